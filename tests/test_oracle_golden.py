@@ -1,0 +1,81 @@
+"""CPU: pin the oracle restatement (oracle/render.py, oracle/knn.py) against golden vectors
+produced by the REAL reference code (tests/golden/make_golden.py)."""
+import pytest
+import torch
+
+from oracle import render as orc
+from oracle.knn import exact_knn, squared_dist_f32
+from helpers import GOLDEN_CASES, Golden, rel_l2
+
+
+def _run(g, dtype=torch.float32):
+    geo = g.t('geo_feats').clone().requires_grad_(True)
+    col = g.t('col_feats').clone().requires_grad_(True)
+    o = g.t('rays_o').clone().requires_grad_(g.is_tracker)
+    d = g.t('rays_d').clone().requires_grad_(g.is_tracker)
+    W = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in g.weights.items()}
+    ef = g.t('exposure_feat').clone().requires_grad_(True) if g.has('exposure_feat') else None
+    dyn = g.t('dynamic_r') if g.has('dynamic_r') else None
+    depth, var, rgb, valid, aux = orc.render_rays(
+        W, g.ocfg, o, d, g.t('gt_depth'), geo, col, g.t('cloud'), g.stage,
+        is_tracker=g.is_tracker, dynamic_r=dyn, exposure_feat=ef, dtype=dtype)
+    loss = (g.t('up_depth').to(dtype) * depth).sum() + (g.t('up_rgb').to(dtype) * rgb).sum()
+    loss.backward()
+    return dict(depth=depth, var=var, rgb=rgb, valid=valid, geo=geo, col=col, o=o, d=d, W=W, ef=ef)
+
+
+@pytest.mark.parametrize('name', GOLDEN_CASES)
+def test_forward_matches_reference(name):
+    g = Golden(name)
+    r = _run(g)
+    assert torch.equal(r['valid'], g.t('valid'))
+    torch.testing.assert_close(r['depth'].detach(), g.t('depth'), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(r['rgb'].detach(), g.t('rgb'), rtol=1e-4, atol=2e-6)
+    torch.testing.assert_close(r['var'].detach(), g.t('var'), rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize('name', GOLDEN_CASES)
+def test_gradients_match_reference(name):
+    g = Golden(name)
+    r = _run(g)
+    # two fp32 formulations of the same math agree to ~1e-4
+    assert rel_l2(r['geo'].grad, g.t('g_geo_feats')) < 2e-4
+    if g.stage == 'color':
+        assert rel_l2(r['col'].grad, g.t('g_col_feats')) < 3e-4
+    if g.is_tracker:
+        assert rel_l2(r['o'].grad, g.t('g_rays_o')) < 1e-3
+        assert rel_l2(r['d'].grad, g.t('g_rays_d')) < 1e-3
+    if g.has('g_exposure_feat'):
+        assert rel_l2(r['ef'].grad, g.t('g_exposure_feat')) < 1e-4
+    for k, gref in g.param_grads.items():
+        got = r['W'][k].grad
+        if got is None:
+            assert gref.abs().max() == 0, k
+            continue
+        assert rel_l2(got, gref) < 5e-4, k
+
+
+def test_fp64_truth_close_to_fp32():
+    g = Golden('replica_color_mapper')
+    r32, r64 = _run(g, torch.float32), _run(g, torch.float64)
+    assert rel_l2(r32['depth'], r64['depth']) < 1e-6
+    assert rel_l2(r32['rgb'], r64['rgb']) < 1e-4
+    assert rel_l2(r32['geo'].grad, r64['geo'].grad) < 5e-4
+
+
+def test_exact_knn_properties():
+    gen = torch.Generator().manual_seed(0)
+    cloud = torch.rand(500, 3, generator=gen)
+    cloud[10] = cloud[3]                      # duplicate point -> tie broken by lower id
+    q = torch.rand(64, 3, generator=gen)
+    q[0] = cloud[3]
+    D, I = exact_knn(q, cloud, 8)
+    full = squared_dist_f32(q, cloud)
+    assert (D[:, 1:] >= D[:, :-1]).all()
+    assert torch.equal(D, torch.gather(full, 1, I))
+    srt = torch.sort(full, dim=1, stable=True)
+    assert torch.equal(srt.values[:, :8], D)
+    assert torch.equal(srt.indices[:, :8], I)
+    assert I[0, 0] == 3 and I[0, 1] == 10
+    D2, I2 = exact_knn(q, cloud[:5], 8)       # N < K -> padded
+    assert (I2[:, 5:] == -1).all() and (D2[:, 5:] > 1e38).all()
