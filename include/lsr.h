@@ -1,0 +1,190 @@
+/*
+ * lsr.h -- C ABI of the B200-native Loopy-SLAM neural-point renderer ("lsr").
+ *
+ * The reference (eriksandstroem/Loopy-SLAM @ 95eb3bd) has no FFI for this path: its render hot
+ * path is pure PyTorch + faiss-gpu.  This header is the boundary a maintainer would bind with
+ * ctypes to replace, per entry point:
+ *
+ *   lsr_grid_build / lsr_knn_query   NeuralPointCloud index lifecycle + find_neighbors_faiss
+ *                                    src/neural_point.py:67-72,1382-1392,1623-1627 / :1659-1708
+ *   lsr_sample_rays(_bwd)            get_samples -> get_sample_uv -> select_uv -> get_rays_from_uv
+ *                                    src/common.py:237-259,160-172,123-138,104-120
+ *   lsr_pose_fwd / lsr_pose_bwd      get_camera_from_tensor / quad2rotation  src/common.py:301-343
+ *   lsr_render_fwd                   Renderer.render_batch_ray + eval_points + NICER.forward +
+ *                                    raw2outputs_nerf_color
+ *                                    src/utils/Renderer.py:24-201, src/conv_onet/models/decoder.py:573-626,
+ *                                    src/common.py:382-422
+ *   lsr_render_bwd                   the autograd backward of the above (loss.backward(),
+ *                                    src/Mapper.py:722, src/Tracker.py:193)
+ *
+ * Conventions: all pointers are DEVICE pointers unless stated; fp32 row-major contiguous;
+ * every call is asynchronous on `stream`; return value 0 = LSR_OK, otherwise an error code for
+ * lsr_strerror().  The library allocates nothing: workspaces are caller-supplied and sized by
+ * the *_bytes queries.  Thread-safe per workspace; not across workspaces sharing one stream.
+ * No CPU fallback exists: without a CUDA device every compute entry returns LSR_ERR_CUDA.
+ */
+#ifndef LSR_H_
+#define LSR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* lsr_stream_t;   /* == cudaStream_t */
+
+enum {
+  LSR_OK = 0,
+  LSR_ERR_ARG = 1,        /* bad argument (null pointer, unsupported dimension, misaligned offset) */
+  LSR_ERR_WORKSPACE = 2,  /* workspace too small */
+  LSR_ERR_CUDA = 3,       /* CUDA runtime error (launch failure, no device) */
+  LSR_ERR_UNSUPPORTED = 4 /* configuration outside the supported envelope */
+};
+
+/* stage (decoder.py:592-626) */
+enum { LSR_STAGE_GEOMETRY = 0, LSR_STAGE_COLOR = 1 };
+
+/* LsrParams.flags */
+enum {
+  LSR_FLAG_REL_POS = 1,          /* model.encode_rel_pos_in_col   (decoder.py:477-485)          */
+  LSR_FLAG_DYNAMIC_R = 2,        /* use_dynamic_radius: per-ray float64 radii (Appendix D)      */
+  LSR_FLAG_SKIP_ZERO_DEPTH = 4   /* rendering.skip_zero_depth_pixel (Renderer.py:199-200)       */
+};
+
+/* LsrParams.rgb_mode: what happens to the colour head output (decoder.py:534-546) */
+enum {
+  LSR_RGB_SIGMOID = 0,           /* rgb = sigmoid(out)                                           */
+  LSR_RGB_RAW = 1,               /* encode_exposure, exposure_feat None: pre-sigmoid (:541-542)  */
+  LSR_RGB_AFFINE_SIGMOID = 2     /* encode_exposure, tracker: sigmoid(out @ A + t) (:535-540)    */
+};
+
+/* grad_flags of lsr_render_bwd: which gradient sinks are wanted (needs_input_grad pruning) */
+enum {
+  LSR_GRAD_GEO_FEATS = 1,   /* d_geo_feats  (N, C)                                               */
+  LSR_GRAD_COL_FEATS = 2,   /* d_col_feats  (N, C)                                               */
+  LSR_GRAD_GEO_W = 4,       /* geometry decoder weights (off when mapping.fix_geo_decoder)       */
+  LSR_GRAD_GEO_B = 8,       /* geo_decoder.embedder._B (trains even with fix_geo_decoder,        */
+                            /*   src/Mapper.py:536-540)                                          */
+  LSR_GRAD_COL_W = 16,      /* colour decoder weights incl. embedder_rel_pos._B                  */
+  LSR_GRAD_RAYS = 32,       /* d_rays_o, d_rays_d (tracker / BA: pose gradient)                  */
+  LSR_GRAD_AFFINE = 64      /* d_exposure_affine (12)                                            */
+};
+
+typedef struct LsrParams {
+  int32_t n_surface;        /* S  rendering.N_surface (1..8; 5 in every shipped config)          */
+  int32_t nn_num;           /* K  pointcloud.nn_num   (must be 8)                                */
+  int32_t min_nn_num;       /*    pointcloud.min_nn_num                                          */
+  int32_t c_dim;            /* C  model.c_dim         (must be 32)                               */
+  float near_end_surface;   /*    rendering.near_end_surface                                     */
+  float far_end_surface;    /*    rendering.far_end_surface                                      */
+  float near_end;           /*    rendering.near_end  (zero-depth rays)                          */
+  float sigmoid_coef;       /*    renderer.sigmoid_coefficient                                   */
+  double radius_query;      /*    pointcloud.radius_query (fixed radius, squared in double)      */
+  int32_t flags;            /*    LSR_FLAG_*                                                     */
+  int32_t rgb_mode;         /*    LSR_RGB_*                                                      */
+} LsrParams;
+
+/*
+ * Decoder weights: ONE flat fp32 device blob plus element offsets of every tensor inside it
+ * (nn.Linear weights are (out,in) row-major exactly as in NICER.state_dict()).  Every offset
+ * must be a multiple of 4 elements (16 B) -- the host mirror lays the blob out that way and makes
+ * the nn.Parameters views into it.  Gradients are returned in a blob of identical layout.
+ * Appendix B of SURVEY.md lists the reference tensors these correspond to.
+ */
+typedef struct LsrWeights {
+  const float* blob;
+  int64_t n_elems;
+  /* geo_decoder (decoder.py:106-288), hidden 32, embedding 93 */
+  int32_t g_fc_w[5], g_fc_b[5];      /* fc_c.i            (32,32) / (32)                          */
+  int32_t g_B;                       /* embedder._B       (3,93)                                  */
+  int32_t g_lin_w[5], g_lin_b[5];    /* pts_linears.i     (32,93)(32,32)(32,32)(32,125)(32,32)    */
+  int32_t g_out_w, g_out_b;          /* output_linear     (1,32) / (1)                            */
+  /* color_decoder (decoder.py:345-546), hidden 128, embedding 2*20 */
+  int32_t c_fc_w[5], c_fc_b[5];      /* fc_c.i            (128,32) / (128)                        */
+  int32_t c_B;                       /* embedder._B       (3,20)  non-persistent, not trained     */
+  int32_t c_Brel;                    /* embedder_rel_pos._B (3,10)                                */
+  int32_t c_nb1_w, c_nb1_b;          /* mlp_col_neighbor.linear1 (128,52) / (128)                 */
+  int32_t c_nb2_w, c_nb2_b;          /* mlp_col_neighbor.linear2 (32,128) / (32)                  */
+  int32_t c_lin_w[5], c_lin_b[5];    /* pts_linears.i     (128,40)(128,128)x2(128,168)(128,128)   */
+  int32_t c_out_w, c_out_b;          /* output_linear     (3,128) / (3)                           */
+} LsrWeights;
+
+int lsr_version(void);
+const char* lsr_strerror(int code);
+/* number of SMs of the current device (grid sizing is done inside; exposed for benches) */
+int lsr_device_sm_count(int* out);
+
+/* ---------------------------------------------------------------- neighbour index (hash grid)
+ * Uniform grid over the cloud's bounding box, cell edge >= `cell` (doubled until the grid has
+ * <= max_cells cells), points counting-sorted by cell (x fastest).  Rebuilt per cloud change
+ * (insertion, PGO move); cheap enough for <= ~1e6 points. */
+int lsr_grid_workspace_bytes(int64_t n_points, int64_t max_cells, size_t* out_bytes);
+int lsr_grid_build(const float* cloud_pos /* N x 3 */, int64_t n_points, float cell, int64_t max_cells,
+                   void* grid_ws, size_t grid_ws_bytes, lsr_stream_t stream);
+
+/* == find_neighbors_faiss: EXACT <=K nearest cloud points with D <= r^2, ascending by (D, id);
+ * D = (dx*dx + dy*dy) + dz*dz in fp32 without FMA; missing entries: I = -1, D = FLT_MAX;
+ * nnum = #{D < r^2} (strict).  r_dyn (P float64, nullable) overrides r_fixed per query. */
+int lsr_knn_query(const void* grid_ws, const float* q /* P x 3 */, const double* r_dyn, double r_fixed,
+                  int64_t n_query, float* D /* P x 8 */, int64_t* I /* P x 8 */, int32_t* nnum /* P */,
+                  lsr_stream_t stream);
+
+/* ---------------------------------------------------------------- pixel -> ray sampling
+ * pix: n int64 indices into the (H1-H0) x (W1-W0) window, row-major (what torch.randint gives
+ * select_uv).  c2w: 3x4 row-major with row stride c2w_ld floats (4 for a (3,4)/(4,4) tensor).
+ * Outputs: rays_o/rays_d (n,3), depth (n), color (n,3), i = column (n) and j = row (n) as int64. */
+int lsr_sample_rays(const float* depth_img, const float* color_img, int32_t H, int32_t W, float fx,
+                    float fy, float cx, float cy, const float* c2w, int32_t c2w_ld, const int64_t* pix,
+                    int64_t n, int32_t H0, int32_t H1, int32_t W0, int32_t W1, float* rays_o,
+                    float* rays_d, float* depth, float* color, int64_t* i_out, int64_t* j_out,
+                    lsr_stream_t stream);
+/* d_c2w (3x4 row-major, 12 floats, overwritten) from d_rays_o/d_rays_d and the pixel coords */
+int lsr_sample_rays_bwd(const float* d_rays_o, const float* d_rays_d, const int64_t* i_pix,
+                        const int64_t* j_pix, int64_t n, float fx, float fy, float cx, float cy,
+                        float* d_c2w, lsr_stream_t stream);
+/* camera tensor [qw qx qy qz tx ty tz] -> c2w 3x4 (unnormalised quaternion, two_s = 2/|q|^2) */
+int lsr_pose_fwd(const float* cam7, float* c2w12, lsr_stream_t stream);
+int lsr_pose_bwd(const float* cam7, const float* d_c2w12, float* d_cam7, lsr_stream_t stream);
+
+/* ---------------------------------------------------------------- fused render
+ * Workspace sizes: `saved` holds the activations the backward needs (0 rows -> forward only),
+ * `scratch` the re-laid-out weights (+ a tile counter). */
+int lsr_render_workspace_bytes(const LsrParams* prm, int64_t n_rays, int stage, size_t* saved_bytes,
+                               size_t* scratch_bytes);
+
+/* far[g] = min(5*mean(d), 1.2*max(d)) over rays [g*group, (g+1)*group)  (Renderer.py:104-121) */
+int lsr_far_bound(const float* gt_depth, int64_t n_rays, int64_t group, float* far_out, lsr_stream_t stream);
+
+/* One fused launch: z-sampling, grid k-NN, IDW gather, geometry MLP, (rel-pos neighbour MLP,)
+ * colour MLP, alpha compositing.  r_query: per-ray float64 radii when LSR_FLAG_DYNAMIC_R.
+ * far_zero: far bound of the z-range used for rays with gt_depth <= 0, one value per group of
+ *   far_group consecutive rays (Renderer.py:102-121 batch statistic; see lsr_far_bound); nullable.
+ * exposure_affine: 12 floats [A row-major 3x3 | t] for LSR_RGB_AFFINE_SIGMOID.
+ * saved == NULL -> inference (render_img); valid: 1 byte per ray. */
+int lsr_render_fwd(const LsrParams* prm, const void* grid_ws, const float* cloud_pos, int64_t n_points,
+                   const float* rays_o, const float* rays_d, const float* gt_depth,
+                   const double* r_query, const float* far_zero, int64_t far_group, int64_t n_rays,
+                   const float* geo_feats, const float* col_feats, const LsrWeights* w,
+                   const float* exposure_affine, int stage, float* depth, float* var, float* rgb,
+                   uint8_t* valid, void* saved, void* scratch, lsr_stream_t stream);
+
+/* Backward of lsr_render_fwd for upstream gradients g_depth (R), g_var (R, nullable), g_rgb (R,3).
+ * is_tracker: neighbour weights depend on the sample position (decoder.py:191-198).
+ * Gradient buffers must be ZEROED by the caller; they are accumulated into with atomics:
+ * d_geo_feats/d_col_feats (N,C), d_weights (layout of w->blob), d_exposure_affine (12),
+ * d_rays_o/d_rays_d (R,3, plain stores).  Unwanted sinks may be NULL (and unset in grad_flags). */
+int lsr_render_bwd(const LsrParams* prm, const void* grid_ws, const float* cloud_pos, int64_t n_points,
+                   const float* rays_o, const float* rays_d, const float* gt_depth,
+                   const double* r_query, int64_t n_rays, const float* geo_feats,
+                   const float* col_feats, const LsrWeights* w, const float* exposure_affine,
+                   int stage, int is_tracker, const void* saved, void* scratch, const float* g_depth,
+                   const float* g_var, const float* g_rgb, int grad_flags, float* d_geo_feats,
+                   float* d_col_feats, float* d_weights, float* d_exposure_affine, float* d_rays_o,
+                   float* d_rays_d, lsr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSR_H_ */

@@ -1,0 +1,869 @@
+// Fused backward render kernel: compositing backward -> colour MLP backward (+ rel-pos neighbour
+// MLP) -> geometry MLP backward -> IDW / Fourier backward -> feature scatter-add, decoder weight
+// gradients (per-tile partial GEMMs + red.global.add.v4), ray gradients.  Mirrors the autograd
+// graph of Renderer.render_batch_ray (/root/reference/src/utils/Renderer.py:71-201) that the
+// reference differentiates with loss.backward() (src/Mapper.py:722, src/Tracker.py:193).
+// Math: SURVEY.md Appendix A ("Backward of step 10") + the chain rule through Appendix A steps 2-7.
+#include "lsr_render.cuh"
+
+namespace lsr {
+
+struct BwdArgs {
+  LsrParams prm;
+  const float* cloud;
+  const float *rays_o, *rays_d, *gt_depth;
+  int R;
+  const float *geo_feats, *col_feats;
+  LsrWeights w;
+  const float* packed;
+  const float* affine;
+  int stage, is_tracker;
+  const float* saved;
+  const float *g_depth, *g_var, *g_rgb;
+  int gflags;
+  float *d_geo, *d_col, *d_w, *d_affine, *d_ro, *d_rd;
+  int rays_per_tile, ntiles;
+};
+
+constexpr int E2_FLOATS = TILE_M * GLD;   // 12800: {sE, sDE} | {sQ, sDQ} | sEg
+constexpr int DQLD = 24;
+constexpr int RED_FLOATS = 320;           // 3*96 dB_geo + 30 dB_rel
+constexpr int BWD_SMEM_FLOATS = TILE_M * DLD + NSTAGE * KC * 128 + 2 * TILE_M * CLD + E2_FLOATS + 3 * TILE_M * KNN +
+                                2 * TILE_M * 4 + TILE_M * KNN + 3 * TILE_M + TILE_M * 4 + RED_FLOATS;
+
+__device__ __forceinline__ float half_warp_sum(float v) {   // sum over the 16 lanes sharing ty
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+
+// dF[idx_k[m]] += w_k * dC[m]  and (tracker) dw_hat_k += dC[m] . F[idx_k[m]]
+__device__ __forceinline__ void scatter_idw(const float* sDC, const int* sIdx, const float* sW, const int* sHas,
+                                            float* sDWh, const float* __restrict__ feats, float* __restrict__ d_feats,
+                                            bool want_feat, bool want_w) {
+  for (int it = threadIdx.x; it < TILE_M * 64; it += NT) {
+    const int q = it & 7, k = (it >> 3) & 7, m = it >> 6;
+    const int idx = sIdx[m * KNN + k];
+    const bool ok = idx >= 0 && sHas[m];
+    const float4 dc = *reinterpret_cast<const float4*>(sDC + m * CLD + q * 4);
+    if (want_feat && ok) {
+      const float wk = sW[m * KNN + k];
+      red_add_v4(d_feats + (size_t)idx * CDIM + q * 4, wk * dc.x, wk * dc.y, wk * dc.z, wk * dc.w);
+    }
+    if (want_w) {
+      float part = 0.f;
+      if (ok) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(feats + (size_t)idx * CDIM) + q);
+        part = dc.x * f.x + dc.y * f.y + dc.z * f.z + dc.w * f.w;
+      }
+      part += __shfl_xor_sync(0xffffffffu, part, 4);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      if (q == 0 && ok) sDWh[m * KNN + k] += part;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NT, 1) render_bwd_kernel(const __grid_constant__ BwdArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* sD = smem;                                   // [128][DLD] (colour) / [128][CLD] view (geometry)
+  float* sB = sD + TILE_M * DLD;
+  float* sC = sB + NSTAGE * KC * 128;
+  float* sDC = sC + TILE_M * CLD;
+  float* sE2 = sDC + TILE_M * CLD;
+  int* sIdx = reinterpret_cast<int*>(sE2 + E2_FLOATS);
+  float* sW = reinterpret_cast<float*>(sIdx + TILE_M * KNN);
+  float* sD8 = sW + TILE_M * KNN;
+  float* sP = sD8 + TILE_M * KNN;
+  float* sDP = sP + TILE_M * 4;
+  float* sDWh = sDP + TILE_M * 4;
+  int* sHas = reinterpret_cast<int*>(sDWh + TILE_M * KNN);
+  float* sWsum = reinterpret_cast<float*>(sHas + TILE_M);
+  float* sDOcc = sWsum + TILE_M;
+  float* sDOut = sDOcc + TILE_M;                      // [m][4]
+  float* sRed = sDOut + TILE_M * 4;
+  float* sE = sE2;                                    // [128][ELD]
+  float* sDE = sE2 + TILE_M * ELD;
+  float* sQ = sE2;                                    // [128][QLD]
+  float* sDQ = sE2 + TILE_M * QLD;                    // [128][DQLD]
+  float* sEg = sE2;                                   // [128][GLD]
+
+  const int tid = threadIdx.x;
+  const int S = a.prm.n_surface;
+  const float* __restrict__ blob = a.w.blob;
+  const float* __restrict__ packed = a.packed;
+  const float* __restrict__ sv = a.saved;
+  const bool color = a.stage == LSR_STAGE_COLOR;
+  const bool relpos = (a.prm.flags & LSR_FLAG_REL_POS) != 0;
+  const bool g_gf = (a.gflags & LSR_GRAD_GEO_FEATS) && a.d_geo;
+  const bool g_cf = (a.gflags & LSR_GRAD_COL_FEATS) && a.d_col && color;
+  const bool g_gw = (a.gflags & LSR_GRAD_GEO_W) && a.d_w;
+  const bool g_gb = ((a.gflags & (LSR_GRAD_GEO_B | LSR_GRAD_GEO_W)) != 0) && a.d_w;
+  const bool g_cw = (a.gflags & LSR_GRAD_COL_W) && a.d_w && color;
+  const bool g_ry = (a.gflags & LSR_GRAD_RAYS) && a.d_ro && a.d_rd;
+  const bool g_af = (a.gflags & LSR_GRAD_AFFINE) && a.d_affine && a.prm.rgb_mode == LSR_RGB_AFFINE_SIGMOID;
+  const bool trk = a.is_tracker && g_ry;              // neighbour weights depend on p
+  const SavedLayout SL = saved_layout(a.R, S, a.stage, a.prm.flags);
+  const size_t Pp = align_up(SL.P, TILE_M) + TILE_M;
+  const WideMap wm;
+  const NarrowMap nm;
+  float* __restrict__ dW = a.d_w;
+
+  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    const int r0 = tile * a.rays_per_tile;
+    const int nr = min(a.rays_per_tile, a.R - r0);
+    const int nrows = nr * S;
+    const size_t p0 = (size_t)r0 * S;
+
+    // ------------------------------------------------------------ 0: per-row state
+    if (tid < TILE_M) {
+      const int m = tid;
+      const bool rv = m < nrows;
+      float4 mi = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rv) mi = reinterpret_cast<const float4*>(sv + SL.misc)[p0 + m];
+#pragma unroll
+      for (int k = 0; k < KNN; ++k) {
+        sIdx[m * KNN + k] = rv ? reinterpret_cast<const int*>(sv + SL.idx)[(p0 + m) * KNN + k] : -1;
+        sW[m * KNN + k] = rv ? sv[SL.w + (p0 + m) * KNN + k] : 0.f;
+        sD8[m * KNN + k] = rv ? sv[SL.D + (p0 + m) * KNN + k] : FLT_MAX;
+        sDWh[m * KNN + k] = 0.f;
+      }
+      float px = 0.f, py = 0.f, pz = 0.f;
+      if (rv) {
+        const int ray = r0 + m / S;
+        px = __fadd_rn(a.rays_o[3 * ray + 0], __fmul_rn(a.rays_d[3 * ray + 0], mi.x));
+        py = __fadd_rn(a.rays_o[3 * ray + 1], __fmul_rn(a.rays_d[3 * ray + 1], mi.x));
+        pz = __fadd_rn(a.rays_o[3 * ray + 2], __fmul_rn(a.rays_d[3 * ray + 2], mi.x));
+      }
+      sP[m * 4 + 0] = px; sP[m * 4 + 1] = py; sP[m * 4 + 2] = pz; sP[m * 4 + 3] = mi.x;
+      sHas[m] = (rv && mi.y > 0.5f) ? 1 : 0;
+      sWsum[m] = mi.z;
+      sDP[m * 4 + 0] = 0.f; sDP[m * 4 + 1] = 0.f; sDP[m * 4 + 2] = 0.f; sDP[m * 4 + 3] = 0.f;
+      sDOcc[m] = 0.f;
+      sDOut[m * 4 + 0] = 0.f; sDOut[m * 4 + 1] = 0.f; sDOut[m * 4 + 2] = 0.f; sDOut[m * 4 + 3] = 0.f;
+    }
+    for (int i = tid; i < RED_FLOATS; i += NT) sRed[i] = 0.f;
+    __syncthreads();
+
+    // ------------------------------------------------------------ 1: compositing backward
+    if (tid < nr) {
+      const int ray = r0 + tid;
+      const float g = a.gt_depth[ray];
+      const float coef = a.prm.sigmoid_coef;
+      const bool nz = g > 0.f;
+      const float gD = nz ? a.g_depth[ray] : 0.f;
+      const float gV = a.g_var ? a.g_var[ray] : 0.f;
+      float gC[3] = {0.f, 0.f, 0.f};
+      if (color && a.g_rgb && (nz || !(a.prm.flags & LSR_FLAG_SKIP_ZERO_DEPTH))) {
+        gC[0] = a.g_rgb[3 * ray + 0]; gC[1] = a.g_rgb[3 * ray + 1]; gC[2] = a.g_rgb[3 * ray + 2];
+      }
+      float al[8], Tv[8], wv[8], zv[8], rg[8][3];
+      float T = 1.f, sw = 0.f, swz = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        if (s < S) {
+          const int m = tid * S + s;
+          const float occ = sHas[m] ? sv[SL.occ + p0 + m] : -100.f;
+          const float alpha = sigmoidf_acc(coef * occ);
+          al[s] = alpha; Tv[s] = T;
+          const float w = alpha * T;
+          wv[s] = w;
+          T = T * ((1.f - alpha) + 1e-10f);
+          zv[s] = sP[m * 4 + 3];
+          float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (color) rs = reinterpret_cast<const float4*>(sv + SL.rgbs)[p0 + m];
+          rg[s][0] = rs.x; rg[s][1] = rs.y; rg[s][2] = rs.z;
+          sw += w; swz += w * zv[s];
+          c0 += w * rs.x; c1 += w * rs.y; c2 += w * rs.z;
+        }
+      }
+      const float wsum = sw + 1e-10f;
+      const float depth = swz / wsum;
+      const float m0 = c0 / wsum, m1 = c1 / wsum, m2 = c2 / wsum;
+      float dvar_ddepth = 0.f;
+#pragma unroll
+      for (int s = 0; s < 8; ++s)
+        if (s < S) dvar_ddepth += -2.f * wv[s] * (zv[s] - depth);
+      const float gDe = gD + gV * dvar_ddepth;
+      float dwv[8];
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        if (s < S) {
+          const float dz = zv[s] - depth;
+          dwv[s] = (gDe * dz + gC[0] * (rg[s][0] - m0) + gC[1] * (rg[s][1] - m1) + gC[2] * (rg[s][2] - m2)) / wsum +
+                   gV * dz * dz;
+        }
+      }
+      float suffix = 0.f;
+#pragma unroll
+      for (int s = 7; s >= 0; --s) {
+        if (s < S) {
+          const int m = tid * S + s;
+          const float dalpha = Tv[s] * dwv[s] - suffix / ((1.f - al[s]) + 1e-10f);
+          suffix += wv[s] * dwv[s];
+          sDOcc[m] = coef * al[s] * (1.f - al[s]) * dalpha;
+          const float f = wv[s] / wsum;
+          sDOut[m * 4 + 0] = gC[0] * f; sDOut[m * 4 + 1] = gC[1] * f; sDOut[m * 4 + 2] = gC[2] * f;
+        }
+      }
+    }
+    __syncthreads();
+
+    if (color) {
+      // ---------------------------------------------------------- colour head activation backward
+      if (tid < TILE_M) {
+        const int m = tid;
+        float d0 = sDOut[m * 4 + 0], d1 = sDOut[m * 4 + 1], d2 = sDOut[m * 4 + 2];
+        float da[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) da[k] = 0.f;
+        if (m < nrows && a.prm.rgb_mode != LSR_RGB_RAW) {
+          const float4 rs = reinterpret_cast<const float4*>(sv + SL.rgbs)[p0 + m];
+          d0 *= rs.x * (1.f - rs.x); d1 *= rs.y * (1.f - rs.y); d2 *= rs.z * (1.f - rs.z);
+          if (a.prm.rgb_mode == LSR_RGB_AFFINE_SIGMOID) {
+            const float4 o = reinterpret_cast<const float4*>(sv + SL.outraw)[p0 + m];
+            const float* Af = a.affine;
+            const float y0 = d0, y1 = d1, y2 = d2;
+            da[0] = o.x * y0; da[1] = o.x * y1; da[2] = o.x * y2;
+            da[3] = o.y * y0; da[4] = o.y * y1; da[5] = o.y * y2;
+            da[6] = o.z * y0; da[7] = o.z * y1; da[8] = o.z * y2;
+            da[9] = y0; da[10] = y1; da[11] = y2;
+            d0 = Af[0] * y0 + Af[1] * y1 + Af[2] * y2;
+            d1 = Af[3] * y0 + Af[4] * y1 + Af[5] * y2;
+            d2 = Af[6] * y0 + Af[7] * y1 + Af[8] * y2;
+          }
+        }
+        sDOut[m * 4 + 0] = d0; sDOut[m * 4 + 1] = d1; sDOut[m * 4 + 2] = d2;
+        if (g_af) {
+#pragma unroll
+          for (int k = 0; k < 12; ++k) {
+            float v = da[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((tid & 31) == 0) atomicAdd(a.d_affine + k, v);
+          }
+        }
+      }
+      // sC <- cc, sE <- e', sDE <- 0
+      for (int it = tid; it < TILE_M * 8; it += NT) {
+        const int m = it >> 3, q = it & 7;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < nrows) v = reinterpret_cast<const float4*>(sv + SL.cc)[(p0 + m) * 8 + q];
+        *reinterpret_cast<float4*>(sC + m * CLD + q * 4) = v;
+      }
+      for (int it = tid; it < TILE_M * EC; it += NT) {
+        const int m = it / EC, j = it - m * EC;
+        const float t0 = TWO_PI_F * sP[m * 4 + 0], t1 = TWO_PI_F * sP[m * 4 + 1], t2 = TWO_PI_F * sP[m * 4 + 2];
+        const float arg = fmaf(t2, blob[a.w.c_B + 2 * EC + j], fmaf(t1, blob[a.w.c_B + EC + j], t0 * blob[a.w.c_B + j]));
+        float sn, cs;
+        sincosf(arg, &sn, &cs);
+        sE[m * ELD + j] = sn;
+        sE[m * ELD + EC + j] = cs;
+      }
+      for (int it = tid; it < TILE_M * ELD; it += NT) sDE[it] = 0.f;
+      __syncthreads();
+
+      if (g_cw) {   // output_linear gradients
+        if (tid < HC) {
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+          for (int m = 0; m < nrows; ++m) {
+            const float h = sv[SL.ch + ((size_t)4 * Pp + p0 + m) * HC + tid];
+            s0 = fmaf(sDOut[m * 4 + 0], h, s0); s1 = fmaf(sDOut[m * 4 + 1], h, s1); s2 = fmaf(sDOut[m * 4 + 2], h, s2);
+          }
+          atomicAdd(dW + a.w.c_out_w + tid, s0);
+          atomicAdd(dW + a.w.c_out_w + HC + tid, s1);
+          atomicAdd(dW + a.w.c_out_w + 2 * HC + tid, s2);
+        } else if (tid < HC + 3) {
+          const int ch = tid - HC;
+          float s = 0.f;
+          for (int m = 0; m < nrows; ++m) s += sDOut[m * 4 + ch];
+          atomicAdd(dW + a.w.c_out_b + ch, s);
+        }
+      }
+      float dH[8][8];
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const int col = wm.col(g);
+        const float4 w0 = *reinterpret_cast<const float4*>(blob + a.w.c_out_w + col);
+        const float4 w1 = *reinterpret_cast<const float4*>(blob + a.w.c_out_w + HC + col);
+        const float4 w2 = *reinterpret_cast<const float4*>(blob + a.w.c_out_w + 2 * HC + col);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = wm.row(i);
+          const float d0 = sDOut[r * 4 + 0], d1 = sDOut[r * 4 + 1], d2 = sDOut[r * 4 + 2];
+          dH[i][g * 4 + 0] = d0 * w0.x + d1 * w1.x + d2 * w2.x;
+          dH[i][g * 4 + 1] = d0 * w0.y + d1 * w1.y + d2 * w2.y;
+          dH[i][g * 4 + 2] = d0 * w0.z + d1 * w1.z + d2 * w2.z;
+          dH[i][g * 4 + 3] = d0 * w0.w + d1 * w1.w + d2 * w2.w;
+        }
+      }
+      float dCacc[4][4];
+      zero_acc(dCacc);
+#pragma unroll 1
+      for (int li = 4; li >= 0; --li) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(sD + wm.row(i) * DLD + wm.col(g)) =
+                make_float4(dH[i][g * 4 + 0], dH[i][g * 4 + 1], dH[i][g * 4 + 2], dH[i][g * 4 + 3]);
+        __syncthreads();
+        if (g_cw) {
+          if (tid < HC) {
+            float s = 0.f;
+            for (int m = 0; m < nrows; ++m) s += sD[m * DLD + tid];
+            atomicAdd(dW + a.w.c_fc_b[li] + tid, s);
+          }
+          float au[4][4];
+          zero_acc(au);
+          tile_gemm<4, 8, 1, false, true>(au, sD, DLD, nrows, sC, CLD, CDIM, sB);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            red_add_v4(dW + a.w.c_fc_w[li] + nm.row(i) * CDIM + nm.col(), au[i][0], au[i][1], au[i][2], au[i][3]);
+        }
+        tile_gemm<4, 8, 1, true, false>(dCacc, sD, DLD, HC, blob + a.w.c_fc_w[li], CDIM, CDIM, sB);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const int col = wm.col(g);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = wm.row(i);
+            float4 dA = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < nrows) {
+              const float4 s4 = *reinterpret_cast<const float4*>(sv + SL.cs + ((size_t)li * Pp + p0 + r) * HC + col);
+              dA = make_float4(dH[i][g * 4 + 0] * softplus100_grad_from_out(s4.x),
+                               dH[i][g * 4 + 1] * softplus100_grad_from_out(s4.y),
+                               dH[i][g * 4 + 2] * softplus100_grad_from_out(s4.z),
+                               dH[i][g * 4 + 3] * softplus100_grad_from_out(s4.w));
+            }
+            *reinterpret_cast<float4*>(sD + r * DLD + col) = dA;
+          }
+        }
+        __syncthreads();
+        if (g_cw) {
+          if (tid < HC) {
+            float s = 0.f;
+            for (int m = 0; m < nrows; ++m) s += sD[m * DLD + tid];
+            atomicAdd(dW + a.w.c_lin_b[li] + tid, s);
+          }
+          if (li == 0 || li == 3) {   // embedding columns of W0 / W3
+            float aw[8][4];
+            zero_acc(aw);
+            tile_gemm<8, 16, 1, false, true>(aw, sD, DLD, nrows, sE, ELD, ECC, sB);
+            const int ldw = li == 0 ? ECC : ECC + HC;
+            if (wm.tx * 4 < ECC) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                red_add_v4(dW + a.w.c_lin_w[li] + wm.row(i) * ldw + wm.tx * 4, aw[i][0], aw[i][1], aw[i][2], aw[i][3]);
+            }
+          }
+          if (li > 0) {
+            float aw[8][8];
+            zero_acc(aw);
+            tile_gemm<8, 16, 2, false, false>(aw, sD, DLD, nrows, sv + SL.ch + ((size_t)(li - 1) * Pp + p0) * HC, HC, HC, sB);
+            const int ldw = li == 3 ? ECC + HC : HC;
+            const int off = li == 3 ? ECC : 0;
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                red_add_v4(dW + a.w.c_lin_w[li] + wm.row(i) * ldw + off + wm.col(g), aw[i][g * 4 + 0], aw[i][g * 4 + 1],
+                           aw[i][g * 4 + 2], aw[i][g * 4 + 3]);
+          }
+        }
+        if (li == 0 || li == 3) {     // d e'
+          float ae[8][4];
+          zero_acc(ae);
+          tile_gemm<8, 16, 1, true, false>(ae, sD, DLD, HC, blob + a.w.c_lin_w[li], li == 3 ? ECC + HC : ECC, ECC, sB);
+          if (wm.tx * 4 < ECC) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float* d = sDE + wm.row(i) * ELD + wm.tx * 4;
+              d[0] += ae[i][0]; d[1] += ae[i][1]; d[2] += ae[i][2]; d[3] += ae[i][3];
+            }
+          }
+        }
+        if (li > 0) {
+          zero_acc(dH);
+          tile_gemm<8, 16, 2, true, false>(dH, sD, DLD, HC, blob + a.w.c_lin_w[li] + (li == 3 ? ECC : 0),
+                                           li == 3 ? ECC + HC : HC, HC, sB);
+        }
+      }
+      __syncthreads();
+      // colour Fourier backward -> dp
+      if (g_ry && tid < TILE_M) {
+        const int m = tid;
+        float q0 = 0.f, q1 = 0.f, q2 = 0.f;
+        for (int j = 0; j < EC; ++j) {
+          const float sn = sE[m * ELD + j], cs = sE[m * ELD + EC + j];
+          const float dar = sDE[m * ELD + j] * cs - sDE[m * ELD + EC + j] * sn;
+          q0 = fmaf(blob[a.w.c_B + j], dar, q0);
+          q1 = fmaf(blob[a.w.c_B + EC + j], dar, q1);
+          q2 = fmaf(blob[a.w.c_B + 2 * EC + j], dar, q2);
+        }
+        sDP[m * 4 + 0] += TWO_PI_F * q0; sDP[m * 4 + 1] += TWO_PI_F * q1; sDP[m * 4 + 2] += TWO_PI_F * q2;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = nm.row(i);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (sHas[r]) v = make_float4(dCacc[i][0], dCacc[i][1], dCacc[i][2], dCacc[i][3]);
+        *reinterpret_cast<float4*>(sDC + r * CLD + nm.col()) = v;
+      }
+      __syncthreads();
+
+      if (relpos) {
+        // ------------------------------------------------------ rel-pos neighbour MLP backward
+        if (g_cw) {
+          float a2[2][8];
+          zero_acc(a2);
+          tile_gemm<2, 16, 2, false, false>(a2, sDC, CLD, nrows, sv + SL.u + p0 * HC, HC, HC, sB);
+#pragma unroll
+          for (int g = 0; g < 2; ++g)
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+              red_add_v4(dW + a.w.c_nb2_w + wm.row(i) * HC + wm.col(g), a2[i][g * 4 + 0], a2[i][g * 4 + 1],
+                         a2[i][g * 4 + 2], a2[i][g * 4 + 3]);
+          if (tid < CDIM) {
+            float s = 0.f;
+            for (int m = 0; m < nrows; ++m) s = fmaf(sDC[m * CLD + tid], sWsum[m], s);
+            atomicAdd(dW + a.w.c_nb2_b + tid, s);
+          }
+        }
+        float dU[8][8];
+        zero_acc(dU);
+        tile_gemm<8, 16, 2, true, false>(dU, sDC, CLD, CDIM, blob + a.w.c_nb2_w, HC, HC, sB);
+        float dV1acc[8][4];
+        zero_acc(dV1acc);
+        float dv1 = 0.f;
+        float dBl[15];
+#pragma unroll
+        for (int k = 0; k < 15; ++k) dBl[k] = 0.f;
+        if (trk && tid < TILE_M) {      // dw_hat_k += dc . v2 (same for every valid k)
+          float rt = 0.f;
+          for (int c = 0; c < CDIM; ++c) rt = fmaf(sDC[tid * CLD + c], blob[a.w.c_nb2_b + c], rt);
+#pragma unroll
+          for (int k = 0; k < KNN; ++k)
+            if (sIdx[tid * KNN + k] >= 0) sDWh[tid * KNN + k] += rt;
+        }
+        for (int m = tid; m < TILE_M; m += NT) {
+          *reinterpret_cast<float4*>(sQ + m * QLD + QD) = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(sQ + m * QLD + QDP) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int k = 0; k < KNN; ++k) {
+          float part[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) part[i] = 0.f;
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const int col = wm.col(g);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = wm.row(i);
+              float4 dA = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (r < nrows) {
+                const float4 sp = *reinterpret_cast<const float4*>(sv + SL.sp + ((p0 + r) * KNN + k) * HC + col);
+                const float wk = sW[r * KNN + k];
+                dA = make_float4(wk * dU[i][g * 4 + 0] * softplus100_grad_from_out(sp.x),
+                                 wk * dU[i][g * 4 + 1] * softplus100_grad_from_out(sp.y),
+                                 wk * dU[i][g * 4 + 2] * softplus100_grad_from_out(sp.z),
+                                 wk * dU[i][g * 4 + 3] * softplus100_grad_from_out(sp.w));
+                part[i] += dU[i][g * 4 + 0] * sp.x + dU[i][g * 4 + 1] * sp.y + dU[i][g * 4 + 2] * sp.z +
+                           dU[i][g * 4 + 3] * sp.w;
+              }
+              *reinterpret_cast<float4*>(sD + r * DLD + col) = dA;
+            }
+          }
+          if (trk) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float v = half_warp_sum(part[i]);
+              const int r = wm.row(i);
+              if (wm.tx == 0 && sIdx[r * KNN + k] >= 0) sDWh[r * KNN + k] += v;
+            }
+          }
+          // rebuild Q_k = [sin(phi) | cos(phi) | F^c[idx_k]]
+          for (int it = tid; it < TILE_M * ER; it += NT) {
+            const int m = it / ER, j = it - m * ER;
+            const int idx = sIdx[m * KNN + k];
+            float sn = 0.f, cs = 0.f;
+            if (idx >= 0) {
+              const float t0 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 0), sP[m * 4 + 0]);
+              const float t1 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 1), sP[m * 4 + 1]);
+              const float t2 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 2), sP[m * 4 + 2]);
+              const float arg = fmaf(t2, blob[a.w.c_Brel + 2 * ER + j],
+                                     fmaf(t1, blob[a.w.c_Brel + ER + j], t0 * blob[a.w.c_Brel + j]));
+              sincosf(arg, &sn, &cs);
+            }
+            sQ[m * QLD + j] = sn;
+            sQ[m * QLD + ER + j] = cs;
+          }
+          for (int it = tid; it < TILE_M * 8; it += NT) {
+            const int m = it >> 3, q = it & 7;
+            const int idx = sIdx[m * KNN + k];
+            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx >= 0) f = __ldg(reinterpret_cast<const float4*>(a.col_feats + (size_t)idx * CDIM) + q);
+            *reinterpret_cast<float4*>(sQ + m * QLD + 2 * ER + q * 4) = f;
+          }
+          __syncthreads();
+          if (g_cw) {
+            tile_gemm<8, 16, 1, false, true>(dV1acc, sD, DLD, nrows, sQ, QLD, QDP, sB);
+            if (tid < HC)
+              for (int m = 0; m < nrows; ++m) dv1 += sD[m * DLD + tid];
+          }
+          float aq[8][4];
+          zero_acc(aq);
+          tile_gemm<8, 16, 1, true, false>(aq, sD, DLD, HC, blob + a.w.c_nb1_w, QD, QD, sB);
+          {
+            const int col = wm.tx * 4;
+            if (col < 2 * ER) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                *reinterpret_cast<float4*>(sDQ + wm.row(i) * DQLD + col) = make_float4(aq[i][0], aq[i][1], aq[i][2], aq[i][3]);
+            } else if (col < QD && g_cf) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int r = wm.row(i);
+                const int idx = sIdx[r * KNN + k];
+                if (idx >= 0 && r < nrows)
+                  red_add_v4(a.d_col + (size_t)idx * CDIM + (col - 2 * ER), aq[i][0], aq[i][1], aq[i][2], aq[i][3]);
+              }
+            }
+          }
+          __syncthreads();
+          if (g_cw || g_ry) {
+            const int m = tid & (TILE_M - 1), half = tid >> 7;
+            const int idx = sIdx[m * KNN + k];
+            if (idx >= 0) {
+              const float t0 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 0), sP[m * 4 + 0]);
+              const float t1 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 1), sP[m * 4 + 1]);
+              const float t2 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 2), sP[m * 4 + 2]);
+              float q0 = 0.f, q1 = 0.f, q2 = 0.f;
+#pragma unroll
+              for (int jj = 0; jj < 5; ++jj) {
+                const int j = half * 5 + jj;
+                const float dphi = sDQ[m * DQLD + j] * sQ[m * QLD + ER + j] - sDQ[m * DQLD + ER + j] * sQ[m * QLD + j];
+                dBl[jj] = fmaf(t0, dphi, dBl[jj]);
+                dBl[5 + jj] = fmaf(t1, dphi, dBl[5 + jj]);
+                dBl[10 + jj] = fmaf(t2, dphi, dBl[10 + jj]);
+                q0 = fmaf(blob[a.w.c_Brel + j], dphi, q0);
+                q1 = fmaf(blob[a.w.c_Brel + ER + j], dphi, q1);
+                q2 = fmaf(blob[a.w.c_Brel + 2 * ER + j], dphi, q2);
+              }
+              if (g_ry) {   // rel = x - p  ->  dp -= d rel
+                atomicAdd(&sDP[m * 4 + 0], -TWO_PI_F * q0);
+                atomicAdd(&sDP[m * 4 + 1], -TWO_PI_F * q1);
+                atomicAdd(&sDP[m * 4 + 2], -TWO_PI_F * q2);
+              }
+            }
+          }
+          __syncthreads();
+        }
+        if (g_cw) {
+          if (wm.tx * 4 < QD) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              red_add_v4(dW + a.w.c_nb1_w + wm.row(i) * QD + wm.tx * 4, dV1acc[i][0], dV1acc[i][1], dV1acc[i][2],
+                         dV1acc[i][3]);
+          }
+          if (tid < HC) atomicAdd(dW + a.w.c_nb1_b + tid, dv1);
+          const int half = tid >> 7;
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int jj = 0; jj < 5; ++jj) atomicAdd(&sRed[3 * EGP + c * ER + half * 5 + jj], dBl[c * 5 + jj]);
+        }
+      } else {
+        scatter_idw(sDC, sIdx, sW, sHas, sDWh, a.col_feats, a.d_col, g_cf, trk);
+      }
+      __syncthreads();
+    }
+
+    // -------------------------------------------------------------- geometry MLP backward
+    {
+      for (int it = tid; it < TILE_M * 8; it += NT) {
+        const int m = it >> 3, q = it & 7;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < nrows) v = reinterpret_cast<const float4*>(sv + SL.cg)[(p0 + m) * 8 + q];
+        *reinterpret_cast<float4*>(sC + m * CLD + q * 4) = v;
+      }
+      if (g_gw) {
+        for (int it = tid; it < TILE_M * EGP; it += NT) {
+          const int m = it / EGP, j = it - m * EGP;
+          float v = 0.f;
+          if (j < EG) {
+            const float t0 = TWO_PI_F * sP[m * 4 + 0], t1 = TWO_PI_F * sP[m * 4 + 1], t2 = TWO_PI_F * sP[m * 4 + 2];
+            v = sinf(fmaf(t2, packed[Packed::gB + 2 * EGP + j], fmaf(t1, packed[Packed::gB + EGP + j], t0 * packed[Packed::gB + j])));
+          }
+          sEg[m * GLD + j] = v;
+        }
+      }
+      __syncthreads();
+      if (g_gw) {
+        if (tid < HG) {
+          float s = 0.f;
+          for (int m = 0; m < nrows; ++m) s = fmaf(sDOcc[m], sv[SL.gh + ((size_t)4 * Pp + p0 + m) * HG + tid], s);
+          atomicAdd(dW + a.w.g_out_w + tid, s);
+        } else if (tid == HG) {
+          float s = 0.f;
+          for (int m = 0; m < nrows; ++m) s += sDOcc[m];
+          atomicAdd(dW + a.w.g_out_b, s);
+        }
+      }
+      float dHg[4][4];
+      {
+        const float4 wo = *reinterpret_cast<const float4*>(blob + a.w.g_out_w + nm.col());
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float d = sDOcc[nm.row(i)];
+          dHg[i][0] = d * wo.x; dHg[i][1] = d * wo.y; dHg[i][2] = d * wo.z; dHg[i][3] = d * wo.w;
+        }
+      }
+      float dCacc[4][4], dEacc[8][8];
+      zero_acc(dCacc);
+      zero_acc(dEacc);
+#pragma unroll 1
+      for (int li = 4; li >= 0; --li) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<float4*>(sD + nm.row(i) * CLD + nm.col()) = make_float4(dHg[i][0], dHg[i][1], dHg[i][2], dHg[i][3]);
+        __syncthreads();
+        if (g_gw) {
+          if (tid < HG) {
+            float s = 0.f;
+            for (int m = 0; m < nrows; ++m) s += sD[m * CLD + tid];
+            atomicAdd(dW + a.w.g_fc_b[li] + tid, s);
+          }
+          float au[1][4];
+          zero_acc(au);
+          tile_gemm<1, 8, 1, false, true>(au, sD, CLD, nrows, sC, CLD, CDIM, sB);
+          red_add_v4(dW + a.w.g_fc_w[li] + nm.ty * CDIM + nm.col(), au[0][0], au[0][1], au[0][2], au[0][3]);
+        }
+        tile_gemm<4, 8, 1, true, false>(dCacc, sD, CLD, HG, blob + a.w.g_fc_w[li], CDIM, CDIM, sB);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = nm.row(i);
+          float4 dA = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r < nrows) {
+            const float4 s4 = *reinterpret_cast<const float4*>(sv + SL.gs + ((size_t)li * Pp + p0 + r) * HG + nm.col());
+            dA = make_float4(s4.x > 0.f ? dHg[i][0] : 0.f, s4.y > 0.f ? dHg[i][1] : 0.f, s4.z > 0.f ? dHg[i][2] : 0.f,
+                             s4.w > 0.f ? dHg[i][3] : 0.f);
+          }
+          *reinterpret_cast<float4*>(sD + r * CLD + nm.col()) = dA;
+        }
+        __syncthreads();
+        if (g_gw) {
+          if (tid < HG) {
+            float s = 0.f;
+            for (int m = 0; m < nrows; ++m) s += sD[m * CLD + tid];
+            atomicAdd(dW + a.w.g_lin_b[li] + tid, s);
+          }
+          if (li == 1 || li == 2 || li == 4) {
+            float aw[1][4];
+            zero_acc(aw);
+            tile_gemm<1, 8, 1, false, false>(aw, sD, CLD, nrows, sv + SL.gh + ((size_t)(li - 1) * Pp + p0) * HG, HG, HG, sB);
+            red_add_v4(dW + a.w.g_lin_w[li] + nm.ty * HG + nm.col(), aw[0][0], aw[0][1], aw[0][2], aw[0][3]);
+          } else {
+            if (li == 3) {
+              float aw[1][4];
+              zero_acc(aw);
+              tile_gemm<1, 8, 1, false, false>(aw, sD, CLD, nrows, sv + SL.gh + ((size_t)2 * Pp + p0) * HG, HG, HG, sB);
+              float* d = dW + a.w.g_lin_w[3] + nm.ty * (EG + HG) + EG + nm.col();   // 125-float rows: unaligned
+              atomicAdd(d + 0, aw[0][0]); atomicAdd(d + 1, aw[0][1]); atomicAdd(d + 2, aw[0][2]); atomicAdd(d + 3, aw[0][3]);
+            }
+            float ae2[2][8];
+            zero_acc(ae2);
+            tile_gemm<2, 16, 2, false, true>(ae2, sD, CLD, nrows, sEg, GLD, EGP, sB);
+            const int ldw = li == 3 ? EG + HG : EG;
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+#pragma unroll
+              for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int col = wm.col(g) + j;
+                  if (col < EG) atomicAdd(dW + a.w.g_lin_w[li] + wm.row(i) * ldw + col, ae2[i][g * 4 + j]);
+                }
+          }
+        }
+        if (li == 1 || li == 2 || li == 4) {
+          zero_acc(dHg);
+          tile_gemm<4, 8, 1, true, false>(dHg, sD, CLD, HG, blob + a.w.g_lin_w[li], HG, HG, sB);
+        } else if (li == 3) {
+          zero_acc(dHg);
+          tile_gemm<4, 8, 1, true, false>(dHg, sD, CLD, HG, packed + Packed::gW3n + EGP, 128, HG, sB);
+          tile_gemm<8, 16, 2, true, false>(dEacc, sD, CLD, HG, packed + Packed::gW3n, 128, EGP, sB);
+        } else {
+          tile_gemm<8, 16, 2, true, false>(dEacc, sD, CLD, HG, packed + Packed::gW0n, EGP, EGP, sB);
+        }
+      }
+      // geometry Fourier backward: e_j = sin(arg_j)
+      if (g_gb || g_ry) {
+        float dpr[8][3];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { dpr[i][0] = 0.f; dpr[i][1] = 0.f; dpr[i][2] = 0.f; }
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int col = wm.col(g) + j;
+            if (col < EG) {
+              const float b0 = packed[Packed::gB + col], b1 = packed[Packed::gB + EGP + col],
+                          b2 = packed[Packed::gB + 2 * EGP + col];
+              float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int r = wm.row(i);
+                if (r < nrows) {
+                  const float t0 = TWO_PI_F * sP[r * 4 + 0], t1 = TWO_PI_F * sP[r * 4 + 1], t2 = TWO_PI_F * sP[r * 4 + 2];
+                  const float dar = dEacc[i][g * 4 + j] * cosf(fmaf(t2, b2, fmaf(t1, b1, t0 * b0)));
+                  s0 = fmaf(t0, dar, s0); s1 = fmaf(t1, dar, s1); s2 = fmaf(t2, dar, s2);
+                  dpr[i][0] = fmaf(b0, dar, dpr[i][0]); dpr[i][1] = fmaf(b1, dar, dpr[i][1]);
+                  dpr[i][2] = fmaf(b2, dar, dpr[i][2]);
+                }
+              }
+              if (g_gb) {
+                atomicAdd(&sRed[col], s0); atomicAdd(&sRed[EGP + col], s1); atomicAdd(&sRed[2 * EGP + col], s2);
+              }
+            }
+          }
+        }
+        if (g_ry) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float v0 = half_warp_sum(dpr[i][0]), v1 = half_warp_sum(dpr[i][1]), v2 = half_warp_sum(dpr[i][2]);
+            if (wm.tx == 0) {
+              const int r = wm.row(i);
+              sDP[r * 4 + 0] += TWO_PI_F * v0; sDP[r * 4 + 1] += TWO_PI_F * v1; sDP[r * 4 + 2] += TWO_PI_F * v2;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = nm.row(i);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (sHas[r]) v = make_float4(dCacc[i][0], dCacc[i][1], dCacc[i][2], dCacc[i][3]);
+        *reinterpret_cast<float4*>(sDC + r * CLD + nm.col()) = v;
+      }
+      __syncthreads();
+      scatter_idw(sDC, sIdx, sW, sHas, sDWh, a.geo_feats, a.d_geo, g_gf, trk);
+      __syncthreads();
+    }
+
+    // -------------------------------------------------------------- IDW weight backward (tracker)
+    if (trk && tid < TILE_M && sHas[tid]) {
+      const int m = tid;
+      float wr[KNN], Wt = 0.f, dot = 0.f;
+#pragma unroll
+      for (int k = 0; k < KNN; ++k) {
+        wr[k] = sIdx[m * KNN + k] >= 0 ? 1.0f / (sD8[m * KNN + k] + 1e-10f) : 0.f;
+        Wt += wr[k];
+        dot = fmaf(sDWh[m * KNN + k], sW[m * KNN + k], dot);
+      }
+      const float denom = fmaxf(Wt, 1e-12f);
+      if (!(Wt > 1e-12f)) dot = 0.f;
+      float q0 = 0.f, q1 = 0.f, q2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < KNN; ++k) {
+        const int idx = sIdx[m * KNN + k];
+        if (idx >= 0) {
+          const float dw = (sDWh[m * KNN + k] - dot) / denom;
+          const float dD = -wr[k] * wr[k] * dw;       // w = 1/(D+eps)
+          const float e0 = __ldg(a.cloud + 3 * (size_t)idx + 0) - sP[m * 4 + 0];
+          const float e1 = __ldg(a.cloud + 3 * (size_t)idx + 1) - sP[m * 4 + 1];
+          const float e2 = __ldg(a.cloud + 3 * (size_t)idx + 2) - sP[m * 4 + 2];
+          q0 = fmaf(-2.f * e0, dD, q0); q1 = fmaf(-2.f * e1, dD, q1); q2 = fmaf(-2.f * e2, dD, q2);
+        }
+      }
+      sDP[m * 4 + 0] += q0; sDP[m * 4 + 1] += q1; sDP[m * 4 + 2] += q2;
+    }
+    __syncthreads();
+    // -------------------------------------------------------------- ray gradients + parameter reductions
+    if (g_ry && tid < nr) {
+      float o0 = 0.f, o1 = 0.f, o2 = 0.f, e0 = 0.f, e1 = 0.f, e2 = 0.f;
+      for (int s = 0; s < S; ++s) {
+        const int m = tid * S + s;
+        const float z = sP[m * 4 + 3];
+        o0 += sDP[m * 4 + 0]; o1 += sDP[m * 4 + 1]; o2 += sDP[m * 4 + 2];
+        e0 = fmaf(z, sDP[m * 4 + 0], e0); e1 = fmaf(z, sDP[m * 4 + 1], e1); e2 = fmaf(z, sDP[m * 4 + 2], e2);
+      }
+      const int ray = r0 + tid;
+      a.d_ro[3 * ray + 0] = o0; a.d_ro[3 * ray + 1] = o1; a.d_ro[3 * ray + 2] = o2;
+      a.d_rd[3 * ray + 0] = e0; a.d_rd[3 * ray + 1] = e1; a.d_rd[3 * ray + 2] = e2;
+    }
+    if (g_gb) {
+      for (int i = tid; i < 3 * EGP; i += NT) {
+        const int c = i / EGP, j = i - c * EGP;
+        if (j < EG) atomicAdd(dW + a.w.g_B + c * EG + j, sRed[i]);
+      }
+    }
+    if (g_cw && relpos && tid < 3 * ER) atomicAdd(dW + a.w.c_Brel + tid, sRed[3 * EGP + tid]);
+    __syncthreads();
+  }
+}
+
+int check_weights(const LsrWeights* w);
+int check_params(const LsrParams* p);
+int sm_count();
+
+}  // namespace lsr
+
+using namespace lsr;
+
+extern "C" int lsr_render_bwd(const LsrParams* prm, const void* grid_ws, const float* cloud_pos, int64_t n_points,
+                              const float* rays_o, const float* rays_d, const float* gt_depth,
+                              const double* r_query, int64_t n_rays, const float* geo_feats,
+                              const float* col_feats, const LsrWeights* w, const float* exposure_affine, int stage,
+                              int is_tracker, const void* saved, void* scratch, const float* g_depth,
+                              const float* g_var, const float* g_rgb, int grad_flags, float* d_geo_feats,
+                              float* d_col_feats, float* d_weights, float* d_exposure_affine, float* d_rays_o,
+                              float* d_rays_d, lsr_stream_t stream) {
+  (void)grid_ws; (void)r_query;
+  int rc = check_params(prm);
+  if (rc) return rc;
+  rc = check_weights(w);
+  if (rc) return rc;
+  if (stage != LSR_STAGE_GEOMETRY && stage != LSR_STAGE_COLOR) return LSR_ERR_ARG;
+  if (n_rays < 0 || n_rays > (1ll << 27) || n_points < 0) return LSR_ERR_ARG;
+  if (n_rays == 0) return LSR_OK;
+  if (!saved || !scratch || !rays_o || !rays_d || !gt_depth || !g_depth || !geo_feats) return LSR_ERR_ARG;
+  if (n_points > 0 && !cloud_pos) return LSR_ERR_ARG;
+  if (stage == LSR_STAGE_COLOR && !col_feats) return LSR_ERR_ARG;
+  if (prm->rgb_mode == LSR_RGB_AFFINE_SIGMOID && !exposure_affine) return LSR_ERR_ARG;
+  if ((grad_flags & LSR_GRAD_GEO_FEATS) && !d_geo_feats) return LSR_ERR_ARG;
+  if ((grad_flags & LSR_GRAD_COL_FEATS) && !d_col_feats) return LSR_ERR_ARG;
+  if ((grad_flags & (LSR_GRAD_GEO_W | LSR_GRAD_GEO_B | LSR_GRAD_COL_W)) && !d_weights) return LSR_ERR_ARG;
+  if ((grad_flags & LSR_GRAD_RAYS) && (!d_rays_o || !d_rays_d)) return LSR_ERR_ARG;
+  if ((grad_flags & LSR_GRAD_AFFINE) && !d_exposure_affine) return LSR_ERR_ARG;
+  const int nsm = sm_count();
+  if (nsm <= 0) return LSR_ERR_CUDA;
+
+  BwdArgs a;
+  a.prm = *prm;
+  a.cloud = cloud_pos;
+  a.rays_o = rays_o; a.rays_d = rays_d; a.gt_depth = gt_depth;
+  a.R = (int)n_rays;
+  a.geo_feats = geo_feats; a.col_feats = col_feats;
+  a.w = *w;
+  a.packed = (const float*)scratch;
+  a.affine = exposure_affine;
+  a.stage = stage; a.is_tracker = is_tracker;
+  a.saved = (const float*)saved;
+  a.g_depth = g_depth; a.g_var = g_var; a.g_rgb = g_rgb;
+  a.gflags = grad_flags;
+  a.d_geo = d_geo_feats; a.d_col = d_col_feats; a.d_w = d_weights; a.d_affine = d_exposure_affine;
+  a.d_ro = d_rays_o; a.d_rd = d_rays_d;
+  a.rays_per_tile = TILE_M / prm->n_surface;
+  a.ntiles = (int)((n_rays + a.rays_per_tile - 1) / a.rays_per_tile);
+  const size_t smem = BWD_SMEM_FLOATS * sizeof(float);
+  LSR_CUDA_CHECK(cudaFuncSetAttribute(render_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = a.ntiles < nsm ? a.ntiles : nsm;
+  render_bwd_kernel<<<grid, NT, smem, stream>>>(a);
+  LSR_CUDA_CHECK(cudaGetLastError());
+  return LSR_OK;
+}

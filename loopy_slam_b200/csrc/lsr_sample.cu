@@ -1,0 +1,184 @@
+// Pixel -> ray sampling and quaternion pose kernels (rows a1/a2 of SURVEY.md section 8a).
+//   get_samples / get_sample_uv / select_uv / get_rays_from_uv   /root/reference/src/common.py:104-138,160-172,237-259
+//   quad2rotation / get_camera_from_tensor                       /root/reference/src/common.py:301-343
+// The reference rebuilds a full H x W meshgrid per call and launches ~10 tiny kernels; here one
+// launch turns n pixel indices into rays + gathered depth/colour.
+#include "lsr_common.cuh"
+
+namespace lsr {
+
+__global__ void sample_rays_kernel(const float* __restrict__ depth_img, const float* __restrict__ color_img, int H,
+                                   int W, float fx, float fy, float cx, float cy, const float* __restrict__ c2w,
+                                   int ld, const int64_t* __restrict__ pix, int64_t n, int H0, int H1, int W0,
+                                   int W1, float* __restrict__ rays_o, float* __restrict__ rays_d,
+                                   float* __restrict__ depth, float* __restrict__ color, int64_t* __restrict__ i_out,
+                                   int64_t* __restrict__ j_out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int ww = W1 - W0;
+  int64_t p = pix[t];
+  const int64_t tot = (int64_t)ww * (H1 - H0);
+  p = p < 0 ? 0 : (p >= tot ? tot - 1 : p);   // select_uv clamps (common.py:131)
+  const int h = (int)(p / ww), w = (int)(p - (int64_t)h * ww);
+  const int col = W0 + w, row = H0 + h;
+  const float fi = (float)col, fj = (float)row;
+  // dirs = [(i-cx)/fx, -(j-cy)/fy, -1]   (common.py:113-114)
+  const float d0 = __fdiv_rn(__fsub_rn(fi, cx), fx);
+  const float d1 = -__fdiv_rn(__fsub_rn(fj, cy), fy);
+  const float d2 = -1.0f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {   // rays_d = sum(dirs * R[a,:])  (common.py:117)
+    const float r0 = c2w[a * ld + 0], r1 = c2w[a * ld + 1], r2 = c2w[a * ld + 2];
+    rays_d[3 * t + a] = __fadd_rn(__fadd_rn(__fmul_rn(d0, r0), __fmul_rn(d1, r1)), __fmul_rn(d2, r2));
+    rays_o[3 * t + a] = c2w[a * ld + 3];
+  }
+  const size_t lin = (size_t)row * W + col;
+  if (depth) depth[t] = depth_img ? depth_img[lin] : 0.f;
+  if (color && color_img) {
+    color[3 * t + 0] = color_img[3 * lin + 0];
+    color[3 * t + 1] = color_img[3 * lin + 1];
+    color[3 * t + 2] = color_img[3 * lin + 2];
+  }
+  if (i_out) i_out[t] = col;
+  if (j_out) j_out[t] = row;
+}
+
+__global__ void sample_rays_bwd_kernel(const float* __restrict__ g_o, const float* __restrict__ g_d,
+                                       const int64_t* __restrict__ ip, const int64_t* __restrict__ jp, int64_t n,
+                                       float fx, float fy, float cx, float cy, float* __restrict__ d_c2w) {
+  float acc[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) acc[k] = 0.f;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const float d0 = __fdiv_rn(__fsub_rn((float)ip[t], cx), fx);
+    const float d1 = -__fdiv_rn(__fsub_rn((float)jp[t], cy), fy);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float gd = g_d ? g_d[3 * t + a] : 0.f;
+      acc[a * 4 + 0] = fmaf(gd, d0, acc[a * 4 + 0]);
+      acc[a * 4 + 1] = fmaf(gd, d1, acc[a * 4 + 1]);
+      acc[a * 4 + 2] -= gd;
+      acc[a * 4 + 3] += g_o ? g_o[3 * t + a] : 0.f;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) atomicAdd(d_c2w + k, acc[k]);
+  }
+}
+
+__global__ void pose_fwd_kernel(const float* __restrict__ cam, float* __restrict__ c2w) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float qr = cam[0], qi = cam[1], qj = cam[2], qk = cam[3];
+  const float s = 2.0f / (qr * qr + qi * qi + qj * qj + qk * qk);   // common.py:313
+  c2w[0] = 1.f - s * (qj * qj + qk * qk);
+  c2w[1] = s * (qi * qj - qk * qr);
+  c2w[2] = s * (qi * qk + qj * qr);
+  c2w[3] = cam[4];
+  c2w[4] = s * (qi * qj + qk * qr);
+  c2w[5] = 1.f - s * (qi * qi + qk * qk);
+  c2w[6] = s * (qj * qk - qi * qr);
+  c2w[7] = cam[5];
+  c2w[8] = s * (qi * qk - qj * qr);
+  c2w[9] = s * (qj * qk + qi * qr);
+  c2w[10] = 1.f - s * (qi * qi + qj * qj);
+  c2w[11] = cam[6];
+}
+
+__global__ void pose_bwd_kernel(const float* __restrict__ cam, const float* __restrict__ G, float* __restrict__ d_cam) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float qr = cam[0], qi = cam[1], qj = cam[2], qk = cam[3];
+  const float s = 2.0f / (qr * qr + qi * qi + qj * qj + qk * qk);
+  const float G00 = G[0], G01 = G[1], G02 = G[2], G10 = G[4], G11 = G[5], G12 = G[6], G20 = G[8], G21 = G[9],
+              G22 = G[10];
+  // R = I + s*M(q);  dL/dq_x = -s^2 q_x <G,M> + s <G, dM/dq_x>
+  const float GM = G00 * (-(qj * qj + qk * qk)) + G01 * (qi * qj - qk * qr) + G02 * (qi * qk + qj * qr) +
+                   G10 * (qi * qj + qk * qr) + G11 * (-(qi * qi + qk * qk)) + G12 * (qj * qk - qi * qr) +
+                   G20 * (qi * qk - qj * qr) + G21 * (qj * qk + qi * qr) + G22 * (-(qi * qi + qj * qj));
+  const float dr = -G01 * qk + G02 * qj + G10 * qk - G12 * qi - G20 * qj + G21 * qi;
+  const float di = G01 * qj + G02 * qk + G10 * qj - 2.f * G11 * qi - G12 * qr + G20 * qk + G21 * qr - 2.f * G22 * qi;
+  const float dj = -2.f * G00 * qj + G01 * qi + G02 * qr + G10 * qi + G12 * qk - G20 * qr + G21 * qk - 2.f * G22 * qj;
+  const float dk = -2.f * G00 * qk - G01 * qr + G02 * qi + G10 * qr - 2.f * G11 * qk + G12 * qj + G20 * qi + G21 * qj;
+  d_cam[0] = -s * s * qr * GM + s * dr;
+  d_cam[1] = -s * s * qi * GM + s * di;
+  d_cam[2] = -s * s * qj * GM + s * dj;
+  d_cam[3] = -s * s * qk * GM + s * dk;
+  d_cam[4] = G[3];
+  d_cam[5] = G[7];
+  d_cam[6] = G[11];
+}
+
+}  // namespace lsr
+
+using namespace lsr;
+
+extern "C" int lsr_sample_rays(const float* depth_img, const float* color_img, int32_t H, int32_t W, float fx,
+                               float fy, float cx, float cy, const float* c2w, int32_t c2w_ld, const int64_t* pix,
+                               int64_t n, int32_t H0, int32_t H1, int32_t W0, int32_t W1, float* rays_o,
+                               float* rays_d, float* depth, float* color, int64_t* i_out, int64_t* j_out,
+                               lsr_stream_t stream) {
+  if (n < 0 || H <= 0 || W <= 0 || H0 < 0 || W0 < 0 || H1 > H || W1 > W || H0 >= H1 || W0 >= W1 || c2w_ld < 4)
+    return LSR_ERR_ARG;
+  if (n == 0) return LSR_OK;
+  if (!c2w || !pix || !rays_o || !rays_d) return LSR_ERR_ARG;
+  sample_rays_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(depth_img, color_img, H, W, fx, fy, cx, cy, c2w,
+                                                                     c2w_ld, pix, n, H0, H1, W0, W1, rays_o, rays_d,
+                                                                     depth, color, i_out, j_out);
+  LSR_CUDA_CHECK(cudaGetLastError());
+  return LSR_OK;
+}
+
+extern "C" int lsr_sample_rays_bwd(const float* d_rays_o, const float* d_rays_d, const int64_t* i_pix,
+                                   const int64_t* j_pix, int64_t n, float fx, float fy, float cx, float cy,
+                                   float* d_c2w, lsr_stream_t stream) {
+  if (n < 0 || !d_c2w) return LSR_ERR_ARG;
+  LSR_CUDA_CHECK(cudaMemsetAsync(d_c2w, 0, 12 * sizeof(float), stream));
+  if (n == 0) return LSR_OK;
+  if (!i_pix || !j_pix) return LSR_ERR_ARG;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 296) blocks = 296;
+  sample_rays_bwd_kernel<<<blocks, 256, 0, stream>>>(d_rays_o, d_rays_d, i_pix, j_pix, n, fx, fy, cx, cy, d_c2w);
+  LSR_CUDA_CHECK(cudaGetLastError());
+  return LSR_OK;
+}
+
+extern "C" int lsr_pose_fwd(const float* cam7, float* c2w12, lsr_stream_t stream) {
+  if (!cam7 || !c2w12) return LSR_ERR_ARG;
+  pose_fwd_kernel<<<1, 32, 0, stream>>>(cam7, c2w12);
+  LSR_CUDA_CHECK(cudaGetLastError());
+  return LSR_OK;
+}
+
+extern "C" int lsr_pose_bwd(const float* cam7, const float* d_c2w12, float* d_cam7, lsr_stream_t stream) {
+  if (!cam7 || !d_c2w12 || !d_cam7) return LSR_ERR_ARG;
+  pose_bwd_kernel<<<1, 32, 0, stream>>>(cam7, d_c2w12, d_cam7);
+  LSR_CUDA_CHECK(cudaGetLastError());
+  return LSR_OK;
+}
+
+extern "C" int lsr_version(void) { return 100; }
+
+extern "C" const char* lsr_strerror(int code) {
+  switch (code) {
+    case LSR_OK: return "ok";
+    case LSR_ERR_ARG: return "invalid argument";
+    case LSR_ERR_WORKSPACE: return "workspace too small";
+    case LSR_ERR_CUDA: return "CUDA runtime error";
+    case LSR_ERR_UNSUPPORTED: return "unsupported configuration";
+    default: return "unknown error";
+  }
+}
+
+extern "C" int lsr_device_sm_count(int* out) {
+  if (!out) return LSR_ERR_ARG;
+  int dev = 0, n = 0;
+  LSR_CUDA_CHECK(cudaGetDevice(&dev));
+  LSR_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  *out = n;
+  return LSR_OK;
+}

@@ -1,0 +1,382 @@
+"""Host-side mirror of ``Renderer`` (/root/reference/src/utils/Renderer.py:6-276): same constructor
+and method signatures, so ``src/Mapper.py`` / ``src/Tracker.py`` call it unchanged.  Every method
+drives the fused sm_100a kernels through the C ABI (include/lsr.h); nothing here computes on the
+CPU and there is no PyTorch-eager fallback.
+"""
+import ctypes
+import warnings
+
+import torch
+
+from . import _lib
+from ._lib import lib, check, ptr, stream_ptr
+
+DEFAULT_MAX_CELLS = 1 << 22
+
+
+# ----------------------------------------------------------------------------- neighbour index
+class GridIndex:
+    """Device workspace of one uniform-grid neighbour index (lsr_grid_build)."""
+
+    def __init__(self, cloud_pos, cell, max_cells=DEFAULT_MAX_CELLS):
+        _lib.require_cuda(cloud_pos, 'cloud_pos')
+        cloud = cloud_pos.detach()
+        if cloud.dtype != torch.float32 or not cloud.is_contiguous():
+            cloud = cloud.to(torch.float32).contiguous()
+        self.cloud = cloud.reshape(-1, 3)
+        self.n = self.cloud.shape[0]
+        self.cell = float(cell)
+        self.max_cells = int(max_cells)
+        nbytes = ctypes.c_size_t()
+        check(lib().lsr_grid_workspace_bytes(self.n, self.max_cells, ctypes.byref(nbytes)), 'lsr_grid_workspace_bytes')
+        self.ws = torch.empty(nbytes.value, dtype=torch.uint8, device=cloud.device)
+        check(lib().lsr_grid_build(ptr(self.cloud), self.n, self.cell, self.max_cells, ptr(self.ws), nbytes.value,
+                                   stream_ptr(cloud.device)), 'lsr_grid_build')
+
+    def query(self, pos, radius, dynamic_radius=None):
+        """== find_neighbors_faiss: D (P,8) f32, I (P,8) i64, neighbor_num (P,) i32."""
+        _lib.require_cuda(pos, 'pos')
+        q = pos.detach().to(torch.float32).reshape(-1, 3).contiguous()
+        P = q.shape[0]
+        D = torch.empty(P, 8, dtype=torch.float32, device=q.device)
+        I = torch.empty(P, 8, dtype=torch.int64, device=q.device)
+        n = torch.empty(P, dtype=torch.int32, device=q.device)
+        rd = None
+        if dynamic_radius is not None:
+            rd = dynamic_radius.detach().to(torch.float64).reshape(-1).contiguous()
+            assert rd.shape[0] == P, 'shape mis-match for input points and dynamic radius'
+        check(lib().lsr_knn_query(ptr(self.ws), ptr(q), ptr(rd), float(radius), P, ptr(D), ptr(I), ptr(n),
+                                  stream_ptr(q.device)), 'lsr_knn_query')
+        return D, I, n
+
+
+class _GridCache:
+    """Grid per (cloud tensor identity, version, cell): both callers pass ``cloud_pos`` on every
+    render call (src/Tracker.py:166, src/Mapper.py:686); rebuild only when it changed."""
+
+    def __init__(self):
+        self.key = None
+        self.grid = None
+
+    def get(self, cloud_pos, cell):
+        key = (cloud_pos.data_ptr(), cloud_pos.shape[0], cloud_pos._version, float(cell), str(cloud_pos.device))
+        if key != self.key:
+            self.grid = GridIndex(cloud_pos, cell)
+            self.key = key
+        return self.grid
+
+
+def _grid_for(npc, cloud_pos, cell, cache):
+    g = getattr(npc, 'grid_index', None)
+    if callable(g):          # our NeuralPointCloud keeps its own index in sync with its cloud
+        grid = g()
+        if grid is not None and (cloud_pos is None or cloud_pos.shape[0] == grid.n):
+            return grid
+    if cloud_pos is None:
+        raise RuntimeError('render needs cloud_pos (or an npc exposing grid_index())')
+    return cache.get(cloud_pos, cell)
+
+
+# ----------------------------------------------------------------------------- fused render op
+class _RenderCtx:
+    """Per-call constants shared by forward and backward."""
+    __slots__ = ('prm', 'grid', 'stage', 'is_tracker', 'blob', 'wstruct', 'flat', 'saved', 'scratch', 'R',
+                 'r_query', 'device', 'far_group', 'force_save')
+
+
+def _f32c(t):
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.to(torch.float32).contiguous()
+    return t
+
+
+class _RenderFn(torch.autograd.Function):
+    """depth, var, rgb, valid = lsr_render_fwd(...); backward = lsr_render_bwd(...)."""
+
+    @staticmethod
+    def forward(ctx, rc, rays_o, rays_d, gt_depth, geo_feats, col_feats, affine, far_zero, *params):
+        ctx.set_materialize_grads(False)
+        dev = rays_o.device
+        R = rays_o.shape[0]
+        depth = torch.empty(R, dtype=torch.float32, device=dev)
+        var = torch.empty(R, dtype=torch.float32, device=dev)
+        rgb = torch.empty(R, 3, dtype=torch.float32, device=dev)
+        valid = torch.empty(R, dtype=torch.uint8, device=dev)
+        need_bwd = any(ctx.needs_input_grad) or rc.force_save
+        sb, cb = ctypes.c_size_t(), ctypes.c_size_t()
+        check(lib().lsr_render_workspace_bytes(ctypes.byref(rc.prm), R, rc.stage, ctypes.byref(sb), ctypes.byref(cb)),
+              'lsr_render_workspace_bytes')
+        rc.scratch = torch.empty(cb.value, dtype=torch.uint8, device=dev)
+        rc.saved = torch.empty(sb.value, dtype=torch.uint8, device=dev) if need_bwd else None
+        check(lib().lsr_render_fwd(ctypes.byref(rc.prm), ptr(rc.grid.ws), ptr(rc.grid.cloud), rc.grid.n,
+                                   ptr(rays_o), ptr(rays_d), ptr(gt_depth), ptr(rc.r_query), ptr(far_zero),
+                                   rc.far_group, R, ptr(geo_feats), ptr(col_feats), ctypes.byref(rc.wstruct),
+                                   ptr(affine), rc.stage, ptr(depth), ptr(var), ptr(rgb), ptr(valid),
+                                   ptr(rc.saved), ptr(rc.scratch), stream_ptr(dev)), 'lsr_render_fwd')
+        ctx.rc = rc
+        ctx.param_shapes = [p.shape for p in params]
+        ctx.save_for_backward(rays_o, rays_d, gt_depth, geo_feats, col_feats, affine)
+        ctx.mark_non_differentiable(valid)
+        return depth, var, rgb, valid
+
+    @staticmethod
+    def backward(ctx, g_depth, g_var, g_rgb, _g_valid):
+        rc = ctx.rc
+        rays_o, rays_d, gt_depth, geo_feats, col_feats, affine = ctx.saved_tensors
+        dev = rays_o.device
+        R = rays_o.shape[0]
+        need = ctx.needs_input_grad   # (rc, o, d, gt, geo, col, affine, far, *params)
+        blob = rc.blob
+        flags = 0
+        d_o = d_d = d_geo = d_col = d_aff = d_w = None
+        if need[1] or need[2]:
+            flags |= _lib.GRAD_RAYS
+            d_o = torch.empty(R, 3, dtype=torch.float32, device=dev)
+            d_d = torch.empty(R, 3, dtype=torch.float32, device=dev)
+        if need[4]:
+            flags |= _lib.GRAD_GEO_FEATS
+            d_geo = torch.zeros_like(geo_feats)
+        if need[5] and rc.stage == 1:
+            flags |= _lib.GRAD_COL_FEATS
+            d_col = torch.zeros_like(col_feats)
+        if need[6] and affine is not None:
+            flags |= _lib.GRAD_AFFINE
+            d_aff = torch.zeros(12, dtype=torch.float32, device=dev)
+        pneed = need[8:]
+        if any(pneed):
+            d_w = torch.zeros(blob.n_elems, dtype=torch.float32, device=dev)
+            if any(pneed[k] for k in blob.geo_w_idx):
+                flags |= _lib.GRAD_GEO_W
+            if any(pneed[k] for k in blob.geo_b_idx):
+                flags |= _lib.GRAD_GEO_B
+            if rc.stage == 1 and any(pneed[k] for k in blob.col_w_idx):
+                flags |= _lib.GRAD_COL_W
+        g_depth = _f32c(g_depth) if g_depth is not None else torch.zeros(R, dtype=torch.float32, device=dev)
+        g_var = _f32c(g_var) if g_var is not None else None
+        g_rgb = _f32c(g_rgb) if g_rgb is not None else None
+        check(lib().lsr_render_bwd(ctypes.byref(rc.prm), ptr(rc.grid.ws), ptr(rc.grid.cloud), rc.grid.n,
+                                   ptr(rays_o), ptr(rays_d), ptr(gt_depth), ptr(rc.r_query), R, ptr(geo_feats),
+                                   ptr(col_feats), ctypes.byref(rc.wstruct), ptr(affine), rc.stage,
+                                   1 if rc.is_tracker else 0, ptr(rc.saved), ptr(rc.scratch), ptr(g_depth),
+                                   ptr(g_var), ptr(g_rgb), flags, ptr(d_geo), ptr(d_col), ptr(d_w), ptr(d_aff),
+                                   ptr(d_o), ptr(d_d), stream_ptr(dev)), 'lsr_render_bwd')
+        rc.saved = None
+        pgrads = []
+        for k, (off, n, t) in enumerate(zip(blob.offsets, blob.numels, ctx.param_shapes)):
+            if pneed[k] and d_w is not None:
+                pgrads.append(d_w[off:off + n].view(t))
+            else:
+                pgrads.append(None)
+        return (None, d_o if need[1] else None, d_d if need[2] else None, None, d_geo, d_col, d_aff, None, *pgrads)
+
+
+def _make_params(renderer, decoders, stage, coef):
+    f = decoders.cfg_flags
+    P = _lib.LsrParams()
+    P.n_surface = renderer.N_surface
+    P.nn_num = f['nn_num']
+    P.min_nn_num = f['min_nn_num']
+    P.c_dim = 32
+    P.near_end_surface = renderer.near_end_surface
+    P.far_end_surface = renderer.far_end_surface
+    P.near_end = renderer.near_end
+    P.sigmoid_coef = coef
+    P.radius_query = 0.0
+    flags = 0
+    if f['encode_rel_pos_in_col']:
+        flags |= _lib.FLAG_REL_POS
+    if renderer.use_dynamic_radius:
+        flags |= _lib.FLAG_DYNAMIC_R
+    if renderer.skip_zero_depth_pixel:
+        flags |= _lib.FLAG_SKIP_ZERO_DEPTH
+    P.flags = flags
+    P.rgb_mode = _lib.RGB_SIGMOID
+    return P
+
+
+def fused_render(renderer, npc, decoders, rays_d, rays_o, stage, gt_depth, npc_geo_feats, npc_col_feats,
+                 is_tracker, cloud_pos, dynamic_r_query, exposure_feat, far_group=None, n_surface=None,
+                 force_save=False, return_ctx=False):
+    """The one place that marshals a render call into lsr_render_fwd / lsr_render_bwd."""
+    _lib.require_cuda(rays_o, 'rays_o')
+    dev = rays_o.device
+    if stage not in _lib.LSR_STAGE:
+        raise NotImplementedError(f"stage '{stage}' is not on the fused path (only 'geometry' and 'color')")
+    if not hasattr(decoders, 'blob'):
+        raise TypeError('decoders must be loopy_slam_b200.decoder.NICER (flat weight blob); '
+                        'build it with loopy_slam_b200.config.get_model(cfg)')
+    prm = _make_params(renderer, decoders, stage, float(renderer.sigmoid_coefficient))
+    if n_surface is not None:
+        prm.n_surface = n_surface
+    radius = npc.get_radius_query() if npc is not None and hasattr(npc, 'get_radius_query') else renderer.radius_query
+    prm.radius_query = float(radius)
+    rc = _RenderCtx()
+    rc.prm = prm
+    rc.stage = _lib.LSR_STAGE[stage]
+    rc.is_tracker = bool(is_tracker)
+    rc.r_query = None
+    cell = float(radius)
+    if renderer.use_dynamic_radius:
+        if dynamic_r_query is None:
+            raise ValueError('use_dynamic_radius is set but dynamic_r_query is None')
+        rc.r_query = dynamic_r_query.detach().to(device=dev, dtype=torch.float64).reshape(-1).contiguous()
+        cell = renderer.max_query_radius
+    rc.grid = _grid_for(npc, cloud_pos, cell, renderer._grid_cache)
+    rc.blob = decoders.blob
+    rc.flat, rc.wstruct = rc.blob.ensure(dev)
+    affine = None
+    if decoders.cfg_flags['encode_exposure'] and rc.stage == 1:
+        if exposure_feat is not None:      # decoder.py:535-540 (tracker): affine applied per sample
+            affine = decoders.color_decoder.mlp_exposure(exposure_feat).to(torch.float32).contiguous()
+            prm.rgb_mode = _lib.RGB_AFFINE_SIGMOID
+        else:                              # decoder.py:541-542 (mapper): caller applies it after compositing
+            prm.rgb_mode = _lib.RGB_RAW
+    rays_o, rays_d = _f32c(rays_o), _f32c(rays_d)
+    R = rays_o.shape[0]
+    if gt_depth is None:       # Renderer.py:107-113: no sensor depth -> z in [near_end, 10]
+        gt = torch.zeros(R, dtype=torch.float32, device=dev)
+        far = torch.full((1,), 10.0, dtype=torch.float32, device=dev)
+        fgroup = max(R, 1)
+    else:
+        gt = _f32c(gt_depth.detach().reshape(-1))
+        fgroup = int(far_group) if far_group else max(R, 1)
+        far = torch.empty((R + fgroup - 1) // fgroup if R else 1, dtype=torch.float32, device=dev)
+        check(lib().lsr_far_bound(ptr(gt), R, fgroup, ptr(far), stream_ptr(dev)), 'lsr_far_bound')
+    geo = _f32c(npc_geo_feats)
+    col = _f32c(npc_col_feats) if npc_col_feats is not None else None
+    params = rc.blob.tensors()
+    rc.R = R
+    rc.device = dev
+    rc.far_group = fgroup
+    rc.force_save = bool(force_save)
+    out = _RenderFn.apply(rc, rays_o, rays_d, gt, geo, col, affine, far, *params)
+    if return_ctx:
+        return out, rc
+    return out
+
+
+def _saved_views(rc):
+    """Python mirror of lsr::saved_layout (csrc/lsr_render.cuh): float views into the saved buffer."""
+    S = rc.prm.n_surface
+    P = rc.R * S
+    Pp = (P + 127) // 128 * 128 + 128
+    f = rc.saved.view(torch.float32)
+    o = 0
+    v = {}
+
+    def take(name, n, shape):
+        nonlocal o
+        v[name] = f[o:o + n].view(shape)
+        o += n
+    take('idx', Pp * 8, (Pp, 8)); take('w', Pp * 8, (Pp, 8)); take('D', Pp * 8, (Pp, 8)); take('misc', Pp * 4, (Pp, 4))
+    take('cg', Pp * 32, (Pp, 32)); take('gs', 5 * Pp * 32, (5, Pp, 32)); take('gh', 5 * Pp * 32, (5, Pp, 32))
+    take('occ', Pp, (Pp,))
+    if rc.stage == 1:
+        take('cc', Pp * 32, (Pp, 32)); take('cs', 5 * Pp * 128, (5, Pp, 128)); take('ch', 5 * Pp * 128, (5, Pp, 128))
+        take('rgbs', Pp * 4, (Pp, 4)); take('outraw', Pp * 4, (Pp, 4))
+        if rc.prm.flags & _lib.FLAG_REL_POS:
+            take('u', Pp * 128, (Pp, 128)); take('sp', Pp * 8 * 128, (Pp, 8, 128))
+    return v, P
+
+
+def decode_points(decoders, p, npc, stage, npc_geo_feats, npc_col_feats, pts_num, cloud_pos, dynamic_r_query,
+                  exposure_feat, renderer=None):
+    """NICER.forward semantics (decoder.py:573-610), forward only: runs the fused kernel with one
+    sample per "ray" (origin = the point, direction = 0, so the sample point is the origin exactly)
+    and reads the per-sample occupancy / colour out of the saved activations.
+    -> raw (P,4) [r,g,b,occ-logit], ray_mask (P/pts_num,) bool or None, point_mask (P,) bool."""
+    if renderer is None:
+        renderer = getattr(decoders, '_lsr_renderer', None)
+        if renderer is None:
+            raise RuntimeError('NICER.forward needs a Renderer: call Renderer.eval_points(...)')
+    pts = _f32c(p.detach().reshape(-1, 3))
+    with torch.no_grad():
+        P = pts.shape[0]
+        ones = torch.ones(P, dtype=torch.float32, device=pts.device)
+        dyn = dynamic_r_query
+        _, rc = fused_render(renderer, npc, decoders, torch.zeros_like(pts), pts, stage, ones, npc_geo_feats,
+                             npc_col_feats, False, cloud_pos, dyn, exposure_feat, n_surface=1, force_save=True,
+                             return_ctx=True)
+        v, n = _saved_views(rc)
+        occ = v['occ'][:n].clone()
+        has = v['misc'][:n, 1] > 0.5
+        rgb = v['rgbs'][:n, :3].clone() if rc.stage == 1 else torch.zeros(n, 3, device=pts.device)
+        raw = torch.cat([rgb, occ[:, None]], -1)
+    ray_mask = None
+    if pts_num:
+        ray_mask = ~(has.view(-1, pts_num).sum(1) < int(decoders.cfg_flags['N_surface'] / 2 + 1))
+    return raw, ray_mask, has
+
+
+class Renderer(object):
+    """Mirror of the reference Renderer (Renderer.py:6-22) -- same cfg keys, same attributes."""
+
+    def __init__(self, cfg, args, slam, points_batch_size=500000, ray_batch_size=3000):
+        self.ray_batch_size = ray_batch_size
+        self.points_batch_size = points_batch_size
+        self.N_surface = cfg['rendering']['N_surface']
+        self.near_end_surface = cfg['rendering']['near_end_surface']
+        self.far_end_surface = cfg['rendering']['far_end_surface']
+        self.sample_near_pcl = cfg['rendering']['sample_near_pcl']
+        self.skip_zero_depth_pixel = cfg['rendering']['skip_zero_depth_pixel']
+        self.near_end = cfg['rendering']['near_end']
+        self.use_dynamic_radius = cfg['use_dynamic_radius']
+        self.crop_edge = 0 if cfg['cam']['crop_edge'] is None else cfg['cam']['crop_edge']
+        self.H, self.W, self.fx, self.fy, self.cx, self.cy = slam.H, slam.W, slam.fx, slam.fy, slam.cx, slam.cy
+        self.radius_query = cfg['pointcloud']['radius_query']
+        pc = cfg['pointcloud']
+        # largest radius the dynamic-radius map can produce (Tracker.py:243-258): r_add_max * ratio
+        self.max_query_radius = float(pc.get('radius_add_max', 0.08)) * float(pc.get('radius_query_ratio', 2))
+        self.sigmoid_coefficient = cfg['rendering'].get('sigmoid_coef_mapper', 0.1)   # callers overwrite it
+        self._grid_cache = _GridCache()
+        if self.sample_near_pcl:
+            warnings.warn('rendering.sample_near_pcl=True: zero-depth rays use the npc-guided z-range only if the '
+                          'npc provides sample_near_pcl(); every shipped dataset config turns it off')
+
+    # -- Renderer.py:24-69
+    def eval_points(self, p, decoders, npc, stage='color', device=None, npc_geo_feats=None, npc_col_feats=None,
+                    is_tracker=False, cloud_pos=None, pts_views_d=None, ray_pts_num=None, dynamic_r_query=None,
+                    exposure_feat=None):
+        assert torch.is_tensor(p)
+        raw, ray_mask, point_mask = decode_points(decoders, p, npc, stage, npc_geo_feats, npc_col_feats,
+                                                  ray_pts_num, cloud_pos, dynamic_r_query, exposure_feat,
+                                                  renderer=self)
+        return raw, ray_mask, point_mask
+
+    # -- Renderer.py:71-201
+    def render_batch_ray(self, npc, decoders, rays_d, rays_o, device, stage, gt_depth=None, npc_geo_feats=None,
+                         npc_col_feats=None, is_tracker=False, cloud_pos=None, dynamic_r_query=None,
+                         exposure_feat=None):
+        """-> depth (R,), uncertainty (R,), color (R,3), valid_ray_mask (R,) bool; differentiable w.r.t.
+        rays, feature tables, decoder parameters and exposure_feat."""
+        if gt_depth is not None and torch.numel(gt_depth) == 0:
+            warnings.warn('tensor gt_depth is empty, info:')      # Renderer.py:122-128
+            gt_depth = None
+        if self.sample_near_pcl and gt_depth is not None and hasattr(npc, 'sample_near_pcl'):
+            return self._render_with_near_pcl(npc, decoders, rays_d, rays_o, stage, gt_depth, npc_geo_feats,
+                                              npc_col_feats, is_tracker, cloud_pos, dynamic_r_query, exposure_feat)
+        depth, var, rgb, valid = fused_render(self, npc, decoders, rays_d, rays_o, stage, gt_depth, npc_geo_feats,
+                                              npc_col_feats, is_tracker, cloud_pos, dynamic_r_query, exposure_feat)
+        return depth, var, rgb, valid.bool()
+
+    def _render_with_near_pcl(self, *a):
+        raise NotImplementedError('rendering.sample_near_pcl=True is not on the fused path yet '
+                                  '(off in configs/Replica, TUM_RGBD, ScanNet)')
+
+    # -- Renderer.py:203-276
+    def render_img(self, npc, decoders, c2w, device, stage, gt_depth=None, npc_geo_feats=None, npc_col_feats=None,
+                   dynamic_r_query=None, cloud_pos=None, exposure_feat=None):
+        """Full-image forward render in ONE fused launch (the reference loops over 3000-ray tiles).
+        -> depth (H,W) f64, uncertainty (H,W) f64, color (H,W,3) f32."""
+        from .common import get_rays
+        with torch.no_grad():
+            H, W = self.H, self.W
+            rays_o, rays_d = get_rays(H, W, self.fx, self.fy, self.cx, self.cy, c2w, device)
+            rays_o = rays_o.reshape(-1, 3)
+            rays_d = rays_d.reshape(-1, 3)
+            dyn = dynamic_r_query.reshape(-1) if (self.use_dynamic_radius and dynamic_r_query is not None) else None
+            gt = gt_depth.reshape(-1) if gt_depth is not None else None
+            depth, var, rgb, _ = fused_render(self, npc, decoders, rays_d, rays_o, stage, gt, npc_geo_feats,
+                                              npc_col_feats, False, cloud_pos, dyn, exposure_feat,
+                                              far_group=self.ray_batch_size)
+            return depth.double().reshape(H, W), var.double().reshape(H, W), rgb.reshape(H, W, 3)

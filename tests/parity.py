@@ -1,0 +1,136 @@
+"""CUDA-vs-oracle parity harness shared by the GPU tests and __graft_entry__.smoke()."""
+import copy
+
+import torch
+
+import loopy_slam_b200 as L
+from oracle import render as orc
+from helpers import Golden, rel_l2
+
+
+class SlamLike:
+    def __init__(self, H, W, fx, fy, cx, cy):
+        self.H, self.W, self.fx, self.fy, self.cx, self.cy = int(H), int(W), float(fx), float(fy), float(cx), float(cy)
+
+
+def cfg_from_ocfg(ocfg):
+    cfg = L.default_cfg('replica')
+    cfg['use_dynamic_radius'] = ocfg.use_dynamic_radius
+    cfg['model']['encode_rel_pos_in_col'] = ocfg.encode_rel_pos_in_col
+    cfg['model']['encode_exposure'] = ocfg.encode_exposure
+    r = cfg['rendering']
+    r['N_surface'], r['near_end'] = ocfg.N_surface, ocfg.near_end
+    r['near_end_surface'], r['far_end_surface'] = ocfg.near_end_surface, ocfg.far_end_surface
+    r['sigmoid_coef_mapper'] = r['sigmoid_coef_tracker'] = ocfg.sigmoid_coef
+    r['skip_zero_depth_pixel'] = ocfg.skip_zero_depth_pixel
+    r['sample_near_pcl'] = False
+    cfg['pointcloud']['radius_query'] = ocfg.radius_query
+    cfg['pointcloud']['min_nn_num'] = ocfg.min_nn_num
+    return cfg
+
+
+def build_model(cfg, weights, device):
+    torch.manual_seed(0)
+    model = L.get_model(cfg)
+    sd = {k: v for k, v in weights.items() if k != 'color_decoder.embedder._B'}
+    model.load_state_dict(sd, strict=True)
+    model.color_decoder.embedder._B = weights['color_decoder.embedder._B'].clone()
+    return model.to(device)
+
+
+def run_cuda(g, device='cuda:0', param_grads=True):
+    """Run our fused path on a golden scene -> dict of outputs and gradients (CPU tensors)."""
+    cfg = cfg_from_ocfg(g.ocfg)
+    H, W, fx, fy, cx, cy = g.raw['intrinsics']
+    model = build_model(cfg, g.weights, device)
+    for p in model.parameters():
+        p.requires_grad_(param_grads)
+    renderer = L.Renderer(cfg, None, SlamLike(H, W, fx, fy, cx, cy))
+    renderer.sigmoid_coefficient = g.ocfg.sigmoid_coef
+    cloud = g.t('cloud').to(device)
+    geo = g.t('geo_feats').to(device).requires_grad_(True)
+    col = g.t('col_feats').to(device).requires_grad_(True)
+    o = g.t('rays_o').to(device).requires_grad_(g.is_tracker)
+    d = g.t('rays_d').to(device).requires_grad_(g.is_tracker)
+    ef = g.t('exposure_feat').to(device).requires_grad_(True) if g.has('exposure_feat') else None
+    dyn = g.t('dynamic_r').to(device) if g.has('dynamic_r') else None
+
+    class NPC:   # the reference passes its npc proxy; only get_radius_query is needed here
+        def get_radius_query(self_inner):
+            return g.ocfg.radius_query
+    depth, var, rgb, valid = renderer.render_batch_ray(
+        NPC(), model, d, o, device, g.stage, gt_depth=g.t('gt_depth').to(device), npc_geo_feats=geo,
+        npc_col_feats=col, is_tracker=g.is_tracker, cloud_pos=cloud, dynamic_r_query=dyn, exposure_feat=ef)
+    loss = (g.t('up_depth').to(device) * depth).sum() + (g.t('up_rgb').to(device) * rgb).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    out = dict(depth=depth.detach().cpu(), var=var.detach().cpu(), rgb=rgb.detach().cpu(), valid=valid.cpu(),
+               g_geo=geo.grad.cpu() if geo.grad is not None else None,
+               g_col=col.grad.cpu() if col.grad is not None else None,
+               g_o=o.grad.cpu() if o.grad is not None else None, g_d=d.grad.cpu() if d.grad is not None else None,
+               g_ef=ef.grad.cpu() if ef is not None and ef.grad is not None else None,
+               g_w={k: p.grad.detach().cpu() for k, p in model.named_parameters() if p.grad is not None})
+    return out
+
+
+def run_oracle(g, dtype):
+    geo = g.t('geo_feats').clone().requires_grad_(True)
+    col = g.t('col_feats').clone().requires_grad_(True)
+    o = g.t('rays_o').clone().requires_grad_(g.is_tracker)
+    d = g.t('rays_d').clone().requires_grad_(g.is_tracker)
+    W = {k: v.clone().requires_grad_(True) for k, v in g.weights.items()}
+    ef = g.t('exposure_feat').clone().requires_grad_(True) if g.has('exposure_feat') else None
+    dyn = g.t('dynamic_r') if g.has('dynamic_r') else None
+    depth, var, rgb, valid, aux = orc.render_rays(W, g.ocfg, o, d, g.t('gt_depth'), geo, col, g.t('cloud'), g.stage,
+                                                  is_tracker=g.is_tracker, dynamic_r=dyn, exposure_feat=ef, dtype=dtype)
+    loss = (g.t('up_depth').to(dtype) * depth).sum() + (g.t('up_rgb').to(dtype) * rgb).sum()
+    loss.backward()
+    return dict(depth=depth.detach(), var=var.detach(), rgb=rgb.detach(), valid=valid, g_geo=geo.grad, g_col=col.grad,
+                g_o=o.grad, g_d=d.grad, g_ef=None if ef is None else ef.grad,
+                g_w={k: v.grad for k, v in W.items() if v.grad is not None}, aux=aux)
+
+
+def grad_ok(ours, truth64, oracle32, floor=1e-4):
+    """SURVEY.md 8c criterion: L2-relative error vs the fp64 restatement must be
+    <= max(1e-4, 2 x the fp32 oracle's own error vs fp64).  -> (ok, err_ours, err_oracle)"""
+    e_ours = rel_l2(ours, truth64)
+    e_orc = rel_l2(oracle32, truth64)
+    return e_ours <= max(floor, 2 * e_orc), e_ours, e_orc
+
+
+def run_case_cuda_vs_oracle(name, device='cuda:0', verbose=False):
+    g = Golden(name)
+    ours = run_cuda(g, device)
+    o32, o64 = run_oracle(g, torch.float32), run_oracle(g, torch.float64)
+    res = {'ok': True}
+    res['valid_equal'] = bool(torch.equal(ours['valid'].bool(), o32['valid']))
+    res['depth'] = rel_l2(ours['depth'], o32['depth'])
+    res['rgb'] = rel_l2(ours['rgb'], o32['rgb'])
+    res['var'] = rel_l2(ours['var'], o32['var'])
+    res['ok'] &= res['valid_equal'] and res['depth'] < 1e-4 and res['rgb'] < 1e-4 and res['var'] < 1e-4
+    for key in ('g_geo', 'g_col', 'g_o', 'g_d', 'g_ef'):
+        if ours[key] is None or o64[key] is None:
+            continue
+        if o64[key].abs().max() == 0:
+            ok = bool(ours[key].abs().max() == 0)
+            res[key] = 0.0
+        else:
+            ok, e, eo = grad_ok(ours[key], o64[key], o32[key])
+            res[key], res[key + '_oracle'] = e, eo
+        res['ok'] &= ok
+    worst = 0.0
+    for k, gw in ours['g_w'].items():
+        if k not in o64['g_w']:
+            if gw.abs().max() > 0:
+                res['ok'] = False
+                res['unexpected_grad_' + k] = float(gw.abs().max())
+            continue
+        ok, e, eo = grad_ok(gw, o64['g_w'][k], o32['g_w'][k])
+        worst = max(worst, e)
+        if not ok:
+            res['ok'] = False
+            res['bad_' + k] = (e, eo)
+    res['g_w_worst'] = worst
+    if verbose:
+        print(name, res)
+    return res

@@ -1,0 +1,91 @@
+"""GPU, BASELINE.json full sizes (R = 4992 rays, N = 2e5 points): size-independent properties,
+since the oracle cannot be run at this size in seconds:
+  * neighbour sets of a random subsample == exact k-NN oracle on that subsample (bit-exact),
+  * ray-shard invariance: rendering two halves == rendering the whole batch (bit-exact forward;
+    this is the property the multi-GPU ray sharding relies on),
+  * linearity of the backward in the upstream gradients,
+  * rendered depth lies inside the sampled z-band of its ray."""
+import pytest
+import torch
+
+import loopy_slam_b200 as L
+from loopy_slam_b200.stream import SyntheticRoom, build_point_cloud, sample_batch
+from oracle.knn import exact_knn, radius_sq, FLT_MAX
+from parity import SlamLike
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+@pytest.fixture(scope='module')
+def scene():
+    room = SyntheticRoom()
+    cloud, geo, col = build_point_cloud(room, 200000, frame_stride=40, pixels_per_frame=20000)
+    o, d, g, c = sample_batch(room, list(range(0, 480, 40)), 416, seed=7)
+    cfg = L.default_cfg('replica')
+    torch.manual_seed(1219)
+    model = L.get_model(cfg).to(DEV)
+    rend = L.Renderer(cfg, None, SlamLike(room.H, room.W, room.fx, room.fy, room.cx, room.cy))
+    rend.sigmoid_coefficient = 0.1
+    return dict(cloud=cloud.to(DEV), geo=geo.to(DEV), col=col.to(DEV), o=o.to(DEV), d=d.to(DEV), g=g.to(DEV),
+                c=c.to(DEV), model=model, rend=rend, cfg=cfg)
+
+
+class NPC:
+    def get_radius_query(self):
+        return 0.08
+
+
+def _render(sc, sl=slice(None), stage='color', grads=False, up=None):
+    geo = sc['geo'].clone().requires_grad_(grads)
+    col = sc['col'].clone().requires_grad_(grads)
+    out = sc['rend'].render_batch_ray(NPC(), sc['model'], sc['d'][sl], sc['o'][sl], DEV, stage, gt_depth=sc['g'][sl],
+                                      npc_geo_feats=geo, npc_col_feats=col, cloud_pos=sc['cloud'])
+    if grads:
+        (out[0] * up[0]).sum().add((out[2] * up[1]).sum()).backward()
+        return out, geo.grad, col.grad
+    return out
+
+
+def test_fullsize_neighbours_exact(scene):
+    sc = scene
+    from loopy_slam_b200.renderer import GridIndex
+    grid = GridIndex(sc['cloud'], 0.08)
+    gen = torch.Generator().manual_seed(0)
+    sel = torch.randint(0, sc['o'].shape[0], (300,), generator=gen)
+    pts = (sc['o'][sel] + sc['d'][sel] * sc['g'][sel, None]).cpu()
+    D, I, nn = grid.query(pts.to(DEV), 0.08)
+    Dr, Ir = exact_knn(pts, sc['cloud'].cpu(), 8, chunk=64)
+    keep = ~(Dr > radius_sq(0.08))
+    assert torch.equal(I.cpu(), torch.where(keep, Ir, torch.full_like(Ir, -1)))
+    assert torch.equal(D.cpu(), torch.where(keep, Dr, torch.full_like(Dr, FLT_MAX)))
+    assert nn.float().mean() > 4
+
+
+def test_fullsize_shard_invariance_and_band(scene):
+    sc = scene
+    R = sc['o'].shape[0]
+    assert R > 4500
+    with torch.no_grad():
+        whole = _render(sc)
+        a, b = _render(sc, slice(0, R // 2)), _render(sc, slice(R // 2, R))
+    for k in range(4):
+        assert torch.equal(whole[k], torch.cat([a[k], b[k]])), k
+    depth, var, rgb, valid = whole
+    assert valid.float().mean() > 0.9
+    v = valid
+    assert (depth[v] >= 0.98 * sc['g'][v] * (1 - 1e-5)).all() and (depth[v] <= 1.02 * sc['g'][v] * (1 + 1e-5)).all()
+    assert (rgb >= 0).all() and (rgb <= 1).all() and torch.isfinite(var).all()
+
+
+def test_fullsize_backward_linearity(scene):
+    sc = scene
+    R = sc['o'].shape[0]
+    gen = torch.Generator().manual_seed(5)
+    u1 = (torch.randn(R, generator=gen).to(DEV), torch.randn(R, 3, generator=gen).to(DEV))
+    u2 = (torch.randn(R, generator=gen).to(DEV), torch.randn(R, 3, generator=gen).to(DEV))
+    _, g1, c1 = _render(sc, grads=True, up=u1)
+    _, g2, c2 = _render(sc, grads=True, up=u2)
+    _, g3, c3 = _render(sc, grads=True, up=(2 * u1[0] - u2[0], 2 * u1[1] - u2[1]))
+    assert (g3 - (2 * g1 - g2)).norm() / g3.norm() < 1e-5
+    assert (c3 - (2 * c1 - c2)).norm() / c3.norm() < 1e-5

@@ -1,0 +1,213 @@
+"""GPU parity tests: the fused sm_100a path (through the C ABI) vs the oracle and the
+reference-generated golden vectors.  Tolerances: forward <= 1e-4 relative vs the
+fp32 oracle, masks exact, neighbour index sets bit-exact, gradients <= max(1e-4, 2x the fp32
+oracle's own error) vs the fp64 restatement."""
+import numpy as np
+import pytest
+import torch
+
+import loopy_slam_b200 as L
+from helpers import GOLDEN_CASES, Golden, rel_l2
+from oracle.knn import exact_knn, neighbor_num, radius_sq, FLT_MAX
+from parity import run_case_cuda_vs_oracle, run_cuda, cfg_from_ocfg, build_model, SlamLike
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _inradius(D, I, r2):
+    if r2.dtype == torch.float64:
+        keep = ~(D.to(torch.float64) > r2) & (I >= 0)
+    else:
+        keep = ~(D > r2) & (I >= 0)
+    return torch.where(keep, D, torch.full_like(D, FLT_MAX)), torch.where(keep, I, torch.full_like(I, -1))
+
+
+@pytest.mark.parametrize('n,p,cell,maxc', [(5000, 3000, 0.08, 1 << 22), (7, 200, 0.08, 1 << 22), (0, 50, 0.08, 1 << 10),
+                                            (20000, 4000, 0.05, 1 << 12), (3000, 2000, 0.16, 1 << 22)])
+def test_knn_bit_exact(n, p, cell, maxc):
+    gen = torch.Generator().manual_seed(n + p)
+    cloud = torch.rand(n, 3, generator=gen) * torch.tensor([2.0, 1.5, 1.0]) - 0.5
+    if n > 100:
+        cloud[10] = cloud[3]
+        cloud[11] = cloud[3]                       # duplicates: tie-break by lower id
+    q = torch.rand(p, 3, generator=gen) * torch.tensor([2.2, 1.7, 1.2]) - 0.6
+    if n > 100:
+        q[0] = cloud[3]
+        q[1] = cloud[50] + torch.tensor([0.08, 0.0, 0.0])   # a point (nearly) exactly at r
+    from loopy_slam_b200.renderer import GridIndex
+    grid = GridIndex(cloud.to(DEV), cell, max_cells=maxc)
+    for radius, dyn in ((0.08, None), (0.04, None), (0.08, 'dyn')):
+        dr = None
+        if dyn:
+            dr = 0.04 + 0.12 * torch.rand(p, generator=gen, dtype=torch.float64)
+        D, I, nn = grid.query(q.to(DEV), radius, None if dr is None else dr.to(DEV))
+        D, I, nn = D.cpu(), I.cpu(), nn.cpu()
+        Dr, Ir = exact_knn(q, cloud, 8)
+        r2 = radius_sq(radius, dr)
+        De, Ie = _inradius(Dr, Ir, r2)
+        assert torch.equal(I, Ie), (radius, dyn)
+        assert torch.equal(D, De)
+        assert torch.equal(nn, neighbor_num(Dr, r2))
+
+
+@pytest.mark.parametrize('name', GOLDEN_CASES)
+def test_render_matches_oracle_and_fp64_truth(name):
+    res = run_case_cuda_vs_oracle(name, DEV, verbose=True)
+    assert res['ok'], res
+
+
+@pytest.mark.parametrize('name', GOLDEN_CASES)
+def test_render_matches_reference_golden(name):
+    """Directly against the numbers the real reference produced (tests/golden/make_golden.py)."""
+    g = Golden(name)
+    ours = run_cuda(g, DEV)
+    assert torch.equal(ours['valid'].bool(), g.t('valid'))
+    torch.testing.assert_close(ours['depth'], g.t('depth'), rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(ours['rgb'], g.t('rgb'), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(ours['var'], g.t('var'), rtol=1e-3, atol=1e-7)
+    assert rel_l2(ours['g_geo'], g.t('g_geo_feats')) < 5e-4
+    if g.stage == 'color':
+        assert rel_l2(ours['g_col'], g.t('g_col_feats')) < 5e-4
+    if g.is_tracker:
+        assert rel_l2(ours['g_o'], g.t('g_rays_o')) < 2e-3
+        assert rel_l2(ours['g_d'], g.t('g_rays_d')) < 2e-3
+    if g.has('g_exposure_feat'):
+        assert rel_l2(ours['g_ef'], g.t('g_exposure_feat')) < 5e-4
+    for k, ref in g.param_grads.items():
+        if k not in ours['g_w']:
+            assert ref.abs().max() == 0, k
+            continue
+        assert rel_l2(ours['g_w'][k], ref) < 1e-3, k
+
+
+def test_grad_pruning_flags():
+    """needs_input_grad pruning: with frozen decoders and constant rays only feature grads come back."""
+    g = Golden('replica_color_mapper')
+    full = run_cuda(g, DEV, param_grads=True)
+    pruned = run_cuda(g, DEV, param_grads=False)
+    assert pruned['g_w'] == {}
+    assert rel_l2(pruned['g_geo'], full['g_geo']) < 1e-5   # atomics reorder only
+    assert rel_l2(pruned['g_col'], full['g_col']) < 1e-5
+    torch.testing.assert_close(pruned['depth'], full['depth'], rtol=0, atol=0)
+
+
+def test_sample_rays_and_pose_match_torch():
+    gen = torch.Generator().manual_seed(3)
+    H, W, fx, fy, cx, cy = 68, 120, 60.0, 61.0, 59.5, 33.5
+    depth = torch.rand(H, W, generator=gen) + 0.5
+    depth[::5, ::7] = 0
+    color = torch.rand(H, W, 3, generator=gen)
+    cam = torch.tensor([0.9, 0.1, -0.2, 0.3, 0.5, -0.4, 1.2], requires_grad=True)
+    cam_g = cam.detach().clone().to(DEV).requires_grad_(True)
+    # ours
+    torch.manual_seed(5)
+    c2w_g = L.get_camera_from_tensor(cam_g)
+    ro, rd, sd, sc, i, j = L.get_samples(4, H - 4, 6, W - 6, 500, H, W, fx, fy, cx, cy, c2w_g, depth.to(DEV),
+                                         color.to(DEV), DEV, depth_filter=True, return_index=True)
+    up = torch.randn(rd.shape, generator=torch.Generator().manual_seed(9))
+    ((rd * up.to(DEV)).sum() + (ro * up.to(DEV) * 0.5).sum()).backward()
+    # torch restatement of common.py:104-120,301-343 on the same pixels
+    c2w = torch.cat([L.quad2rotation(cam[None, :4])[0], cam[4:, None]], 1)
+    ii, jj = i.cpu().float(), j.cpu().float()
+    dirs = torch.stack([(ii - cx) / fx, -(jj - cy) / fy, -torch.ones_like(ii)], -1)
+    rd_t = torch.sum(dirs[:, None, :] * c2w[:3, :3], -1)
+    ro_t = c2w[:3, -1].expand(rd_t.shape)
+    ((rd_t * up).sum() + (ro_t * up * 0.5).sum()).backward()
+    torch.testing.assert_close(rd.detach().cpu(), rd_t.detach(), rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(ro.detach().cpu(), ro_t.detach(), rtol=0, atol=1e-7)
+    assert (sd > 0).all() and torch.equal(sd.cpu(), depth[j.cpu(), i.cpu()])
+    torch.testing.assert_close(sc.cpu(), color[j.cpu(), i.cpu()])
+    assert (i >= 6).all() and (i < W - 6).all() and (j >= 4).all() and (j < H - 4).all()
+    assert rel_l2(cam_g.grad, cam.grad) < 1e-5
+
+
+def test_render_img_matches_tiled_oracle():
+    """render_img (one fused launch, per-3000-ray far statistics) vs the oracle run tile by tile."""
+    from oracle import render as orc
+    g = Golden('replica_color_sparse_zero_depth')
+    cfg = cfg_from_ocfg(g.ocfg)
+    gen = torch.Generator().manual_seed(21)
+    H, W = 24, 30
+    fx = fy = 20.0
+    cx, cy = 14.5, 11.5
+    model = build_model(cfg, g.weights, DEV)
+    rend = L.Renderer(cfg, None, SlamLike(H, W, fx, fy, cx, cy), ray_batch_size=100)
+    rend.sigmoid_coefficient = g.ocfg.sigmoid_coef
+    gdc = Golden('replica_color_mapper')     # dense cloud, camera from its first ray origin
+    cloud, geo, col = gdc.t('cloud'), gdc.t('geo_feats'), gdc.t('col_feats')
+    c2w = torch.eye(4)
+    c2w[:3, 3] = gdc.t('rays_o')[0]
+    dvec = gdc.t('rays_d')[0]
+    zc = -dvec / dvec.norm()
+    xc = torch.linalg.cross(torch.tensor([0., 0., 1.]), zc)
+    xc = xc / xc.norm()
+    c2w[:3, 0], c2w[:3, 1], c2w[:3, 2] = xc, torch.linalg.cross(zc, xc), zc
+    gt = 0.4 + torch.rand(H, W, generator=gen) * 0.8
+    gt[::4, ::3] = 0.0
+
+    class NPC:
+        def get_radius_query(self):
+            return g.ocfg.radius_query
+    d_img, v_img, c_img = rend.render_img(NPC(), model, c2w.to(DEV), DEV, 'color', gt_depth=gt.to(DEV),
+                                          npc_geo_feats=geo.to(DEV), npc_col_feats=col.to(DEV), cloud_pos=cloud.to(DEV))
+    assert d_img.dtype == torch.float64 and d_img.shape == (H, W) and c_img.shape == (H, W, 3)
+    ro, rd = L.get_rays(H, W, fx, fy, cx, cy, c2w.to(DEV), DEV)
+    ro, rd = ro.reshape(-1, 3).cpu(), rd.reshape(-1, 3).cpu()
+    W_ = {k: v for k, v in g.weights.items()}
+    outs = []
+    for s in range(0, H * W, 100):
+        dd, vv, cc, _, _ = orc.render_rays(W_, g.ocfg, ro[s:s + 100], rd[s:s + 100], gt.reshape(-1)[s:s + 100], geo, col,
+                                           cloud, 'color')
+        outs.append((dd, vv, cc))
+    d_ref = torch.cat([o[0] for o in outs]).reshape(H, W)
+    c_ref = torch.cat([o[2] for o in outs]).reshape(H, W, 3)
+    assert (d_img.cpu()[gt == 0] == 0).all()
+    torch.testing.assert_close(d_img.cpu().float(), d_ref, rtol=2e-4, atol=1e-5)
+    torch.testing.assert_close(c_img.cpu(), c_ref, rtol=2e-3, atol=2e-4)
+
+
+def test_eval_points_matches_oracle_decode():
+    from oracle import render as orc
+    g = Golden('replica_color_mapper')
+    cfg = cfg_from_ocfg(g.ocfg)
+    model = build_model(cfg, g.weights, DEV)
+    H, W, fx, fy, cx, cy = g.raw['intrinsics']
+    rend = L.Renderer(cfg, None, SlamLike(H, W, fx, fy, cx, cy))
+    o32 = __import__('parity').run_oracle(g, torch.float32)
+    pts = o32['aux']['p']
+
+    class NPC:
+        def get_radius_query(self):
+            return g.ocfg.radius_query
+    raw, ray_mask, point_mask = rend.eval_points(pts.to(DEV), model, NPC(), 'color', DEV, g.t('geo_feats').to(DEV),
+                                                 g.t('col_feats').to(DEV), False, g.t('cloud').to(DEV), None,
+                                                 ray_pts_num=5)
+    ref_raw = o32['aux']['raw'].reshape(-1, 4)
+    has = o32['aux']['has']
+    assert torch.equal(point_mask.cpu(), has)
+    assert torch.equal(ray_mask.cpu(), o32['valid'])
+    torch.testing.assert_close(raw.cpu()[has][:, :3], ref_raw[has][:, :3], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(raw.cpu()[has][:, 3], ref_raw[has][:, 3], rtol=1e-3, atol=1e-3)
+
+
+def test_neural_point_cloud_insert_and_query():
+    cfg = L.default_cfg('replica')
+    cfg['mapping']['device'] = DEV
+    npc = L.NeuralPointCloud(cfg)
+    gen = torch.Generator().manual_seed(4)
+    o = torch.zeros(400, 3)
+    d = torch.randn(400, 3, generator=gen)
+    d = d / d.norm(dim=1, keepdim=True)
+    dep = 1.0 + 0.2 * torch.rand(400, generator=gen)
+    col = torch.rand(400, 3, generator=gen)
+    n1 = int(npc.add_neural_points(o.to(DEV), d.to(DEV), dep.to(DEV), col.to(DEV)))
+    assert n1 == 400 and npc.pts_num() == 1200
+    n2 = int(npc.add_neural_points(o.to(DEV), d.to(DEV), dep.to(DEV), col.to(DEV)))   # same locations again
+    assert n2 == 0 and npc.pts_num() == 1200
+    D, I, nn = npc.find_neighbors_faiss((o + d * dep[:, None]).to(DEV), step='query')
+    Dr, Ir = exact_knn(o + d * dep[:, None], npc.cloud_pos_tensor().cpu(), 8)
+    r2 = radius_sq(0.08)
+    _, Ie = _inradius(Dr, Ir, r2)
+    assert torch.equal(I.cpu(), Ie) and (nn >= 1).all()
+    assert npc.get_geo_feats().shape == (1200, 32) and abs(float(npc.get_geo_feats().std()) - 0.1) < 0.01
