@@ -59,7 +59,7 @@ struct PackJob {
   int gap_at, gap;           // input index k >= gap_at is shifted by +gap in the destination
   int transpose;             // 1: dst[k'][n]  0: dst[n][k']
 };
-constexpr int MAX_PACK_JOBS = 24;
+constexpr int MAX_PACK_JOBS = 32;
 struct PackJobs { PackJob j[MAX_PACK_JOBS]; int n; };
 
 // ------------------------------------------------------------------ saved activations (global)

@@ -487,6 +487,7 @@ __global__ void far_bound_kernel(const float* __restrict__ g, int64_t R, int64_t
 // host side ------------------------------------------------------------------------------------
 static void add_job(PackJobs& J, int src, int n_out, int n_in, int dst, int dst_rows, int dst_ld, int transpose,
                     int gap_at = 1 << 30, int gap = 0) {
+  if (J.n >= MAX_PACK_JOBS) return;   // guarded by the static job list in launch_pack (25 jobs)
   PackJob& j = J.j[J.n++];
   j.src = src; j.n_out = n_out; j.n_in = n_in; j.dst = dst; j.dst_rows = dst_rows; j.dst_ld = dst_ld;
   j.gap_at = gap_at; j.gap = gap; j.transpose = transpose;

@@ -1,0 +1,97 @@
+"""Multi-GPU data parallelism of the render hot path.
+
+Rays are independent given replicated {cloud positions, feature tables, decoder weights}
+(<= N*(12+256) B ~ 0.27 GB at N = 1e6), so the path shards by RAYS: one process per GPU
+(torch.distributed, NCCL over NVLink/NVSwitch), every rank renders its own slice of the
+iteration's rays with the fused kernels, and ONE all-reduce(sum) per optimiser step over a flat
+buffer [d_geo_feats(n_sel x 32) | d_col_feats(n_sel x 32) | decoder grads | pose grad] makes the
+gradients identical everywhere; every rank then applies the same Adam step, so the replicas stay
+in sync without any broadcast.  The reference losses are *sums* over rays (src/Mapper.py:693-717,
+src/Tracker.py:183-188), so sharded-sum + all-reduce is exact up to fp32 addition order.
+
+Batch-global statistics that must not be sharded (the mapper's inside_mask uses the batch median,
+src/Mapper.py:674-676) are computed on the full batch before slicing -- see shard_rays().
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from torchrun's env (RANK/WORLD_SIZE/LOCAL_RANK/MASTER_*).
+    Returns (rank, world, local_rank).  World size 1 (no env) needs no process group."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+        if backend == 'nccl':
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def shard_bounds(n, rank, world):
+    """Contiguous slice [lo, hi) of n rays owned by `rank` (per-frame sub-batches stay contiguous,
+    needed by the per-frame exposure slices of src/Mapper.py:700-714)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_rays(tensors, rank, world):
+    """Slice every (R, ...) tensor of a ray batch to this rank's contiguous share."""
+    n = tensors[0].shape[0]
+    lo, hi = shard_bounds(n, rank, world)
+    return [t[lo:hi] if t is not None else None for t in tensors]
+
+
+class GradAllReducer:
+    """One all-reduce per optimiser step over a persistent flat fp32 buffer."""
+
+    def __init__(self, params, group=None):
+        self.params = [p for p in params]
+        self.group = group
+        self.numel = sum(p.numel() for p in self.params)
+        self.flat = None
+
+    def _ensure(self, device):
+        if self.flat is None or self.flat.device != device or self.flat.numel() != self.numel:
+            self.flat = torch.zeros(self.numel, dtype=torch.float32, device=device)
+        return self.flat
+
+    def allreduce_(self):
+        """Sum .grad of all params across ranks in place (missing grads count as zero)."""
+        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return 0
+        dev = next((p.grad.device for p in self.params if p.grad is not None), self.params[0].device)
+        flat = self._ensure(dev)
+        off = 0
+        views = []
+        for p in self.params:
+            n = p.numel()
+            v = flat[off:off + n]
+            if p.grad is None:
+                v.zero_()
+            else:
+                v.copy_(p.grad.reshape(-1))
+            views.append(v)
+            off += n
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        for p, v in zip(self.params, views):
+            if p.grad is None:
+                p.grad = v.view(p.shape).clone()
+            else:
+                p.grad.copy_(v.view(p.shape))
+        return flat.numel() * 4
+
+
+def max_over_ranks(value, device):
+    """Max of a python float over ranks (device-side timing is reported as the max over ranks)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

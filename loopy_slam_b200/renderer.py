@@ -81,7 +81,24 @@ def _grid_for(npc, cloud_pos, cell, cache):
 class _RenderCtx:
     """Per-call constants shared by forward and backward."""
     __slots__ = ('prm', 'grid', 'stage', 'is_tracker', 'blob', 'wstruct', 'flat', 'saved', 'scratch', 'R',
-                 'r_query', 'device', 'far_group', 'force_save')
+                 'r_query', 'device', 'far_group', 'force_save', 'timing')
+
+
+def _tick(timing):
+    """Optional CUDA-event bracket around one C-ABI launch (bench.py: Renderer._timing = {...})."""
+    if timing is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def _tock(timing, key, start):
+    if timing is None:
+        return
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    timing[key].append((start, e))
 
 
 def _f32c(t):
@@ -108,11 +125,13 @@ class _RenderFn(torch.autograd.Function):
               'lsr_render_workspace_bytes')
         rc.scratch = torch.empty(cb.value, dtype=torch.uint8, device=dev)
         rc.saved = torch.empty(sb.value, dtype=torch.uint8, device=dev) if need_bwd else None
+        ev = _tick(rc.timing)
         check(lib().lsr_render_fwd(ctypes.byref(rc.prm), ptr(rc.grid.ws), ptr(rc.grid.cloud), rc.grid.n,
                                    ptr(rays_o), ptr(rays_d), ptr(gt_depth), ptr(rc.r_query), ptr(far_zero),
                                    rc.far_group, R, ptr(geo_feats), ptr(col_feats), ctypes.byref(rc.wstruct),
                                    ptr(affine), rc.stage, ptr(depth), ptr(var), ptr(rgb), ptr(valid),
                                    ptr(rc.saved), ptr(rc.scratch), stream_ptr(dev)), 'lsr_render_fwd')
+        _tock(rc.timing, 'fwd', ev)
         ctx.rc = rc
         ctx.param_shapes = [p.shape for p in params]
         ctx.save_for_backward(rays_o, rays_d, gt_depth, geo_feats, col_feats, affine)
@@ -154,12 +173,14 @@ class _RenderFn(torch.autograd.Function):
         g_depth = _f32c(g_depth) if g_depth is not None else torch.zeros(R, dtype=torch.float32, device=dev)
         g_var = _f32c(g_var) if g_var is not None else None
         g_rgb = _f32c(g_rgb) if g_rgb is not None else None
+        ev = _tick(rc.timing)
         check(lib().lsr_render_bwd(ctypes.byref(rc.prm), ptr(rc.grid.ws), ptr(rc.grid.cloud), rc.grid.n,
                                    ptr(rays_o), ptr(rays_d), ptr(gt_depth), ptr(rc.r_query), R, ptr(geo_feats),
                                    ptr(col_feats), ctypes.byref(rc.wstruct), ptr(affine), rc.stage,
                                    1 if rc.is_tracker else 0, ptr(rc.saved), ptr(rc.scratch), ptr(g_depth),
                                    ptr(g_var), ptr(g_rgb), flags, ptr(d_geo), ptr(d_col), ptr(d_w), ptr(d_aff),
                                    ptr(d_o), ptr(d_d), stream_ptr(dev)), 'lsr_render_bwd')
+        _tock(rc.timing, 'bwd', ev)
         rc.saved = None
         pgrads = []
         for k, (off, n, t) in enumerate(zip(blob.offsets, blob.numels, ctx.param_shapes)):
@@ -249,6 +270,7 @@ def fused_render(renderer, npc, decoders, rays_d, rays_o, stage, gt_depth, npc_g
     rc.device = dev
     rc.far_group = fgroup
     rc.force_save = bool(force_save)
+    rc.timing = getattr(renderer, '_timing', None)
     out = _RenderFn.apply(rc, rays_o, rays_d, gt, geo, col, affine, far, *params)
     if return_ctx:
         return out, rc

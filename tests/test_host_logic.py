@@ -1,0 +1,97 @@
+"""CPU: host-side logic that needs no GPU -- weight-blob aliasing, config mirror, stream generator,
+frustum selection, decoder/state_dict compatibility with the reference layout."""
+import numpy as np
+import pytest
+import torch
+
+import loopy_slam_b200 as L
+from loopy_slam_b200.frustum import get_mask_from_c2w
+from loopy_slam_b200.stream import SyntheticRoom, build_point_cloud, sample_batch
+from helpers import Golden
+
+
+def test_state_dict_matches_reference_layout():
+    cfg = L.default_cfg('replica')
+    m = L.get_model(cfg)
+    g = Golden('replica_color_mapper')
+    ref = {k: v.shape for k, v in g.weights.items() if k != 'color_decoder.embedder._B'}
+    ours = {k: v.shape for k, v in m.state_dict().items()}
+    assert list(ours.keys()) == list(ref.keys())          # same names, same ORDER (Appendix B offsets)
+    assert ours == ref
+    assert sum(p.numel() for p in m.parameters()) == 127447
+    assert m.color_decoder.embedder._B.shape == (3, 20) and not isinstance(m.color_decoder.embedder._B, torch.nn.Parameter)
+    cfg2 = L.default_cfg('scannet')
+    m2 = L.get_model(cfg2)
+    assert 'color_decoder.mlp_exposure.linear2.weight' in m2.state_dict()
+
+
+def test_weight_blob_aliases_parameters_and_survives_updates():
+    cfg = L.default_cfg('replica')
+    m = L.get_model(cfg)
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    flat, W = m.blob.ensure('cpu')
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, before[k]), k                 # values preserved
+    for t, off in zip(m.blob.tensors(), m.blob.offsets):
+        assert off % 4 == 0 and t.data_ptr() == flat.data_ptr() + 4 * off
+    assert W.n_elems == m.blob.n_elems and W.c_lin_w[3] == m.blob.offsets[[e[0] + str(e[1]) for e in m.blob.entries].index('c_lin_w3')]
+    # an in-place optimiser step is visible through the blob without re-packing
+    opt = torch.optim.SGD([m.color_decoder.pts_linears[1].weight], lr=1.0)
+    m.color_decoder.pts_linears[1].weight.grad = torch.ones_like(m.color_decoder.pts_linears[1].weight)
+    opt.step()
+    off = W.c_lin_w[1]
+    assert torch.equal(flat[off:off + 128 * 128].view(128, 128), m.color_decoder.pts_linears[1].weight.detach())
+    flat2, _ = m.blob.ensure('cpu')
+    assert flat2.data_ptr() == flat.data_ptr()              # no rebuild when aliasing is intact
+    # load_state_dict copies in place -> aliasing intact; replacing .data breaks it -> rebuilt
+    m.load_state_dict(before)
+    assert m.blob.ensure('cpu')[0].data_ptr() == flat.data_ptr()
+    m.geo_decoder.output_linear.weight.data = torch.zeros(1, 32)
+    flat3, _ = m.blob.ensure('cpu')
+    assert flat3.data_ptr() != flat.data_ptr()
+    assert float(flat3[m.blob.struct.g_out_w:m.blob.struct.g_out_w + 32].abs().sum()) == 0
+
+
+def test_config_mirror_inherit(tmp_path):
+    base = tmp_path / 'base.yaml'
+    mid = tmp_path / 'mid.yaml'
+    leaf = tmp_path / 'leaf.yaml'
+    base.write_text('a: 1\nsub:\n  x: 1\n  y: 2\n')
+    mid.write_text('sub:\n  y: 3\n')
+    leaf.write_text(f'inherit_from: {mid}\nsub:\n  z: 4\n')
+    cfg = L.load_config(str(leaf), str(base))
+    assert cfg['a'] == 1 and cfg['sub'] == {'x': 1, 'y': 3, 'z': 4}
+    d = L.default_cfg('scannet')
+    assert d['model']['encode_exposure'] and d['rendering']['near_end_surface'] == 0.96 and d['use_dynamic_radius']
+    assert not L.default_cfg('replica')['use_dynamic_radius']
+
+
+def test_synthetic_stream_geometry():
+    room = SyntheticRoom(H=48, W=64, fx=40., fy=40., cx=31.5, cy=23.5, n_frames=100, half=(1.0, 0.8, 0.6))
+    color, depth, c2w = room.frame(3)
+    assert color.shape == (48, 64, 3) and depth.shape == (48, 64) and c2w.shape == (4, 4)
+    assert 0 < float((depth == 0).float().mean()) < 0.05 and float(color.min()) >= 0 and float(color.max()) <= 1
+    R = c2w[:3, :3].double()
+    assert torch.allclose(R @ R.t(), torch.eye(3, dtype=torch.float64), atol=1e-6)
+    o, d, g, c = sample_batch(room, [3], 200, seed=1)
+    hit = o + d * g[:, None]
+    on_wall = ((hit.abs() - torch.tensor([1.0, 0.8, 0.6])).abs() < 1e-4).any(1)
+    assert on_wall.all()
+    cloud, geo, col = build_point_cloud(room, 900, pixels_per_frame=500, frame_ids=[3], max_frames=10)
+    assert cloud.shape[0] <= 900 and cloud.shape[0] % 3 == 0 and geo.shape == (cloud.shape[0], 32)
+    assert abs(float(geo.std()) - 0.1) < 0.02
+
+
+def test_frustum_selection_cpu():
+    room = SyntheticRoom(H=48, W=64, fx=40., fy=40., cx=31.5, cy=23.5, n_frames=100, half=(1.0, 0.8, 0.6), hole_frac=0.0)
+    color, depth, c2w = room.frame(0)
+    o, d, g, _ = sample_batch(room, [0], 300, seed=2)
+    surf = o + d * g[:, None]
+    behind = o - d * g[:, None]                  # behind the camera
+    pts = torch.cat([surf, behind, surf + 3.0 * d])   # visible | behind | far beyond the wall
+    idx = get_mask_from_c2w(pts, c2w, depth, room.H, room.W, room.fx, room.fy, room.cx, room.cy, edge=0)
+    sel = torch.zeros(pts.shape[0], dtype=torch.bool)
+    sel[idx] = True
+    assert sel[:surf.shape[0]].float().mean() > 0.9
+    assert not sel[surf.shape[0]:2 * surf.shape[0]].any()
+    assert sel[2 * surf.shape[0]:].float().mean() < 0.1
