@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'liblsr.so')
+LIB_PATH = os.environ.get('LSR_LIB', os.path.join(_HERE, 'liblsr.so'))   # LSR_LIB: A/B experiments only
 
 LSR_STAGE = {'geometry': 0, 'color': 1}
 FLAG_REL_POS, FLAG_DYNAMIC_R, FLAG_SKIP_ZERO_DEPTH = 1, 2, 4

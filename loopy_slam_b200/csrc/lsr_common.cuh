@@ -138,6 +138,85 @@ __device__ __forceinline__ void knn_walk(const GridView& g, float px, float py, 
   }
   out.cnt = cnt;
 }
+// Warp-cooperative version of knn_walk: the 32 lanes of one warp search for ONE query point.
+// Lanes fetch the (cy,cz) cell ranges in parallel, the candidates of all ranges are enumerated 32 at
+// a time (coalesced float4 loads inside a range), and the running top-8 by (D, id) lives in lanes
+// 0..7 (lane k = k-th nearest).  Selection = 8 rounds of REDUX min over (D bits, id).  Same exact
+// arithmetic, predicate and tie-break as knn_walk / the oracle.
+constexpr unsigned KNN_INF = 0x7f800000u;   // +inf bits; squared distances are >= 0 so bit order == value order
+constexpr int KNN_NOID = 0x7fffffff;
+
+__device__ __forceinline__ void knn_warp(const GridView& g, float px, float py, float pz, float rr, bool dyn,
+                                         float r2f, double r2d, unsigned& bestD, int& bestI) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  bestD = KNN_INF;
+  bestI = KNN_NOID;
+  const GridHeader* h = g.hdr;
+  if (h->n_points <= 0) return;
+  const float inv = h->inv_cell;
+  const float ox = h->origin[0], oy = h->origin[1], oz = h->origin[2];
+  const int dx = h->dims[0], dy = h->dims[1], dz = h->dims[2];
+  const int x0 = max(cell_coord_raw(px - rr, ox, inv), 0), x1 = min(cell_coord_raw(px + rr, ox, inv), dx - 1);
+  const int y0 = max(cell_coord_raw(py - rr, oy, inv), 0), y1 = min(cell_coord_raw(py + rr, oy, inv), dy - 1);
+  const int z0 = max(cell_coord_raw(pz - rr, oz, inv), 0), z1 = min(cell_coord_raw(pz + rr, oz, inv), dz - 1);
+  if (x0 > x1 || y0 > y1 || z0 > z1) return;
+  const int ny = y1 - y0 + 1, nranges = ny * (z1 - z0 + 1);
+  for (int rc0 = 0; rc0 < nranges; rc0 += 32) {
+    const int r = rc0 + lane;
+    int beg = 0, cnt = 0;
+    if (r < nranges) {
+      const int cz = z0 + r / ny, cy = y0 + r % ny;
+      const int base = (cz * dy + cy) * dx;
+      beg = __ldg(g.cell_start + base + x0);
+      cnt = __ldg(g.cell_start + base + x1 + 1) - beg;
+    }
+    int inc = cnt;   // inclusive prefix sum of the range sizes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(FULL, inc, o);
+      if (lane >= o) inc += v;
+    }
+    const int T = __shfl_sync(FULL, inc, 31);
+    const int nr_here = min(32, nranges - rc0);
+    for (int j0 = 0; j0 < T; j0 += 32) {
+      const int j = j0 + lane;
+      int rsel = 0;
+      for (int q = 0; q < nr_here; ++q) rsel += (__shfl_sync(FULL, inc, q) <= j) ? 1 : 0;
+      rsel = min(rsel, 31);
+      const int inc_sel = __shfl_sync(FULL, inc, rsel), cnt_sel = __shfl_sync(FULL, cnt, rsel);
+      const int beg_sel = __shfl_sync(FULL, beg, rsel);
+      unsigned cD = KNN_INF;
+      int cI = KNN_NOID;
+      if (j < T) {
+        const float4 q4 = __ldg(g.sorted + beg_sel + (j - (inc_sel - cnt_sel)));
+        const float D = sqdist_rn(q4.x, q4.y, q4.z, px, py, pz);
+        const bool outside = dyn ? ((double)D > r2d) : (D > r2f);
+        if (!outside) { cD = __float_as_uint(D); cI = __float_as_int(q4.w); }
+      }
+      const unsigned b7D = __shfl_sync(FULL, bestD, KNN - 1);
+      const int b7I = __shfl_sync(FULL, bestI, KNN - 1);
+      if (!__any_sync(FULL, (cD < b7D) || (cD == b7D && cI < b7I))) continue;
+      unsigned oD = lane < KNN ? bestD : KNN_INF;
+      int oI = lane < KNN ? bestI : KNN_NOID;
+      unsigned nD = KNN_INF;
+      int nI = KNN_NOID;
+#pragma unroll
+      for (int k = 0; k < KNN; ++k) {
+        const bool c_lt = (cD < oD) || (cD == oD && cI < oI);
+        const unsigned lD = c_lt ? cD : oD;
+        const int lI = c_lt ? cI : oI;
+        const unsigned mD = __reduce_min_sync(FULL, lD);
+        const int mI = __reduce_min_sync(FULL, lD == mD ? lI : KNN_NOID);
+        if (lane == k) { nD = mD; nI = mI; }
+        if (cD == mD && cI == mI) { cD = KNN_INF; cI = KNN_NOID; }
+        else if (oD == mD && oI == mI) { oD = KNN_INF; oI = KNN_NOID; }
+      }
+      bestD = nD;
+      bestI = nI;
+    }
+  }
+}
 #endif  // __CUDACC__
 
 }  // namespace lsr

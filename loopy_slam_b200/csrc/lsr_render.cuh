@@ -5,8 +5,16 @@
 
 namespace lsr {
 
-constexpr int NT = 256;        // threads per CTA (8 warps), one CTA per SM
-constexpr int TILE_M = 128;    // sample rows per tile
+#ifndef LSR_TILE_M
+#define LSR_TILE_M 128
+#endif
+constexpr int TILE_M = LSR_TILE_M;   // sample rows per tile (64: two CTAs per SM; 128: one)
+constexpr int NT = 2 * TILE_M;       // threads per CTA; the 8x8 / 4x4 register micro-tiles cover TILE_M rows
+constexpr int CTAS_PER_SM = TILE_M == 64 ? 2 : 1;
+constexpr int RSW = NT / 16;         // row stride of the WIDE thread map (16 threads across the columns)
+constexpr int RSN = NT / 8;          // row stride of the NARROW thread map (8 threads across the columns)
+constexpr int TMW32 = 32 / RSW;      // rows per thread when a WIDE-mapped output has only 32 rows
+constexpr int TMN32 = 32 / RSN;      // same for NARROW
 constexpr int KC = 16;         // contraction rows per streamed chunk
 constexpr int NSTAGE = 3;      // cp.async ring depth
 constexpr int HG = 32;         // geometry decoder hidden width  (decoder.py:566)
@@ -66,13 +74,14 @@ struct PackJobs { PackJob j[MAX_PACK_JOBS]; int n; };
 // Row p = ray*S + s.  Offsets in floats from the saved base.
 struct SavedLayout {
   size_t idx, w, D, misc, cg, cc, gs, gh, occ, cs, ch, u, sp, rgbs, outraw, total;
-  size_t P;
+  size_t P, Pp;
 };
 __host__ __device__ inline SavedLayout saved_layout(int64_t R, int S, int stage, int flags) {
   SavedLayout L;
   const size_t P = (size_t)R * S;
-  const size_t Pp = align_up(P, TILE_M) + TILE_M;
+  const size_t Pp = align_up(P, 128) + 128;   // row pitch of every plane (independent of the tile height)
   L.P = P;
+  L.Pp = Pp;
   size_t o = 0;
   L.idx = o;   o += Pp * KNN;
   L.w = o;     o += Pp * KNN;
@@ -131,6 +140,14 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+// DRAM -> L2 prefetch of `nrows` rows of `row_floats` floats (one request per 128-byte line)
+__device__ __forceinline__ void prefetch_rows_l2(const float* base, int nrows, int row_floats) {
+  const int lines_per_row = row_floats / 32;
+  for (int l = threadIdx.x; l < nrows * lines_per_row; l += NT)
+    prefetch_l2(base + (size_t)(l / lines_per_row) * row_floats + (l % lines_per_row) * 32);
 }
 
 // ------------------------------------------------------------------ tile GEMM
@@ -256,16 +273,16 @@ __device__ __forceinline__ void zero_acc(float (&acc)[TM][NC]) {
 }
 
 // thread -> tile coordinates of the two mappings used everywhere
-struct WideMap {    // 16 x 16 threads, 8 rows x (4 + 4) cols per thread -> 128 x 128
+struct WideMap {    // 16 x (NT/16) threads, 8 rows x (4 + 4) cols per thread -> TILE_M x 128
   int tx, ty;
   __device__ WideMap() : tx(threadIdx.x & 15), ty(threadIdx.x >> 4) {}
-  __device__ int row(int i) const { return ty + 16 * i; }
+  __device__ int row(int i) const { return ty + RSW * i; }
   __device__ int col(int g) const { return g * 64 + tx * 4; }   // first of 4 consecutive columns
 };
-struct NarrowMap {  // 8 x 32 threads, 4 rows x 4 cols per thread -> 128 x 32
+struct NarrowMap {  // 8 x (NT/8) threads, 4 rows x 4 cols per thread -> TILE_M x 32
   int tx, ty;
   __device__ NarrowMap() : tx(threadIdx.x & 7), ty(threadIdx.x >> 3) {}
-  __device__ int row(int i) const { return ty + 32 * i; }
+  __device__ int row(int i) const { return ty + RSN * i; }
   __device__ int col() const { return tx * 4; }
 };
 #endif  // __CUDACC__

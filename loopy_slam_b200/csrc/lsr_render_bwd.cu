@@ -66,7 +66,7 @@ __device__ __forceinline__ void scatter_idw(const float* sDC, const int* sIdx, c
   }
 }
 
-__global__ void __launch_bounds__(NT, 1) render_bwd_kernel(const __grid_constant__ BwdArgs a) {
+__global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __grid_constant__ BwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* sD = smem;                                   // [128][DLD] (colour) / [128][CLD] view (geometry)
   float* sB = sD + TILE_M * DLD;
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(NT, 1) render_bwd_kernel(const __grid_constant
   const bool g_af = (a.gflags & LSR_GRAD_AFFINE) && a.d_affine && a.prm.rgb_mode == LSR_RGB_AFFINE_SIGMOID;
   const bool trk = a.is_tracker && g_ry;              // neighbour weights depend on p
   const SavedLayout SL = saved_layout(a.R, S, a.stage, a.prm.flags);
-  const size_t Pp = align_up(SL.P, TILE_M) + TILE_M;
+  const size_t Pp = SL.Pp;
   const WideMap wm;
   const NarrowMap nm;
   float* __restrict__ dW = a.d_w;
@@ -266,20 +266,20 @@ __global__ void __launch_bounds__(NT, 1) render_bwd_kernel(const __grid_constant
       __syncthreads();
 
       if (g_cw) {   // output_linear gradients
-        if (tid < HC) {
+        for (int c = tid; c < HC; c += NT) {
           float s0 = 0.f, s1 = 0.f, s2 = 0.f;
           for (int m = 0; m < nrows; ++m) {
-            const float h = sv[SL.ch + ((size_t)4 * Pp + p0 + m) * HC + tid];
+            const float h = sv[SL.ch + ((size_t)4 * Pp + p0 + m) * HC + c];
             s0 = fmaf(sDOut[m * 4 + 0], h, s0); s1 = fmaf(sDOut[m * 4 + 1], h, s1); s2 = fmaf(sDOut[m * 4 + 2], h, s2);
           }
-          atomicAdd(dW + a.w.c_out_w + tid, s0);
-          atomicAdd(dW + a.w.c_out_w + HC + tid, s1);
-          atomicAdd(dW + a.w.c_out_w + 2 * HC + tid, s2);
-        } else if (tid < HC + 3) {
-          const int ch = tid - HC;
+          atomicAdd(dW + a.w.c_out_w + c, s0);
+          atomicAdd(dW + a.w.c_out_w + HC + c, s1);
+          atomicAdd(dW + a.w.c_out_w + 2 * HC + c, s2);
+        }
+        if (tid < 3) {
           float s = 0.f;
-          for (int m = 0; m < nrows; ++m) s += sDOut[m * 4 + ch];
-          atomicAdd(dW + a.w.c_out_b + ch, s);
+          for (int m = 0; m < nrows; ++m) s += sDOut[m * 4 + tid];
+          atomicAdd(dW + a.w.c_out_b + tid, s);
         }
       }
       float dH[8][8];
@@ -303,6 +303,10 @@ __global__ void __launch_bounds__(NT, 1) render_bwd_kernel(const __grid_constant
       zero_acc(dCacc);
 #pragma unroll 1
       for (int li = 4; li >= 0; --li) {
+        // DRAM -> L2 prefetch of the saved tiles this layer will read (softplus outputs now, the
+        // previous layer's h as the dW operand later)
+        prefetch_rows_l2(sv + SL.cs + ((size_t)li * Pp + p0) * HC, nrows, HC);
+        if (g_cw && li > 0) prefetch_rows_l2(sv + SL.ch + ((size_t)(li - 1) * Pp + p0) * HC, nrows, HC);
 #pragma unroll
         for (int g = 0; g < 2; ++g)
 #pragma unroll
@@ -311,10 +315,10 @@ __global__ void __launch_bounds__(NT, 1) render_bwd_kernel(const __grid_constant
                 make_float4(dH[i][g * 4 + 0], dH[i][g * 4 + 1], dH[i][g * 4 + 2], dH[i][g * 4 + 3]);
         __syncthreads();
         if (g_cw) {
-          if (tid < HC) {
+          for (int c = tid; c < HC; c += NT) {
             float s = 0.f;
-            for (int m = 0; m < nrows; ++m) s += sD[m * DLD + tid];
-            atomicAdd(dW + a.w.c_fc_b[li] + tid, s);
+            for (int m = 0; m < nrows; ++m) s += sD[m * DLD + c];
+            atomicAdd(dW + a.w.c_fc_b[li] + c, s);
           }
           float au[4][4];
           zero_acc(au);
@@ -327,26 +331,31 @@ __global__ void __launch_bounds__(NT, 1) render_bwd_kernel(const __grid_constant
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           const int col = wm.col(g);
+          float4 s4[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {      // all loads first: 8 independent 16 B requests in flight
+            const int r = wm.row(i);
+            s4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < nrows) s4[i] = __ldcs(reinterpret_cast<const float4*>(sv + SL.cs + ((size_t)li * Pp + p0 + r) * HC + col));
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int r = wm.row(i);
             float4 dA = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < nrows) {
-              const float4 s4 = *reinterpret_cast<const float4*>(sv + SL.cs + ((size_t)li * Pp + p0 + r) * HC + col);
-              dA = make_float4(dH[i][g * 4 + 0] * softplus100_grad_from_out(s4.x),
-                               dH[i][g * 4 + 1] * softplus100_grad_from_out(s4.y),
-                               dH[i][g * 4 + 2] * softplus100_grad_from_out(s4.z),
-                               dH[i][g * 4 + 3] * softplus100_grad_from_out(s4.w));
-            }
+            if (r < nrows)
+              dA = make_float4(dH[i][g * 4 + 0] * softplus100_grad_from_out(s4[i].x),
+                               dH[i][g * 4 + 1] * softplus100_grad_from_out(s4[i].y),
+                               dH[i][g * 4 + 2] * softplus100_grad_from_out(s4[i].z),
+                               dH[i][g * 4 + 3] * softplus100_grad_from_out(s4[i].w));
             *reinterpret_cast<float4*>(sD + r * DLD + col) = dA;
           }
         }
         __syncthreads();
         if (g_cw) {
-          if (tid < HC) {
+          for (int c = tid; c < HC; c += NT) {
             float s = 0.f;
-            for (int m = 0; m < nrows; ++m) s += sD[m * DLD + tid];
-            atomicAdd(dW + a.w.c_lin_b[li] + tid, s);
+            for (int m = 0; m < nrows; ++m) s += sD[m * DLD + c];
+            atomicAdd(dW + a.w.c_lin_b[li] + c, s);
           }
           if (li == 0 || li == 3) {   // embedding columns of W0 / W3
             float aw[8][4];
@@ -417,13 +426,13 @@ __global__ void __launch_bounds__(NT, 1) render_bwd_kernel(const __grid_constant
       if (relpos) {
         // ------------------------------------------------------ rel-pos neighbour MLP backward
         if (g_cw) {
-          float a2[2][8];
+          float a2[TMW32][8];
           zero_acc(a2);
-          tile_gemm<2, 16, 2, false, false>(a2, sDC, CLD, nrows, sv + SL.u + p0 * HC, HC, HC, sB);
+          tile_gemm<TMW32, 16, 2, false, false>(a2, sDC, CLD, nrows, sv + SL.u + p0 * HC, HC, HC, sB);
 #pragma unroll
           for (int g = 0; g < 2; ++g)
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
+            for (int i = 0; i < TMW32; ++i)
               red_add_v4(dW + a.w.c_nb2_w + wm.row(i) * HC + wm.col(g), a2[i][g * 4 + 0], a2[i][g * 4 + 1],
                          a2[i][g * 4 + 2], a2[i][g * 4 + 3]);
           if (tid < CDIM) {
@@ -432,6 +441,7 @@ __global__ void __launch_bounds__(NT, 1) render_bwd_kernel(const __grid_constant
             atomicAdd(dW + a.w.c_nb2_b + tid, s);
           }
         }
+        prefetch_rows_l2(sv + SL.sp + p0 * KNN * HC, nrows * KNN, HC);
         float dU[8][8];
         zero_acc(dU);
         tile_gemm<8, 16, 2, true, false>(dU, sDC, CLD, CDIM, blob + a.w.c_nb2_w, HC, HC, sB);
@@ -461,12 +471,19 @@ __global__ void __launch_bounds__(NT, 1) render_bwd_kernel(const __grid_constant
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const int col = wm.col(g);
+            float4 sp4[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = wm.row(i);
+              sp4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (r < nrows) sp4[i] = __ldcs(reinterpret_cast<const float4*>(sv + SL.sp + ((p0 + r) * KNN + k) * HC + col));
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int r = wm.row(i);
               float4 dA = make_float4(0.f, 0.f, 0.f, 0.f);
               if (r < nrows) {
-                const float4 sp = *reinterpret_cast<const float4*>(sv + SL.sp + ((p0 + r) * KNN + k) * HC + col);
+                const float4 sp = sp4[i];
                 const float wk = sW[r * KNN + k];
                 dA = make_float4(wk * dU[i][g * 4 + 0] * softplus100_grad_from_out(sp.x),
                                  wk * dU[i][g * 4 + 1] * softplus100_grad_from_out(sp.y),
@@ -536,7 +553,7 @@ __global__ void __launch_bounds__(NT, 1) render_bwd_kernel(const __grid_constant
           }
           __syncthreads();
           if (g_cw || g_ry) {
-            const int m = tid & (TILE_M - 1), half = tid >> 7;
+            const int m = tid % TILE_M, half = tid / TILE_M;   // NT == 2 * TILE_M
             const int idx = sIdx[m * KNN + k];
             if (idx >= 0) {
               const float t0 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 0), sP[m * 4 + 0]);
@@ -571,11 +588,16 @@ __global__ void __launch_bounds__(NT, 1) render_bwd_kernel(const __grid_constant
                          dV1acc[i][3]);
           }
           if (tid < HC) atomicAdd(dW + a.w.c_nb1_b + tid, dv1);
-          const int half = tid >> 7;
+          const int half = tid / TILE_M;     // uniform per warp (TILE_M is a multiple of 32)
 #pragma unroll
           for (int c = 0; c < 3; ++c)
 #pragma unroll
-            for (int jj = 0; jj < 5; ++jj) atomicAdd(&sRed[3 * EGP + c * ER + half * 5 + jj], dBl[c * 5 + jj]);
+            for (int jj = 0; jj < 5; ++jj) {
+              float v = dBl[c * 5 + jj];
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+              if ((tid & 31) == 0) atomicAdd(&sRed[3 * EGP + c * ER + half * 5 + jj], v);
+            }
         }
       } else {
         scatter_idw(sDC, sIdx, sW, sHas, sDWh, a.col_feats, a.d_col, g_cf, trk);
@@ -623,6 +645,7 @@ __global__ void __launch_bounds__(NT, 1) render_bwd_kernel(const __grid_constant
           dHg[i][0] = d * wo.x; dHg[i][1] = d * wo.y; dHg[i][2] = d * wo.z; dHg[i][3] = d * wo.w;
         }
       }
+      for (int li = 0; li < 5; ++li) prefetch_rows_l2(sv + SL.gs + ((size_t)li * Pp + p0) * HG, nrows, HG);
       float dCacc[4][4], dEacc[8][8];
       zero_acc(dCacc);
       zero_acc(dEacc);
@@ -638,10 +661,12 @@ __global__ void __launch_bounds__(NT, 1) render_bwd_kernel(const __grid_constant
             for (int m = 0; m < nrows; ++m) s += sD[m * CLD + tid];
             atomicAdd(dW + a.w.g_fc_b[li] + tid, s);
           }
-          float au[1][4];
+          float au[TMN32][4];
           zero_acc(au);
-          tile_gemm<1, 8, 1, false, true>(au, sD, CLD, nrows, sC, CLD, CDIM, sB);
-          red_add_v4(dW + a.w.g_fc_w[li] + nm.ty * CDIM + nm.col(), au[0][0], au[0][1], au[0][2], au[0][3]);
+          tile_gemm<TMN32, 8, 1, false, true>(au, sD, CLD, nrows, sC, CLD, CDIM, sB);
+#pragma unroll
+          for (int i = 0; i < TMN32; ++i)
+            red_add_v4(dW + a.w.g_fc_w[li] + nm.row(i) * CDIM + nm.col(), au[i][0], au[i][1], au[i][2], au[i][3]);
         }
         tile_gemm<4, 8, 1, true, false>(dCacc, sD, CLD, HG, blob + a.w.g_fc_w[li], CDIM, CDIM, sB);
 #pragma unroll
@@ -663,26 +688,31 @@ __global__ void __launch_bounds__(NT, 1) render_bwd_kernel(const __grid_constant
             atomicAdd(dW + a.w.g_lin_b[li] + tid, s);
           }
           if (li == 1 || li == 2 || li == 4) {
-            float aw[1][4];
+            float aw[TMN32][4];
             zero_acc(aw);
-            tile_gemm<1, 8, 1, false, false>(aw, sD, CLD, nrows, sv + SL.gh + ((size_t)(li - 1) * Pp + p0) * HG, HG, HG, sB);
-            red_add_v4(dW + a.w.g_lin_w[li] + nm.ty * HG + nm.col(), aw[0][0], aw[0][1], aw[0][2], aw[0][3]);
+            tile_gemm<TMN32, 8, 1, false, false>(aw, sD, CLD, nrows, sv + SL.gh + ((size_t)(li - 1) * Pp + p0) * HG, HG, HG, sB);
+#pragma unroll
+            for (int i = 0; i < TMN32; ++i)
+              red_add_v4(dW + a.w.g_lin_w[li] + nm.row(i) * HG + nm.col(), aw[i][0], aw[i][1], aw[i][2], aw[i][3]);
           } else {
             if (li == 3) {
-              float aw[1][4];
+              float aw[TMN32][4];
               zero_acc(aw);
-              tile_gemm<1, 8, 1, false, false>(aw, sD, CLD, nrows, sv + SL.gh + ((size_t)2 * Pp + p0) * HG, HG, HG, sB);
-              float* d = dW + a.w.g_lin_w[3] + nm.ty * (EG + HG) + EG + nm.col();   // 125-float rows: unaligned
-              atomicAdd(d + 0, aw[0][0]); atomicAdd(d + 1, aw[0][1]); atomicAdd(d + 2, aw[0][2]); atomicAdd(d + 3, aw[0][3]);
+              tile_gemm<TMN32, 8, 1, false, false>(aw, sD, CLD, nrows, sv + SL.gh + ((size_t)2 * Pp + p0) * HG, HG, HG, sB);
+#pragma unroll
+              for (int i = 0; i < TMN32; ++i) {
+                float* d = dW + a.w.g_lin_w[3] + nm.row(i) * (EG + HG) + EG + nm.col();   // 125-float rows: unaligned
+                atomicAdd(d + 0, aw[i][0]); atomicAdd(d + 1, aw[i][1]); atomicAdd(d + 2, aw[i][2]); atomicAdd(d + 3, aw[i][3]);
+              }
             }
-            float ae2[2][8];
+            float ae2[TMW32][8];
             zero_acc(ae2);
-            tile_gemm<2, 16, 2, false, true>(ae2, sD, CLD, nrows, sEg, GLD, EGP, sB);
+            tile_gemm<TMW32, 16, 2, false, true>(ae2, sD, CLD, nrows, sEg, GLD, EGP, sB);
             const int ldw = li == 3 ? EG + HG : EG;
 #pragma unroll
             for (int g = 0; g < 2; ++g)
 #pragma unroll
-              for (int i = 0; i < 2; ++i)
+              for (int i = 0; i < TMW32; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const int col = wm.col(g) + j;
@@ -862,7 +892,8 @@ extern "C" int lsr_render_bwd(const LsrParams* prm, const void* grid_ws, const f
   a.ntiles = (int)((n_rays + a.rays_per_tile - 1) / a.rays_per_tile);
   const size_t smem = BWD_SMEM_FLOATS * sizeof(float);
   LSR_CUDA_CHECK(cudaFuncSetAttribute(render_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = a.ntiles < nsm ? a.ntiles : nsm;
+  const int slots = nsm * CTAS_PER_SM;
+  const int grid = a.ntiles < slots ? a.ntiles : slots;
   render_bwd_kernel<<<grid, NT, smem, stream>>>(a);
   LSR_CUDA_CHECK(cudaGetLastError());
   return LSR_OK;

@@ -60,7 +60,7 @@ __device__ __forceinline__ float linspace_f32(float start, float end, int S, int
 constexpr int FWD_SMEM_FLOATS = TILE_M * XLD + TILE_M * CLD + NSTAGE * KC * 128 + TILE_M * KNN * 2 +
                                 TILE_M * 4 + TILE_M * 3 + TILE_M * 4;
 
-__global__ void __launch_bounds__(NT, 1) render_fwd_kernel(const __grid_constant__ FwdArgs a) {
+__global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __grid_constant__ FwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* sX = smem;
   float* sC = sX + TILE_M * XLD;
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(NT, 1) render_fwd_kernel(const __grid_constant
   const bool dynr = (a.prm.flags & LSR_FLAG_DYNAMIC_R) != 0;
   const bool save = a.saved != nullptr;
   const SavedLayout SL = saved_layout(a.R, S, a.stage, a.prm.flags);
-  const size_t Pp = align_up(SL.P, TILE_M) + TILE_M;   // row pitch of the per-layer saved planes
+  const size_t Pp = SL.Pp;   // row pitch of the per-layer saved planes
   const GridHeader* gh_ = reinterpret_cast<const GridHeader*>(a.grid);
   const GridView gv = grid_view(a.grid, gh_->n_points, gh_->max_cells);
   const WideMap wm;
@@ -95,15 +95,14 @@ __global__ void __launch_bounds__(NT, 1) render_fwd_kernel(const __grid_constant
     const size_t p0 = (size_t)r0 * S;
 
     // ---------------------------------------------------------------- A: sample points + k-NN
-    if (tid < TILE_M) {
-      const int m = tid;
+    // one warp per sample row (lane k < 8 ends up owning the k-th neighbour)
+    for (int m = tid >> 5; m < TILE_M; m += NT / 32) {
+      const int lane = tid & 31;
       const bool rowvalid = m < nrows;
-      float px = 0.f, py = 0.f, pz = 0.f, z = 0.f;
-      Knn8 kn;
-#pragma unroll
-      for (int k = 0; k < KNN; ++k) { kn.D[k] = INFINITY; kn.I[k] = 0x7fffffff; }
-      kn.cnt = 0;
-      int ns = 0;
+      float px = 0.f, py = 0.f, pz = 0.f, z = 0.f, r2f = 0.f;
+      double r2d = 0.0;
+      unsigned bD = KNN_INF;
+      int bI = KNN_NOID;
       if (rowvalid) {
         const int rl = m / S, s = m - rl * S, ray = r0 + rl;
         const float g = a.gt_depth[ray];
@@ -119,40 +118,39 @@ __global__ void __launch_bounds__(NT, 1) render_fwd_kernel(const __grid_constant
         py = __fadd_rn(a.rays_o[3 * ray + 1], __fmul_rn(a.rays_d[3 * ray + 1], z));
         pz = __fadd_rn(a.rays_o[3 * ray + 2], __fmul_rn(a.rays_d[3 * ray + 2], z));
         const double r = dynr ? a.r_query[ray] : a.prm.radius_query;
-        const double r2d = r * r;
-        const float r2f = (float)r2d;
-        knn_walk(gv, px, py, pz, (float)r * 1.00001f + 1e-7f, dynr, r2f, r2d, kn);
-#pragma unroll
-        for (int k = 0; k < KNN; ++k)
-          if (k < kn.cnt) ns += dynr ? ((double)kn.D[k] < r2d) : (kn.D[k] < r2f);   // neural_point.py:1701-1706
+        r2d = r * r;
+        r2f = (float)r2d;
+        knn_warp(gv, px, py, pz, (float)r * 1.00001f + 1e-7f, dynr, r2f, r2d, bD, bI);
       }
-      float wraw[KNN], wsum = 0.f;
+      const bool vk = lane < KNN && bD != KNN_INF;
+      const float Dk = __uint_as_float(bD);
+      const bool strict = vk && (dynr ? ((double)Dk < r2d) : (Dk < r2f));        // neural_point.py:1701-1706
+      const int ns = __popc(__ballot_sync(0xffffffffu, strict));
+      const int cnt = __popc(__ballot_sync(0xffffffffu, vk));
+      const float wraw = vk ? 1.0f / (Dk + 1e-10f) : 0.f;                        // decoder.py:210,217-220
+      float wsum = 0.f;
 #pragma unroll
-      for (int k = 0; k < KNN; ++k) {   // decoder.py:210,217-220
-        wraw[k] = (k < kn.cnt) ? 1.0f / (kn.D[k] + 1e-10f) : 0.f;
-        wsum += wraw[k];
-      }
-      const float denom = fmaxf(wsum, 1e-12f);
-      const int has = (rowvalid && ns >= a.prm.min_nn_num) ? 1 : 0;   // decoder.py:204
+      for (int k = 0; k < KNN; ++k) wsum += __shfl_sync(0xffffffffu, wraw, k);
+      const float wn = wraw / fmaxf(wsum, 1e-12f);
       float wn_sum = 0.f;
 #pragma unroll
-      for (int k = 0; k < KNN; ++k) {
-        const float wn = wraw[k] / denom;
-        wn_sum += wn;
-        sIdx[m * KNN + k] = (k < kn.cnt) ? kn.I[k] : -1;
-        sW[m * KNN + k] = wn;
+      for (int k = 0; k < KNN; ++k) wn_sum += __shfl_sync(0xffffffffu, wn, k);
+      const int has = (rowvalid && ns >= a.prm.min_nn_num) ? 1 : 0;             // decoder.py:204
+      if (lane < KNN) {
+        sIdx[m * KNN + lane] = vk ? bI : -1;
+        sW[m * KNN + lane] = wn;
         if (save && rowvalid) {
-          reinterpret_cast<int*>(a.saved + SL.idx)[(p0 + m) * KNN + k] = (k < kn.cnt) ? kn.I[k] : -1;
-          a.saved[SL.w + (p0 + m) * KNN + k] = wn;
-          a.saved[SL.D + (p0 + m) * KNN + k] = (k < kn.cnt) ? kn.D[k] : FLT_MAX;
+          reinterpret_cast<int*>(a.saved + SL.idx)[(p0 + m) * KNN + lane] = vk ? bI : -1;
+          a.saved[SL.w + (p0 + m) * KNN + lane] = wn;
+          a.saved[SL.D + (p0 + m) * KNN + lane] = vk ? Dk : FLT_MAX;
         }
       }
-      sP[m * 4 + 0] = px; sP[m * 4 + 1] = py; sP[m * 4 + 2] = pz; sP[m * 4 + 3] = z;
-      sHas[m] = has;
-      sWsum[m] = wn_sum;
-      if (save && rowvalid) {
-        float4 mi = make_float4(z, (float)has, wn_sum, (float)kn.cnt);
-        reinterpret_cast<float4*>(a.saved + SL.misc)[p0 + m] = mi;
+      if (lane == 0) {
+        *reinterpret_cast<float4*>(sP + m * 4) = make_float4(px, py, pz, z);
+        sHas[m] = has;
+        sWsum[m] = wn_sum;
+        if (save && rowvalid)
+          reinterpret_cast<float4*>(a.saved + SL.misc)[p0 + m] = make_float4(z, (float)has, wn_sum, (float)cnt);
       }
     }
     __syncthreads();
@@ -608,7 +606,8 @@ extern "C" int lsr_render_fwd(const LsrParams* prm, const void* grid_ws, const f
   a.ntiles = (int)((n_rays + a.rays_per_tile - 1) / a.rays_per_tile);
   const size_t smem = FWD_SMEM_FLOATS * sizeof(float);
   LSR_CUDA_CHECK(cudaFuncSetAttribute(render_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = a.ntiles < nsm ? a.ntiles : nsm;
+  const int slots = nsm * CTAS_PER_SM;
+  const int grid = a.ntiles < slots ? a.ntiles : slots;
   render_fwd_kernel<<<grid, NT, smem, stream>>>(a);
   LSR_CUDA_CHECK(cudaGetLastError());
   return LSR_OK;
