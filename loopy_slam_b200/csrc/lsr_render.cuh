@@ -6,15 +6,19 @@
 namespace lsr {
 
 #ifndef LSR_TILE_M
-#define LSR_TILE_M 128
+#define LSR_TILE_M 64
 #endif
-constexpr int TILE_M = LSR_TILE_M;   // sample rows per tile (64: two CTAs per SM; 128: one)
-constexpr int NT = 2 * TILE_M;       // threads per CTA; the 8x8 / 4x4 register micro-tiles cover TILE_M rows
+constexpr int TILE_M = LSR_TILE_M;   // sample rows per tile (64: two CTAs = 16 warps per SM; 128: one CTA)
+constexpr int NT = 256;              // threads per CTA
 constexpr int CTAS_PER_SM = TILE_M == 64 ? 2 : 1;
 constexpr int RSW = NT / 16;         // row stride of the WIDE thread map (16 threads across the columns)
 constexpr int RSN = NT / 8;          // row stride of the NARROW thread map (8 threads across the columns)
-constexpr int TMW32 = 32 / RSW;      // rows per thread when a WIDE-mapped output has only 32 rows
-constexpr int TMN32 = 32 / RSN;      // same for NARROW
+constexpr int TMA = TILE_M / RSW;    // rows per thread of a WIDE-mapped ACTIVATION tile (TILE_M rows)
+constexpr int TMNA = TILE_M / RSN;   // same, NARROW map
+constexpr int TMW = 128 / RSW;       // rows per thread of a WIDE-mapped 128-row weight-gradient tile
+constexpr int TMN128 = 128 / RSN;    // same, NARROW map
+constexpr int TMW32 = 32 / RSW;      // 32-row outputs, WIDE map
+constexpr int TMN32 = 32 / RSN;      // 32-row outputs, NARROW map
 constexpr int KC = 16;         // contraction rows per streamed chunk
 constexpr int NSTAGE = 3;      // cp.async ring depth
 constexpr int HG = 32;         // geometry decoder hidden width  (decoder.py:566)

@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
           atomicAdd(dW + a.w.c_out_b + tid, s);
         }
       }
-      float dH[8][8];
+      float dH[TMA][8];
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
         const int col = wm.col(g);
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
         const float4 w1 = *reinterpret_cast<const float4*>(blob + a.w.c_out_w + HC + col);
         const float4 w2 = *reinterpret_cast<const float4*>(blob + a.w.c_out_w + 2 * HC + col);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < TMA; ++i) {
           const int r = wm.row(i);
           const float d0 = sDOut[r * 4 + 0], d1 = sDOut[r * 4 + 1], d2 = sDOut[r * 4 + 2];
           dH[i][g * 4 + 0] = d0 * w0.x + d1 * w1.x + d2 * w2.x;
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
           dH[i][g * 4 + 3] = d0 * w0.w + d1 * w1.w + d2 * w2.w;
         }
       }
-      float dCacc[4][4];
+      float dCacc[TMNA][4];
       zero_acc(dCacc);
 #pragma unroll 1
       for (int li = 4; li >= 0; --li) {
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
 #pragma unroll
         for (int g = 0; g < 2; ++g)
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
+          for (int i = 0; i < TMA; ++i)
             *reinterpret_cast<float4*>(sD + wm.row(i) * DLD + wm.col(g)) =
                 make_float4(dH[i][g * 4 + 0], dH[i][g * 4 + 1], dH[i][g * 4 + 2], dH[i][g * 4 + 3]);
         __syncthreads();
@@ -320,26 +320,26 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
             for (int m = 0; m < nrows; ++m) s += sD[m * DLD + c];
             atomicAdd(dW + a.w.c_fc_b[li] + c, s);
           }
-          float au[4][4];
+          float au[TMN128][4];
           zero_acc(au);
-          tile_gemm<4, 8, 1, false, true>(au, sD, DLD, nrows, sC, CLD, CDIM, sB);
+          tile_gemm<TMN128, 8, 1, false, true>(au, sD, DLD, nrows, sC, CLD, CDIM, sB);
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+          for (int i = 0; i < TMN128; ++i)
             red_add_v4(dW + a.w.c_fc_w[li] + nm.row(i) * CDIM + nm.col(), au[i][0], au[i][1], au[i][2], au[i][3]);
         }
-        tile_gemm<4, 8, 1, true, false>(dCacc, sD, DLD, HC, blob + a.w.c_fc_w[li], CDIM, CDIM, sB);
+        tile_gemm<TMNA, 8, 1, true, false>(dCacc, sD, DLD, HC, blob + a.w.c_fc_w[li], CDIM, CDIM, sB);
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           const int col = wm.col(g);
-          float4 s4[8];
+          float4 s4[TMA];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {      // all loads first: 8 independent 16 B requests in flight
+          for (int i = 0; i < TMA; ++i) {      // all loads first: 8 independent 16 B requests in flight
             const int r = wm.row(i);
             s4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r < nrows) s4[i] = __ldcs(reinterpret_cast<const float4*>(sv + SL.cs + ((size_t)li * Pp + p0 + r) * HC + col));
           }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < TMA; ++i) {
             const int r = wm.row(i);
             float4 dA = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r < nrows)
@@ -358,37 +358,37 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
             atomicAdd(dW + a.w.c_lin_b[li] + c, s);
           }
           if (li == 0 || li == 3) {   // embedding columns of W0 / W3
-            float aw[8][4];
+            float aw[TMW][4];
             zero_acc(aw);
-            tile_gemm<8, 16, 1, false, true>(aw, sD, DLD, nrows, sE, ELD, ECC, sB);
+            tile_gemm<TMW, 16, 1, false, true>(aw, sD, DLD, nrows, sE, ELD, ECC, sB);
             const int ldw = li == 0 ? ECC : ECC + HC;
             if (wm.tx * 4 < ECC) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
+              for (int i = 0; i < TMW; ++i)
                 red_add_v4(dW + a.w.c_lin_w[li] + wm.row(i) * ldw + wm.tx * 4, aw[i][0], aw[i][1], aw[i][2], aw[i][3]);
             }
           }
           if (li > 0) {
-            float aw[8][8];
+            float aw[TMW][8];
             zero_acc(aw);
-            tile_gemm<8, 16, 2, false, false>(aw, sD, DLD, nrows, sv + SL.ch + ((size_t)(li - 1) * Pp + p0) * HC, HC, HC, sB);
+            tile_gemm<TMW, 16, 2, false, false>(aw, sD, DLD, nrows, sv + SL.ch + ((size_t)(li - 1) * Pp + p0) * HC, HC, HC, sB);
             const int ldw = li == 3 ? ECC + HC : HC;
             const int off = li == 3 ? ECC : 0;
 #pragma unroll
             for (int g = 0; g < 2; ++g)
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
+              for (int i = 0; i < TMW; ++i)
                 red_add_v4(dW + a.w.c_lin_w[li] + wm.row(i) * ldw + off + wm.col(g), aw[i][g * 4 + 0], aw[i][g * 4 + 1],
                            aw[i][g * 4 + 2], aw[i][g * 4 + 3]);
           }
         }
         if (li == 0 || li == 3) {     // d e'
-          float ae[8][4];
+          float ae[TMA][4];
           zero_acc(ae);
-          tile_gemm<8, 16, 1, true, false>(ae, sD, DLD, HC, blob + a.w.c_lin_w[li], li == 3 ? ECC + HC : ECC, ECC, sB);
+          tile_gemm<TMA, 16, 1, true, false>(ae, sD, DLD, HC, blob + a.w.c_lin_w[li], li == 3 ? ECC + HC : ECC, ECC, sB);
           if (wm.tx * 4 < ECC) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < TMA; ++i) {
               float* d = sDE + wm.row(i) * ELD + wm.tx * 4;
               d[0] += ae[i][0]; d[1] += ae[i][1]; d[2] += ae[i][2]; d[3] += ae[i][3];
             }
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
         }
         if (li > 0) {
           zero_acc(dH);
-          tile_gemm<8, 16, 2, true, false>(dH, sD, DLD, HC, blob + a.w.c_lin_w[li] + (li == 3 ? ECC : 0),
+          tile_gemm<TMA, 16, 2, true, false>(dH, sD, DLD, HC, blob + a.w.c_lin_w[li] + (li == 3 ? ECC : 0),
                                            li == 3 ? ECC + HC : HC, HC, sB);
         }
       }
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
         sDP[m * 4 + 0] += TWO_PI_F * q0; sDP[m * 4 + 1] += TWO_PI_F * q1; sDP[m * 4 + 2] += TWO_PI_F * q2;
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < TMNA; ++i) {
         const int r = nm.row(i);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (sHas[r]) v = make_float4(dCacc[i][0], dCacc[i][1], dCacc[i][2], dCacc[i][3]);
@@ -442,10 +442,10 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
           }
         }
         prefetch_rows_l2(sv + SL.sp + p0 * KNN * HC, nrows * KNN, HC);
-        float dU[8][8];
+        float dU[TMA][8];
         zero_acc(dU);
-        tile_gemm<8, 16, 2, true, false>(dU, sDC, CLD, CDIM, blob + a.w.c_nb2_w, HC, HC, sB);
-        float dV1acc[8][4];
+        tile_gemm<TMA, 16, 2, true, false>(dU, sDC, CLD, CDIM, blob + a.w.c_nb2_w, HC, HC, sB);
+        float dV1acc[TMW][4];
         zero_acc(dV1acc);
         float dv1 = 0.f;
         float dBl[15];
@@ -465,21 +465,21 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
         __syncthreads();
 #pragma unroll 1
         for (int k = 0; k < KNN; ++k) {
-          float part[8];
+          float part[TMA];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) part[i] = 0.f;
+          for (int i = 0; i < TMA; ++i) part[i] = 0.f;
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const int col = wm.col(g);
-            float4 sp4[8];
+            float4 sp4[TMA];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < TMA; ++i) {
               const int r = wm.row(i);
               sp4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
               if (r < nrows) sp4[i] = __ldcs(reinterpret_cast<const float4*>(sv + SL.sp + ((p0 + r) * KNN + k) * HC + col));
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < TMA; ++i) {
               const int r = wm.row(i);
               float4 dA = make_float4(0.f, 0.f, 0.f, 0.f);
               if (r < nrows) {
@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
           }
           if (trk) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < TMA; ++i) {
               const float v = half_warp_sum(part[i]);
               const int r = wm.row(i);
               if (wm.tx == 0 && sIdx[r * KNN + k] >= 0) sDWh[r * KNN + k] += v;
@@ -528,22 +528,22 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
           }
           __syncthreads();
           if (g_cw) {
-            tile_gemm<8, 16, 1, false, true>(dV1acc, sD, DLD, nrows, sQ, QLD, QDP, sB);
+            tile_gemm<TMW, 16, 1, false, true>(dV1acc, sD, DLD, nrows, sQ, QLD, QDP, sB);
             if (tid < HC)
               for (int m = 0; m < nrows; ++m) dv1 += sD[m * DLD + tid];
           }
-          float aq[8][4];
+          float aq[TMA][4];
           zero_acc(aq);
-          tile_gemm<8, 16, 1, true, false>(aq, sD, DLD, HC, blob + a.w.c_nb1_w, QD, QD, sB);
+          tile_gemm<TMA, 16, 1, true, false>(aq, sD, DLD, HC, blob + a.w.c_nb1_w, QD, QD, sB);
           {
             const int col = wm.tx * 4;
             if (col < 2 * ER) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
+              for (int i = 0; i < TMA; ++i)
                 *reinterpret_cast<float4*>(sDQ + wm.row(i) * DQLD + col) = make_float4(aq[i][0], aq[i][1], aq[i][2], aq[i][3]);
             } else if (col < QD && g_cf) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
+              for (int i = 0; i < TMA; ++i) {
                 const int r = wm.row(i);
                 const int idx = sIdx[r * KNN + k];
                 if (idx >= 0 && r < nrows)
@@ -552,8 +552,8 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
             }
           }
           __syncthreads();
-          if (g_cw || g_ry) {
-            const int m = tid % TILE_M, half = tid / TILE_M;   // NT == 2 * TILE_M
+          if ((g_cw || g_ry) && tid < 2 * TILE_M) {
+            const int m = tid % TILE_M, half = tid / TILE_M;
             const int idx = sIdx[m * KNN + k];
             if (idx >= 0) {
               const float t0 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 0), sP[m * 4 + 0]);
@@ -583,12 +583,12 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
         if (g_cw) {
           if (wm.tx * 4 < QD) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < TMW; ++i)
               red_add_v4(dW + a.w.c_nb1_w + wm.row(i) * QD + wm.tx * 4, dV1acc[i][0], dV1acc[i][1], dV1acc[i][2],
                          dV1acc[i][3]);
           }
           if (tid < HC) atomicAdd(dW + a.w.c_nb1_b + tid, dv1);
-          const int half = tid / TILE_M;     // uniform per warp (TILE_M is a multiple of 32)
+          const int half = (tid / TILE_M) & 1;   // uniform per warp; warps beyond 2*TILE_M threads carry zeros
 #pragma unroll
           for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -636,23 +636,23 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
           atomicAdd(dW + a.w.g_out_b, s);
         }
       }
-      float dHg[4][4];
+      float dHg[TMNA][4];
       {
         const float4 wo = *reinterpret_cast<const float4*>(blob + a.w.g_out_w + nm.col());
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < TMNA; ++i) {
           const float d = sDOcc[nm.row(i)];
           dHg[i][0] = d * wo.x; dHg[i][1] = d * wo.y; dHg[i][2] = d * wo.z; dHg[i][3] = d * wo.w;
         }
       }
       for (int li = 0; li < 5; ++li) prefetch_rows_l2(sv + SL.gs + ((size_t)li * Pp + p0) * HG, nrows, HG);
-      float dCacc[4][4], dEacc[8][8];
+      float dCacc[TMNA][4], dEacc[TMA][8];
       zero_acc(dCacc);
       zero_acc(dEacc);
 #pragma unroll 1
       for (int li = 4; li >= 0; --li) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < TMNA; ++i)
           *reinterpret_cast<float4*>(sD + nm.row(i) * CLD + nm.col()) = make_float4(dHg[i][0], dHg[i][1], dHg[i][2], dHg[i][3]);
         __syncthreads();
         if (g_gw) {
@@ -668,9 +668,9 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
           for (int i = 0; i < TMN32; ++i)
             red_add_v4(dW + a.w.g_fc_w[li] + nm.row(i) * CDIM + nm.col(), au[i][0], au[i][1], au[i][2], au[i][3]);
         }
-        tile_gemm<4, 8, 1, true, false>(dCacc, sD, CLD, HG, blob + a.w.g_fc_w[li], CDIM, CDIM, sB);
+        tile_gemm<TMNA, 8, 1, true, false>(dCacc, sD, CLD, HG, blob + a.w.g_fc_w[li], CDIM, CDIM, sB);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < TMNA; ++i) {
           const int r = nm.row(i);
           float4 dA = make_float4(0.f, 0.f, 0.f, 0.f);
           if (r < nrows) {
@@ -722,20 +722,20 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
         }
         if (li == 1 || li == 2 || li == 4) {
           zero_acc(dHg);
-          tile_gemm<4, 8, 1, true, false>(dHg, sD, CLD, HG, blob + a.w.g_lin_w[li], HG, HG, sB);
+          tile_gemm<TMNA, 8, 1, true, false>(dHg, sD, CLD, HG, blob + a.w.g_lin_w[li], HG, HG, sB);
         } else if (li == 3) {
           zero_acc(dHg);
-          tile_gemm<4, 8, 1, true, false>(dHg, sD, CLD, HG, packed + Packed::gW3n + EGP, 128, HG, sB);
-          tile_gemm<8, 16, 2, true, false>(dEacc, sD, CLD, HG, packed + Packed::gW3n, 128, EGP, sB);
+          tile_gemm<TMNA, 8, 1, true, false>(dHg, sD, CLD, HG, packed + Packed::gW3n + EGP, 128, HG, sB);
+          tile_gemm<TMA, 16, 2, true, false>(dEacc, sD, CLD, HG, packed + Packed::gW3n, 128, EGP, sB);
         } else {
-          tile_gemm<8, 16, 2, true, false>(dEacc, sD, CLD, HG, packed + Packed::gW0n, EGP, EGP, sB);
+          tile_gemm<TMA, 16, 2, true, false>(dEacc, sD, CLD, HG, packed + Packed::gW0n, EGP, EGP, sB);
         }
       }
       // geometry Fourier backward: e_j = sin(arg_j)
       if (g_gb || g_ry) {
-        float dpr[8][3];
+        float dpr[TMA][3];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { dpr[i][0] = 0.f; dpr[i][1] = 0.f; dpr[i][2] = 0.f; }
+        for (int i = 0; i < TMA; ++i) { dpr[i][0] = 0.f; dpr[i][1] = 0.f; dpr[i][2] = 0.f; }
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
 #pragma unroll
@@ -746,7 +746,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
                           b2 = packed[Packed::gB + 2 * EGP + col];
               float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
+              for (int i = 0; i < TMA; ++i) {
                 const int r = wm.row(i);
                 if (r < nrows) {
                   const float t0 = TWO_PI_F * sP[r * 4 + 0], t1 = TWO_PI_F * sP[r * 4 + 1], t2 = TWO_PI_F * sP[r * 4 + 2];
@@ -764,7 +764,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
         }
         if (g_ry) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < TMA; ++i) {
             const float v0 = half_warp_sum(dpr[i][0]), v1 = half_warp_sum(dpr[i][1]), v2 = half_warp_sum(dpr[i][2]);
             if (wm.tx == 0) {
               const int r = wm.row(i);
@@ -774,7 +774,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
         }
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < TMNA; ++i) {
         const int r = nm.row(i);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (sHas[r]) v = make_float4(dCacc[i][0], dCacc[i][1], dCacc[i][2], dCacc[i][3]);

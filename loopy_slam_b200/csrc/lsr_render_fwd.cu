@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
     }
     // geometry MLP: h = relu(W x + b) + U c + u  (decoder.py:275-283)
     {
-      float acc[4][4];
+      float acc[TMNA][4];
       const int col = nm.col();
 #pragma unroll 1
       for (int li = 0; li < 5; ++li) {
@@ -197,10 +197,10 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
         const int wt = li == 0 ? Packed::gW0t : li == 1 ? Packed::gW1t : li == 2 ? Packed::gW2t
                      : li == 3 ? Packed::gW3t : Packed::gW4t;
         zero_acc(acc);
-        tile_gemm<4, 8, 1, true, false>(acc, A, XLD, Kc, packed + wt, HG, HG, sB);
+        tile_gemm<TMNA, 8, 1, true, false>(acc, A, XLD, Kc, packed + wt, HG, HG, sB);
         const float4 b = *reinterpret_cast<const float4*>(blob + a.w.g_lin_b[li] + col);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < TMNA; ++i) {
           acc[i][0] = fmaxf(acc[i][0] + b.x, 0.f); acc[i][1] = fmaxf(acc[i][1] + b.y, 0.f);
           acc[i][2] = fmaxf(acc[i][2] + b.z, 0.f); acc[i][3] = fmaxf(acc[i][3] + b.w, 0.f);
           const int r = nm.row(i);
@@ -208,10 +208,10 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
             *reinterpret_cast<float4*>(a.saved + SL.gs + ((size_t)li * Pp + p0 + r) * HG + col) =
                 make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
         }
-        tile_gemm<4, 8, 1, true, false>(acc, sC, CLD, CDIM, packed + Packed::gUt + li * CDIM * HG, HG, HG, sB);
+        tile_gemm<TMNA, 8, 1, true, false>(acc, sC, CLD, CDIM, packed + Packed::gUt + li * CDIM * HG, HG, HG, sB);
         const float4 u = *reinterpret_cast<const float4*>(blob + a.w.g_fc_b[li] + col);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < TMNA; ++i) {
           const int r = nm.row(i);
           const float4 h = make_float4(acc[i][0] + u.x, acc[i][1] + u.y, acc[i][2] + u.z, acc[i][3] + u.w);
           *reinterpret_cast<float4*>(sX + r * XLD + EGP + col) = h;
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
     if (color) {
       // -------------------------------------------------------------- D: colour feature
       if (relpos) {   // decoder.py:477-488
-        float uacc[8][8], acc[8][8];
+        float uacc[TMA][8], acc[TMA][8];
         zero_acc(uacc);
         for (int m = tid; m < TILE_M; m += NT)
           *reinterpret_cast<float4*>(sX + m * XLD + QD) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -262,13 +262,13 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
             *reinterpret_cast<float4*>(sX + m * XLD + 2 * ER + q * 4) = f;
           }
           zero_acc(acc);
-          tile_gemm<8, 16, 2, true, false>(acc, sX, XLD, QDP, packed + Packed::V1t, HC, HC, sB);
+          tile_gemm<TMA, 16, 2, true, false>(acc, sX, XLD, QDP, packed + Packed::V1t, HC, HC, sB);
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const int col = wm.col(g);
             const float4 b = *reinterpret_cast<const float4*>(blob + a.w.c_nb1_b + col);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < TMA; ++i) {
               const int r = wm.row(i);
               const float wk = sW[r * KNN + k];
               const float4 sp = make_float4(softplus100(acc[i][g * 4 + 0] + b.x), softplus100(acc[i][g * 4 + 1] + b.y),
@@ -286,20 +286,20 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
         for (int g = 0; g < 2; ++g) {
           const int col = wm.col(g);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < TMA; ++i) {
             const int r = wm.row(i);
             const float4 u = make_float4(uacc[i][g * 4 + 0], uacc[i][g * 4 + 1], uacc[i][g * 4 + 2], uacc[i][g * 4 + 3]);
             *reinterpret_cast<float4*>(sX + r * XLD + col) = u;
             if (save && r < nrows) *reinterpret_cast<float4*>(a.saved + SL.u + (p0 + r) * HC + col) = u;
           }
         }
-        float c4[4][4];
+        float c4[TMNA][4];
         zero_acc(c4);
-        tile_gemm<4, 8, 1, true, false>(c4, sX, XLD, HC, packed + Packed::V2t, CDIM, CDIM, sB);
+        tile_gemm<TMNA, 8, 1, true, false>(c4, sX, XLD, HC, packed + Packed::V2t, CDIM, CDIM, sB);
         const int col = nm.col();
         const float4 v2 = *reinterpret_cast<const float4*>(blob + a.w.c_nb2_b + col);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < TMNA; ++i) {
           const int r = nm.row(i);
           const float ws = sWsum[r];
           float4 cc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
         sX[m * XLD + EC + j] = cs;
       }
       {
-        float acc[8][8];
+        float acc[TMA][8];
 #pragma unroll 1
         for (int li = 0; li < 5; ++li) {
           const float* A = (li == 0 || li == 3) ? sX : sX + ECC;
@@ -348,13 +348,13 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
           const int wt = li == 0 ? Packed::cW0t : li == 1 ? Packed::cW1t : li == 2 ? Packed::cW2t
                        : li == 3 ? Packed::cW3t : Packed::cW4t;
           zero_acc(acc);
-          tile_gemm<8, 16, 2, true, false>(acc, A, XLD, Kc, packed + wt, HC, HC, sB);
+          tile_gemm<TMA, 16, 2, true, false>(acc, A, XLD, Kc, packed + wt, HC, HC, sB);
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const int col = wm.col(g);
             const float4 b = *reinterpret_cast<const float4*>(blob + a.w.c_lin_b[li] + col);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < TMA; ++i) {
               acc[i][g * 4 + 0] = softplus100(acc[i][g * 4 + 0] + b.x);
               acc[i][g * 4 + 1] = softplus100(acc[i][g * 4 + 1] + b.y);
               acc[i][g * 4 + 2] = softplus100(acc[i][g * 4 + 2] + b.z);
@@ -365,13 +365,13 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
                     make_float4(acc[i][g * 4 + 0], acc[i][g * 4 + 1], acc[i][g * 4 + 2], acc[i][g * 4 + 3]);
             }
           }
-          tile_gemm<8, 16, 2, true, false>(acc, sC, CLD, CDIM, packed + Packed::cUt + li * CDIM * HC, HC, HC, sB);
+          tile_gemm<TMA, 16, 2, true, false>(acc, sC, CLD, CDIM, packed + Packed::cUt + li * CDIM * HC, HC, HC, sB);
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const int col = wm.col(g);
             const float4 u = *reinterpret_cast<const float4*>(blob + a.w.c_fc_b[li] + col);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < TMA; ++i) {
               const int r = wm.row(i);
               const float4 h = make_float4(acc[i][g * 4 + 0] + u.x, acc[i][g * 4 + 1] + u.y,
                                            acc[i][g * 4 + 2] + u.z, acc[i][g * 4 + 3] + u.w);
