@@ -39,7 +39,7 @@ constexpr int CLD = 36;        // interpolated feature c (32)
 constexpr int DLD = 132;       // backward: dA / dH tile (128)
 constexpr int ELD = 44;        // backward: e' (40) and dE'
 constexpr int QLD = 60;        // backward: Q_k (56)
-constexpr int GLD = 100;       // backward: geometry e (96)
+constexpr int GLD = 96;        // backward: geometry e (96), only staged when geometry weights train
 
 // ------------------------------------------------------------------ packed weights (scratch)
 // Transposed ([in][out], "contraction-major") copies for the forward GEMMs and zero-padded copies of
@@ -163,6 +163,165 @@ __device__ __forceinline__ void prefetch_rows_l2(const float* base, int nrows, i
 //     !B_SMEM : global memory, streamed through a 3-stage cp.async ring of KC-row chunks in sBuf
 //   Columns >= ncols_valid (multiple of 4) contribute zeros.  All NT threads must call; ends with
 //   __syncthreads() so callers may immediately overwrite A or reuse sBuf.
+//
+// Default implementation: tensor cores with an error-compensated 3xTF32 split.  Every fp32 operand
+// x is split into hi = x with the low 13 mantissa bits cleared (exactly what the tensor core reads of
+// an fp32 word) and lo = x - hi (exact), and each product is evaluated as hi*hi + lo*hi + hi*lo with
+// fp32 accumulation: relative error ~2^-21 per operand, i.e. fp32-grade (the 1e-4 parity contract
+// rules out single-pass TF32).  mma.sync.m16n8k8 (HMMA.1688.F32.TF32) measured on this
+// B200 at 478 MAC/clk/SM = 3.9x the FFMA pipe (tools/mma_rate.cu), i.e. 1.3x FFMA peak after the 3x
+// split but with ~4x fewer issued instructions and ~3x less shared-memory traffic per MAC.
+// The 8 warps tile the output as 2 (rows) x 4 (cols): warp (wm, wn) owns 16-row tiles wm, wm+2, ... and
+// 8-column tiles wn, wn+4, ...; the fragments are then re-laid-out through shared memory (32 rows per
+// pass) into the WIDE / NARROW per-thread register tiles every epilogue of the kernels is written for.
+// Define LSR_FFMA_GEMM to compile the plain FP32 FFMA version instead (A/B comparisons only).
+constexpr int SB_LD_PAD = 8;                         // chunk / staging row pitch = cols + 8 (== 8 mod 32)
+constexpr int SB_FLOATS = NSTAGE * KC * (128 + SB_LD_PAD);
+
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void split_tf32(float x, unsigned& hi, unsigned& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+#ifndef LSR_FFMA_GEMM
+template <int TM, int TXN, int NCG, bool A_ROWMAJOR, bool B_SMEM>
+__device__ __forceinline__ void tile_gemm(float (&acc)[TM][NCG * 4], const float* __restrict__ A, int lda,
+                                          int Kc, const float* __restrict__ B, int ldb, int ncols_valid,
+                                          float* sBuf) {
+  constexpr int NCOLS = TXN * 4 * NCG;      // 32 / 64 / 128 output columns
+  constexpr int RS = NT / TXN;
+  constexpr int M_OUT = TM * RS;            // 32 / 64 / 128 output rows
+  constexpr int MTT = M_OUT / 16;           // 16-row tiles in the output
+  constexpr int MI = (MTT + 1) / 2;         //   per warp
+  constexpr int NTT = NCOLS / 8;            // 8-column tiles in the output
+  constexpr int NJ = (NTT + 3) / 4;         //   per warp
+  constexpr int CLD_ = NCOLS + SB_LD_PAD;   // chunk row pitch
+  static_assert(NT == 256 && M_OUT % 32 == 0, "tile_gemm thread layout");
+  const int tid = threadIdx.x;
+  const int tx = tid % TXN, ty = tid / TXN;
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int wm = warp >> 2, wn = warp & 3;
+
+  float c[MI][NJ][4];
+#pragma unroll
+  for (int i = 0; i < MI; ++i)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) { c[i][j][0] = 0.f; c[i][j][1] = 0.f; c[i][j][2] = 0.f; c[i][j][3] = 0.f; }
+
+  // one k8 step: A fragments from A (shared), B fragments from bs (shared, row pitch bld)
+  auto k8_step = [&](int k, const float* bs, int bld, int kb) {
+    unsigned ah[MI][4], al[MI][4];
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+      const int r0 = (wm + 2 * i) * 16 + g;
+      float a0, a1, a2, a3;
+      if (A_ROWMAJOR) {
+        a0 = A[(size_t)r0 * lda + k + t];       a1 = A[(size_t)(r0 + 8) * lda + k + t];
+        a2 = A[(size_t)r0 * lda + k + t + 4];   a3 = A[(size_t)(r0 + 8) * lda + k + t + 4];
+      } else {
+        a0 = A[(size_t)(k + t) * lda + r0];     a1 = A[(size_t)(k + t) * lda + r0 + 8];
+        a2 = A[(size_t)(k + t + 4) * lda + r0]; a3 = A[(size_t)(k + t + 4) * lda + r0 + 8];
+      }
+      if (MTT % 2 && wm + 2 * i >= MTT) { a0 = 0.f; a1 = 0.f; a2 = 0.f; a3 = 0.f; }
+      split_tf32(a0, ah[i][0], al[i][0]); split_tf32(a1, ah[i][1], al[i][1]);
+      split_tf32(a2, ah[i][2], al[i][2]); split_tf32(a3, ah[i][3], al[i][3]);
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int n0 = (wn + 4 * j) * 8 + g;
+      float b0 = 0.f, b1 = 0.f;
+      if ((NTT % 4 == 0 || wn + 4 * j < NTT) && (!B_SMEM || (wn + 4 * j) * 8 < ncols_valid)) {
+        b0 = bs[(size_t)(kb + t) * bld + n0];
+        b1 = bs[(size_t)(kb + t + 4) * bld + n0];
+      }
+      unsigned bh[2], bl[2];
+      split_tf32(b0, bh[0], bl[0]);
+      split_tf32(b1, bh[1], bl[1]);
+#pragma unroll
+      for (int i = 0; i < MI; ++i) {
+        mma_tf32_16x8x8(c[i][j], al[i], bh);
+        mma_tf32_16x8x8(c[i][j], ah[i], bl);
+        mma_tf32_16x8x8(c[i][j], ah[i], bh);
+      }
+    }
+  };
+
+  if constexpr (B_SMEM) {
+    __syncthreads();   // A / B tiles written by the caller must be visible
+    const int K8 = (Kc + 7) / 8;
+    for (int k8 = 0; k8 < K8; ++k8) k8_step(k8 * 8, B, ldb, k8 * 8);
+    __syncthreads();
+  } else {
+    constexpr int PIECES = KC * NCOLS / 4;   // float4 pieces per chunk
+    constexpr int PPR = NCOLS / 4;           // pieces per chunk row
+    const int nchunks = (Kc + KC - 1) / KC;
+    auto prefetch = [&](int chunk) {
+      if (chunk < nchunks) {
+        float* dst = sBuf + (chunk % NSTAGE) * (KC * CLD_);
+        const int k0 = chunk * KC;
+        for (int p = tid; p < PIECES; p += NT) {
+          const int row = p / PPR, c4 = p % PPR;
+          float* d = dst + row * CLD_ + c4 * 4;
+          if (k0 + row < Kc && c4 * 4 < ncols_valid) {
+            cp_async16(d, B + (size_t)(k0 + row) * ldb + c4 * 4);
+          } else {
+            *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      }
+      cp_async_commit();
+    };
+    prefetch(0);
+    prefetch(1);
+    for (int cix = 0; cix < nchunks; ++cix) {
+      cp_async_wait<1>();
+      __syncthreads();          // chunk visible to all; everyone is done with the previous chunk's buffer
+      prefetch(cix + 2);
+      const float* sb = sBuf + (cix % NSTAGE) * (KC * CLD_);
+      const int k0 = cix * KC;
+      k8_step(k0, sb, CLD_, 0);
+      if (k0 + 8 < Kc) k8_step(k0 + 8, sb, CLD_, 8);
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+  }
+
+  // fragments -> per-thread register tiles, 32 output rows per pass through sBuf
+  float* stage = sBuf;
+#pragma unroll
+  for (int p = 0; p < M_OUT / 32; ++p) {
+    if (MTT % 2 == 0 || wm + 2 * p < MTT) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int nt = wn + 4 * j;
+        if (NTT % 4 == 0 || nt < NTT) {
+          *reinterpret_cast<float2*>(stage + (wm * 16 + g) * CLD_ + nt * 8 + 2 * t) = make_float2(c[p][j][0], c[p][j][1]);
+          *reinterpret_cast<float2*>(stage + (wm * 16 + g + 8) * CLD_ + nt * 8 + 2 * t) = make_float2(c[p][j][2], c[p][j][3]);
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      if ((ty + RS * i) / 32 == p) {     // RS = 16: i in {2p, 2p+1};  RS = 32: i == p  (folds at compile time per i)
+        const int rl = ty + RS * i - 32 * p;
+#pragma unroll
+        for (int gq = 0; gq < NCG; ++gq) {
+          const float4 v = *reinterpret_cast<const float4*>(stage + rl * CLD_ + gq * TXN * 4 + tx * 4);
+          acc[i][gq * 4 + 0] += v.x; acc[i][gq * 4 + 1] += v.y; acc[i][gq * 4 + 2] += v.z; acc[i][gq * 4 + 3] += v.w;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+#else
 template <int TM, int TXN, int NCG, bool A_ROWMAJOR, bool B_SMEM>
 __device__ __forceinline__ void tile_gemm(float (&acc)[TM][NCG * 4], const float* __restrict__ A, int lda,
                                           int Kc, const float* __restrict__ B, int ldb, int ncols_valid,
@@ -267,6 +426,8 @@ __device__ __forceinline__ void tile_gemm(float (&acc)[TM][NCG * 4], const float
     __syncthreads();
   }
 }
+
+#endif  // LSR_FFMA_GEMM
 
 template <int TM, int NC>
 __device__ __forceinline__ void zero_acc(float (&acc)[TM][NC]) {

@@ -25,10 +25,11 @@ struct BwdArgs {
   int rays_per_tile, ntiles;
 };
 
-constexpr int E2_FLOATS = TILE_M * GLD;   // 12800: {sE, sDE} | {sQ, sDQ} | sEg
+constexpr int E2_FLOATS = 2 * TILE_M * ELD;   // {sE, sDE} | {sQ, sDQ}
+static_assert(TILE_M * (QLD + 24) <= E2_FLOATS && TILE_M * (CLD + GLD) <= TILE_M * DLD, "smem aliasing");
 constexpr int DQLD = 24;
 constexpr int RED_FLOATS = 320;           // 3*96 dB_geo + 30 dB_rel
-constexpr int BWD_SMEM_FLOATS = TILE_M * DLD + NSTAGE * KC * 128 + 2 * TILE_M * CLD + E2_FLOATS + 3 * TILE_M * KNN +
+constexpr int BWD_SMEM_FLOATS = TILE_M * DLD + SB_FLOATS + 2 * TILE_M * CLD + E2_FLOATS + 3 * TILE_M * KNN +
                                 2 * TILE_M * 4 + TILE_M * KNN + 3 * TILE_M + TILE_M * 4 + RED_FLOATS;
 
 __device__ __forceinline__ float half_warp_sum(float v) {   // sum over the 16 lanes sharing ty
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
   extern __shared__ __align__(16) float smem[];
   float* sD = smem;                                   // [128][DLD] (colour) / [128][CLD] view (geometry)
   float* sB = sD + TILE_M * DLD;
-  float* sC = sB + NSTAGE * KC * 128;
+  float* sC = sB + SB_FLOATS;
   float* sDC = sC + TILE_M * CLD;
   float* sE2 = sDC + TILE_M * CLD;
   int* sIdx = reinterpret_cast<int*>(sE2 + E2_FLOATS);
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
   float* sDE = sE2 + TILE_M * ELD;
   float* sQ = sE2;                                    // [128][QLD]
   float* sDQ = sE2 + TILE_M * QLD;                    // [128][DQLD]
-  float* sEg = sE2;                                   // [128][GLD]
+  float* sEg = sD + TILE_M * CLD;                     // [TILE_M][GLD], behind the [TILE_M][CLD] view of sD (geometry phase)
 
   const int tid = threadIdx.x;
   const int S = a.prm.n_surface;

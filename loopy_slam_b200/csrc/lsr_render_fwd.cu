@@ -57,7 +57,7 @@ __device__ __forceinline__ float linspace_f32(float start, float end, int S, int
                      : __fsub_rn(end, __fmul_rn(step, (float)(S - 1 - s)));
 }
 
-constexpr int FWD_SMEM_FLOATS = TILE_M * XLD + TILE_M * CLD + NSTAGE * KC * 128 + TILE_M * KNN * 2 +
+constexpr int FWD_SMEM_FLOATS = TILE_M * XLD + TILE_M * CLD + SB_FLOATS + TILE_M * KNN * 2 +
                                 TILE_M * 4 + TILE_M * 3 + TILE_M * 4;
 
 __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __grid_constant__ FwdArgs a) {
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
   float* sX = smem;
   float* sC = sX + TILE_M * XLD;
   float* sB = sC + TILE_M * CLD;
-  int* sIdx = reinterpret_cast<int*>(sB + NSTAGE * KC * 128);
+  int* sIdx = reinterpret_cast<int*>(sB + SB_FLOATS);
   float* sW = reinterpret_cast<float*>(sIdx + TILE_M * KNN);
   float* sP = sW + TILE_M * KNN;          // [m][4] = px,py,pz,z
   float* sOcc = sP + TILE_M * 4;
