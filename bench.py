@@ -46,38 +46,46 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region: one streaming `nvidia-smi -lms`
+    subprocess (started before warm-up so it is already sampling), rows kept between start()/stop()."""
 
-    def __init__(self, index=0):
-        self.rows, self.stop_flag, self.index = [], False, index
-        self.t = threading.Thread(target=self._run, daemon=True)
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0, period_ms=20):
+        self.rows, self.keep, self.proc = [], False, None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={index}', f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', str(period_ms)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
 
     def _run(self):
-        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}', '--format=csv,noheader,nounits'],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(',')])
-            except Exception:
-                pass
-            time.sleep(0.2)
+        for line in self.proc.stdout:
+            if self.keep:
+                self.rows.append([x.strip() for x in line.split(',')])
 
     def start(self):
-        self.t.start()
+        self.keep = True
 
     def stop(self):
-        self.stop_flag = True
-        self.t.join(timeout=3)
-        if not self.rows:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        self.keep = False
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        rows = [r for r in self.rows if len(r) >= 6 and r[0].isdigit()]
+        if not rows:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        sm = sorted(int(r[0]) for r in rows)
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for k, n in enumerate(names) if any(r[2 + k].lower().startswith('active') for r in self.rows)]
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                'reasons': reasons, 'samples': len(self.rows)}
+        reasons = [n for k, n in enumerate(names) if any(r[2 + k].lower().startswith('active') for r in rows)]
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': int(rows[0][1]) if rows[0][1].isdigit() else None,
+                'reasons': reasons, 'samples': len(rows)}
 
 
 def build_scene(n_points, cache=True):
@@ -178,10 +186,10 @@ def run_lsr(args, rank, world, local):
             torch.distributed.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local) if rank == 0 else None
     for w in range(args.warmup):
         step(dev_batches[w % len(dev_batches)])
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
     launches[0] = 0
@@ -339,8 +347,8 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=30)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='lsr', choices=['lsr', 'reference'])
     ap.add_argument('--stage', default='color', choices=['color', 'geometry'])
     ap.add_argument('--n-points', type=int, default=N_POINTS)
@@ -349,6 +357,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == 'reference':
+        args.steps, args.warmup = min(args.steps, 5), min(args.warmup, 3)     # each step = seconds of CPU work
         rank = int(os.environ.get('RANK', '0'))
         return run_reference(args, rank, int(os.environ.get('WORLD_SIZE', '1')))
     from loopy_slam_b200 import parallel

@@ -179,8 +179,7 @@ constexpr int SB_LD_PAD = 8;                         // chunk / staging row pitc
 constexpr int SB_FLOATS = NSTAGE * KC * (128 + SB_LD_PAD);
 
 __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
@@ -214,41 +213,54 @@ __device__ __forceinline__ void tile_gemm(float (&acc)[TM][NCG * 4], const float
 #pragma unroll
     for (int j = 0; j < NJ; ++j) { c[i][j][0] = 0.f; c[i][j][1] = 0.f; c[i][j][2] = 0.f; c[i][j][3] = 0.f; }
 
-  // one k8 step: A fragments from A (shared), B fragments from bs (shared, row pitch bld)
+  // one k8 step: A fragments from A (shared), B fragments from bs (shared, row pitch bld).
+  // The three partial products of one accumulator are issued in three separate sweeps over the
+  // (i, j) tiles so that consecutive HMMAs never depend on each other.
+  const float* Abase = A_ROWMAJOR ? A + (size_t)(wm * 16 + g) * lda + t : A + (size_t)t * lda + wm * 16 + g;
   auto k8_step = [&](int k, const float* bs, int bld, int kb) {
-    unsigned ah[MI][4], al[MI][4];
-#pragma unroll
-    for (int i = 0; i < MI; ++i) {
-      const int r0 = (wm + 2 * i) * 16 + g;
-      float a0, a1, a2, a3;
-      if (A_ROWMAJOR) {
-        a0 = A[(size_t)r0 * lda + k + t];       a1 = A[(size_t)(r0 + 8) * lda + k + t];
-        a2 = A[(size_t)r0 * lda + k + t + 4];   a3 = A[(size_t)(r0 + 8) * lda + k + t + 4];
-      } else {
-        a0 = A[(size_t)(k + t) * lda + r0];     a1 = A[(size_t)(k + t) * lda + r0 + 8];
-        a2 = A[(size_t)(k + t + 4) * lda + r0]; a3 = A[(size_t)(k + t + 4) * lda + r0 + 8];
-      }
-      if (MTT % 2 && wm + 2 * i >= MTT) { a0 = 0.f; a1 = 0.f; a2 = 0.f; a3 = 0.f; }
-      split_tf32(a0, ah[i][0], al[i][0]); split_tf32(a1, ah[i][1], al[i][1]);
-      split_tf32(a2, ah[i][2], al[i][2]); split_tf32(a3, ah[i][3], al[i][3]);
-    }
+    unsigned bh[NJ][2], bl[NJ][2];
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-      const int n0 = (wn + 4 * j) * 8 + g;
       float b0 = 0.f, b1 = 0.f;
       if ((NTT % 4 == 0 || wn + 4 * j < NTT) && (!B_SMEM || (wn + 4 * j) * 8 < ncols_valid)) {
-        b0 = bs[(size_t)(kb + t) * bld + n0];
-        b1 = bs[(size_t)(kb + t + 4) * bld + n0];
+        const float* bp = bs + (size_t)(kb + t) * bld + (wn + 4 * j) * 8 + g;
+        b0 = bp[0];
+        b1 = bp[4 * bld];
       }
-      unsigned bh[2], bl[2];
-      split_tf32(b0, bh[0], bl[0]);
-      split_tf32(b1, bh[1], bl[1]);
+      split_tf32(b0, bh[j][0], bl[j][0]);
+      split_tf32(b1, bh[j][1], bl[j][1]);
+    }
 #pragma unroll
-      for (int i = 0; i < MI; ++i) {
-        mma_tf32_16x8x8(c[i][j], al[i], bh);
-        mma_tf32_16x8x8(c[i][j], ah[i], bl);
-        mma_tf32_16x8x8(c[i][j], ah[i], bh);
+    for (int i0 = 0; i0 < MI; i0 += 2) {
+      constexpr int IB = MI >= 2 ? 2 : 1;
+      unsigned ah[IB][4], al[IB][4];
+#pragma unroll
+      for (int ii = 0; ii < IB; ++ii) {
+        const int i = i0 + ii;
+        float a0, a1, a2, a3;
+        if (A_ROWMAJOR) {
+          const float* ap = Abase + (size_t)(32 * i) * lda + k;
+          a0 = ap[0]; a1 = ap[8 * lda]; a2 = ap[4]; a3 = ap[8 * lda + 4];
+        } else {
+          const float* ap = Abase + (size_t)k * lda + 32 * i;
+          a0 = ap[0]; a1 = ap[8]; a2 = ap[4 * lda]; a3 = ap[4 * lda + 8];
+        }
+        if (MTT % 2 && wm + 2 * i >= MTT) { a0 = 0.f; a1 = 0.f; a2 = 0.f; a3 = 0.f; }
+        split_tf32(a0, ah[ii][0], al[ii][0]); split_tf32(a1, ah[ii][1], al[ii][1]);
+        split_tf32(a2, ah[ii][2], al[ii][2]); split_tf32(a3, ah[ii][3], al[ii][3]);
       }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+#pragma unroll
+        for (int ii = 0; ii < IB; ++ii) mma_tf32_16x8x8(c[i0 + ii][j], al[ii], bh[j]);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+#pragma unroll
+        for (int ii = 0; ii < IB; ++ii) mma_tf32_16x8x8(c[i0 + ii][j], ah[ii], bl[j]);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+#pragma unroll
+        for (int ii = 0; ii < IB; ++ii) mma_tf32_16x8x8(c[i0 + ii][j], ah[ii], bh[j]);
     }
   };
 
