@@ -112,6 +112,23 @@ __host__ __device__ inline SavedLayout saved_layout(int64_t R, int S, int stage,
 }
 
 #ifdef __CUDACC__
+#ifdef LSR_PHASE_TIMING
+// debug-only per-phase cycle accounting (tools/phase_timing.py); never compiled into the product build
+extern __device__ unsigned long long lsr_phase_cycles[2][16];
+#define LSR_PHASE_BEGIN() long long _pt_last = clock64();
+#define LSR_PHASE(kernel, k)                                                         \
+  do {                                                                               \
+    __syncthreads();                                                                 \
+    if (threadIdx.x == 0) {                                                          \
+      const long long _n = clock64();                                                \
+      atomicAdd(&lsr_phase_cycles[kernel][k], (unsigned long long)(_n - _pt_last));  \
+      _pt_last = _n;                                                                 \
+    }                                                                                \
+  } while (0)
+#else
+#define LSR_PHASE_BEGIN()
+#define LSR_PHASE(kernel, k)
+#endif
 // ------------------------------------------------------------------ small math
 __device__ __forceinline__ float softplus100(float x) {
   // torch.nn.Softplus(beta=100, threshold=20): x if 100x > 20 else log1p(exp(100x))/100

@@ -8,6 +8,10 @@
 
 namespace lsr {
 
+#ifdef LSR_PHASE_TIMING
+extern __device__ unsigned long long lsr_phase_cycles[2][16];
+#endif
+
 struct BwdArgs {
   LsrParams prm;
   const float* cloud;
@@ -118,6 +122,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
     const int nrows = nr * S;
     const size_t p0 = (size_t)r0 * S;
 
+    LSR_PHASE_BEGIN();
     // ------------------------------------------------------------ 0: per-row state
     if (tid < TILE_M) {
       const int m = tid;
@@ -212,6 +217,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
     }
     __syncthreads();
 
+    LSR_PHASE(1, 0);   // load state + compositing backward
     if (color) {
       // ---------------------------------------------------------- colour head activation backward
       if (tid < TILE_M) {
@@ -300,6 +306,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
           dH[i][g * 4 + 3] = d0 * w0.w + d1 * w1.w + d2 * w2.w;
         }
       }
+      LSR_PHASE(1, 1);   // head backward + setup
       float dCacc[TMNA][4];
       zero_acc(dCacc);
 #pragma unroll 1
@@ -401,6 +408,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
                                            li == 3 ? ECC + HC : HC, HC, sB);
         }
       }
+      LSR_PHASE(1, 2);   // colour trunk backward
       __syncthreads();
       // colour Fourier backward -> dp
       if (g_ry && tid < TILE_M) {
@@ -424,6 +432,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
       }
       __syncthreads();
 
+      LSR_PHASE(1, 3);   // fourier bwd + dC
       if (relpos) {
         // ------------------------------------------------------ rel-pos neighbour MLP backward
         if (g_cw) {
@@ -606,6 +615,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
       __syncthreads();
     }
 
+    LSR_PHASE(1, 4);   // rel-pos backward / colour scatter
     // -------------------------------------------------------------- geometry MLP backward
     {
       for (int it = tid; it < TILE_M * 8; it += NT) {
@@ -786,6 +796,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
       __syncthreads();
     }
 
+    LSR_PHASE(1, 5);   // geometry backward + scatter
     // -------------------------------------------------------------- IDW weight backward (tracker)
     if (trk && tid < TILE_M && sHas[tid]) {
       const int m = tid;
@@ -845,6 +856,13 @@ int sm_count();
 }  // namespace lsr
 
 using namespace lsr;
+
+#ifdef LSR_PHASE_TIMING
+extern "C" int lsr_debug_phase_cycles(unsigned long long* out32) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out32, lsr_phase_cycles, sizeof(unsigned long long) * 32) == cudaSuccess ? 0 : 3;
+}
+#endif
 
 extern "C" int lsr_render_bwd(const LsrParams* prm, const void* grid_ws, const float* cloud_pos, int64_t n_points,
                               const float* rays_o, const float* rays_d, const float* gt_depth,

@@ -10,6 +10,10 @@
 
 namespace lsr {
 
+#ifdef LSR_PHASE_TIMING
+__device__ unsigned long long lsr_phase_cycles[2][16];
+#endif
+
 struct FwdArgs {
   LsrParams prm;
   const void* grid;
@@ -94,6 +98,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
     const int nrows = nr * S;
     const size_t p0 = (size_t)r0 * S;
 
+    LSR_PHASE_BEGIN();
     // ---------------------------------------------------------------- A: sample points + k-NN
     // one warp per sample row (lane k < 8 ends up owning the k-th neighbour)
     for (int m = tid >> 5; m < TILE_M; m += NT / 32) {
@@ -155,6 +160,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
     }
     __syncthreads();
 
+    LSR_PHASE(0, 0);   // knn
     // ---------------------------------------------------------------- B: geometry feature (IDW gather)
     for (int it = tid; it < TILE_M * 8; it += NT) {
       const int m = it >> 3, q = it & 7;
@@ -186,6 +192,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
       }
       sX[m * XLD + j] = v;
     }
+    LSR_PHASE(0, 1);   // gather + fourier
     // geometry MLP: h = relu(W x + b) + U c + u  (decoder.py:275-283)
     {
       float acc[TMNA][4];
@@ -230,6 +237,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
       __syncthreads();
     }
 
+    LSR_PHASE(0, 2);   // geometry MLP
     if (color) {
       // -------------------------------------------------------------- D: colour feature
       if (relpos) {   // decoder.py:477-488
@@ -329,6 +337,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
         }
       }
       __syncthreads();
+      LSR_PHASE(0, 3);   // rel-pos neighbour MLP / colour gather
       // -------------------------------------------------------------- E: colour trunk (decoder.py:515-533)
       for (int it = tid; it < TILE_M * EC; it += NT) {
         const int m = it / EC, j = it - m * EC;
@@ -383,6 +392,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
         }
       }
       __syncthreads();
+      LSR_PHASE(0, 4);   // colour trunk
       // colour head (decoder.py:533-546)
       for (int it = tid; it < TILE_M * 3; it += NT) {
         const int m = it % TILE_M, ch = it / TILE_M;
@@ -417,6 +427,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
       __syncthreads();
     }
 
+    LSR_PHASE(0, 5);   // colour head
     // ---------------------------------------------------------------- F: compositing (common.py:402-422)
     if (tid < nr) {
       const int ray = r0 + tid;
@@ -454,6 +465,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
       a.valid[ray] = (nhas >= S / 2 + 1) ? 1 : 0;            // decoder.py:259-260
     }
     __syncthreads();
+    LSR_PHASE(0, 6);   // compositing
   }
 }
 
