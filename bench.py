@@ -220,6 +220,56 @@ def run_lsr(args, rank, world, local):
     clocks = sampler.stop() if sampler else None
     h2d = sum(t.numel() * t.element_size() for t in host_batches[0])
 
+    extra = {}
+    if world == 1 and not args.no_extra:
+        def timed(fn, n):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize(dev)
+            evs2 = []
+            for k in range(n):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); fn(k); e1.record()
+                evs2.append((e0, e1))
+            torch.cuda.synchronize(dev)
+            return sum(a.elapsed_time(b) for a, b in evs2) / n
+        n_extra = max(10, args.steps // 4)
+        # (1) mapper iteration, stage 'geometry' (40 % of the mapping iterations, src/Mapper.py:588-591)
+        stage_saved = stage
+
+        def geo_step(k=0):
+            o, d, g, c = dev_batches[k % len(dev_batches)]
+            for p in train_params:
+                p.grad = None
+            gtab = npc_geo.index_put((indices,), geo_leaf)
+            depth, var, color, valid = rend.render_batch_ray(npc, model, d, o, dev, 'geometry', gt_depth=g,
+                                                             npc_geo_feats=gtab, npc_col_feats=npc_col,
+                                                             is_tracker=False, cloud_pos=cloud)
+            mapper_loss(depth, color, valid, g, c, 'geometry').backward()
+        ms = timed(geo_step, n_extra)
+        extra['mapper_geometry_stage'] = {'rays_per_s': R / (ms * 1e-3), 'ms_per_step': ms, 'rays': R}
+        # (2) tracking iteration (src/Tracker.py:102-197): 1500 rays, stage 'color', is_tracker, frozen decoders,
+        #     gradient to the ray origins/directions (-> pose)
+        for p in model.parameters():
+            p.requires_grad_(False)
+        tr_batches = [[t[:1500].clone() for t in b] for b in dev_batches]
+
+        def trk_step(k=0):
+            o, d, g, c = tr_batches[k % len(tr_batches)]
+            o = o.detach().requires_grad_(True)
+            d = d.detach().requires_grad_(True)
+            depth, var, color, valid = rend.render_batch_ray(npc, model, d, o, dev, 'color', gt_depth=g,
+                                                             npc_geo_feats=npc_geo, npc_col_feats=npc_col,
+                                                             is_tracker=True, cloud_pos=cloud)
+            unc = var.detach()
+            m = ((g > 0) & valid).float()
+            loss = (torch.clamp(torch.abs(g - depth) / torch.sqrt(unc + 1e-10), 0.0, 1e3) * m).sum() \
+                + 0.5 * (torch.abs(c - color) * m[:, None]).sum()
+            loss.backward()
+        ms = timed(trk_step, n_extra)
+        extra['tracker_iteration'] = {'rays_per_s': 1500 / (ms * 1e-3), 'ms_per_step': ms, 'rays': 1500}
+
     if rank != 0:
         return
     peak, peak_src, peaks = load_peaks()
@@ -248,11 +298,17 @@ def run_lsr(args, rank, world, local):
         'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
                      'frac': ach / peak, 'traffic': None, 'peak_source': peak_src,
                      'algorithmic_bytes_per_launch': bytes_dom,
-                     'note': 'arithmetic intensity ~190 FLOP/B: the kernels are FP32-FMA bound, see fp32_fma'},
+                     'note': 'HBM fraction as defined in BASELINE.md section 3; arithmetic intensity ~190 FLOP/B puts both '
+                             'fused kernels on the tensor/issue side of the roofline, see "tensor"'},
+        'tensor': {'algorithmic_tflops': flops_step / ((t_f + t_b) * 1e-3) / 1e12 if t_f + t_b > 0 else 0,
+                   'executed_tflops_3xtf32': 3 * flops_step / ((t_f + t_b) * 1e-3) / 1e12 if t_f + t_b > 0 else 0,
+                   'peak_tf32_mma_sync_tflops_measured': 278.0, 'peak_bf16_tflops_measured': peaks.get('bf16_tflops'),
+                   'note': 'MLP contractions run as error-compensated 3xTF32 mma.sync (HMMA.1688.F32.TF32); 278 TFLOP/s '
+                           'is this path\'s measured issue peak on B200 (tools/mma_rate.cu)'},
         'kernels': {'render_fwd_ms': t_f, 'render_bwd_ms': t_b,
                     'fwd_bwd_GBps': R * BYTES_RAY_ALL[stage] / ((t_f + t_b) * 1e-3) / 1e9 if t_f + t_b > 0 else 0},
-        'fp32_fma': {'algorithmic_tflops': flops_step / ((t_f + t_b) * 1e-3) / 1e12 if t_f + t_b > 0 else 0,
-                     'peak_tflops_at_clock': fp32_peak, 'sm_mhz': sm_mhz},
+        'fp32_fma_peak_tflops_at_clock': fp32_peak,
+        'extra': extra,
         'clocks': clocks, 'loss': loss_host,
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -353,6 +409,7 @@ def main():
     ap.add_argument('--stage', default='color', choices=['color', 'geometry'])
     ap.add_argument('--n-points', type=int, default=N_POINTS)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extra', action='store_true', help='skip the geometry-stage / tracker side measurements')
     ap.add_argument('--cpu-budget', type=float, default=20.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -10,6 +10,7 @@
  *   lsr_sample_rays(_bwd)            get_samples -> get_sample_uv -> select_uv -> get_rays_from_uv
  *                                    src/common.py:237-259,160-172,123-138,104-120
  *   lsr_pose_fwd / lsr_pose_bwd      get_camera_from_tensor / quad2rotation  src/common.py:301-343
+ *   lsr_dynamic_radius               per-frame radius maps  src/Tracker.py:243-258, src/Mapper.py:854-869
  *   lsr_render_fwd                   Renderer.render_batch_ray + eval_points + NICER.forward +
  *                                    raw2outputs_nerf_color
  *                                    src/utils/Renderer.py:24-201, src/conv_onet/models/decoder.py:573-626,
@@ -147,6 +148,13 @@ int lsr_sample_rays_bwd(const float* d_rays_o, const float* d_rays_d, const int6
 /* camera tensor [qw qx qy qz tx ty tz] -> c2w 3x4 (unnormalised quaternion, two_s = 2/|q|^2) */
 int lsr_pose_fwd(const float* cam7, float* c2w12, lsr_stream_t stream);
 int lsr_pose_bwd(const float* cam7, const float* d_c2w12, float* d_cam7, lsr_stream_t stream);
+
+/* Per-frame dynamic radius maps (use_dynamic_radius, src/Tracker.py:243-258, src/Mapper.py:854-869):
+ * grey -> Sobel magnitude -> clip to [0, thr] -> linear map on [0, 0.01, thr]; r_add / r_query are (H,W)
+ * float64 like the reference's numpy path.  Exactly one of color_f32 / color_f64 ((H,W,3)) is non-NULL. */
+int lsr_dynamic_radius(const float* color_f32, const double* color_f64, int32_t H, int32_t W, double thr,
+                       double r_add_max, double r_add_min, double ratio, double* r_add, double* r_query,
+                       lsr_stream_t stream);
 
 /* ---------------------------------------------------------------- fused render
  * Workspace sizes: `saved` holds the activations the backward needs (0 rows -> forward only),

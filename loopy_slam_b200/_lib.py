@@ -20,7 +20,7 @@ GRAD_GEO_FEATS, GRAD_COL_FEATS, GRAD_GEO_W, GRAD_GEO_B, GRAD_COL_W, GRAD_RAYS, G
 EXPORTS = [
     'lsr_version', 'lsr_strerror', 'lsr_device_sm_count', 'lsr_grid_workspace_bytes', 'lsr_grid_build',
     'lsr_knn_query', 'lsr_sample_rays', 'lsr_sample_rays_bwd', 'lsr_pose_fwd', 'lsr_pose_bwd',
-    'lsr_render_workspace_bytes', 'lsr_far_bound', 'lsr_render_fwd', 'lsr_render_bwd',
+    'lsr_render_workspace_bytes', 'lsr_far_bound', 'lsr_render_fwd', 'lsr_render_bwd', 'lsr_dynamic_radius',
 ]
 
 
@@ -71,6 +71,7 @@ def lib():
         L.lsr_render_workspace_bytes.argtypes = [ctypes.POINTER(LsrParams), i64, ctypes.c_int,
                                                  ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]
         L.lsr_far_bound.argtypes = [vp, i64, i64, vp, vp]
+        L.lsr_dynamic_radius.argtypes = [vp, vp, i32, i32, f64, f64, f64, f64, vp, vp, vp]
         L.lsr_render_fwd.argtypes = [ctypes.POINTER(LsrParams), vp, vp, i64, vp, vp, vp, vp, vp, i64, i64, vp, vp,
                                      ctypes.POINTER(LsrWeights), vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp]
         L.lsr_render_bwd.argtypes = [ctypes.POINTER(LsrParams), vp, vp, i64, vp, vp, vp, vp, i64, vp, vp,

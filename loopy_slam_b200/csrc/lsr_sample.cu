@@ -113,9 +113,54 @@ __global__ void pose_bwd_kernel(const float* __restrict__ cam, const float* __re
   d_cam[6] = G[11];
 }
 
+// Per-frame dynamic radius maps: grey -> Sobel magnitude -> clip -> piecewise
+// linear map to r_add / r_query, float64 like the reference's numpy path
+// (/root/reference/src/Tracker.py:243-258, src/Mapper.py:854-869: skimage rgb2gray + sobel_h/sobel_v
+// (reflect borders, smoothing [1,2,1]/4) + scipy interp1d on [0, 0.01, thr]).
+template <typename T>
+__global__ void dynamic_radius_kernel(const T* __restrict__ color, int H, int W, double thr, double r_add_max,
+                                      double r_add_min, double ratio, double* __restrict__ r_add,
+                                      double* __restrict__ r_query) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  auto refl = [](int i, int n) { return i < 0 ? -i - 1 : (i >= n ? 2 * n - 1 - i : i); };   // scipy 'reflect'
+  double g[3][3];
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const size_t p = ((size_t)refl(y + dy, H) * W + refl(x + dx, W)) * 3;
+      g[dy + 1][dx + 1] = 0.2125 * (double)color[p] + 0.7154 * (double)color[p + 1] + 0.0721 * (double)color[p + 2];
+    }
+  const double gy = ((g[2][0] - g[0][0]) + 2.0 * (g[2][1] - g[0][1]) + (g[2][2] - g[0][2])) * 0.25;
+  const double gx = ((g[0][2] - g[0][0]) + 2.0 * (g[1][2] - g[1][0]) + (g[2][2] - g[2][0])) * 0.25;
+  double m = sqrt(gx * gx + gy * gy);
+  m = fmin(fmax(m, 0.0), thr);
+  auto map = [&](double hi, double lo) {   // interp1d([0, 0.01, thr], [hi, hi, lo])
+    if (m <= 0.01) return hi;
+    return (lo - hi) / (thr - 0.01) * (m - 0.01) + hi;
+  };
+  const size_t o = (size_t)y * W + x;
+  r_add[o] = map(r_add_max, r_add_min);
+  r_query[o] = map(ratio * r_add_max, ratio * r_add_min);
+}
+
 }  // namespace lsr
 
 using namespace lsr;
+
+extern "C" int lsr_dynamic_radius(const float* color_f32, const double* color_f64, int32_t H, int32_t W, double thr,
+                                  double r_add_max, double r_add_min, double ratio, double* r_add, double* r_query,
+                                  lsr_stream_t stream) {
+  if (H <= 0 || W <= 0 || (!color_f32 && !color_f64) || !r_add || !r_query || !(thr > 0.01)) return LSR_ERR_ARG;
+  const dim3 blk(32, 8), grd((W + 31) / 32, (H + 7) / 8);
+  if (color_f64)
+    dynamic_radius_kernel<double><<<grd, blk, 0, stream>>>(color_f64, H, W, thr, r_add_max, r_add_min, ratio, r_add, r_query);
+  else
+    dynamic_radius_kernel<float><<<grd, blk, 0, stream>>>(color_f32, H, W, thr, r_add_max, r_add_min, ratio, r_add, r_query);
+  LSR_CUDA_CHECK(cudaGetLastError());
+  return LSR_OK;
+}
 
 extern "C" int lsr_sample_rays(const float* depth_img, const float* color_img, int32_t H, int32_t W, float fx,
                                float fy, float cx, float cy, const float* c2w, int32_t c2w_ld, const int64_t* pix,

@@ -211,3 +211,77 @@ def test_neural_point_cloud_insert_and_query():
     _, Ie = _inradius(Dr, Ir, r2)
     assert torch.equal(I.cpu(), Ie) and (nn >= 1).all()
     assert npc.get_geo_feats().shape == (1200, 32) and abs(float(npc.get_geo_feats().std()) - 0.1) < 0.01
+
+
+def test_dynamic_radius_map_matches_numpy_restatement():
+    """vs a scipy/numpy restatement of skimage 0.19.3 rgb2gray + sobel_h/sobel_v (reflect) + interp1d
+    (src/Tracker.py:243-258).  skimage itself is not installed: pinned to its documented kernels."""
+    from scipy import ndimage as ndi
+    from loopy_slam_b200.radius_map import dynamic_radius_maps
+    cfg = L.default_cfg('tum')
+    gen = torch.Generator().manual_seed(8)
+    img = torch.rand(37, 53, 3, generator=gen, dtype=torch.float64)
+    img[10:20, 5:30] = 0.3                                  # flat patch -> r_max
+    gray = img.numpy() @ np.array([0.2125, 0.7154, 0.0721])
+    smooth, edge = np.array([1., 2., 1.]) / 4.0, np.array([1., 0., -1.])
+    gy = ndi.convolve(gray, np.outer(edge, smooth), mode='reflect')
+    gx = ndi.convolve(gray, np.outer(smooth, edge), mode='reflect')
+    mag = np.clip(np.sqrt(gx ** 2 + gy ** 2), 0.0, 0.15)
+    ref_add = np.interp(mag, [0, 0.01, 0.15], [0.08, 0.08, 0.02])
+    ref_q = np.interp(mag, [0, 0.01, 0.15], [0.16, 0.16, 0.04])
+    for dt in (torch.float64, torch.float32):
+        ra, rq = dynamic_radius_maps(img.to(DEV, dt), cfg)
+        assert ra.dtype == torch.float64 and ra.shape == (37, 53)
+        tol = 1e-12 if dt == torch.float64 else 1e-6
+        np.testing.assert_allclose(ra.cpu().numpy(), ref_add, rtol=0, atol=tol)
+        np.testing.assert_allclose(rq.cpu().numpy(), ref_q, rtol=0, atol=2 * tol)
+    assert float(ra[12, 10]) == 0.08
+
+
+def test_edge_cases_empty_and_tiny():
+    """R = 0 rays, empty cloud, N < 8 points, gt_depth=None, N_surface != 5."""
+    cfg = L.default_cfg('replica')
+    torch.manual_seed(3)
+    model = L.get_model(cfg).to(DEV)
+    rend = L.Renderer(cfg, None, SlamLike(64, 64, 40., 40., 31.5, 31.5))
+    rend.sigmoid_coefficient = 0.1
+
+    class NPC:
+        def get_radius_query(self):
+            return 0.08
+    gen = torch.Generator().manual_seed(1)
+    cloud5 = (torch.rand(5, 3, generator=gen) * 0.05).to(DEV)
+    feats5 = torch.randn(5, 32, generator=gen).to(DEV)
+    o = torch.zeros(7, 3, device=DEV)
+    d = torch.tensor([[0.01, 0.01, 1.0]], device=DEV).repeat(7, 1) * 0.02
+    g = torch.ones(7, device=DEV)
+    # N < 8: every neighbour list is padded, all five points are within the radius of the first samples
+    dep, var, rgb, valid = rend.render_batch_ray(NPC(), model, d, o, DEV, 'color', gt_depth=g, npc_geo_feats=feats5,
+                                                 npc_col_feats=feats5, cloud_pos=cloud5)
+    assert torch.isfinite(dep).all() and torch.isfinite(rgb).all() and valid.dtype == torch.bool and valid.all()
+    # empty cloud: nothing has neighbours -> invalid rays, finite outputs
+    dep, var, rgb, valid = rend.render_batch_ray(NPC(), model, d, o, DEV, 'geometry', gt_depth=g,
+                                                 npc_geo_feats=torch.zeros(0, 32, device=DEV),
+                                                 npc_col_feats=torch.zeros(0, 32, device=DEV),
+                                                 cloud_pos=torch.zeros(0, 3, device=DEV))
+    assert (~valid).all() and torch.isfinite(dep).all()
+    # R = 0
+    dep, var, rgb, valid = rend.render_batch_ray(NPC(), model, d[:0], o[:0], DEV, 'color', gt_depth=g[:0],
+                                                 npc_geo_feats=feats5, npc_col_feats=feats5, cloud_pos=cloud5)
+    assert dep.shape == (0,) and rgb.shape == (0, 3)
+    # gt_depth None: z in [near_end, 10], depth forced to 0 (Renderer.py:107-113,197-198)
+    dep, var, rgb, valid = rend.render_batch_ray(NPC(), model, d, o, DEV, 'color', gt_depth=None, npc_geo_feats=feats5,
+                                                 npc_col_feats=feats5, cloud_pos=cloud5)
+    assert (dep == 0).all() and torch.isfinite(var).all()
+    # N_surface = 3 (tile = 21 rays x 3 samples)
+    cfg3 = L.default_cfg('replica')
+    cfg3['rendering']['N_surface'] = 3
+    model3 = L.get_model(cfg3).to(DEV)
+    rend3 = L.Renderer(cfg3, None, SlamLike(64, 64, 40., 40., 31.5, 31.5))
+    rend3.sigmoid_coefficient = 0.1
+    geo = feats5.clone().requires_grad_(True)
+    dep, var, rgb, valid = rend3.render_batch_ray(NPC(), model3, d, o, DEV, 'color', gt_depth=g, npc_geo_feats=geo,
+                                                  npc_col_feats=feats5, cloud_pos=cloud5)
+    (dep.sum() + rgb.sum()).backward()
+    assert torch.isfinite(geo.grad).all() and geo.grad.abs().sum() > 0
+    assert ((dep >= 0.98 * g - 1e-5) & (dep <= 1.02 * g + 1e-5)).all()
