@@ -880,9 +880,9 @@ extern "C" int lsr_render_bwd(const LsrParams* prm, const void* grid_ws, const f
   if (stage != LSR_STAGE_GEOMETRY && stage != LSR_STAGE_COLOR) return LSR_ERR_ARG;
   if (n_rays < 0 || n_rays > (1ll << 27) || n_points < 0) return LSR_ERR_ARG;
   if (n_rays == 0) return LSR_OK;
-  if (!saved || !scratch || !rays_o || !rays_d || !gt_depth || !g_depth || !geo_feats) return LSR_ERR_ARG;
-  if (n_points > 0 && !cloud_pos) return LSR_ERR_ARG;
-  if (stage == LSR_STAGE_COLOR && !col_feats) return LSR_ERR_ARG;
+  if (!saved || !scratch || !rays_o || !rays_d || !gt_depth || !g_depth) return LSR_ERR_ARG;
+  if (n_points > 0 && (!cloud_pos || !geo_feats)) return LSR_ERR_ARG;
+  if (n_points > 0 && stage == LSR_STAGE_COLOR && !col_feats) return LSR_ERR_ARG;
   if (prm->rgb_mode == LSR_RGB_AFFINE_SIGMOID && !exposure_affine) return LSR_ERR_ARG;
   if ((grad_flags & LSR_GRAD_GEO_FEATS) && !d_geo_feats) return LSR_ERR_ARG;
   if ((grad_flags & LSR_GRAD_COL_FEATS) && !d_col_feats) return LSR_ERR_ARG;

@@ -590,9 +590,9 @@ extern "C" int lsr_render_fwd(const LsrParams* prm, const void* grid_ws, const f
   if (stage != LSR_STAGE_GEOMETRY && stage != LSR_STAGE_COLOR) return LSR_ERR_ARG;
   if (!grid_ws || !scratch || n_rays < 0 || n_rays > (1ll << 27) || n_points < 0) return LSR_ERR_ARG;
   if (n_rays == 0) return LSR_OK;
-  if (!rays_o || !rays_d || !gt_depth || !depth || !var || !rgb || !valid || !geo_feats) return LSR_ERR_ARG;
-  if (n_points > 0 && !cloud_pos) return LSR_ERR_ARG;
-  if (stage == LSR_STAGE_COLOR && !col_feats) return LSR_ERR_ARG;
+  if (!rays_o || !rays_d || !gt_depth || !depth || !var || !rgb || !valid) return LSR_ERR_ARG;
+  if (n_points > 0 && (!cloud_pos || !geo_feats)) return LSR_ERR_ARG;
+  if (n_points > 0 && stage == LSR_STAGE_COLOR && !col_feats) return LSR_ERR_ARG;
   if ((prm->flags & LSR_FLAG_DYNAMIC_R) && !r_query) return LSR_ERR_ARG;
   if (prm->rgb_mode == LSR_RGB_AFFINE_SIGMOID && !exposure_affine) return LSR_ERR_ARG;
   const int nsm = sm_count();

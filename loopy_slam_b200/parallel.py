@@ -49,28 +49,43 @@ def shard_rays(tensors, rank, world):
 
 
 class GradAllReducer:
-    """One all-reduce per optimiser step over a persistent flat fp32 buffer."""
+    """One gradient exchange per optimiser step.  Small tensors (decoder weights, pose) travel in ONE
+    flat fp32 buffer; tensors above ``big_numel`` (the two trainable feature sub-blocks, ~9 MB each)
+    are all-reduced in place -- staging them through the flat buffer would cost two extra full
+    copies per step.  All collectives are issued back to back (async) and waited for together."""
 
-    def __init__(self, params, group=None):
+    def __init__(self, params, group=None, big_numel=1 << 18):
         self.params = [p for p in params]
         self.group = group
-        self.numel = sum(p.numel() for p in self.params)
+        self.big_numel = big_numel
+        self.small = [p for p in self.params if p.numel() < big_numel]
+        self.big = [p for p in self.params if p.numel() >= big_numel]
+        self.numel = sum(p.numel() for p in self.small)
         self.flat = None
 
     def _ensure(self, device):
         if self.flat is None or self.flat.device != device or self.flat.numel() != self.numel:
-            self.flat = torch.zeros(self.numel, dtype=torch.float32, device=device)
+            self.flat = torch.zeros(max(self.numel, 1), dtype=torch.float32, device=device)
         return self.flat
 
     def allreduce_(self):
-        """Sum .grad of all params across ranks in place (missing grads count as zero)."""
+        """Sum .grad of all params across ranks in place (missing grads count as zero).  Returns the
+        number of bytes exchanged per rank."""
         if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
             return 0
         dev = next((p.grad.device for p in self.params if p.grad is not None), self.params[0].device)
+        works, nbytes = [], 0
+        for p in self.big:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+            works.append(dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            if g is not p.grad:
+                p.grad = g
+            nbytes += g.numel() * 4
         flat = self._ensure(dev)
-        off = 0
-        views = []
-        for p in self.params:
+        off, views = 0, []
+        for p in self.small:
             n = p.numel()
             v = flat[off:off + n]
             if p.grad is None:
@@ -79,13 +94,17 @@ class GradAllReducer:
                 v.copy_(p.grad.reshape(-1))
             views.append(v)
             off += n
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-        for p, v in zip(self.params, views):
+        if self.small:
+            works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            nbytes += self.numel * 4
+        for w in works:
+            w.wait()
+        for p, v in zip(self.small, views):
             if p.grad is None:
                 p.grad = v.view(p.shape).clone()
             else:
                 p.grad.copy_(v.view(p.shape))
-        return flat.numel() * 4
+        return nbytes
 
 
 def max_over_ranks(value, device):
