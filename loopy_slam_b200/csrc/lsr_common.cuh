@@ -178,11 +178,16 @@ __device__ __forceinline__ void knn_warp(const GridView& g, float px, float py, 
       if (lane >= o) inc += v;
     }
     const int T = __shfl_sync(FULL, inc, 31);
-    const int nr_here = min(32, nranges - rc0);
     for (int j0 = 0; j0 < T; j0 += 32) {
       const int j = j0 + lane;
+      // range of candidate j = number of ranges whose inclusive prefix is <= j: binary search over the
+      // (non-decreasing) prefix held one-per-lane; lanes beyond the last range hold T > j
       int rsel = 0;
-      for (int q = 0; q < nr_here; ++q) rsel += (__shfl_sync(FULL, inc, q) <= j) ? 1 : 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const int v = __shfl_sync(FULL, inc, rsel + step - 1);
+        if (v <= j) rsel += step;
+      }
       rsel = min(rsel, 31);
       const int inc_sel = __shfl_sync(FULL, inc, rsel), cnt_sel = __shfl_sync(FULL, cnt, rsel);
       const int beg_sel = __shfl_sync(FULL, beg, rsel);

@@ -130,14 +130,27 @@ extern __device__ unsigned long long lsr_phase_cycles[2][16];
 #define LSR_PHASE(kernel, k)
 #endif
 // ------------------------------------------------------------------ small math
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float softplus100(float x) {
   // torch.nn.Softplus(beta=100, threshold=20): x if 100x > 20 else log1p(exp(100x))/100
-  const float y = 100.f * x;
 #ifdef LSR_ACCURATE_MATH
+  const float y = 100.f * x;
   return y > 20.f ? x : log1pf(expf(y)) * 0.01f;
 #else
-  // MUFU path: |abs err| ~ 1e-8 on values that are added to O(0.1) activations
-  return y > 20.f ? x : __logf(1.f + __expf(y)) * 0.01f;
+  // two MUFU ops: log(1 + e^(100x))/100 = lg2(1 + 2^(x * 100 log2 e)) * (ln 2 / 100); absolute error
+  // ~1e-8 on values that are added to O(0.1) activations (the 1e-4 parity bar is relative to those)
+  const float e = ex2_approx(x * 144.26950408889634f);
+  const float sp = lg2_approx(1.f + e) * 0.0069314718055994531f;
+  return x > 0.2f ? x : sp;
 #endif
 }
 // d softplus100 / dx = sigmoid(100x) = 1 - exp(-100*softplus100(x))
@@ -145,7 +158,7 @@ __device__ __forceinline__ float softplus100_grad_from_out(float sp) {
 #ifdef LSR_ACCURATE_MATH
   return 1.f - expf(-100.f * sp);
 #else
-  return 1.f - __expf(-100.f * sp);
+  return 1.f - ex2_approx(sp * -144.26950408889634f);
 #endif
 }
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.f / (1.f + expf(-x)); }
