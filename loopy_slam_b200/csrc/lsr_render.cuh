@@ -222,7 +222,9 @@ __device__ __forceinline__ void split_tf32(float x, unsigned& hi, unsigned& lo) 
 template <int TM, int TXN, int NCG, bool A_ROWMAJOR, bool B_SMEM>
 __device__ __forceinline__ void tile_gemm(float (&acc)[TM][NCG * 4], const float* __restrict__ A, int lda,
                                           int Kc, const float* __restrict__ B, int ldb, int ncols_valid,
-                                          float* sBuf) {
+                                          float* sBuf, int mvalid = 1 << 30) {
+  // mvalid: output rows >= mvalid are not needed (short tiles); their 16-row MMA tiles are skipped and
+  // come out as zeros
   constexpr int NCOLS = TXN * 4 * NCG;      // 32 / 64 / 128 output columns
   constexpr int RS = NT / TXN;
   constexpr int M_OUT = TM * RS;            // 32 / 64 / 128 output rows
@@ -263,9 +265,12 @@ __device__ __forceinline__ void tile_gemm(float (&acc)[TM][NCG * 4], const float
 #pragma unroll
     for (int i0 = 0; i0 < MI; i0 += 2) {
       constexpr int IB = MI >= 2 ? 2 : 1;
+      if ((wm + 2 * i0) * 16 >= mvalid) break;             // warp-uniform: this and all later row tiles are unused
+      const bool second = IB > 1 && (wm + 2 * (i0 + 1)) * 16 < mvalid;
       unsigned ah[IB][4], al[IB][4];
 #pragma unroll
       for (int ii = 0; ii < IB; ++ii) {
+        if (ii == 1 && !second) break;
         const int i = i0 + ii;
         float a0, a1, a2, a3;
         if (A_ROWMAJOR) {
@@ -279,18 +284,27 @@ __device__ __forceinline__ void tile_gemm(float (&acc)[TM][NCG * 4], const float
         split_tf32(a0, ah[ii][0], al[ii][0]); split_tf32(a1, ah[ii][1], al[ii][1]);
         split_tf32(a2, ah[ii][2], al[ii][2]); split_tf32(a3, ah[ii][3], al[ii][3]);
       }
+      if (IB == 1 || second) {
 #pragma unroll
-      for (int j = 0; j < NJ; ++j)
+        for (int j = 0; j < NJ; ++j)
 #pragma unroll
-        for (int ii = 0; ii < IB; ++ii) mma_tf32_16x8x8(c[i0 + ii][j], al[ii], bh[j]);
+          for (int ii = 0; ii < IB; ++ii) mma_tf32_16x8x8(c[i0 + ii][j], al[ii], bh[j]);
 #pragma unroll
-      for (int j = 0; j < NJ; ++j)
+        for (int j = 0; j < NJ; ++j)
 #pragma unroll
-        for (int ii = 0; ii < IB; ++ii) mma_tf32_16x8x8(c[i0 + ii][j], ah[ii], bl[j]);
+          for (int ii = 0; ii < IB; ++ii) mma_tf32_16x8x8(c[i0 + ii][j], ah[ii], bl[j]);
 #pragma unroll
-      for (int j = 0; j < NJ; ++j)
+        for (int j = 0; j < NJ; ++j)
 #pragma unroll
-        for (int ii = 0; ii < IB; ++ii) mma_tf32_16x8x8(c[i0 + ii][j], ah[ii], bh[j]);
+          for (int ii = 0; ii < IB; ++ii) mma_tf32_16x8x8(c[i0 + ii][j], ah[ii], bh[j]);
+      } else {                                             // only the first row tile of the pair is live
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) mma_tf32_16x8x8(c[i0][j], al[0], bh[j]);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) mma_tf32_16x8x8(c[i0][j], ah[0], bl[j]);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) mma_tf32_16x8x8(c[i0][j], ah[0], bh[j]);
+      }
     }
   };
 
@@ -367,7 +381,8 @@ __device__ __forceinline__ void tile_gemm(float (&acc)[TM][NCG * 4], const float
 template <int TM, int TXN, int NCG, bool A_ROWMAJOR, bool B_SMEM>
 __device__ __forceinline__ void tile_gemm(float (&acc)[TM][NCG * 4], const float* __restrict__ A, int lda,
                                           int Kc, const float* __restrict__ B, int ldb, int ncols_valid,
-                                          float* sBuf) {
+                                          float* sBuf, int mvalid = 1 << 30) {
+  (void)mvalid;
   constexpr int NCOLS = TXN * 4 * NCG;
   constexpr int RS = NT / TXN;
   const int tid = threadIdx.x;

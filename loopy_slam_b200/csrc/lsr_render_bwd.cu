@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
           for (int i = 0; i < TMN128; ++i)
             red_add_v4(dW + a.w.c_fc_w[li] + nm.row(i) * CDIM + nm.col(), au[i][0], au[i][1], au[i][2], au[i][3]);
         }
-        tile_gemm<TMNA, 8, 1, true, false>(dCacc, sD, DLD, HC, blob + a.w.c_fc_w[li], CDIM, CDIM, sB);
+        tile_gemm<TMNA, 8, 1, true, false>(dCacc, sD, DLD, HC, blob + a.w.c_fc_w[li], CDIM, CDIM, sB, nrows);
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           const int col = wm.col(g);
@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
         if (li == 0 || li == 3) {     // d e'
           float ae[TMA][4];
           zero_acc(ae);
-          tile_gemm<TMA, 16, 1, true, false>(ae, sD, DLD, HC, blob + a.w.c_lin_w[li], li == 3 ? ECC + HC : ECC, ECC, sB);
+          tile_gemm<TMA, 16, 1, true, false>(ae, sD, DLD, HC, blob + a.w.c_lin_w[li], li == 3 ? ECC + HC : ECC, ECC, sB, nrows);
           if (wm.tx * 4 < ECC) {
 #pragma unroll
             for (int i = 0; i < TMA; ++i) {
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
         if (li > 0) {
           zero_acc(dH);
           tile_gemm<TMA, 16, 2, true, false>(dH, sD, DLD, HC, blob + a.w.c_lin_w[li] + (li == 3 ? ECC : 0),
-                                           li == 3 ? ECC + HC : HC, HC, sB);
+                                           li == 3 ? ECC + HC : HC, HC, sB, nrows);
         }
       }
       LSR_PHASE(1, 2);   // colour trunk backward
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
         prefetch_rows_l2(sv + SL.sp + p0 * KNN * HC, nrows * KNN, HC);
         float dU[TMA][8];
         zero_acc(dU);
-        tile_gemm<TMA, 16, 2, true, false>(dU, sDC, CLD, CDIM, blob + a.w.c_nb2_w, HC, HC, sB);
+        tile_gemm<TMA, 16, 2, true, false>(dU, sDC, CLD, CDIM, blob + a.w.c_nb2_w, HC, HC, sB, nrows);
         float dV1acc[TMW][4];
         zero_acc(dV1acc);
         float dv1 = 0.f;
@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
           }
           float aq[TMA][4];
           zero_acc(aq);
-          tile_gemm<TMA, 16, 1, true, false>(aq, sD, DLD, HC, blob + a.w.c_nb1_w, QD, QD, sB);
+          tile_gemm<TMA, 16, 1, true, false>(aq, sD, DLD, HC, blob + a.w.c_nb1_w, QD, QD, sB, nrows);
           {
             const int col = wm.tx * 4;
             if (col < 2 * ER) {
@@ -679,7 +679,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
           for (int i = 0; i < TMN32; ++i)
             red_add_v4(dW + a.w.g_fc_w[li] + nm.row(i) * CDIM + nm.col(), au[i][0], au[i][1], au[i][2], au[i][3]);
         }
-        tile_gemm<TMNA, 8, 1, true, false>(dCacc, sD, CLD, HG, blob + a.w.g_fc_w[li], CDIM, CDIM, sB);
+        tile_gemm<TMNA, 8, 1, true, false>(dCacc, sD, CLD, HG, blob + a.w.g_fc_w[li], CDIM, CDIM, sB, nrows);
 #pragma unroll
         for (int i = 0; i < TMNA; ++i) {
           const int r = nm.row(i);
@@ -733,13 +733,13 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
         }
         if (li == 1 || li == 2 || li == 4) {
           zero_acc(dHg);
-          tile_gemm<TMNA, 8, 1, true, false>(dHg, sD, CLD, HG, blob + a.w.g_lin_w[li], HG, HG, sB);
+          tile_gemm<TMNA, 8, 1, true, false>(dHg, sD, CLD, HG, blob + a.w.g_lin_w[li], HG, HG, sB, nrows);
         } else if (li == 3) {
           zero_acc(dHg);
-          tile_gemm<TMNA, 8, 1, true, false>(dHg, sD, CLD, HG, packed + Packed::gW3n + EGP, 128, HG, sB);
-          tile_gemm<TMA, 16, 2, true, false>(dEacc, sD, CLD, HG, packed + Packed::gW3n, 128, EGP, sB);
+          tile_gemm<TMNA, 8, 1, true, false>(dHg, sD, CLD, HG, packed + Packed::gW3n + EGP, 128, HG, sB, nrows);
+          tile_gemm<TMA, 16, 2, true, false>(dEacc, sD, CLD, HG, packed + Packed::gW3n, 128, EGP, sB, nrows);
         } else {
-          tile_gemm<TMA, 16, 2, true, false>(dEacc, sD, CLD, HG, packed + Packed::gW0n, EGP, EGP, sB);
+          tile_gemm<TMA, 16, 2, true, false>(dEacc, sD, CLD, HG, packed + Packed::gW0n, EGP, EGP, sB, nrows);
         }
       }
       // geometry Fourier backward: e_j = sin(arg_j)
@@ -852,6 +852,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
 int check_weights(const LsrWeights* w);
 int check_params(const LsrParams* p);
 int sm_count();
+int balanced_rays_per_tile(int64_t n_rays, int n_surface, int nsm);
 
 }  // namespace lsr
 
@@ -907,7 +908,7 @@ extern "C" int lsr_render_bwd(const LsrParams* prm, const void* grid_ws, const f
   a.gflags = grad_flags;
   a.d_geo = d_geo_feats; a.d_col = d_col_feats; a.d_w = d_weights; a.d_affine = d_exposure_affine;
   a.d_ro = d_rays_o; a.d_rd = d_rays_d;
-  a.rays_per_tile = TILE_M / prm->n_surface;
+  a.rays_per_tile = balanced_rays_per_tile(n_rays, prm->n_surface, nsm);
   a.ntiles = (int)((n_rays + a.rays_per_tile - 1) / a.rays_per_tile);
   const size_t smem = BWD_SMEM_FLOATS * sizeof(float);
   LSR_CUDA_CHECK(cudaFuncSetAttribute(render_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

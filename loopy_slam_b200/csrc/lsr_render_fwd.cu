@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
         const int wt = li == 0 ? Packed::gW0t : li == 1 ? Packed::gW1t : li == 2 ? Packed::gW2t
                      : li == 3 ? Packed::gW3t : Packed::gW4t;
         zero_acc(acc);
-        tile_gemm<TMNA, 8, 1, true, false>(acc, A, XLD, Kc, packed + wt, HG, HG, sB);
+        tile_gemm<TMNA, 8, 1, true, false>(acc, A, XLD, Kc, packed + wt, HG, HG, sB, nrows);
         const float4 b = *reinterpret_cast<const float4*>(blob + a.w.g_lin_b[li] + col);
 #pragma unroll
         for (int i = 0; i < TMNA; ++i) {
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
             *reinterpret_cast<float4*>(a.saved + SL.gs + ((size_t)li * Pp + p0 + r) * HG + col) =
                 make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
         }
-        tile_gemm<TMNA, 8, 1, true, false>(acc, sC, CLD, CDIM, packed + Packed::gUt + li * CDIM * HG, HG, HG, sB);
+        tile_gemm<TMNA, 8, 1, true, false>(acc, sC, CLD, CDIM, packed + Packed::gUt + li * CDIM * HG, HG, HG, sB, nrows);
         const float4 u = *reinterpret_cast<const float4*>(blob + a.w.g_fc_b[li] + col);
 #pragma unroll
         for (int i = 0; i < TMNA; ++i) {
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
             *reinterpret_cast<float4*>(sX + m * XLD + 2 * ER + q * 4) = f;
           }
           zero_acc(acc);
-          tile_gemm<TMA, 16, 2, true, false>(acc, sX, XLD, QDP, packed + Packed::V1t, HC, HC, sB);
+          tile_gemm<TMA, 16, 2, true, false>(acc, sX, XLD, QDP, packed + Packed::V1t, HC, HC, sB, nrows);
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const int col = wm.col(g);
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
         }
         float c4[TMNA][4];
         zero_acc(c4);
-        tile_gemm<TMNA, 8, 1, true, false>(c4, sX, XLD, HC, packed + Packed::V2t, CDIM, CDIM, sB);
+        tile_gemm<TMNA, 8, 1, true, false>(c4, sX, XLD, HC, packed + Packed::V2t, CDIM, CDIM, sB, nrows);
         const int col = nm.col();
         const float4 v2 = *reinterpret_cast<const float4*>(blob + a.w.c_nb2_b + col);
 #pragma unroll
@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
           const int wt = li == 0 ? Packed::cW0t : li == 1 ? Packed::cW1t : li == 2 ? Packed::cW2t
                        : li == 3 ? Packed::cW3t : Packed::cW4t;
           zero_acc(acc);
-          tile_gemm<TMA, 16, 2, true, false>(acc, A, XLD, Kc, packed + wt, HC, HC, sB);
+          tile_gemm<TMA, 16, 2, true, false>(acc, A, XLD, Kc, packed + wt, HC, HC, sB, nrows);
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const int col = wm.col(g);
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
                     make_float4(acc[i][g * 4 + 0], acc[i][g * 4 + 1], acc[i][g * 4 + 2], acc[i][g * 4 + 3]);
             }
           }
-          tile_gemm<TMA, 16, 2, true, false>(acc, sC, CLD, CDIM, packed + Packed::cUt + li * CDIM * HC, HC, HC, sB);
+          tile_gemm<TMA, 16, 2, true, false>(acc, sC, CLD, CDIM, packed + Packed::cUt + li * CDIM * HC, HC, HC, sB, nrows);
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const int col = wm.col(g);
@@ -544,6 +544,19 @@ int check_params(const LsrParams* p) {
   return LSR_OK;
 }
 
+// Rays per tile: the largest tile that fits TILE_M rows, shrunk so that the tiles fill whole waves of
+// (SMs x CTAs/SM) evenly -- short tiles skip their unused 16-row MMA tiles, so two even waves of 3/4
+// tiles beat one full wave plus a 40 % one.  Forward and backward must agree (saved-row order).
+int balanced_rays_per_tile(int64_t n_rays, int n_surface, int nsm) {
+  const int rmax = TILE_M / n_surface;
+  const int64_t slots = (int64_t)nsm * CTAS_PER_SM;
+  const int64_t waves = (n_rays + rmax * slots - 1) / (rmax * slots);
+  int64_t rpt = (n_rays + waves * slots - 1) / (waves * slots);
+  if (rpt < 1) rpt = 1;
+  if (rpt > rmax) rpt = rmax;
+  return (int)rpt;
+}
+
 int sm_count() {
   static int cached = 0;
   if (cached) return cached;
@@ -614,7 +627,7 @@ extern "C" int lsr_render_fwd(const LsrParams* prm, const void* grid_ws, const f
   a.stage = stage;
   a.depth = depth; a.var = var; a.rgb = rgb; a.valid = valid;
   a.saved = (float*)saved;
-  a.rays_per_tile = TILE_M / prm->n_surface;
+  a.rays_per_tile = balanced_rays_per_tile(n_rays, prm->n_surface, nsm);
   a.ntiles = (int)((n_rays + a.rays_per_tile - 1) / a.rays_per_tile);
   const size_t smem = FWD_SMEM_FLOATS * sizeof(float);
   LSR_CUDA_CHECK(cudaFuncSetAttribute(render_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
