@@ -6,6 +6,7 @@
 //   Renderer.render_batch_ray   /root/reference/src/utils/Renderer.py:71-201
 //   NICER / MLP_geometry / MLP_color   /root/reference/src/conv_onet/models/decoder.py:106-626
 //   raw2outputs_nerf_color      /root/reference/src/common.py:382-422
+#include <cstdlib>
 #include "lsr_render.cuh"
 
 namespace lsr {
@@ -549,6 +550,10 @@ int check_params(const LsrParams* p) {
 // tiles beat one full wave plus a 40 % one.  Forward and backward must agree (saved-row order).
 int balanced_rays_per_tile(int64_t n_rays, int n_surface, int nsm) {
   const int rmax = TILE_M / n_surface;
+  if (const char* e = getenv("LSR_DEBUG_RAYS_PER_TILE")) {   // tuning experiments only
+    const int v = atoi(e);
+    if (v >= 1 && v <= rmax) return v;
+  }
   const int64_t slots = (int64_t)nsm * CTAS_PER_SM;
   const int64_t waves = (n_rays + rmax * slots - 1) / (rmax * slots);
   int64_t rpt = (n_rays + waves * slots - 1) / (waves * slots);
