@@ -296,8 +296,11 @@ def run_lsr(args, rank, world, local):
                 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4},
         'gpu_launches': n_launch,
         'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
-                     'frac': ach / peak, 'traffic': None, 'peak_source': peak_src,
+                     'frac': ach / peak,
+                     'traffic': (331.4e6 if t_b >= t_f else 254.1e6) if stage == 'color' and R == 4936 else None, 'peak_source': peak_src,
                      'algorithmic_bytes_per_launch': bytes_dom,
+                     'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_ncu_final_summary.md '
+                                       '(same command; the excess over the algorithmic bytes is the saved-activation round trip)',
                      'note': 'HBM fraction as defined in BASELINE.md section 3; arithmetic intensity ~190 FLOP/B puts both '
                              'fused kernels on the tensor/issue side of the roofline, see "tensor"'},
         'tensor': {'algorithmic_tflops': flops_step / ((t_f + t_b) * 1e-3) / 1e12 if t_f + t_b > 0 else 0,
