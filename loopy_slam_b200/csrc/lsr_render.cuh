@@ -19,8 +19,14 @@ constexpr int TMW = 128 / RSW;       // rows per thread of a WIDE-mapped 128-row
 constexpr int TMN128 = 128 / RSN;    // same, NARROW map
 constexpr int TMW32 = 32 / RSW;      // 32-row outputs, WIDE map
 constexpr int TMN32 = 32 / RSN;      // 32-row outputs, NARROW map
-constexpr int KC = 16;         // contraction rows per streamed chunk
-constexpr int NSTAGE = 3;      // cp.async ring depth
+#ifndef LSR_KC
+#define LSR_KC 16
+#endif
+#ifndef LSR_NSTAGE
+#define LSR_NSTAGE 3
+#endif
+constexpr int KC = LSR_KC;         // contraction rows per streamed chunk (multiple of 8)
+constexpr int NSTAGE = LSR_NSTAGE; // cp.async ring depth (>= 2)
 constexpr int HG = 32;         // geometry decoder hidden width  (decoder.py:566)
 constexpr int HC = 128;        // colour decoder hidden width    (decoder.py:561,569)
 constexpr int EG = 93;         // geometry Fourier features      (decoder.py:151)
@@ -333,16 +339,17 @@ __device__ __forceinline__ void tile_gemm(float (&acc)[TM][NCG * 4], const float
       }
       cp_async_commit();
     };
-    prefetch(0);
-    prefetch(1);
+#pragma unroll
+    for (int st = 0; st < NSTAGE - 1; ++st) prefetch(st);
     for (int cix = 0; cix < nchunks; ++cix) {
-      cp_async_wait<1>();
+      cp_async_wait<NSTAGE - 2>();
       __syncthreads();          // chunk visible to all; everyone is done with the previous chunk's buffer
-      prefetch(cix + 2);
+      prefetch(cix + NSTAGE - 1);
       const float* sb = sBuf + (cix % NSTAGE) * (KC * CLD_);
       const int k0 = cix * KC;
-      k8_step(k0, sb, CLD_, 0);
-      if (k0 + 8 < Kc) k8_step(k0 + 8, sb, CLD_, 8);
+#pragma unroll
+      for (int kb = 0; kb < KC; kb += 8)
+        if (k0 + kb < Kc) k8_step(k0 + kb, sb, CLD_, kb);
     }
     cp_async_wait<0>();
     __syncthreads();
@@ -431,12 +438,12 @@ __device__ __forceinline__ void tile_gemm(float (&acc)[TM][NCG * 4], const float
       }
       cp_async_commit();
     };
-    prefetch(0);
-    prefetch(1);
+#pragma unroll
+    for (int st = 0; st < NSTAGE - 1; ++st) prefetch(st);
     for (int c = 0; c < nchunks; ++c) {
-      cp_async_wait<1>();
+      cp_async_wait<NSTAGE - 2>();
       __syncthreads();          // chunk c visible to all; everyone is done with chunk c-1's buffer
-      prefetch(c + 2);
+      prefetch(c + NSTAGE - 1);
       const float* sb = sBuf + (c % NSTAGE) * (KC * NCOLS);
       const int k0 = c * KC;
       const int kmax = min(KC, Kc - k0);

@@ -7,6 +7,9 @@
 //   NICER / MLP_geometry / MLP_color   /root/reference/src/conv_onet/models/decoder.py:106-626
 //   raw2outputs_nerf_color      /root/reference/src/common.py:382-422
 #include <cstdlib>
+// the forward kernel has shared memory to spare: 32-row weight chunks, two stages -> half the barriers per GEMM
+#define LSR_KC 32
+#define LSR_NSTAGE 2
 #include "lsr_render.cuh"
 
 namespace lsr {
