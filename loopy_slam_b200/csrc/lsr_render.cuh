@@ -225,31 +225,41 @@ __device__ __forceinline__ void split_tf32(float x, unsigned& hi, unsigned& lo) 
 }
 
 #ifndef LSR_FFMA_GEMM
-template <int TM, int TXN, int NCG, bool A_ROWMAJOR, bool B_SMEM>
-__device__ __forceinline__ void tile_gemm(float (&acc)[TM][NCG * 4], const float* __restrict__ A, int lda,
-                                          int Kc, const float* __restrict__ B, int ldb, int ncols_valid,
-                                          float* sBuf, int mvalid = 1 << 30) {
-  // mvalid: output rows >= mvalid are not needed (short tiles); their 16-row MMA tiles are skipped and
-  // come out as zeros
-  constexpr int NCOLS = TXN * 4 * NCG;      // 32 / 64 / 128 output columns
-  constexpr int RS = NT / TXN;
-  constexpr int M_OUT = TM * RS;            // 32 / 64 / 128 output rows
-  constexpr int MTT = M_OUT / 16;           // 16-row tiles in the output
-  constexpr int MI = (MTT + 1) / 2;         //   per warp
-  constexpr int NTT = NCOLS / 8;            // 8-column tiles in the output
-  constexpr int NJ = (NTT + 3) / 4;         //   per warp
+// Accumulator fragments of an M_OUT x NCOLS output tile, distributed over the 8 warps as 2 (rows) x 4
+// (cols): warp (wm, wn) owns 16-row tiles wm, wm+2, ... and 8-column tiles wn, wn+4, ...; inside a
+// fragment, thread (g = lane/4, t = lane%4) holds rows g, g+8 and columns 2t, 2t+1.
+template <int M_OUT, int NCOLS>
+struct FragTile {
+  static constexpr int MTT = M_OUT / 16, NTT = NCOLS / 8;
+  static constexpr int MI = (MTT + 1) / 2, NJ = (NTT + 3) / 4;
+  float c[MI][NJ][4];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) { c[i][j][0] = 0.f; c[i][j][1] = 0.f; c[i][j][2] = 0.f; c[i][j][3] = 0.f; }
+  }
+  // row of the (c[i][j][2h], c[i][j][2h+1]) pair and its first column
+  __device__ __forceinline__ static int row(int i, int h) {
+    return (((threadIdx.x >> 5) >> 2) + 2 * i) * 16 + ((threadIdx.x & 31) >> 2) + 8 * h;
+  }
+  __device__ __forceinline__ static int col(int j) { return (((threadIdx.x >> 5) & 3) + 4 * j) * 8 + 2 * (threadIdx.x & 3); }
+  __device__ __forceinline__ static bool col_ok(int j) { return NTT % 4 == 0 || ((threadIdx.x >> 5) & 3) + 4 * j < NTT; }
+};
+
+// c += A . B on the tensor cores (3xTF32); semantics of the operands as in tile_gemm below.  Ends with
+// __syncthreads().  mvalid: output rows >= mvalid are not needed, their 16-row MMA tiles are skipped.
+template <int M_OUT, int NCOLS, bool A_ROWMAJOR, bool B_SMEM>
+__device__ __forceinline__ void mma_core(float (&c)[FragTile<M_OUT, NCOLS>::MI][FragTile<M_OUT, NCOLS>::NJ][4],
+                                         const float* __restrict__ A, int lda, int Kc, const float* __restrict__ B,
+                                         int ldb, int ncols_valid, float* sBuf, int mvalid) {
+  constexpr int MTT = M_OUT / 16, NTT = NCOLS / 8;
+  constexpr int MI = (MTT + 1) / 2, NJ = (NTT + 3) / 4;
   constexpr int CLD_ = NCOLS + SB_LD_PAD;   // chunk row pitch
-  static_assert(NT == 256 && M_OUT % 32 == 0, "tile_gemm thread layout");
+  static_assert(NT == 256 && M_OUT % 32 == 0, "mma_core thread layout");
   const int tid = threadIdx.x;
-  const int tx = tid % TXN, ty = tid / TXN;
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int wm = warp >> 2, wn = warp & 3;
-
-  float c[MI][NJ][4];
-#pragma unroll
-  for (int i = 0; i < MI; ++i)
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) { c[i][j][0] = 0.f; c[i][j][1] = 0.f; c[i][j][2] = 0.f; c[i][j][3] = 0.f; }
 
   // one k8 step: A fragments from A (shared), B fragments from bs (shared, row pitch bld).
   // The three partial products of one accumulator are issued in three separate sweeps over the
@@ -354,6 +364,27 @@ __device__ __forceinline__ void tile_gemm(float (&acc)[TM][NCG * 4], const float
     cp_async_wait<0>();
     __syncthreads();
   }
+
+}
+
+template <int TM, int TXN, int NCG, bool A_ROWMAJOR, bool B_SMEM>
+__device__ __forceinline__ void tile_gemm(float (&acc)[TM][NCG * 4], const float* __restrict__ A, int lda,
+                                          int Kc, const float* __restrict__ B, int ldb, int ncols_valid,
+                                          float* sBuf, int mvalid = 1 << 30) {
+  constexpr int NCOLS = TXN * 4 * NCG;      // 32 / 64 / 128 output columns
+  constexpr int RS = NT / TXN;
+  constexpr int M_OUT = TM * RS;            // 32 / 64 / 128 output rows
+  constexpr int MTT = M_OUT / 16, NTT = NCOLS / 8;
+  constexpr int NJ = (NTT + 3) / 4;
+  constexpr int CLD_ = NCOLS + SB_LD_PAD;
+  const int tid = threadIdx.x;
+  const int tx = tid % TXN, ty = tid / TXN;
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int wm = warp >> 2, wn = warp & 3;
+  FragTile<M_OUT, NCOLS> f;
+  f.zero();
+  mma_core<M_OUT, NCOLS, A_ROWMAJOR, B_SMEM>(f.c, A, lda, Kc, B, ldb, ncols_valid, sBuf, mvalid);
+  float (&c)[FragTile<M_OUT, NCOLS>::MI][NJ][4] = f.c;
 
   // fragments -> per-thread register tiles, 32 output rows per pass through sBuf
   float* stage = sBuf;

@@ -197,37 +197,49 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
       sX[m * XLD + j] = v;
     }
     LSR_PHASE(0, 1);   // gather + fourier
-    // geometry MLP: h = relu(W x + b) + U c + u  (decoder.py:275-283)
+    // geometry MLP: h = relu(W x + b) + U c + u  (decoder.py:275-283); epilogues work directly on the MMA
+    // accumulator fragments (rows g / g+8, column pairs 2t, 2t+1)
     {
-      float acc[TMNA][4];
-      const int col = nm.col();
+      typedef FragTile<TILE_M, HG> FG;
+      FG f;
 #pragma unroll 1
       for (int li = 0; li < 5; ++li) {
         const float* A = (li == 0 || li == 3) ? sX : sX + EGP;
         const int Kc = (li == 0) ? EGP : (li == 3 ? 128 : HG);
         const int wt = li == 0 ? Packed::gW0t : li == 1 ? Packed::gW1t : li == 2 ? Packed::gW2t
                      : li == 3 ? Packed::gW3t : Packed::gW4t;
-        zero_acc(acc);
-        tile_gemm<TMNA, 8, 1, true, false>(acc, A, XLD, Kc, packed + wt, HG, HG, sB, nrows);
-        const float4 b = *reinterpret_cast<const float4*>(blob + a.w.g_lin_b[li] + col);
+        f.zero();
+        mma_core<TILE_M, HG, true, false>(f.c, A, XLD, Kc, packed + wt, HG, HG, sB, nrows);
 #pragma unroll
-        for (int i = 0; i < TMNA; ++i) {
-          acc[i][0] = fmaxf(acc[i][0] + b.x, 0.f); acc[i][1] = fmaxf(acc[i][1] + b.y, 0.f);
-          acc[i][2] = fmaxf(acc[i][2] + b.z, 0.f); acc[i][3] = fmaxf(acc[i][3] + b.w, 0.f);
-          const int r = nm.row(i);
-          if (save && r < nrows)
-            *reinterpret_cast<float4*>(a.saved + SL.gs + ((size_t)li * Pp + p0 + r) * HG + col) =
-                make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        for (int j = 0; j < FG::NJ; ++j) {
+          const int col = FG::col(j);
+          const float2 b = *reinterpret_cast<const float2*>(blob + a.w.g_lin_b[li] + col);
+#pragma unroll
+          for (int i = 0; i < FG::MI; ++i)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int r = FG::row(i, h);
+              const float v0 = fmaxf(f.c[i][j][2 * h] + b.x, 0.f), v1 = fmaxf(f.c[i][j][2 * h + 1] + b.y, 0.f);
+              f.c[i][j][2 * h] = v0; f.c[i][j][2 * h + 1] = v1;
+              if (save && r < nrows)
+                *reinterpret_cast<float2*>(a.saved + SL.gs + ((size_t)li * Pp + p0 + r) * HG + col) = make_float2(v0, v1);
+            }
         }
-        tile_gemm<TMNA, 8, 1, true, false>(acc, sC, CLD, CDIM, packed + Packed::gUt + li * CDIM * HG, HG, HG, sB, nrows);
-        const float4 u = *reinterpret_cast<const float4*>(blob + a.w.g_fc_b[li] + col);
+        mma_core<TILE_M, HG, true, false>(f.c, sC, CLD, CDIM, packed + Packed::gUt + li * CDIM * HG, HG, HG, sB, nrows);
 #pragma unroll
-        for (int i = 0; i < TMNA; ++i) {
-          const int r = nm.row(i);
-          const float4 h = make_float4(acc[i][0] + u.x, acc[i][1] + u.y, acc[i][2] + u.z, acc[i][3] + u.w);
-          *reinterpret_cast<float4*>(sX + r * XLD + EGP + col) = h;
-          if (save && r < nrows)
-            *reinterpret_cast<float4*>(a.saved + SL.gh + ((size_t)li * Pp + p0 + r) * HG + col) = h;
+        for (int j = 0; j < FG::NJ; ++j) {
+          const int col = FG::col(j);
+          const float2 u = *reinterpret_cast<const float2*>(blob + a.w.g_fc_b[li] + col);
+#pragma unroll
+          for (int i = 0; i < FG::MI; ++i)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int r = FG::row(i, h);
+              const float2 hv = make_float2(f.c[i][j][2 * h] + u.x, f.c[i][j][2 * h + 1] + u.y);
+              *reinterpret_cast<float2*>(sX + r * XLD + EGP + col) = hv;
+              if (save && r < nrows)
+                *reinterpret_cast<float2*>(a.saved + SL.gh + ((size_t)li * Pp + p0 + r) * HG + col) = hv;
+            }
         }
       }
       __syncthreads();
@@ -245,8 +257,9 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
     if (color) {
       // -------------------------------------------------------------- D: colour feature
       if (relpos) {   // decoder.py:477-488
-        float uacc[TMA][8], acc[TMA][8];
-        zero_acc(uacc);
+        typedef FragTile<TILE_M, HC> FW;
+        FW uf, f;
+        uf.zero();
         for (int m = tid; m < TILE_M; m += NT)
           *reinterpret_cast<float4*>(sX + m * XLD + QD) = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
@@ -273,52 +286,58 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
             if (idx >= 0) f = __ldg(reinterpret_cast<const float4*>(a.col_feats + (size_t)idx * CDIM) + q);
             *reinterpret_cast<float4*>(sX + m * XLD + 2 * ER + q * 4) = f;
           }
-          zero_acc(acc);
-          tile_gemm<TMA, 16, 2, true, false>(acc, sX, XLD, QDP, packed + Packed::V1t, HC, HC, sB, nrows);
+          f.zero();
+          mma_core<TILE_M, HC, true, false>(f.c, sX, XLD, QDP, packed + Packed::V1t, HC, HC, sB, nrows);
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            const int col = wm.col(g);
-            const float4 b = *reinterpret_cast<const float4*>(blob + a.w.c_nb1_b + col);
+          for (int j = 0; j < FW::NJ; ++j) {
+            const int col = FW::col(j);
+            const float2 b = *reinterpret_cast<const float2*>(blob + a.w.c_nb1_b + col);
 #pragma unroll
-            for (int i = 0; i < TMA; ++i) {
-              const int r = wm.row(i);
-              const float wk = sW[r * KNN + k];
-              const float4 sp = make_float4(softplus100(acc[i][g * 4 + 0] + b.x), softplus100(acc[i][g * 4 + 1] + b.y),
-                                            softplus100(acc[i][g * 4 + 2] + b.z), softplus100(acc[i][g * 4 + 3] + b.w));
-              uacc[i][g * 4 + 0] = fmaf(wk, sp.x, uacc[i][g * 4 + 0]);
-              uacc[i][g * 4 + 1] = fmaf(wk, sp.y, uacc[i][g * 4 + 1]);
-              uacc[i][g * 4 + 2] = fmaf(wk, sp.z, uacc[i][g * 4 + 2]);
-              uacc[i][g * 4 + 3] = fmaf(wk, sp.w, uacc[i][g * 4 + 3]);
-              if (save && r < nrows)
-                *reinterpret_cast<float4*>(a.saved + SL.sp + ((p0 + r) * KNN + k) * HC + col) = sp;
+            for (int i = 0; i < FW::MI; ++i)
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int r = FW::row(i, h);
+                const float wk = sW[r * KNN + k];
+                const float s0 = softplus100(f.c[i][j][2 * h] + b.x), s1 = softplus100(f.c[i][j][2 * h + 1] + b.y);
+                uf.c[i][j][2 * h] = fmaf(wk, s0, uf.c[i][j][2 * h]);
+                uf.c[i][j][2 * h + 1] = fmaf(wk, s1, uf.c[i][j][2 * h + 1]);
+                if (save && r < nrows)
+                  *reinterpret_cast<float2*>(a.saved + SL.sp + ((p0 + r) * KNN + k) * HC + col) = make_float2(s0, s1);
+              }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < FW::NJ; ++j) {
+          const int col = FW::col(j);
+#pragma unroll
+          for (int i = 0; i < FW::MI; ++i)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int r = FW::row(i, h);
+              const float2 u = make_float2(uf.c[i][j][2 * h], uf.c[i][j][2 * h + 1]);
+              *reinterpret_cast<float2*>(sX + r * XLD + col) = u;
+              if (save && r < nrows) *reinterpret_cast<float2*>(a.saved + SL.u + (p0 + r) * HC + col) = u;
             }
-          }
         }
+        typedef FragTile<TILE_M, CDIM> FC;
+        FC c4;
+        c4.zero();
+        mma_core<TILE_M, CDIM, true, false>(c4.c, sX, XLD, HC, packed + Packed::V2t, CDIM, CDIM, sB, nrows);
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const int col = wm.col(g);
+        for (int j = 0; j < FC::NJ; ++j) {
+          const int col = FC::col(j);
+          const float2 v2 = *reinterpret_cast<const float2*>(blob + a.w.c_nb2_b + col);
 #pragma unroll
-          for (int i = 0; i < TMA; ++i) {
-            const int r = wm.row(i);
-            const float4 u = make_float4(uacc[i][g * 4 + 0], uacc[i][g * 4 + 1], uacc[i][g * 4 + 2], uacc[i][g * 4 + 3]);
-            *reinterpret_cast<float4*>(sX + r * XLD + col) = u;
-            if (save && r < nrows) *reinterpret_cast<float4*>(a.saved + SL.u + (p0 + r) * HC + col) = u;
-          }
-        }
-        float c4[TMNA][4];
-        zero_acc(c4);
-        tile_gemm<TMNA, 8, 1, true, false>(c4, sX, XLD, HC, packed + Packed::V2t, CDIM, CDIM, sB, nrows);
-        const int col = nm.col();
-        const float4 v2 = *reinterpret_cast<const float4*>(blob + a.w.c_nb2_b + col);
+          for (int i = 0; i < FC::MI; ++i)
 #pragma unroll
-        for (int i = 0; i < TMNA; ++i) {
-          const int r = nm.row(i);
-          const float ws = sWsum[r];
-          float4 cc = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (sHas[r]) cc = make_float4(fmaf(v2.x, ws, c4[i][0]), fmaf(v2.y, ws, c4[i][1]),
-                                        fmaf(v2.z, ws, c4[i][2]), fmaf(v2.w, ws, c4[i][3]));
-          *reinterpret_cast<float4*>(sC + r * CLD + col) = cc;
-          if (save && r < nrows) *reinterpret_cast<float4*>(a.saved + SL.cc + (p0 + r) * CDIM + col) = cc;
+            for (int h = 0; h < 2; ++h) {
+              const int r = FC::row(i, h);
+              const float ws = sWsum[r];
+              float2 cc = make_float2(0.f, 0.f);
+              if (sHas[r]) cc = make_float2(fmaf(v2.x, ws, c4.c[i][j][2 * h]), fmaf(v2.y, ws, c4.c[i][j][2 * h + 1]));
+              *reinterpret_cast<float2*>(sC + r * CLD + col) = cc;
+              if (save && r < nrows) *reinterpret_cast<float2*>(a.saved + SL.cc + (p0 + r) * CDIM + col) = cc;
+            }
         }
       } else {        // decoder.py:476,487-488
         for (int it = tid; it < TILE_M * 8; it += NT) {
@@ -353,45 +372,46 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
         sX[m * XLD + EC + j] = cs;
       }
       {
-        float acc[TMA][8];
+        typedef FragTile<TILE_M, HC> FW;
+        FW f;
 #pragma unroll 1
         for (int li = 0; li < 5; ++li) {
           const float* A = (li == 0 || li == 3) ? sX : sX + ECC;
           const int Kc = (li == 0) ? ECC : (li == 3 ? ECC + HC : HC);
           const int wt = li == 0 ? Packed::cW0t : li == 1 ? Packed::cW1t : li == 2 ? Packed::cW2t
                        : li == 3 ? Packed::cW3t : Packed::cW4t;
-          zero_acc(acc);
-          tile_gemm<TMA, 16, 2, true, false>(acc, A, XLD, Kc, packed + wt, HC, HC, sB, nrows);
+          f.zero();
+          mma_core<TILE_M, HC, true, false>(f.c, A, XLD, Kc, packed + wt, HC, HC, sB, nrows);
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            const int col = wm.col(g);
-            const float4 b = *reinterpret_cast<const float4*>(blob + a.w.c_lin_b[li] + col);
+          for (int j = 0; j < FW::NJ; ++j) {
+            const int col = FW::col(j);
+            const float2 b = *reinterpret_cast<const float2*>(blob + a.w.c_lin_b[li] + col);
 #pragma unroll
-            for (int i = 0; i < TMA; ++i) {
-              acc[i][g * 4 + 0] = softplus100(acc[i][g * 4 + 0] + b.x);
-              acc[i][g * 4 + 1] = softplus100(acc[i][g * 4 + 1] + b.y);
-              acc[i][g * 4 + 2] = softplus100(acc[i][g * 4 + 2] + b.z);
-              acc[i][g * 4 + 3] = softplus100(acc[i][g * 4 + 3] + b.w);
-              const int r = wm.row(i);
-              if (save && r < nrows)
-                *reinterpret_cast<float4*>(a.saved + SL.cs + ((size_t)li * Pp + p0 + r) * HC + col) =
-                    make_float4(acc[i][g * 4 + 0], acc[i][g * 4 + 1], acc[i][g * 4 + 2], acc[i][g * 4 + 3]);
-            }
+            for (int i = 0; i < FW::MI; ++i)
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int r = FW::row(i, h);
+                const float s0 = softplus100(f.c[i][j][2 * h] + b.x), s1 = softplus100(f.c[i][j][2 * h + 1] + b.y);
+                f.c[i][j][2 * h] = s0; f.c[i][j][2 * h + 1] = s1;
+                if (save && r < nrows)
+                  *reinterpret_cast<float2*>(a.saved + SL.cs + ((size_t)li * Pp + p0 + r) * HC + col) = make_float2(s0, s1);
+              }
           }
-          tile_gemm<TMA, 16, 2, true, false>(acc, sC, CLD, CDIM, packed + Packed::cUt + li * CDIM * HC, HC, HC, sB, nrows);
+          mma_core<TILE_M, HC, true, false>(f.c, sC, CLD, CDIM, packed + Packed::cUt + li * CDIM * HC, HC, HC, sB, nrows);
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            const int col = wm.col(g);
-            const float4 u = *reinterpret_cast<const float4*>(blob + a.w.c_fc_b[li] + col);
+          for (int j = 0; j < FW::NJ; ++j) {
+            const int col = FW::col(j);
+            const float2 u = *reinterpret_cast<const float2*>(blob + a.w.c_fc_b[li] + col);
 #pragma unroll
-            for (int i = 0; i < TMA; ++i) {
-              const int r = wm.row(i);
-              const float4 h = make_float4(acc[i][g * 4 + 0] + u.x, acc[i][g * 4 + 1] + u.y,
-                                           acc[i][g * 4 + 2] + u.z, acc[i][g * 4 + 3] + u.w);
-              *reinterpret_cast<float4*>(sX + r * XLD + ECC + col) = h;
-              if (save && r < nrows)
-                *reinterpret_cast<float4*>(a.saved + SL.ch + ((size_t)li * Pp + p0 + r) * HC + col) = h;
-            }
+            for (int i = 0; i < FW::MI; ++i)
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int r = FW::row(i, h);
+                const float2 hv = make_float2(f.c[i][j][2 * h] + u.x, f.c[i][j][2 * h + 1] + u.y);
+                *reinterpret_cast<float2*>(sX + r * XLD + ECC + col) = hv;
+                if (save && r < nrows)
+                  *reinterpret_cast<float2*>(a.saved + SL.ch + ((size_t)li * Pp + p0 + r) * HC + col) = hv;
+              }
           }
         }
       }
