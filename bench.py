@@ -110,9 +110,9 @@ def build_scene(n_points, cache=True):
     return room, sc
 
 
-def mapper_loss(depth, color, valid, gt_depth, gt_color, stage, w_color=0.1):
-    """src/Mapper.py:689-720 (sum-L1 depth + 0.1 sum-L1 colour over gt>0 & valid & ~nan) written with
-    mask multiplication instead of boolean indexing (no host sync)."""
+def mapper_loss_eager(depth, color, valid, gt_depth, gt_color, stage, w_color=0.1):
+    """src/Mapper.py:689-720 as plain torch ops (kept for A/B: --eager-loss); the default step uses the fused
+    lsr_mapper_loss kernel through loopy_slam_b200.mapper_loss."""
     m = ((gt_depth > 0) & valid & (~torch.isnan(depth))).to(depth.dtype)
     loss = (torch.abs(gt_depth - depth) * m).sum()
     if stage == 'color':
@@ -171,12 +171,15 @@ def run_lsr(args, rank, world, local):
         rend._timing = timing if timed else None
         depth, var, color, valid = rend.render_batch_ray(npc, model, d, o, dev, stage, gt_depth=g, npc_geo_feats=gtab,
                                                          npc_col_feats=ctab, is_tracker=False, cloud_pos=cloud)
-        loss = mapper_loss(depth, color, valid, g, c, stage)
+        if args.eager_loss:
+            loss = mapper_loss_eager(depth, color, valid, g, c, stage)
+        else:
+            loss = L.mapper_loss(depth, color, valid, g, c, stage, 0.1)[0]     # fused lsr_mapper_loss (src/Mapper.py:689-720)
         loss.backward()
         rend._timing = None
         if world > 1:
             reducer.allreduce_()
-        launches[0] += 4            # far_bound + pack + render_fwd + render_bwd (ours); torch ops not counted
+        launches[0] += 5            # far_bound + pack + render_fwd + mapper_loss + render_bwd (ours); torch ops not counted
         return loss
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
@@ -246,7 +249,7 @@ def run_lsr(args, rank, world, local):
             depth, var, color, valid = rend.render_batch_ray(npc, model, d, o, dev, 'geometry', gt_depth=g,
                                                              npc_geo_feats=gtab, npc_col_feats=npc_col,
                                                              is_tracker=False, cloud_pos=cloud)
-            mapper_loss(depth, color, valid, g, c, 'geometry').backward()
+            L.mapper_loss(depth, color, valid, g, c, 'geometry', 0.1)[0].backward()
         ms = timed(geo_step, n_extra)
         extra['mapper_geometry_stage'] = {'rays_per_s': R / (ms * 1e-3), 'ms_per_step': ms, 'rays': R}
         # (2) tracking iteration (src/Tracker.py:102-197): 1500 rays, stage 'color', is_tracker, frozen decoders,
@@ -262,11 +265,7 @@ def run_lsr(args, rank, world, local):
             depth, var, color, valid = rend.render_batch_ray(npc, model, d, o, dev, 'color', gt_depth=g,
                                                              npc_geo_feats=npc_geo, npc_col_feats=npc_col,
                                                              is_tracker=True, cloud_pos=cloud)
-            unc = var.detach()
-            m = ((g > 0) & valid).float()
-            loss = (torch.clamp(torch.abs(g - depth) / torch.sqrt(unc + 1e-10), 0.0, 1e3) * m).sum() \
-                + 0.5 * (torch.abs(c - color) * m[:, None]).sum()
-            loss.backward()
+            L.tracker_loss(depth, var, color, g, c, True, True, 0.5)[0].backward()     # src/Tracker.py:171-193
         ms = timed(trk_step, n_extra)
         extra['tracker_iteration'] = {'rays_per_s': 1500 / (ms * 1e-3), 'ms_per_step': ms, 'rays': 1500}
 
@@ -346,7 +345,7 @@ def _oracle_step(orc, ocfg, W, grid, sc, batch, stage):
     geo = sc['geo'].clone().requires_grad_(True)
     col = sc['col'].clone().requires_grad_(True)
     depth, var, rgb, valid, _ = orc.render_rays(Wl, ocfg, o, d, g, geo, col, sc['cloud'], stage, knn=knn)
-    loss = mapper_loss(depth, rgb, valid, g, c, stage)
+    loss = mapper_loss_eager(depth, rgb, valid, g, c, stage)
     loss.backward()
     return time.perf_counter() - t0
 
@@ -411,6 +410,7 @@ def main():
     ap.add_argument('--stage', default='color', choices=['color', 'geometry'])
     ap.add_argument('--n-points', type=int, default=N_POINTS)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--eager-loss', action='store_true', help='A/B: the mapper loss as ~30 torch ops instead of lsr_mapper_loss')
     ap.add_argument('--no-extra', action='store_true', help='skip the geometry-stage / tracker side measurements')
     ap.add_argument('--cpu-budget', type=float, default=20.0)
     args = ap.parse_args()

@@ -17,6 +17,8 @@
  *                                    src/common.py:382-422
  *   lsr_render_bwd                   the autograd backward of the above (loss.backward(),
  *                                    src/Mapper.py:722, src/Tracker.py:193)
+ *   lsr_mapper_loss                  mapper loss + its gradient wrt (depth, rgb)   src/Mapper.py:689-693,713-720
+ *   lsr_tracker_resid / _loss        tracker outlier statistic, loss + gradient     src/Tracker.py:171-191
  *
  * Conventions: all pointers are DEVICE pointers unless stated; fp32 row-major contiguous;
  * every call is asynchronous on `stream`; return value 0 = LSR_OK, otherwise an error code for
@@ -191,6 +193,34 @@ int lsr_render_bwd(const LsrParams* prm, const void* grid_ws, const float* cloud
                    const float* g_var, const float* g_rgb, int grad_flags, float* d_geo_feats,
                    float* d_col_feats, float* d_weights, float* d_exposure_affine, float* d_rays_o,
                    float* d_rays_d, lsr_stream_t stream);
+
+/* ---------------------------------------------------------------- fused losses
+ * One pass over the (R,) render outputs -> loss terms AND the upstream gradients lsr_render_bwd consumes.
+ * loss3 = [loss, geo_loss, color_loss] (fp32, device).  d_depth (R) / d_rgb (R,3) are dloss/d(depth|rgb)
+ * for an upstream gradient of 1 (the caller scales them by grad_output).  scratch: lsr_loss_scratch_bytes
+ * bytes, owned by the call sequence (mapper: one call; tracker: resid then loss). */
+int lsr_loss_scratch_bytes(size_t* bytes);
+
+/* src/Mapper.py:689-693,713-720: mask = gt_depth > 0 & valid & !isnan(depth) (valid nullable = all true);
+ * geo = sum |gt_depth - depth|, color = sum |gt_rgb - rgb| over the mask; loss = geo (+ w_color * color when
+ * stage == LSR_STAGE_COLOR; rgb / gt_rgb / d_rgb may be NULL in stage geometry). */
+int lsr_mapper_loss(const float* depth, const float* rgb, const uint8_t* valid, const float* gt_depth,
+                    const float* gt_rgb, int64_t n_rays, int stage, float w_color, void* scratch, float* loss3,
+                    float* d_depth, float* d_rgb, lsr_stream_t stream);
+
+/* src/Tracker.py:175-180: tmp = |gt_depth - depth| (/ sqrt(var + 1e-10) when handle_dynamic), written to
+ * tmp (R); its sum is kept in scratch for the 10*mean(tmp) threshold of lsr_tracker_loss. */
+int lsr_tracker_resid(const float* depth, const float* var, const float* gt_depth, int64_t n_rays,
+                      int handle_dynamic, void* scratch, float* tmp, lsr_stream_t stream);
+
+/* src/Tracker.py:171-191: mask = tmp < thr & gt_depth > 0 & !isnan(depth) & !isnan(var), thr = *thr (device,
+ * e.g. 10*median(tmp)) or 10*mean(tmp) from lsr_tracker_resid when thr == NULL; geo = sum clamp(|gt_depth -
+ * depth| / sqrt(var + 1e-10), 0, 1e3), color = sum |gt_rgb - rgb|; loss = geo + (use_color ? w_color*color : 0).
+ * var is detached (no gradient).  mask_out: nullable, 1 byte per ray. */
+int lsr_tracker_loss(const float* depth, const float* var, const float* rgb, const float* gt_depth,
+                     const float* gt_rgb, const float* tmp, int64_t n_rays, const float* thr, int use_color,
+                     float w_color, void* scratch, float* loss3, float* d_depth, float* d_rgb, uint8_t* mask_out,
+                     lsr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -21,6 +21,7 @@ EXPORTS = [
     'lsr_version', 'lsr_strerror', 'lsr_device_sm_count', 'lsr_grid_workspace_bytes', 'lsr_grid_build',
     'lsr_knn_query', 'lsr_sample_rays', 'lsr_sample_rays_bwd', 'lsr_pose_fwd', 'lsr_pose_bwd',
     'lsr_render_workspace_bytes', 'lsr_far_bound', 'lsr_render_fwd', 'lsr_render_bwd', 'lsr_dynamic_radius',
+    'lsr_loss_scratch_bytes', 'lsr_mapper_loss', 'lsr_tracker_resid', 'lsr_tracker_loss',
 ]
 
 
@@ -77,6 +78,10 @@ def lib():
         L.lsr_render_bwd.argtypes = [ctypes.POINTER(LsrParams), vp, vp, i64, vp, vp, vp, vp, i64, vp, vp,
                                      ctypes.POINTER(LsrWeights), vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp,
                                      ctypes.c_int, vp, vp, vp, vp, vp, vp, vp]
+        L.lsr_loss_scratch_bytes.argtypes = [ctypes.POINTER(ctypes.c_size_t)]
+        L.lsr_mapper_loss.argtypes = [vp, vp, vp, vp, vp, i64, ctypes.c_int, f32, vp, vp, vp, vp, vp]
+        L.lsr_tracker_resid.argtypes = [vp, vp, vp, i64, ctypes.c_int, vp, vp, vp]
+        L.lsr_tracker_loss.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp, ctypes.c_int, f32, vp, vp, vp, vp, vp, vp]
         for name in EXPORTS:
             if name not in ('lsr_strerror',):
                 getattr(L, name).restype = ctypes.c_int

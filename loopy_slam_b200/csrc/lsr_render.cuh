@@ -224,6 +224,39 @@ __device__ __forceinline__ void split_tf32(float x, unsigned& hi, unsigned& lo) 
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
+// One KC-row chunk of a streamed B operand -> ring stage (chunk % NSTAGE); always commits a group.
+template <int NCOLS>
+__device__ __forceinline__ void ring_prefetch_chunk(const float* __restrict__ B, int ldb, int Kc, int ncols_valid,
+                                                    float* sBuf, int chunk) {
+  constexpr int CLD_ = NCOLS + SB_LD_PAD;
+  constexpr int PIECES = KC * NCOLS / 4;   // float4 pieces per chunk
+  constexpr int PPR = NCOLS / 4;           // pieces per chunk row
+  const int nchunks = (Kc + KC - 1) / KC;
+  if (chunk < nchunks) {
+    float* dst = sBuf + (chunk % NSTAGE) * (KC * CLD_);
+    const int k0 = chunk * KC;
+    for (int p = threadIdx.x; p < PIECES; p += NT) {
+      const int row = p / PPR, c4 = p % PPR;
+      float* d = dst + row * CLD_ + c4 * 4;
+      if (k0 + row < Kc && c4 * 4 < ncols_valid) {
+        cp_async16(d, B + (size_t)(k0 + row) * ldb + c4 * 4);
+      } else {
+        *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+  cp_async_commit();
+}
+// Issue the ring prologue (chunks 0 .. NSTAGE-2) of the NEXT streamed GEMM early -- typically right
+// before an epilogue -- so the L2 latency of its first weight chunk hides behind that epilogue.  The
+// matching mma_core / tile_gemm call must then pass PRE = true.  Only legal when the ring is idle
+// (i.e. after the previous mma_core / tile_gemm returned).
+template <int NCOLS>
+__device__ __forceinline__ void gemm_prefetch(const float* __restrict__ B, int ldb, int Kc, int ncols_valid, float* sBuf) {
+#pragma unroll
+  for (int st = 0; st < NSTAGE - 1; ++st) ring_prefetch_chunk<NCOLS>(B, ldb, Kc, ncols_valid, sBuf, st);
+}
+
 #ifndef LSR_FFMA_GEMM
 // Accumulator fragments of an M_OUT x NCOLS output tile, distributed over the 8 warps as 2 (rows) x 4
 // (cols): warp (wm, wn) owns 16-row tiles wm, wm+2, ... and 8-column tiles wn, wn+4, ...; inside a
@@ -249,7 +282,7 @@ struct FragTile {
 
 // c += A . B on the tensor cores (3xTF32); semantics of the operands as in tile_gemm below.  Ends with
 // __syncthreads().  mvalid: output rows >= mvalid are not needed, their 16-row MMA tiles are skipped.
-template <int M_OUT, int NCOLS, bool A_ROWMAJOR, bool B_SMEM>
+template <int M_OUT, int NCOLS, bool A_ROWMAJOR, bool B_SMEM, bool PRE = false>
 __device__ __forceinline__ void mma_core(float (&c)[FragTile<M_OUT, NCOLS>::MI][FragTile<M_OUT, NCOLS>::NJ][4],
                                          const float* __restrict__ A, int lda, int Kc, const float* __restrict__ B,
                                          int ldb, int ncols_valid, float* sBuf, int mvalid) {
@@ -333,24 +366,11 @@ __device__ __forceinline__ void mma_core(float (&c)[FragTile<M_OUT, NCOLS>::MI][
     constexpr int PIECES = KC * NCOLS / 4;   // float4 pieces per chunk
     constexpr int PPR = NCOLS / 4;           // pieces per chunk row
     const int nchunks = (Kc + KC - 1) / KC;
-    auto prefetch = [&](int chunk) {
-      if (chunk < nchunks) {
-        float* dst = sBuf + (chunk % NSTAGE) * (KC * CLD_);
-        const int k0 = chunk * KC;
-        for (int p = tid; p < PIECES; p += NT) {
-          const int row = p / PPR, c4 = p % PPR;
-          float* d = dst + row * CLD_ + c4 * 4;
-          if (k0 + row < Kc && c4 * 4 < ncols_valid) {
-            cp_async16(d, B + (size_t)(k0 + row) * ldb + c4 * 4);
-          } else {
-            *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-      }
-      cp_async_commit();
-    };
+    auto prefetch = [&](int chunk) { ring_prefetch_chunk<NCOLS>(B, ldb, Kc, ncols_valid, sBuf, chunk); };
+    if (!PRE) {
 #pragma unroll
-    for (int st = 0; st < NSTAGE - 1; ++st) prefetch(st);
+      for (int st = 0; st < NSTAGE - 1; ++st) prefetch(st);
+    }
     for (int cix = 0; cix < nchunks; ++cix) {
       cp_async_wait<NSTAGE - 2>();
       __syncthreads();          // chunk visible to all; everyone is done with the previous chunk's buffer
@@ -367,7 +387,7 @@ __device__ __forceinline__ void mma_core(float (&c)[FragTile<M_OUT, NCOLS>::MI][
 
 }
 
-template <int TM, int TXN, int NCG, bool A_ROWMAJOR, bool B_SMEM>
+template <int TM, int TXN, int NCG, bool A_ROWMAJOR, bool B_SMEM, bool PRE = false>
 __device__ __forceinline__ void tile_gemm(float (&acc)[TM][NCG * 4], const float* __restrict__ A, int lda,
                                           int Kc, const float* __restrict__ B, int ldb, int ncols_valid,
                                           float* sBuf, int mvalid = 1 << 30) {
@@ -383,7 +403,7 @@ __device__ __forceinline__ void tile_gemm(float (&acc)[TM][NCG * 4], const float
   const int wm = warp >> 2, wn = warp & 3;
   FragTile<M_OUT, NCOLS> f;
   f.zero();
-  mma_core<M_OUT, NCOLS, A_ROWMAJOR, B_SMEM>(f.c, A, lda, Kc, B, ldb, ncols_valid, sBuf, mvalid);
+  mma_core<M_OUT, NCOLS, A_ROWMAJOR, B_SMEM, PRE>(f.c, A, lda, Kc, B, ldb, ncols_valid, sBuf, mvalid);
   float (&c)[FragTile<M_OUT, NCOLS>::MI][NJ][4] = f.c;
 
   // fragments -> per-thread register tiles, 32 output rows per pass through sBuf

@@ -209,7 +209,9 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
         const int wt = li == 0 ? Packed::gW0t : li == 1 ? Packed::gW1t : li == 2 ? Packed::gW2t
                      : li == 3 ? Packed::gW3t : Packed::gW4t;
         f.zero();
-        mma_core<TILE_M, HG, true, false>(f.c, A, XLD, Kc, packed + wt, HG, HG, sB, nrows);
+        if (li == 0) mma_core<TILE_M, HG, true, false>(f.c, A, XLD, Kc, packed + wt, HG, HG, sB, nrows);
+        else         mma_core<TILE_M, HG, true, false, true>(f.c, A, XLD, Kc, packed + wt, HG, HG, sB, nrows);
+        gemm_prefetch<HG>(packed + Packed::gUt + li * CDIM * HG, HG, CDIM, HG, sB);   // fc_c weights fly during the epilogue
 #pragma unroll
         for (int j = 0; j < FG::NJ; ++j) {
           const int col = FG::col(j);
@@ -225,7 +227,12 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
                 *reinterpret_cast<float2*>(a.saved + SL.gs + ((size_t)li * Pp + p0 + r) * HG + col) = make_float2(v0, v1);
             }
         }
-        mma_core<TILE_M, HG, true, false>(f.c, sC, CLD, CDIM, packed + Packed::gUt + li * CDIM * HG, HG, HG, sB, nrows);
+        mma_core<TILE_M, HG, true, false, true>(f.c, sC, CLD, CDIM, packed + Packed::gUt + li * CDIM * HG, HG, HG, sB, nrows);
+        if (li < 4) {   // next layer's weights
+          const int kn = (li + 1 == 3) ? 128 : HG;
+          const int wn_ = li + 1 == 1 ? Packed::gW1t : li + 1 == 2 ? Packed::gW2t : li + 1 == 3 ? Packed::gW3t : Packed::gW4t;
+          gemm_prefetch<HG>(packed + wn_, HG, kn, HG, sB);
+        }
 #pragma unroll
         for (int j = 0; j < FG::NJ; ++j) {
           const int col = FG::col(j);
@@ -264,6 +271,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
           *reinterpret_cast<float4*>(sX + m * XLD + QD) = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
         for (int k = 0; k < KNN; ++k) {
+          gemm_prefetch<HC>(packed + Packed::V1t, HC, QDP, HC, sB);   // V1 chunk flies while Q_k is built
           for (int it = tid; it < TILE_M * ER; it += NT) {
             const int m = it / ER, j = it - m * ER;
             const int idx = sIdx[m * KNN + k];
@@ -287,7 +295,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
             *reinterpret_cast<float4*>(sX + m * XLD + 2 * ER + q * 4) = f;
           }
           f.zero();
-          mma_core<TILE_M, HC, true, false>(f.c, sX, XLD, QDP, packed + Packed::V1t, HC, HC, sB, nrows);
+          mma_core<TILE_M, HC, true, false, true>(f.c, sX, XLD, QDP, packed + Packed::V1t, HC, HC, sB, nrows);
 #pragma unroll
           for (int j = 0; j < FW::NJ; ++j) {
             const int col = FW::col(j);
@@ -306,6 +314,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
               }
           }
         }
+        gemm_prefetch<CDIM>(packed + Packed::V2t, CDIM, HC, CDIM, sB);
 #pragma unroll
         for (int j = 0; j < FW::NJ; ++j) {
           const int col = FW::col(j);
@@ -322,7 +331,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
         typedef FragTile<TILE_M, CDIM> FC;
         FC c4;
         c4.zero();
-        mma_core<TILE_M, CDIM, true, false>(c4.c, sX, XLD, HC, packed + Packed::V2t, CDIM, CDIM, sB, nrows);
+        mma_core<TILE_M, CDIM, true, false, true>(c4.c, sX, XLD, HC, packed + Packed::V2t, CDIM, CDIM, sB, nrows);
 #pragma unroll
         for (int j = 0; j < FC::NJ; ++j) {
           const int col = FC::col(j);
@@ -381,7 +390,9 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
           const int wt = li == 0 ? Packed::cW0t : li == 1 ? Packed::cW1t : li == 2 ? Packed::cW2t
                        : li == 3 ? Packed::cW3t : Packed::cW4t;
           f.zero();
-          mma_core<TILE_M, HC, true, false>(f.c, A, XLD, Kc, packed + wt, HC, HC, sB, nrows);
+          if (li == 0) mma_core<TILE_M, HC, true, false>(f.c, A, XLD, Kc, packed + wt, HC, HC, sB, nrows);
+          else         mma_core<TILE_M, HC, true, false, true>(f.c, A, XLD, Kc, packed + wt, HC, HC, sB, nrows);
+          gemm_prefetch<HC>(packed + Packed::cUt + li * CDIM * HC, HC, CDIM, HC, sB);   // fc_c weights fly during the epilogue
 #pragma unroll
           for (int j = 0; j < FW::NJ; ++j) {
             const int col = FW::col(j);
@@ -397,7 +408,12 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
                   *reinterpret_cast<float2*>(a.saved + SL.cs + ((size_t)li * Pp + p0 + r) * HC + col) = make_float2(s0, s1);
               }
           }
-          mma_core<TILE_M, HC, true, false>(f.c, sC, CLD, CDIM, packed + Packed::cUt + li * CDIM * HC, HC, HC, sB, nrows);
+          mma_core<TILE_M, HC, true, false, true>(f.c, sC, CLD, CDIM, packed + Packed::cUt + li * CDIM * HC, HC, HC, sB, nrows);
+          if (li < 4) {   // next layer's weights
+            const int kn = (li + 1 == 3) ? ECC + HC : HC;
+            const int wn_ = li + 1 == 1 ? Packed::cW1t : li + 1 == 2 ? Packed::cW2t : li + 1 == 3 ? Packed::cW3t : Packed::cW4t;
+            gemm_prefetch<HC>(packed + wn_, HC, kn, HC, sB);
+          }
 #pragma unroll
           for (int j = 0; j < FW::NJ; ++j) {
             const int col = FW::col(j);

@@ -38,7 +38,7 @@ def build_model(cfg, weights, device):
     return model.to(device)
 
 
-def run_cuda(g, device='cuda:0', param_grads=True):
+def run_cuda(g, device='cuda:0', param_grads=True, loss_fn=None):
     """Run our fused path on a golden scene -> dict of outputs and gradients (CPU tensors)."""
     cfg = cfg_from_ocfg(g.ocfg)
     H, W, fx, fy, cx, cy = g.raw['intrinsics']
@@ -61,10 +61,15 @@ def run_cuda(g, device='cuda:0', param_grads=True):
     depth, var, rgb, valid = renderer.render_batch_ray(
         NPC(), model, d, o, device, g.stage, gt_depth=g.t('gt_depth').to(device), npc_geo_feats=geo,
         npc_col_feats=col, is_tracker=g.is_tracker, cloud_pos=cloud, dynamic_r_query=dyn, exposure_feat=ef)
-    loss = (g.t('up_depth').to(device) * depth).sum() + (g.t('up_rgb').to(device) * rgb).sum()
+    if loss_fn is None:
+        loss = (g.t('up_depth').to(device) * depth).sum() + (g.t('up_rgb').to(device) * rgb).sum()
+    else:   # a caller-style loss on (depth, var, rgb, valid, gt_depth, gt_color); gt_color synthesised from up_rgb
+        loss = loss_fn(depth, var, rgb, valid, g.t('gt_depth').to(device), (g.t('up_rgb').abs() % 1.0).to(device))
     loss.backward()
     torch.cuda.synchronize()
-    out = dict(depth=depth.detach().cpu(), var=var.detach().cpu(), rgb=rgb.detach().cpu(), valid=valid.cpu(),
+    out = dict(loss=float(loss),
+               grads={k: v.grad.detach().cpu() for k, v in (('geo', geo), ('col', col)) if v.grad is not None},
+               depth=depth.detach().cpu(), var=var.detach().cpu(), rgb=rgb.detach().cpu(), valid=valid.cpu(),
                g_geo=geo.grad.cpu() if geo.grad is not None else None,
                g_col=col.grad.cpu() if col.grad is not None else None,
                g_o=o.grad.cpu() if o.grad is not None else None, g_d=d.grad.cpu() if d.grad is not None else None,

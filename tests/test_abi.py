@@ -49,6 +49,9 @@ def test_argument_validation_without_gpu(lib):
     assert lib.lsr_render_workspace_bytes(ctypes.byref(prm), 10, 1, ctypes.byref(sb), ctypes.byref(cb)) == 4
     assert lib.lsr_strerror(4) == b'unsupported configuration'
     assert lib.lsr_pose_fwd(None, None, None) == 1
+    assert lib.lsr_loss_scratch_bytes(ctypes.byref(out)) == 0 and out.value >= 32
+    assert lib.lsr_mapper_loss(None, None, None, None, None, 10, 1, 0.1, None, None, None, None, None) == 1
+    assert lib.lsr_tracker_loss(None, None, None, None, None, None, 10, None, 1, 0.5, None, None, None, None, None, None) == 1
 
 
 def test_no_cpu_fallback():
