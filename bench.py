@@ -156,6 +156,7 @@ def run_lsr(args, rank, world, local):
     model.geo_decoder.embedder._B.requires_grad_(True)
     train_params = [p for p in model.parameters() if p.requires_grad] + [geo_leaf, col_leaf]
     reducer = parallel.GradAllReducer(train_params)
+    subset = L.FeatureSubset(indices, npc_geo.shape[0])      # built once per mapped frame, like `indices` itself
     dev_batches = [[t.to(dev) for t in b] for b in sc['batches']]
     host_batches = [[t.pin_memory() for t in b] for b in sc['batches']]
     R = dev_batches[0][0].shape[0]
@@ -166,11 +167,18 @@ def run_lsr(args, rank, world, local):
         o, d, g, c = batch
         for p in train_params:
             p.grad = None
-        gtab = npc_geo.index_put((indices,), geo_leaf)              # src/Mapper.py:581-582
-        ctab = npc_col.index_put((indices,), col_leaf)
         rend._timing = timing if timed else None
-        depth, var, color, valid = rend.render_batch_ray(npc, model, d, o, dev, stage, gt_depth=g, npc_geo_feats=gtab,
-                                                         npc_col_feats=ctab, is_tracker=False, cloud_pos=cloud)
+        if args.index_put:      # the reference's literal flow: table[indices] = leaf every iteration (src/Mapper.py:581-582)
+            gtab = npc_geo.index_put((indices,), geo_leaf)
+            ctab = npc_col.index_put((indices,), col_leaf)
+            depth, var, color, valid = rend.render_batch_ray(npc, model, d, o, dev, stage, gt_depth=g,
+                                                             npc_geo_feats=gtab, npc_col_feats=ctab, is_tracker=False,
+                                                             cloud_pos=cloud)
+        else:                   # same sub-block, read through lsr's row_remap (no table rewrite, leaf-sized gradients)
+            depth, var, color, valid = rend.render_batch_ray(npc, model, d, o, dev, stage, gt_depth=g,
+                                                             npc_geo_feats=npc_geo, npc_col_feats=npc_col,
+                                                             is_tracker=False, cloud_pos=cloud,
+                                                             feat_subset=(subset, geo_leaf, col_leaf))
         if args.eager_loss:
             loss = mapper_loss_eager(depth, color, valid, g, c, stage)
         else:
@@ -245,10 +253,10 @@ def run_lsr(args, rank, world, local):
             o, d, g, c = dev_batches[k % len(dev_batches)]
             for p in train_params:
                 p.grad = None
-            gtab = npc_geo.index_put((indices,), geo_leaf)
             depth, var, color, valid = rend.render_batch_ray(npc, model, d, o, dev, 'geometry', gt_depth=g,
-                                                             npc_geo_feats=gtab, npc_col_feats=npc_col,
-                                                             is_tracker=False, cloud_pos=cloud)
+                                                             npc_geo_feats=npc_geo, npc_col_feats=npc_col,
+                                                             is_tracker=False, cloud_pos=cloud,
+                                                             feat_subset=(subset, geo_leaf, col_leaf))
             L.mapper_loss(depth, color, valid, g, c, 'geometry', 0.1)[0].backward()
         ms = timed(geo_step, n_extra)
         extra['mapper_geometry_stage'] = {'rays_per_s': R / (ms * 1e-3), 'ms_per_step': ms, 'rays': R}
@@ -290,6 +298,9 @@ def run_lsr(args, rank, world, local):
                    'rays_per_step_per_gpu': R, 'n_surface': S, 'n_points': int(cloud.shape[0]),
                    'n_trainable_rows': int(indices.shape[0]), 'image': f'{room.H}x{room.W}', 'frames_per_batch': N_FRAMES,
                    'parallelism': f'ray-shard dp{world} (replicated cloud+weights, 1 NCCL all-reduce/step)',
+                   'feature_subblock': 'index_put into the tables every step (src/Mapper.py:581-582)' if args.index_put
+                                       else 'lsr row_remap + leaf blocks (same rows, no table rewrite)',
+                   'loss': 'torch ops' if args.eager_loss else 'lsr_mapper_loss',
                    'l2': 'flushed between timed steps (256 MiB memset outside the event pairs)'},
         'e2e': {'value': world * R / (e2e_ms * 1e-3), 'unit': 'rays/s', 'ms_per_step': e2e_ms,
                 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4},
@@ -410,6 +421,8 @@ def main():
     ap.add_argument('--stage', default='color', choices=['color', 'geometry'])
     ap.add_argument('--n-points', type=int, default=N_POINTS)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--index-put', action='store_true',
+                    help='A/B: rewrite the feature tables every step (src/Mapper.py:581-582) instead of lsr row_remap')
     ap.add_argument('--eager-loss', action='store_true', help='A/B: the mapper loss as ~30 torch ops instead of lsr_mapper_loss')
     ap.add_argument('--no-extra', action='store_true', help='skip the geometry-stage / tracker side measurements')
     ap.add_argument('--cpu-budget', type=float, default=20.0)

@@ -172,11 +172,16 @@ int lsr_far_bound(const float* gt_depth, int64_t n_rays, int64_t group, float* f
  * far_zero: far bound of the z-range used for rays with gt_depth <= 0, one value per group of
  *   far_group consecutive rays (Renderer.py:102-121 batch statistic; see lsr_far_bound); nullable.
  * exposure_affine: 12 floats [A row-major 3x3 | t] for LSR_RGB_AFFINE_SIGMOID.
- * saved == NULL -> inference (render_img); valid: 1 byte per ray. */
+ * saved == NULL -> inference (render_img); valid: 1 byte per ray.
+ * row_remap (nullable, int32 per point): rows with row_remap[id] = j >= 0 read their features from the
+ *   compact leaf blocks geo_leaf / col_leaf (n_sel,C) row j instead of the tables -- the optimised
+ *   sub-block of src/Mapper.py:502-505, WITHOUT the per-iteration table[indices] = leaf index_put of
+ *   src/Mapper.py:581-582 (and without the (N,C) gradient tables + gather of its backward). */
 int lsr_render_fwd(const LsrParams* prm, const void* grid_ws, const float* cloud_pos, int64_t n_points,
                    const float* rays_o, const float* rays_d, const float* gt_depth,
                    const double* r_query, const float* far_zero, int64_t far_group, int64_t n_rays,
-                   const float* geo_feats, const float* col_feats, const LsrWeights* w,
+                   const float* geo_feats, const float* col_feats, const int32_t* row_remap,
+                   const float* geo_leaf, const float* col_leaf, const LsrWeights* w,
                    const float* exposure_affine, int stage, float* depth, float* var, float* rgb,
                    uint8_t* valid, void* saved, void* scratch, lsr_stream_t stream);
 
@@ -184,11 +189,14 @@ int lsr_render_fwd(const LsrParams* prm, const void* grid_ws, const float* cloud
  * is_tracker: neighbour weights depend on the sample position (decoder.py:191-198).
  * Gradient buffers must be ZEROED by the caller; they are accumulated into with atomics:
  * d_geo_feats/d_col_feats (N,C), d_weights (layout of w->blob), d_exposure_affine (12),
- * d_rays_o/d_rays_d (R,3, plain stores).  Unwanted sinks may be NULL (and unset in grad_flags). */
+ * d_rays_o/d_rays_d (R,3, plain stores).  Unwanted sinks may be NULL (and unset in grad_flags).
+ * With row_remap, d_geo_feats / d_col_feats are the (n_sel,C) gradients of geo_leaf / col_leaf; rows that
+ * are not remapped are not trainable and receive nothing. */
 int lsr_render_bwd(const LsrParams* prm, const void* grid_ws, const float* cloud_pos, int64_t n_points,
                    const float* rays_o, const float* rays_d, const float* gt_depth,
                    const double* r_query, int64_t n_rays, const float* geo_feats,
-                   const float* col_feats, const LsrWeights* w, const float* exposure_affine,
+                   const float* col_feats, const int32_t* row_remap, const float* geo_leaf,
+                   const float* col_leaf, const LsrWeights* w, const float* exposure_affine,
                    int stage, int is_tracker, const void* saved, void* scratch, const float* g_depth,
                    const float* g_var, const float* g_rgb, int grad_flags, float* d_geo_feats,
                    float* d_col_feats, float* d_weights, float* d_exposure_affine, float* d_rays_o,

@@ -11,7 +11,7 @@ All arithmetic runs in hand-written CUDA (csrc/) behind the C ABI of include/lsr
 from . import _lib  # noqa: F401
 from .config import get_model, load_config, default_cfg  # noqa: F401
 from .decoder import NICER  # noqa: F401
-from .renderer import Renderer, GridIndex  # noqa: F401
+from .renderer import Renderer, GridIndex, FeatureSubset  # noqa: F401
 from .neural_point import NeuralPointCloud  # noqa: F401
 from .loss import mapper_loss, tracker_loss  # noqa: F401
 from .common import (get_samples, get_rays, get_rays_from_uv, get_camera_from_tensor, quad2rotation,  # noqa: F401

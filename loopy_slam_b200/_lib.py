@@ -74,8 +74,10 @@ def lib():
         L.lsr_far_bound.argtypes = [vp, i64, i64, vp, vp]
         L.lsr_dynamic_radius.argtypes = [vp, vp, i32, i32, f64, f64, f64, f64, vp, vp, vp]
         L.lsr_render_fwd.argtypes = [ctypes.POINTER(LsrParams), vp, vp, i64, vp, vp, vp, vp, vp, i64, i64, vp, vp,
+                                     vp, vp, vp,
                                      ctypes.POINTER(LsrWeights), vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp]
         L.lsr_render_bwd.argtypes = [ctypes.POINTER(LsrParams), vp, vp, i64, vp, vp, vp, vp, i64, vp, vp,
+                                     vp, vp, vp,
                                      ctypes.POINTER(LsrWeights), vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp,
                                      ctypes.c_int, vp, vp, vp, vp, vp, vp, vp]
         L.lsr_loss_scratch_bytes.argtypes = [ctypes.POINTER(ctypes.c_size_t)]

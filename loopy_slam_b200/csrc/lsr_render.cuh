@@ -224,6 +224,26 @@ __device__ __forceinline__ void split_tf32(float x, unsigned& hi, unsigned& lo) 
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
+// Feature rows may live in two places: the full (N,C) table, or -- for the rows the mapper is optimising --
+// a compact (n_sel,C) leaf block addressed through row_remap[id] >= 0 (replaces the per-iteration
+// table[indices] = leaf index_put of src/Mapper.py:581-582 and the gather in its backward).
+__device__ __forceinline__ const float* feat_row(const float* __restrict__ table, const float* __restrict__ leaf,
+                                                 const int32_t* __restrict__ remap, int idx) {
+  if (remap != nullptr) {
+    const int j = __ldg(remap + idx);
+    if (j >= 0) return leaf + (size_t)j * CDIM;
+  }
+  return table + (size_t)idx * CDIM;
+}
+// gradient row of point idx, or nullptr when the row is not trainable (remap given and remap[idx] < 0)
+__device__ __forceinline__ float* grad_row(float* __restrict__ d, const int32_t* __restrict__ remap, int idx) {
+  if (remap != nullptr) {
+    const int j = __ldg(remap + idx);
+    return j >= 0 ? d + (size_t)j * CDIM : nullptr;
+  }
+  return d + (size_t)idx * CDIM;
+}
+
 // One KC-row chunk of a streamed B operand -> ring stage (chunk % NSTAGE); always commits a group.
 template <int NCOLS>
 __device__ __forceinline__ void ring_prefetch_chunk(const float* __restrict__ B, int ldb, int Kc, int ncols_valid,

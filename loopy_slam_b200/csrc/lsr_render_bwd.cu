@@ -18,6 +18,8 @@ struct BwdArgs {
   const float *rays_o, *rays_d, *gt_depth;
   int R;
   const float *geo_feats, *col_feats;
+  const int32_t* remap;
+  const float *geo_leaf, *col_leaf;
   LsrWeights w;
   const float* packed;
   const float* affine;
@@ -46,8 +48,9 @@ __device__ __forceinline__ float half_warp_sum(float v) {   // sum over the 16 l
 
 // dF[idx_k[m]] += w_k * dC[m]  and (tracker) dw_hat_k += dC[m] . F[idx_k[m]]
 __device__ __forceinline__ void scatter_idw(const float* sDC, const int* sIdx, const float* sW, const int* sHas,
-                                            float* sDWh, const float* __restrict__ feats, float* __restrict__ d_feats,
-                                            bool want_feat, bool want_w) {
+                                            float* sDWh, const float* __restrict__ feats,
+                                            const float* __restrict__ leaf, const int32_t* __restrict__ remap,
+                                            float* __restrict__ d_feats, bool want_feat, bool want_w) {
   for (int it = threadIdx.x; it < TILE_M * 64; it += NT) {
     const int q = it & 7, k = (it >> 3) & 7, m = it >> 6;
     const int idx = sIdx[m * KNN + k];
@@ -55,12 +58,13 @@ __device__ __forceinline__ void scatter_idw(const float* sDC, const int* sIdx, c
     const float4 dc = *reinterpret_cast<const float4*>(sDC + m * CLD + q * 4);
     if (want_feat && ok) {
       const float wk = sW[m * KNN + k];
-      red_add_v4(d_feats + (size_t)idx * CDIM + q * 4, wk * dc.x, wk * dc.y, wk * dc.z, wk * dc.w);
+      float* dst = grad_row(d_feats, remap, idx);
+      if (dst) red_add_v4(dst + q * 4, wk * dc.x, wk * dc.y, wk * dc.z, wk * dc.w);
     }
     if (want_w) {
       float part = 0.f;
       if (ok) {
-        const float4 f = __ldg(reinterpret_cast<const float4*>(feats + (size_t)idx * CDIM) + q);
+        const float4 f = __ldg(reinterpret_cast<const float4*>(feat_row(feats, leaf, remap, idx)) + q);
         part = dc.x * f.x + dc.y * f.y + dc.z * f.z + dc.w * f.w;
       }
       part += __shfl_xor_sync(0xffffffffu, part, 4);
@@ -533,7 +537,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
             const int m = it >> 3, q = it & 7;
             const int idx = sIdx[m * KNN + k];
             float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (idx >= 0) f = __ldg(reinterpret_cast<const float4*>(a.col_feats + (size_t)idx * CDIM) + q);
+            if (idx >= 0) f = __ldg(reinterpret_cast<const float4*>(feat_row(a.col_feats, a.col_leaf, a.remap, idx)) + q);
             *reinterpret_cast<float4*>(sQ + m * QLD + 2 * ER + q * 4) = f;
           }
           __syncthreads();
@@ -556,8 +560,10 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
               for (int i = 0; i < TMA; ++i) {
                 const int r = wm.row(i);
                 const int idx = sIdx[r * KNN + k];
-                if (idx >= 0 && r < nrows)
-                  red_add_v4(a.d_col + (size_t)idx * CDIM + (col - 2 * ER), aq[i][0], aq[i][1], aq[i][2], aq[i][3]);
+                if (idx >= 0 && r < nrows) {
+                  float* dst = grad_row(a.d_col, a.remap, idx);
+                  if (dst) red_add_v4(dst + (col - 2 * ER), aq[i][0], aq[i][1], aq[i][2], aq[i][3]);
+                }
               }
             }
           }
@@ -610,7 +616,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
             }
         }
       } else {
-        scatter_idw(sDC, sIdx, sW, sHas, sDWh, a.col_feats, a.d_col, g_cf, trk);
+        scatter_idw(sDC, sIdx, sW, sHas, sDWh, a.col_feats, a.col_leaf, a.remap, a.d_col, g_cf, trk);
       }
       __syncthreads();
     }
@@ -792,7 +798,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
         *reinterpret_cast<float4*>(sDC + r * CLD + nm.col()) = v;
       }
       __syncthreads();
-      scatter_idw(sDC, sIdx, sW, sHas, sDWh, a.geo_feats, a.d_geo, g_gf, trk);
+      scatter_idw(sDC, sIdx, sW, sHas, sDWh, a.geo_feats, a.geo_leaf, a.remap, a.d_geo, g_gf, trk);
       __syncthreads();
     }
 
@@ -868,7 +874,8 @@ extern "C" int lsr_debug_phase_cycles(unsigned long long* out32) {
 extern "C" int lsr_render_bwd(const LsrParams* prm, const void* grid_ws, const float* cloud_pos, int64_t n_points,
                               const float* rays_o, const float* rays_d, const float* gt_depth,
                               const double* r_query, int64_t n_rays, const float* geo_feats,
-                              const float* col_feats, const LsrWeights* w, const float* exposure_affine, int stage,
+                              const float* col_feats, const int32_t* row_remap, const float* geo_leaf,
+                              const float* col_leaf, const LsrWeights* w, const float* exposure_affine, int stage,
                               int is_tracker, const void* saved, void* scratch, const float* g_depth,
                               const float* g_var, const float* g_rgb, int grad_flags, float* d_geo_feats,
                               float* d_col_feats, float* d_weights, float* d_exposure_affine, float* d_rays_o,
@@ -884,6 +891,7 @@ extern "C" int lsr_render_bwd(const LsrParams* prm, const void* grid_ws, const f
   if (!saved || !scratch || !rays_o || !rays_d || !gt_depth || !g_depth) return LSR_ERR_ARG;
   if (n_points > 0 && (!cloud_pos || !geo_feats)) return LSR_ERR_ARG;
   if (n_points > 0 && stage == LSR_STAGE_COLOR && !col_feats) return LSR_ERR_ARG;
+  if (row_remap && (!geo_leaf || (stage == LSR_STAGE_COLOR && !col_leaf))) return LSR_ERR_ARG;
   if (prm->rgb_mode == LSR_RGB_AFFINE_SIGMOID && !exposure_affine) return LSR_ERR_ARG;
   if ((grad_flags & LSR_GRAD_GEO_FEATS) && !d_geo_feats) return LSR_ERR_ARG;
   if ((grad_flags & LSR_GRAD_COL_FEATS) && !d_col_feats) return LSR_ERR_ARG;
@@ -899,6 +907,7 @@ extern "C" int lsr_render_bwd(const LsrParams* prm, const void* grid_ws, const f
   a.rays_o = rays_o; a.rays_d = rays_d; a.gt_depth = gt_depth;
   a.R = (int)n_rays;
   a.geo_feats = geo_feats; a.col_feats = col_feats;
+  a.remap = row_remap; a.geo_leaf = geo_leaf; a.col_leaf = col_leaf;
   a.w = *w;
   a.packed = (const float*)scratch;
   a.affine = exposure_affine;

@@ -28,6 +28,8 @@ struct FwdArgs {
   int far_group;
   int R;
   const float *geo_feats, *col_feats;
+  const int32_t* remap;
+  const float *geo_leaf, *col_leaf;
   LsrWeights w;
   const float* packed;
   const float* affine;
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
           const int idx = sIdx[m * KNN + k];
           if (idx >= 0) {
             const float w = sW[m * KNN + k];
-            const float4 f = __ldg(reinterpret_cast<const float4*>(a.geo_feats + (size_t)idx * CDIM) + q);
+            const float4 f = __ldg(reinterpret_cast<const float4*>(feat_row(a.geo_feats, a.geo_leaf, a.remap, idx)) + q);
             acc.x = fmaf(w, f.x, acc.x); acc.y = fmaf(w, f.y, acc.y);
             acc.z = fmaf(w, f.z, acc.z); acc.w = fmaf(w, f.w, acc.w);
           }
@@ -291,7 +293,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
             const int m = it >> 3, q = it & 7;
             const int idx = sIdx[m * KNN + k];
             float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (idx >= 0) f = __ldg(reinterpret_cast<const float4*>(a.col_feats + (size_t)idx * CDIM) + q);
+            if (idx >= 0) f = __ldg(reinterpret_cast<const float4*>(feat_row(a.col_feats, a.col_leaf, a.remap, idx)) + q);
             *reinterpret_cast<float4*>(sX + m * XLD + 2 * ER + q * 4) = f;
           }
           f.zero();
@@ -358,7 +360,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
               const int idx = sIdx[m * KNN + k];
               if (idx >= 0) {
                 const float w = sW[m * KNN + k];
-                const float4 f = __ldg(reinterpret_cast<const float4*>(a.col_feats + (size_t)idx * CDIM) + q);
+                const float4 f = __ldg(reinterpret_cast<const float4*>(feat_row(a.col_feats, a.col_leaf, a.remap, idx)) + q);
                 acc.x = fmaf(w, f.x, acc.x); acc.y = fmaf(w, f.y, acc.y);
                 acc.z = fmaf(w, f.z, acc.z); acc.w = fmaf(w, f.w, acc.w);
               }
@@ -637,7 +639,8 @@ extern "C" int lsr_far_bound(const float* gt_depth, int64_t n_rays, int64_t grou
 extern "C" int lsr_render_fwd(const LsrParams* prm, const void* grid_ws, const float* cloud_pos, int64_t n_points,
                               const float* rays_o, const float* rays_d, const float* gt_depth,
                               const double* r_query, const float* far_zero, int64_t far_group, int64_t n_rays,
-                              const float* geo_feats, const float* col_feats, const LsrWeights* w,
+                              const float* geo_feats, const float* col_feats, const int32_t* row_remap,
+                              const float* geo_leaf, const float* col_leaf, const LsrWeights* w,
                               const float* exposure_affine, int stage, float* depth, float* var, float* rgb,
                               uint8_t* valid, void* saved, void* scratch, lsr_stream_t stream) {
   int rc = check_params(prm);
@@ -650,6 +653,7 @@ extern "C" int lsr_render_fwd(const LsrParams* prm, const void* grid_ws, const f
   if (!rays_o || !rays_d || !gt_depth || !depth || !var || !rgb || !valid) return LSR_ERR_ARG;
   if (n_points > 0 && (!cloud_pos || !geo_feats)) return LSR_ERR_ARG;
   if (n_points > 0 && stage == LSR_STAGE_COLOR && !col_feats) return LSR_ERR_ARG;
+  if (row_remap && (!geo_leaf || (stage == LSR_STAGE_COLOR && !col_leaf))) return LSR_ERR_ARG;
   if ((prm->flags & LSR_FLAG_DYNAMIC_R) && !r_query) return LSR_ERR_ARG;
   if (prm->rgb_mode == LSR_RGB_AFFINE_SIGMOID && !exposure_affine) return LSR_ERR_ARG;
   const int nsm = sm_count();
@@ -665,6 +669,7 @@ extern "C" int lsr_render_fwd(const LsrParams* prm, const void* grid_ws, const f
   a.far_group = (int)(far_group > 0 ? (far_group < (1ll << 30) ? far_group : (1ll << 30)) : 1);
   a.R = (int)n_rays;
   a.geo_feats = geo_feats; a.col_feats = col_feats;
+  a.remap = row_remap; a.geo_leaf = geo_leaf; a.col_leaf = col_leaf;
   a.w = *w;
   a.packed = (const float*)scratch;
   a.affine = exposure_affine;

@@ -81,7 +81,7 @@ def _grid_for(npc, cloud_pos, cell, cache):
 class _RenderCtx:
     """Per-call constants shared by forward and backward."""
     __slots__ = ('prm', 'grid', 'stage', 'is_tracker', 'blob', 'wstruct', 'flat', 'saved', 'scratch', 'R',
-                 'r_query', 'device', 'far_group', 'force_save', 'timing')
+                 'r_query', 'device', 'far_group', 'force_save', 'timing', 'remap')
 
 
 def _tick(timing):
@@ -107,11 +107,33 @@ def _f32c(t):
     return t
 
 
+class FeatureSubset:
+    """The trainable sub-block of the feature tables (src/Mapper.py:498-505): `indices` are the table rows
+    whose features live in the compact leaf tensors passed with it.  Holds the (N,) int32 row->leaf-row map
+    the kernels read (built once per frame, when the reference builds `indices`).  Passing
+    `feat_subset=(subset, geo_leaf, col_leaf)` to Renderer.render_batch_ray replaces the per-iteration
+    `npc_geo_feats[indices] = geo_pcl_grad` / `npc_col_feats[indices] = color_pcl_grad` index_puts
+    (src/Mapper.py:581-582) and the table-sized gradients + gathers of their backward."""
+
+    def __init__(self, indices, n_points, device=None):
+        idx = torch.as_tensor(indices, dtype=torch.int64, device=device).reshape(-1)
+        if not idx.is_cuda:
+            raise RuntimeError('FeatureSubset: indices must live on (or be sent to) a CUDA device')
+        self.indices = idx
+        self.n_points = int(n_points)
+        self.remap = torch.full((self.n_points,), -1, dtype=torch.int32, device=idx.device)
+        self.remap[idx] = torch.arange(idx.numel(), dtype=torch.int32, device=idx.device)
+
+    def __len__(self):
+        return int(self.indices.numel())
+
+
 class _RenderFn(torch.autograd.Function):
     """depth, var, rgb, valid = lsr_render_fwd(...); backward = lsr_render_bwd(...)."""
 
     @staticmethod
-    def forward(ctx, rc, rays_o, rays_d, gt_depth, geo_feats, col_feats, affine, far_zero, *params):
+    def forward(ctx, rc, rays_o, rays_d, gt_depth, geo_feats, col_feats, affine, far_zero, geo_leaf, col_leaf,
+                *params):
         ctx.set_materialize_grads(False)
         dev = rays_o.device
         R = rays_o.shape[0]
@@ -128,23 +150,25 @@ class _RenderFn(torch.autograd.Function):
         ev = _tick(rc.timing)
         check(lib().lsr_render_fwd(ctypes.byref(rc.prm), ptr(rc.grid.ws), ptr(rc.grid.cloud), rc.grid.n,
                                    ptr(rays_o), ptr(rays_d), ptr(gt_depth), ptr(rc.r_query), ptr(far_zero),
-                                   rc.far_group, R, ptr(geo_feats), ptr(col_feats), ctypes.byref(rc.wstruct),
+                                   rc.far_group, R, ptr(geo_feats), ptr(col_feats), ptr(rc.remap), ptr(geo_leaf),
+                                   ptr(col_leaf), ctypes.byref(rc.wstruct),
                                    ptr(affine), rc.stage, ptr(depth), ptr(var), ptr(rgb), ptr(valid),
                                    ptr(rc.saved), ptr(rc.scratch), stream_ptr(dev)), 'lsr_render_fwd')
         _tock(rc.timing, 'fwd', ev)
         ctx.rc = rc
         ctx.param_shapes = [p.shape for p in params]
-        ctx.save_for_backward(rays_o, rays_d, gt_depth, geo_feats, col_feats, affine)
+        ctx.save_for_backward(rays_o, rays_d, gt_depth, geo_feats, col_feats, affine, geo_leaf, col_leaf)
         ctx.mark_non_differentiable(valid)
         return depth, var, rgb, valid
 
     @staticmethod
     def backward(ctx, g_depth, g_var, g_rgb, _g_valid):
         rc = ctx.rc
-        rays_o, rays_d, gt_depth, geo_feats, col_feats, affine = ctx.saved_tensors
+        rays_o, rays_d, gt_depth, geo_feats, col_feats, affine, geo_leaf, col_leaf = ctx.saved_tensors
         dev = rays_o.device
         R = rays_o.shape[0]
-        need = ctx.needs_input_grad   # (rc, o, d, gt, geo, col, affine, far, *params)
+        need = ctx.needs_input_grad   # (rc, o, d, gt, geo, col, affine, far, geo_leaf, col_leaf, *params)
+        sub = rc.remap is not None    # feature gradients go to the leaf blocks, the tables are constants
         blob = rc.blob
         flags = 0
         d_o = d_d = d_geo = d_col = d_aff = d_w = None
@@ -152,16 +176,16 @@ class _RenderFn(torch.autograd.Function):
             flags |= _lib.GRAD_RAYS
             d_o = torch.empty(R, 3, dtype=torch.float32, device=dev)
             d_d = torch.empty(R, 3, dtype=torch.float32, device=dev)
-        if need[4]:
+        if (need[8] if sub else need[4]):
             flags |= _lib.GRAD_GEO_FEATS
-            d_geo = torch.zeros_like(geo_feats)
-        if need[5] and rc.stage == 1:
+            d_geo = torch.zeros_like(geo_leaf if sub else geo_feats)
+        if (need[9] if sub else need[5]) and rc.stage == 1:
             flags |= _lib.GRAD_COL_FEATS
-            d_col = torch.zeros_like(col_feats)
+            d_col = torch.zeros_like(col_leaf if sub else col_feats)
         if need[6] and affine is not None:
             flags |= _lib.GRAD_AFFINE
             d_aff = torch.zeros(12, dtype=torch.float32, device=dev)
-        pneed = need[8:]
+        pneed = need[10:]
         if any(pneed):
             d_w = torch.zeros(blob.n_elems, dtype=torch.float32, device=dev)
             if any(pneed[k] for k in blob.geo_w_idx):
@@ -176,7 +200,8 @@ class _RenderFn(torch.autograd.Function):
         ev = _tick(rc.timing)
         check(lib().lsr_render_bwd(ctypes.byref(rc.prm), ptr(rc.grid.ws), ptr(rc.grid.cloud), rc.grid.n,
                                    ptr(rays_o), ptr(rays_d), ptr(gt_depth), ptr(rc.r_query), R, ptr(geo_feats),
-                                   ptr(col_feats), ctypes.byref(rc.wstruct), ptr(affine), rc.stage,
+                                   ptr(col_feats), ptr(rc.remap), ptr(geo_leaf), ptr(col_leaf),
+                                   ctypes.byref(rc.wstruct), ptr(affine), rc.stage,
                                    1 if rc.is_tracker else 0, ptr(rc.saved), ptr(rc.scratch), ptr(g_depth),
                                    ptr(g_var), ptr(g_rgb), flags, ptr(d_geo), ptr(d_col), ptr(d_w), ptr(d_aff),
                                    ptr(d_o), ptr(d_d), stream_ptr(dev)), 'lsr_render_bwd')
@@ -188,7 +213,11 @@ class _RenderFn(torch.autograd.Function):
                 pgrads.append(d_w[off:off + n].view(t))
             else:
                 pgrads.append(None)
-        return (None, d_o if need[1] else None, d_d if need[2] else None, None, d_geo, d_col, d_aff, None, *pgrads)
+        if sub:
+            return (None, d_o if need[1] else None, d_d if need[2] else None, None, None, None, d_aff, None,
+                    d_geo, d_col, *pgrads)
+        return (None, d_o if need[1] else None, d_d if need[2] else None, None, d_geo, d_col, d_aff, None,
+                None, None, *pgrads)
 
 
 def _make_params(renderer, decoders, stage, coef):
@@ -217,7 +246,7 @@ def _make_params(renderer, decoders, stage, coef):
 
 def fused_render(renderer, npc, decoders, rays_d, rays_o, stage, gt_depth, npc_geo_feats, npc_col_feats,
                  is_tracker, cloud_pos, dynamic_r_query, exposure_feat, far_group=None, n_surface=None,
-                 force_save=False, return_ctx=False):
+                 force_save=False, return_ctx=False, feat_subset=None):
     """The one place that marshals a render call into lsr_render_fwd / lsr_render_bwd."""
     _lib.require_cuda(rays_o, 'rays_o')
     dev = rays_o.device
@@ -266,12 +295,25 @@ def fused_render(renderer, npc, decoders, rays_d, rays_o, stage, gt_depth, npc_g
     geo = _f32c(npc_geo_feats)
     col = _f32c(npc_col_feats) if npc_col_feats is not None else None
     params = rc.blob.tensors()
+    rc.remap = geo_leaf = col_leaf = None
+    if feat_subset is not None:
+        subset, geo_leaf, col_leaf = feat_subset
+        if npc_geo_feats.requires_grad or (npc_col_feats is not None and npc_col_feats.requires_grad):
+            raise ValueError('with feat_subset the feature tables are constants: gradients go to the leaf blocks')
+        if subset.n_points != geo.shape[0] or subset.remap.device != dev:
+            raise ValueError('feat_subset was built for a different table size / device')
+        if geo_leaf.shape != (len(subset), 32) or (col is not None and rc.stage == 1 and
+                                                   (col_leaf is None or col_leaf.shape != (len(subset), 32))):
+            raise ValueError('feat_subset leaf blocks must be (len(indices), 32)')
+        rc.remap = subset.remap
+        geo_leaf = _f32c(geo_leaf)
+        col_leaf = _f32c(col_leaf) if col_leaf is not None else None
     rc.R = R
     rc.device = dev
     rc.far_group = fgroup
     rc.force_save = bool(force_save)
     rc.timing = getattr(renderer, '_timing', None)
-    out = _RenderFn.apply(rc, rays_o, rays_d, gt, geo, col, affine, far, *params)
+    out = _RenderFn.apply(rc, rays_o, rays_d, gt, geo, col, affine, far, geo_leaf, col_leaf, *params)
     if return_ctx:
         return out, rc
     return out
@@ -368,9 +410,10 @@ class Renderer(object):
     # -- Renderer.py:71-201
     def render_batch_ray(self, npc, decoders, rays_d, rays_o, device, stage, gt_depth=None, npc_geo_feats=None,
                          npc_col_feats=None, is_tracker=False, cloud_pos=None, dynamic_r_query=None,
-                         exposure_feat=None):
+                         exposure_feat=None, feat_subset=None):
         """-> depth (R,), uncertainty (R,), color (R,3), valid_ray_mask (R,) bool; differentiable w.r.t.
-        rays, feature tables, decoder parameters and exposure_feat."""
+        rays, feature tables, decoder parameters and exposure_feat.  feat_subset (extension, optional):
+        (FeatureSubset, geo_leaf, col_leaf) -- see FeatureSubset."""
         if gt_depth is not None and torch.numel(gt_depth) == 0:
             warnings.warn('tensor gt_depth is empty, info:')      # Renderer.py:122-128
             gt_depth = None
@@ -378,7 +421,8 @@ class Renderer(object):
             return self._render_with_near_pcl(npc, decoders, rays_d, rays_o, stage, gt_depth, npc_geo_feats,
                                               npc_col_feats, is_tracker, cloud_pos, dynamic_r_query, exposure_feat)
         depth, var, rgb, valid = fused_render(self, npc, decoders, rays_d, rays_o, stage, gt_depth, npc_geo_feats,
-                                              npc_col_feats, is_tracker, cloud_pos, dynamic_r_query, exposure_feat)
+                                              npc_col_feats, is_tracker, cloud_pos, dynamic_r_query, exposure_feat,
+                                              feat_subset=feat_subset)
         return depth, var, rgb, valid.bool()
 
     def _render_with_near_pcl(self, *a):

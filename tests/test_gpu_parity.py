@@ -285,3 +285,60 @@ def test_edge_cases_empty_and_tiny():
     (dep.sum() + rgb.sum()).backward()
     assert torch.isfinite(geo.grad).all() and geo.grad.abs().sum() > 0
     assert ((dep >= 0.98 * g - 1e-5) & (dep <= 1.02 * g + 1e-5)).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['replica_color_mapper', 'tum_color_mapper_dynr'])
+def test_feature_subset_equals_index_put_flow(name):
+    """row_remap / leaf blocks (FeatureSubset) == the reference's table[indices] = leaf flow
+    (src/Mapper.py:581-582): identical forward, leaf gradients == gathered table gradients."""
+    if name not in GOLDEN_CASES:
+        pytest.skip('golden case not present')
+    g = Golden(name)
+    dev = torch.device('cuda:0')
+    cfg = cfg_from_ocfg(g.ocfg)
+    H, W, fx, fy, cx, cy = g.raw['intrinsics']
+    model = build_model(cfg, g.weights, dev)
+    rend = L.Renderer(cfg, None, SlamLike(H, W, fx, fy, cx, cy))
+    rend.sigmoid_coefficient = g.ocfg.sigmoid_coef
+    cloud = g.t('cloud').to(dev)
+    N = cloud.shape[0]
+    gen = torch.Generator().manual_seed(5)
+    indices = torch.randperm(N, generator=gen)[: (2 * N) // 3].to(dev)          # a third of the rows is frozen
+    geo_tab, col_tab = g.t('geo_feats').to(dev), g.t('col_feats').to(dev)
+    dyn = g.t('dynamic_r').to(dev) if g.has('dynamic_r') else None
+
+    class NPC:
+        def get_radius_query(self_inner):
+            return g.ocfg.radius_query
+
+    def run(use_subset):
+        for p in model.parameters():
+            p.grad = None
+        geo_leaf = (geo_tab[indices] + 0.01).clone().requires_grad_(True)        # leaf differs from the stale table rows
+        col_leaf = (col_tab[indices] - 0.02).clone().requires_grad_(True)
+        kw = dict(gt_depth=g.t('gt_depth').to(dev), is_tracker=False, cloud_pos=cloud, dynamic_r_query=dyn)
+        if use_subset:
+            sub = L.FeatureSubset(indices, N)
+            out = rend.render_batch_ray(NPC(), model, g.t('rays_d').to(dev), g.t('rays_o').to(dev), dev, g.stage,
+                                        npc_geo_feats=geo_tab, npc_col_feats=col_tab,
+                                        feat_subset=(sub, geo_leaf, col_leaf), **kw)
+        else:
+            gt_, ct_ = geo_tab.index_put((indices,), geo_leaf), col_tab.index_put((indices,), col_leaf)
+            out = rend.render_batch_ray(NPC(), model, g.t('rays_d').to(dev), g.t('rays_o').to(dev), dev, g.stage,
+                                        npc_geo_feats=gt_, npc_col_feats=ct_, **kw)
+        depth, var, rgb, valid = out
+        loss = (g.t('up_depth').to(dev) * depth).sum() + (g.t('up_rgb').to(dev) * rgb).sum()
+        loss.backward()
+        w = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+        return depth.detach(), var.detach(), rgb.detach(), valid, geo_leaf.grad, col_leaf.grad, w
+
+    a, b = run(False), run(True)
+    for x, y in zip(a[:4], b[:4]):
+        assert torch.equal(x, y)
+    for x, y in zip(a[4:6], b[4:6]):
+        assert x is not None and y is not None and float(x.abs().max()) > 0
+        assert rel_l2(y.cpu(), x.cpu()) < 1e-5          # atomics order only
+    assert a[6].keys() == b[6].keys()
+    for k in a[6]:
+        assert rel_l2(b[6][k].cpu(), a[6][k].cpu()) < 1e-4, k
