@@ -82,146 +82,153 @@ __device__ __forceinline__ float sqdist_rn(float ax, float ay, float az, float b
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
-struct Knn8 {
-  float D[KNN];
-  int I[KNN];
-  int cnt;
-};
+// Exact <=8 nearest points with D <= r^2 around a query, ordered by (D, id) lexicographically, found
+// warp-cooperatively: lanes fetch the (cy,cz) rows of the cell neighbourhood in parallel (each row is one
+// contiguous range of the counting-sorted point array), the candidates of all rows are enumerated 32 at a
+// time (coalesced float4 loads inside a row), and the running top-8 lives in lanes 0..7 (lane k = k-th
+// nearest).  Selection = 8 rounds of REDUX min over (D bits, id).
+// dyn: compare in double against r2d (the reference evaluates D < r^2 in float64 when the radius is a
+// float64 tensor, SURVEY.md Appendix D); else in float against r2f.
+constexpr unsigned KNN_INF = 0x7f800000u;   // +inf bits; squared distances are >= 0 so bit order == value order
+constexpr int KNN_NOID = 0x7fffffff;
 
-__device__ __forceinline__ bool knn_less(float d, int i, float D, int I) {
-  return d < D || (d == D && i < I);
+// Conservative lower bound of |p - x| over every x binned into cell c along one axis (0 when p may be
+// inside).  Points land in cell c when floor(fl(fl(x - o) * inv)) == c, i.e. x in [o + c*cell, o + (c+1)*cell)
+// up to a few roundings; `slack` covers those.
+// The first / last cell of an axis also hold whatever the binning clamped into them, so they are
+// unbounded on the outer side.
+__device__ __forceinline__ float slab_dist_lb(float p, float o, float cell, int c, int dim) {
+  const float lo = o + (float)c * cell, hi = lo + cell;
+  const float slack = 1e-6f * (fabsf(p) + fabsf(o) + fabsf(hi - o)) + 1e-7f;
+  const float below = c > 0 ? (lo - slack) - p : 0.f;         // > 0: p is below the slab
+  const float above = c < dim - 1 ? p - (hi + slack) : 0.f;   // > 0: p is above the slab
+  return fmaxf(0.f, fmaxf(below, above));
 }
 
-// Exact <=8 nearest points with D <= r^2 around p, by (D, id) lexicographic order.
-// dyn: compare in double against r2d (reference evaluates D < r^2 in float64 when the radius is a
-// float64 tensor, SURVEY.md Appendix D); else in float against r2f.
-__device__ __forceinline__ void knn_walk(const GridView& g, float px, float py, float pz, float rr,
-                                         bool dyn, float r2f, double r2d, Knn8& out) {
+// NQ independent queries per warp, advanced in lockstep: the cell-range loads and the candidate loads of
+// all NQ queries are issued back to back before any of them is consumed, so one global round trip is
+// shared by NQ searches (the walk is a chain of dependent loads: header -> ranges -> candidates).
+// Per-query results are identical to knn_warp.
+template <int NQ>
+__device__ __forceinline__ void knn_warp_multi(const GridView& g, const float (&px)[NQ], const float (&py)[NQ],
+                                               const float (&pz)[NQ], const float (&rr)[NQ], const bool (&active)[NQ],
+                                               bool dyn, const float (&r2f)[NQ], const double (&r2d)[NQ],
+                                               unsigned (&bestD)[NQ], int (&bestI)[NQ]) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
 #pragma unroll
-  for (int k = 0; k < KNN; ++k) { out.D[k] = INFINITY; out.I[k] = 0x7fffffff; }
-  out.cnt = 0;
+  for (int q = 0; q < NQ; ++q) { bestD[q] = KNN_INF; bestI[q] = KNN_NOID; }
   const GridHeader* h = g.hdr;
-  const int n = h->n_points;
-  if (n <= 0) return;
-  const float inv = h->inv_cell;
+  if (h->n_points <= 0) return;
+  const float inv = h->inv_cell, ce = h->cell;
   const float ox = h->origin[0], oy = h->origin[1], oz = h->origin[2];
   const int dx = h->dims[0], dy = h->dims[1], dz = h->dims[2];
-  int x0 = max(cell_coord_raw(px - rr, ox, inv), 0), x1 = min(cell_coord_raw(px + rr, ox, inv), dx - 1);
-  int y0 = max(cell_coord_raw(py - rr, oy, inv), 0), y1 = min(cell_coord_raw(py + rr, oy, inv), dy - 1);
-  int z0 = max(cell_coord_raw(pz - rr, oz, inv), 0), z1 = min(cell_coord_raw(pz + rr, oz, inv), dz - 1);
-  if (x0 > x1 || y0 > y1 || z0 > z1) return;
-  int cnt = 0;
-  for (int cz = z0; cz <= z1; ++cz) {
-    for (int cy = y0; cy <= y1; ++cy) {
-      const int base = (cz * dy + cy) * dx;
-      const int beg = __ldg(g.cell_start + base + x0);
-      const int end = __ldg(g.cell_start + base + x1 + 1);
-      for (int j = beg; j < end; ++j) {
-        const float4 q = __ldg(g.sorted + j);
-        const float D = sqdist_rn(q.x, q.y, q.z, px, py, pz);
-        const bool outside = dyn ? ((double)D > r2d) : (D > r2f);
-        const int id = __float_as_int(q.w);
-        if (!outside && knn_less(D, id, out.D[KNN - 1], out.I[KNN - 1])) {
-          out.D[KNN - 1] = D;
-          out.I[KNN - 1] = id;
+  int x0[NQ], x1[NQ], y0[NQ], z0[NQ], ny[NQ], nranges[NQ];
+  int maxr = 0;
 #pragma unroll
-          for (int t = KNN - 1; t > 0; --t) {
-            if (knn_less(out.D[t], out.I[t], out.D[t - 1], out.I[t - 1])) {
-              float td = out.D[t]; out.D[t] = out.D[t - 1]; out.D[t - 1] = td;
-              int ti = out.I[t];   out.I[t] = out.I[t - 1]; out.I[t - 1] = ti;
-            }
+  for (int q = 0; q < NQ; ++q) {
+    x0[q] = max(cell_coord_raw(px[q] - rr[q], ox, inv), 0);
+    x1[q] = min(cell_coord_raw(px[q] + rr[q], ox, inv), dx - 1);
+    y0[q] = max(cell_coord_raw(py[q] - rr[q], oy, inv), 0);
+    const int y1 = min(cell_coord_raw(py[q] + rr[q], oy, inv), dy - 1);
+    z0[q] = max(cell_coord_raw(pz[q] - rr[q], oz, inv), 0);
+    const int z1 = min(cell_coord_raw(pz[q] + rr[q], oz, inv), dz - 1);
+    ny[q] = y1 - y0[q] + 1;
+    const bool ok = active[q] && x0[q] <= x1[q] && y0[q] <= y1 && z0[q] <= z1;
+    nranges[q] = ok ? ny[q] * (z1 - z0[q] + 1) : 0;
+    maxr = max(maxr, nranges[q]);
+  }
+  for (int rc0 = 0; rc0 < maxr; rc0 += 32) {
+    const int r = rc0 + lane;
+    int beg[NQ], cnt[NQ], inc[NQ], T[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      beg[q] = 0;
+      cnt[q] = 0;
+      if (r < nranges[q]) {
+        const int cz = z0[q] + r / ny[q], cy = y0[q] + r % ny[q];
+        // rows of cells the query ball cannot reach are skipped, the others are clipped to the chord of
+        // the ball at the row's minimum (y,z) offset: never drops a point with D <= r^2 (bounds are
+        // conservative), only trims the candidate list
+        const float dyl = slab_dist_lb(py[q], oy, ce, cy, dy), dzl = slab_dist_lb(pz[q], oz, ce, cz, dz);
+        const float rem = rr[q] * rr[q] - dyl * dyl - dzl * dzl;
+        if (rem >= 0.f) {
+          const float hx = sqrtf(rem) * 1.000001f + 1e-7f;
+          const int xa = max(x0[q], cell_coord_raw(px[q] - hx, ox, inv));
+          const int xb = min(x1[q], cell_coord_raw(px[q] + hx, ox, inv));
+          if (xa <= xb) {
+            const int base = (cz * dy + cy) * dx;
+            beg[q] = __ldg(g.cell_start + base + xa);
+            cnt[q] = __ldg(g.cell_start + base + xb + 1);
           }
-          cnt = min(cnt + 1, KNN);
+        }
+      }
+    }
+    int maxT = 0;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      cnt[q] -= beg[q];
+      inc[q] = cnt[q];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, inc[q], o);
+        if (lane >= o) inc[q] += v;
+      }
+      T[q] = __shfl_sync(FULL, inc[q], 31);
+      maxT = max(maxT, T[q]);
+    }
+    for (int j0 = 0; j0 < maxT; j0 += 32) {
+      const int j = j0 + lane;
+      float4 q4[NQ];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        int rsel = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+          const int v = __shfl_sync(FULL, inc[q], rsel + step - 1);
+          if (v <= j) rsel += step;
+        }
+        rsel = min(rsel, 31);
+        const int inc_sel = __shfl_sync(FULL, inc[q], rsel), cnt_sel = __shfl_sync(FULL, cnt[q], rsel);
+        const int beg_sel = __shfl_sync(FULL, beg[q], rsel);
+        q4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < T[q]) q4[q] = __ldg(g.sorted + beg_sel + (j - (inc_sel - cnt_sel)));
+      }
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        unsigned cD = KNN_INF;
+        int cI = KNN_NOID;
+        if (j < T[q]) {
+          const float D = sqdist_rn(q4[q].x, q4[q].y, q4[q].z, px[q], py[q], pz[q]);
+          const bool outside = dyn ? ((double)D > r2d[q]) : (D > r2f[q]);
+          if (!outside) { cD = __float_as_uint(D); cI = __float_as_int(q4[q].w); }
+        }
+        const unsigned b7D = __shfl_sync(FULL, bestD[q], KNN - 1);
+        const int b7I = __shfl_sync(FULL, bestI[q], KNN - 1);
+        if (__any_sync(FULL, (cD < b7D) || (cD == b7D && cI < b7I))) {
+          unsigned oD = lane < KNN ? bestD[q] : KNN_INF;
+          int oI = lane < KNN ? bestI[q] : KNN_NOID;
+          unsigned nD = KNN_INF;
+          int nI = KNN_NOID;
+#pragma unroll
+          for (int k = 0; k < KNN; ++k) {
+            const bool c_lt = (cD < oD) || (cD == oD && cI < oI);
+            const unsigned lD = c_lt ? cD : oD;
+            const int lI = c_lt ? cI : oI;
+            const unsigned mD = __reduce_min_sync(FULL, lD);
+            const int mI = __reduce_min_sync(FULL, lD == mD ? lI : KNN_NOID);
+            if (lane == k) { nD = mD; nI = mI; }
+            if (cD == mD && cI == mI) { cD = KNN_INF; cI = KNN_NOID; }
+            else if (oD == mD && oI == mI) { oD = KNN_INF; oI = KNN_NOID; }
+          }
+          bestD[q] = nD;
+          bestI[q] = nI;
         }
       }
     }
   }
-  out.cnt = cnt;
-}
-// Warp-cooperative version of knn_walk: the 32 lanes of one warp search for ONE query point.
-// Lanes fetch the (cy,cz) cell ranges in parallel, the candidates of all ranges are enumerated 32 at
-// a time (coalesced float4 loads inside a range), and the running top-8 by (D, id) lives in lanes
-// 0..7 (lane k = k-th nearest).  Selection = 8 rounds of REDUX min over (D bits, id).  Same exact
-// arithmetic, predicate and tie-break as knn_walk / the oracle.
-constexpr unsigned KNN_INF = 0x7f800000u;   // +inf bits; squared distances are >= 0 so bit order == value order
-constexpr int KNN_NOID = 0x7fffffff;
-
-__device__ __forceinline__ void knn_warp(const GridView& g, float px, float py, float pz, float rr, bool dyn,
-                                         float r2f, double r2d, unsigned& bestD, int& bestI) {
-  const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  bestD = KNN_INF;
-  bestI = KNN_NOID;
-  const GridHeader* h = g.hdr;
-  if (h->n_points <= 0) return;
-  const float inv = h->inv_cell;
-  const float ox = h->origin[0], oy = h->origin[1], oz = h->origin[2];
-  const int dx = h->dims[0], dy = h->dims[1], dz = h->dims[2];
-  const int x0 = max(cell_coord_raw(px - rr, ox, inv), 0), x1 = min(cell_coord_raw(px + rr, ox, inv), dx - 1);
-  const int y0 = max(cell_coord_raw(py - rr, oy, inv), 0), y1 = min(cell_coord_raw(py + rr, oy, inv), dy - 1);
-  const int z0 = max(cell_coord_raw(pz - rr, oz, inv), 0), z1 = min(cell_coord_raw(pz + rr, oz, inv), dz - 1);
-  if (x0 > x1 || y0 > y1 || z0 > z1) return;
-  const int ny = y1 - y0 + 1, nranges = ny * (z1 - z0 + 1);
-  for (int rc0 = 0; rc0 < nranges; rc0 += 32) {
-    const int r = rc0 + lane;
-    int beg = 0, cnt = 0;
-    if (r < nranges) {
-      const int cz = z0 + r / ny, cy = y0 + r % ny;
-      const int base = (cz * dy + cy) * dx;
-      beg = __ldg(g.cell_start + base + x0);
-      cnt = __ldg(g.cell_start + base + x1 + 1) - beg;
-    }
-    int inc = cnt;   // inclusive prefix sum of the range sizes
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(FULL, inc, o);
-      if (lane >= o) inc += v;
-    }
-    const int T = __shfl_sync(FULL, inc, 31);
-    for (int j0 = 0; j0 < T; j0 += 32) {
-      const int j = j0 + lane;
-      // range of candidate j = number of ranges whose inclusive prefix is <= j: binary search over the
-      // (non-decreasing) prefix held one-per-lane; lanes beyond the last range hold T > j
-      int rsel = 0;
-#pragma unroll
-      for (int step = 16; step > 0; step >>= 1) {
-        const int v = __shfl_sync(FULL, inc, rsel + step - 1);
-        if (v <= j) rsel += step;
-      }
-      rsel = min(rsel, 31);
-      const int inc_sel = __shfl_sync(FULL, inc, rsel), cnt_sel = __shfl_sync(FULL, cnt, rsel);
-      const int beg_sel = __shfl_sync(FULL, beg, rsel);
-      unsigned cD = KNN_INF;
-      int cI = KNN_NOID;
-      if (j < T) {
-        const float4 q4 = __ldg(g.sorted + beg_sel + (j - (inc_sel - cnt_sel)));
-        const float D = sqdist_rn(q4.x, q4.y, q4.z, px, py, pz);
-        const bool outside = dyn ? ((double)D > r2d) : (D > r2f);
-        if (!outside) { cD = __float_as_uint(D); cI = __float_as_int(q4.w); }
-      }
-      const unsigned b7D = __shfl_sync(FULL, bestD, KNN - 1);
-      const int b7I = __shfl_sync(FULL, bestI, KNN - 1);
-      if (!__any_sync(FULL, (cD < b7D) || (cD == b7D && cI < b7I))) continue;
-      unsigned oD = lane < KNN ? bestD : KNN_INF;
-      int oI = lane < KNN ? bestI : KNN_NOID;
-      unsigned nD = KNN_INF;
-      int nI = KNN_NOID;
-#pragma unroll
-      for (int k = 0; k < KNN; ++k) {
-        const bool c_lt = (cD < oD) || (cD == oD && cI < oI);
-        const unsigned lD = c_lt ? cD : oD;
-        const int lI = c_lt ? cI : oI;
-        const unsigned mD = __reduce_min_sync(FULL, lD);
-        const int mI = __reduce_min_sync(FULL, lD == mD ? lI : KNN_NOID);
-        if (lane == k) { nD = mD; nI = mI; }
-        if (cD == mD && cI == mI) { cD = KNN_INF; cI = KNN_NOID; }
-        else if (oD == mD && oI == mI) { oD = KNN_INF; oI = KNN_NOID; }
-      }
-      bestD = nD;
-      bestI = nI;
-    }
-  }
 }
 #endif  // __CUDACC__
+
 
 }  // namespace lsr

@@ -178,30 +178,53 @@ __global__ void grid_scatter_kernel(const float* __restrict__ pos, int n, const 
                              __int_as_float(i));
 }
 
-__global__ void knn_query_kernel(const void* ws, const float* __restrict__ q,
-                                 const double* __restrict__ r_dyn, double r_fixed, int64_t P,
-                                 float* __restrict__ D, int64_t* __restrict__ I,
-                                 int32_t* __restrict__ nnum) {
+// one warp per pair of queries (knn_warp_multi<2>); lane k < 8 holds the k-th neighbour
+constexpr int KQ_NT = 256, KQ_NQ = 2;
+__global__ void __launch_bounds__(KQ_NT) knn_query_kernel(const void* ws, const float* __restrict__ q,
+                                                          const double* __restrict__ r_dyn, double r_fixed, int64_t P,
+                                                          float* __restrict__ D, int64_t* __restrict__ I,
+                                                          int32_t* __restrict__ nnum) {
   const GridHeader* h = (const GridHeader*)ws;
   const GridView g = grid_view(ws, h->n_points, h->max_cells);
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * KQ_NT + threadIdx.x) >> 5;
+  const int64_t i0 = warp * KQ_NQ;
+  if (i0 >= P) return;
   const bool dyn = r_dyn != nullptr;
-  const double r = dyn ? r_dyn[i] : r_fixed;
-  const double r2d = r * r;
-  const float r2f = (float)r2d;
-  const float rr = (float)r * 1.00001f + 1e-7f;
-  Knn8 k;
-  knn_walk(g, q[3 * i], q[3 * i + 1], q[3 * i + 2], rr, dyn, r2f, r2d, k);
-  int ns = 0;
+  float px[KQ_NQ], py[KQ_NQ], pz[KQ_NQ], rr[KQ_NQ], r2f[KQ_NQ];
+  double r2d[KQ_NQ];
+  bool act[KQ_NQ];
+  unsigned bD[KQ_NQ];
+  int bI[KQ_NQ];
 #pragma unroll
-  for (int t = 0; t < KNN; ++t) {
-    const bool ok = t < k.cnt;
-    D[i * KNN + t] = ok ? k.D[t] : FLT_MAX;
-    I[i * KNN + t] = ok ? (int64_t)k.I[t] : (int64_t)-1;
-    if (ok) ns += dyn ? ((double)k.D[t] < r2d) : (k.D[t] < r2f);
+  for (int t = 0; t < KQ_NQ; ++t) {
+    const int64_t i = i0 + t;
+    act[t] = i < P;
+    px[t] = py[t] = pz[t] = rr[t] = r2f[t] = 0.f;
+    r2d[t] = 0.0;
+    if (act[t]) {
+      const double r = dyn ? r_dyn[i] : r_fixed;
+      r2d[t] = r * r;
+      r2f[t] = (float)r2d[t];
+      rr[t] = (float)r * 1.00001f + 1e-7f;
+      px[t] = q[3 * i]; py[t] = q[3 * i + 1]; pz[t] = q[3 * i + 2];
+    }
   }
-  nnum[i] = ns;
+  knn_warp_multi<KQ_NQ>(g, px, py, pz, rr, act, dyn, r2f, r2d, bD, bI);
+#pragma unroll
+  for (int t = 0; t < KQ_NQ; ++t) {
+    const int64_t i = i0 + t;
+    if (!act[t]) continue;
+    const bool ok = lane < KNN && bD[t] != KNN_INF;
+    const float Dk = __uint_as_float(bD[t]);
+    const bool strict = ok && (dyn ? ((double)Dk < r2d[t]) : (Dk < r2f[t]));
+    const int ns = __popc(__ballot_sync(0xffffffffu, strict));
+    if (lane < KNN) {
+      D[i * KNN + lane] = ok ? Dk : FLT_MAX;
+      I[i * KNN + lane] = ok ? (int64_t)bI[t] : (int64_t)-1;
+    }
+    if (lane == 0) nnum[i] = ns;
+  }
 }
 
 }  // namespace lsr
@@ -253,7 +276,8 @@ extern "C" int lsr_knn_query(const void* grid_ws, const float* q, const double* 
                              int64_t P, float* D, int64_t* I, int32_t* nnum, lsr_stream_t stream) {
   if (!grid_ws || P < 0 || (P > 0 && (!q || !D || !I || !nnum))) return LSR_ERR_ARG;
   if (P == 0) return LSR_OK;
-  knn_query_kernel<<<(unsigned)((P + 127) / 128), 128, 0, stream>>>(grid_ws, q, r_dyn, r_fixed, P, D, I, nnum);
+  const int64_t per_block = (KQ_NT / 32) * KQ_NQ;
+  knn_query_kernel<<<(unsigned)((P + per_block - 1) / per_block), KQ_NT, 0, stream>>>(grid_ws, q, r_dyn, r_fixed, P, D, I, nnum);
   LSR_CUDA_CHECK(cudaGetLastError());
   return LSR_OK;
 }

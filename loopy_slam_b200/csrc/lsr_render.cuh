@@ -235,6 +235,10 @@ __device__ __forceinline__ const float* feat_row(const float* __restrict__ table
   }
   return table + (size_t)idx * CDIM;
 }
+__device__ __forceinline__ const float* feat_row_cached(const float* __restrict__ table, const float* __restrict__ leaf,
+                                                        int idx, int rem) {   // rem = row_remap[idx] looked up once
+  return rem >= 0 ? leaf + (size_t)rem * CDIM : table + (size_t)idx * CDIM;
+}
 // gradient row of point idx, or nullptr when the row is not trainable (remap given and remap[idx] < 0)
 __device__ __forceinline__ float* grad_row(float* __restrict__ d, const int32_t* __restrict__ remap, int idx) {
   if (remap != nullptr) {

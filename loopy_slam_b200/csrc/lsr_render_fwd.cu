@@ -67,7 +67,7 @@ __device__ __forceinline__ float linspace_f32(float start, float end, int S, int
                      : __fsub_rn(end, __fmul_rn(step, (float)(S - 1 - s)));
 }
 
-constexpr int FWD_SMEM_FLOATS = TILE_M * XLD + TILE_M * CLD + SB_FLOATS + TILE_M * KNN * 2 +
+constexpr int FWD_SMEM_FLOATS = TILE_M * XLD + TILE_M * CLD + SB_FLOATS + TILE_M * KNN * 3 +
                                 TILE_M * 4 + TILE_M * 3 + TILE_M * 4;
 
 __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __grid_constant__ FwdArgs a) {
@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
   float* sWsum = sOcc + TILE_M;
   int* sHas = reinterpret_cast<int*>(sWsum + TILE_M);
   float* sRgb = reinterpret_cast<float*>(sHas + TILE_M);   // [m][4]
+  int* sRem = reinterpret_cast<int*>(sRgb + TILE_M * 4);   // [m][k] leaf row of neighbour k (row_remap), -1 = table
 
   const int tid = threadIdx.x;
   const int S = a.prm.n_surface;
@@ -106,62 +107,76 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
 
     LSR_PHASE_BEGIN();
     // ---------------------------------------------------------------- A: sample points + k-NN
-    // one warp per sample row (lane k < 8 ends up owning the k-th neighbour)
-    for (int m = tid >> 5; m < TILE_M; m += NT / 32) {
+    // one warp per PAIR of sample rows, searched in lockstep (lane k < 8 ends up owning the k-th neighbour)
+    constexpr int NQ = 2;
+    for (int m0 = (tid >> 5) * NQ; m0 < TILE_M; m0 += (NT / 32) * NQ) {
       const int lane = tid & 31;
-      const bool rowvalid = m < nrows;
-      float px = 0.f, py = 0.f, pz = 0.f, z = 0.f, r2f = 0.f;
-      double r2d = 0.0;
-      unsigned bD = KNN_INF;
-      int bI = KNN_NOID;
-      if (rowvalid) {
-        const int rl = m / S, s = m - rl * S, ray = r0 + rl;
-        const float g = a.gt_depth[ray];
-        if (g > 0.f) {   // Renderer.py:140-150
-          const float t = linspace_f32(0.f, 1.f, S, s);
-          const float zn = __fmul_rn(a.prm.near_end_surface, g), zf = __fmul_rn(a.prm.far_end_surface, g);
-          z = __fadd_rn(__fmul_rn(zn, __fsub_rn(1.f, t)), __fmul_rn(zf, t));
-        } else {         // Renderer.py:162-163
-          const float far = a.far_zero ? a.far_zero[ray / a.far_group] : a.prm.near_end;
-          z = linspace_f32(a.prm.near_end, far, S, s);
-        }
-        px = __fadd_rn(a.rays_o[3 * ray + 0], __fmul_rn(a.rays_d[3 * ray + 0], z));   // Renderer.py:167-168
-        py = __fadd_rn(a.rays_o[3 * ray + 1], __fmul_rn(a.rays_d[3 * ray + 1], z));
-        pz = __fadd_rn(a.rays_o[3 * ray + 2], __fmul_rn(a.rays_d[3 * ray + 2], z));
-        const double r = dynr ? a.r_query[ray] : a.prm.radius_query;
-        r2d = r * r;
-        r2f = (float)r2d;
-        knn_warp(gv, px, py, pz, (float)r * 1.00001f + 1e-7f, dynr, r2f, r2d, bD, bI);
-      }
-      const bool vk = lane < KNN && bD != KNN_INF;
-      const float Dk = __uint_as_float(bD);
-      const bool strict = vk && (dynr ? ((double)Dk < r2d) : (Dk < r2f));        // neural_point.py:1701-1706
-      const int ns = __popc(__ballot_sync(0xffffffffu, strict));
-      const int cnt = __popc(__ballot_sync(0xffffffffu, vk));
-      const float wraw = vk ? 1.0f / (Dk + 1e-10f) : 0.f;                        // decoder.py:210,217-220
-      float wsum = 0.f;
+      float px[NQ], py[NQ], pz[NQ], z[NQ], r2f[NQ], rr[NQ];
+      double r2d[NQ];
+      bool rowvalid[NQ];
+      unsigned bD[NQ];
+      int bI[NQ];
 #pragma unroll
-      for (int k = 0; k < KNN; ++k) wsum += __shfl_sync(0xffffffffu, wraw, k);
-      const float wn = wraw / fmaxf(wsum, 1e-12f);
-      float wn_sum = 0.f;
-#pragma unroll
-      for (int k = 0; k < KNN; ++k) wn_sum += __shfl_sync(0xffffffffu, wn, k);
-      const int has = (rowvalid && ns >= a.prm.min_nn_num) ? 1 : 0;             // decoder.py:204
-      if (lane < KNN) {
-        sIdx[m * KNN + lane] = vk ? bI : -1;
-        sW[m * KNN + lane] = wn;
-        if (save && rowvalid) {
-          reinterpret_cast<int*>(a.saved + SL.idx)[(p0 + m) * KNN + lane] = vk ? bI : -1;
-          a.saved[SL.w + (p0 + m) * KNN + lane] = wn;
-          a.saved[SL.D + (p0 + m) * KNN + lane] = vk ? Dk : FLT_MAX;
+      for (int q = 0; q < NQ; ++q) {
+        const int m = m0 + q;
+        rowvalid[q] = m < nrows;
+        px[q] = py[q] = pz[q] = z[q] = r2f[q] = rr[q] = 0.f;
+        r2d[q] = 0.0;
+        if (rowvalid[q]) {
+          const int rl = m / S, s = m - rl * S, ray = r0 + rl;
+          const float g = a.gt_depth[ray];
+          if (g > 0.f) {   // Renderer.py:140-150
+            const float t = linspace_f32(0.f, 1.f, S, s);
+            const float zn = __fmul_rn(a.prm.near_end_surface, g), zf = __fmul_rn(a.prm.far_end_surface, g);
+            z[q] = __fadd_rn(__fmul_rn(zn, __fsub_rn(1.f, t)), __fmul_rn(zf, t));
+          } else {         // Renderer.py:162-163
+            const float far = a.far_zero ? a.far_zero[ray / a.far_group] : a.prm.near_end;
+            z[q] = linspace_f32(a.prm.near_end, far, S, s);
+          }
+          px[q] = __fadd_rn(a.rays_o[3 * ray + 0], __fmul_rn(a.rays_d[3 * ray + 0], z[q]));   // Renderer.py:167-168
+          py[q] = __fadd_rn(a.rays_o[3 * ray + 1], __fmul_rn(a.rays_d[3 * ray + 1], z[q]));
+          pz[q] = __fadd_rn(a.rays_o[3 * ray + 2], __fmul_rn(a.rays_d[3 * ray + 2], z[q]));
+          const double r = dynr ? a.r_query[ray] : a.prm.radius_query;
+          r2d[q] = r * r;
+          r2f[q] = (float)r2d[q];
+          rr[q] = (float)r * 1.00001f + 1e-7f;
         }
       }
-      if (lane == 0) {
-        *reinterpret_cast<float4*>(sP + m * 4) = make_float4(px, py, pz, z);
-        sHas[m] = has;
-        sWsum[m] = wn_sum;
-        if (save && rowvalid)
-          reinterpret_cast<float4*>(a.saved + SL.misc)[p0 + m] = make_float4(z, (float)has, wn_sum, (float)cnt);
+      knn_warp_multi<NQ>(gv, px, py, pz, rr, rowvalid, dynr, r2f, r2d, bD, bI);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int m = m0 + q;
+        const bool vk = lane < KNN && bD[q] != KNN_INF;
+        const float Dk = __uint_as_float(bD[q]);
+        const bool strict = vk && (dynr ? ((double)Dk < r2d[q]) : (Dk < r2f[q]));   // neural_point.py:1701-1706
+        const int ns = __popc(__ballot_sync(0xffffffffu, strict));
+        const int cnt = __popc(__ballot_sync(0xffffffffu, vk));
+        const float wraw = vk ? 1.0f / (Dk + 1e-10f) : 0.f;                        // decoder.py:210,217-220
+        float wsum = 0.f;
+#pragma unroll
+        for (int k = 0; k < KNN; ++k) wsum += __shfl_sync(0xffffffffu, wraw, k);
+        const float wn = wraw / fmaxf(wsum, 1e-12f);
+        float wn_sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < KNN; ++k) wn_sum += __shfl_sync(0xffffffffu, wn, k);
+        const int has = (rowvalid[q] && ns >= a.prm.min_nn_num) ? 1 : 0;           // decoder.py:204
+        if (lane < KNN) {
+          sIdx[m * KNN + lane] = vk ? bI[q] : -1;
+          sRem[m * KNN + lane] = (vk && a.remap != nullptr) ? __ldg(a.remap + bI[q]) : -1;
+          sW[m * KNN + lane] = wn;
+          if (save && rowvalid[q]) {
+            reinterpret_cast<int*>(a.saved + SL.idx)[(p0 + m) * KNN + lane] = vk ? bI[q] : -1;
+            a.saved[SL.w + (p0 + m) * KNN + lane] = wn;
+            a.saved[SL.D + (p0 + m) * KNN + lane] = vk ? Dk : FLT_MAX;
+          }
+        }
+        if (lane == 0) {
+          *reinterpret_cast<float4*>(sP + m * 4) = make_float4(px[q], py[q], pz[q], z[q]);
+          sHas[m] = has;
+          sWsum[m] = wn_sum;
+          if (save && rowvalid[q])
+            reinterpret_cast<float4*>(a.saved + SL.misc)[p0 + m] = make_float4(z[q], (float)has, wn_sum, (float)cnt);
+        }
       }
     }
     __syncthreads();
@@ -177,7 +192,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
           const int idx = sIdx[m * KNN + k];
           if (idx >= 0) {
             const float w = sW[m * KNN + k];
-            const float4 f = __ldg(reinterpret_cast<const float4*>(feat_row(a.geo_feats, a.geo_leaf, a.remap, idx)) + q);
+            const float4 f = __ldg(reinterpret_cast<const float4*>(feat_row_cached(a.geo_feats, a.geo_leaf, idx, sRem[m * KNN + k])) + q);
             acc.x = fmaf(w, f.x, acc.x); acc.y = fmaf(w, f.y, acc.y);
             acc.z = fmaf(w, f.z, acc.z); acc.w = fmaf(w, f.w, acc.w);
           }
@@ -293,7 +308,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
             const int m = it >> 3, q = it & 7;
             const int idx = sIdx[m * KNN + k];
             float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (idx >= 0) f = __ldg(reinterpret_cast<const float4*>(feat_row(a.col_feats, a.col_leaf, a.remap, idx)) + q);
+            if (idx >= 0) f = __ldg(reinterpret_cast<const float4*>(feat_row_cached(a.col_feats, a.col_leaf, idx, sRem[m * KNN + k])) + q);
             *reinterpret_cast<float4*>(sX + m * XLD + 2 * ER + q * 4) = f;
           }
           f.zero();
@@ -360,7 +375,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __gri
               const int idx = sIdx[m * KNN + k];
               if (idx >= 0) {
                 const float w = sW[m * KNN + k];
-                const float4 f = __ldg(reinterpret_cast<const float4*>(feat_row(a.col_feats, a.col_leaf, a.remap, idx)) + q);
+                const float4 f = __ldg(reinterpret_cast<const float4*>(feat_row_cached(a.col_feats, a.col_leaf, idx, sRem[m * KNN + k])) + q);
                 acc.x = fmaf(w, f.x, acc.x); acc.y = fmaf(w, f.y, acc.y);
                 acc.z = fmaf(w, f.z, acc.z); acc.w = fmaf(w, f.w, acc.w);
               }

@@ -4,6 +4,7 @@ drives the fused sm_100a kernels through the C ABI (include/lsr.h); nothing here
 CPU and there is no PyTorch-eager fallback.
 """
 import ctypes
+import os
 import warnings
 
 import torch
@@ -15,17 +16,22 @@ DEFAULT_MAX_CELLS = 1 << 22
 
 
 # ----------------------------------------------------------------------------- neighbour index
+CELL_PER_RADIUS = float(os.environ.get('LSR_CELL_FACTOR', '0.5'))   # grid cell edge / query radius (tuning knob)
+
+
 class GridIndex:
     """Device workspace of one uniform-grid neighbour index (lsr_grid_build)."""
 
     def __init__(self, cloud_pos, cell, max_cells=DEFAULT_MAX_CELLS):
+        """cell: the largest query radius this index will serve; the grid's cell edge is CELL_PER_RADIUS x
+        that (the walk prunes cell rows against the query ball, so finer cells trim the candidate list)."""
         _lib.require_cuda(cloud_pos, 'cloud_pos')
         cloud = cloud_pos.detach()
         if cloud.dtype != torch.float32 or not cloud.is_contiguous():
             cloud = cloud.to(torch.float32).contiguous()
         self.cloud = cloud.reshape(-1, 3)
         self.n = self.cloud.shape[0]
-        self.cell = float(cell)
+        self.cell = float(cell) * CELL_PER_RADIUS
         self.max_cells = int(max_cells)
         nbytes = ctypes.c_size_t()
         check(lib().lsr_grid_workspace_bytes(self.n, self.max_cells, ctypes.byref(nbytes)), 'lsr_grid_workspace_bytes')

@@ -12,7 +12,7 @@ SO = os.path.join(ROOT, 'loopy_slam_b200', 'liblsr_phase.so')
 
 def build():
     csrc = os.path.join(ROOT, 'loopy_slam_b200', 'csrc')
-    srcs = [os.path.join(csrc, f) for f in ('lsr_grid.cu', 'lsr_sample.cu', 'lsr_render_fwd.cu', 'lsr_render_bwd.cu')]
+    srcs = [os.path.join(csrc, f) for f in ('lsr_grid.cu', 'lsr_sample.cu', 'lsr_loss.cu', 'lsr_render_fwd.cu', 'lsr_render_bwd.cu')]
     subprocess.check_call(['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-rdc=true',
                            '-DLSR_PHASE_TIMING', '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '-shared', '-cudart', 'static',
                            '-o', SO] + srcs)
@@ -27,7 +27,8 @@ if __name__ == '__main__':
     import torch
     import bench
     from loopy_slam_b200 import _lib
-    sys.argv = ['bench.py', '--steps', '10', '--warmup', '3', '--no-cpu-baseline']
+    sys.argv = ['bench.py', '--steps', '10', '--warmup', '3', '--no-cpu-baseline', '--no-extra'] + \
+        [a for a in sys.argv[1:] if a not in ('--build', '--build-only')]
     bench.main()
     torch.cuda.synchronize()
     rt = ctypes.CDLL('libcudart.so.12') if False else None
@@ -43,4 +44,4 @@ if __name__ == '__main__':
         tot = sum(buf[k * 16 + i] for i in range(16)) or 1
         print(['render_fwd', 'render_bwd'][k], 'phase share of CTA-cycles:')
         for i, n in enumerate(names[k]):
-            print(f'   {n:24s} {100.0 * buf[k * 16 + i] / tot:5.1f}%')
+            print(f'   {n:24s} {100.0 * buf[k * 16 + i] / tot:5.1f}%   {buf[k * 16 + i] / 1e6:9.2f} Mcycles')
