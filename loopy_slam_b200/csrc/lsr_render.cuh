@@ -248,6 +248,9 @@ __device__ __forceinline__ float* grad_row(float* __restrict__ d, const int32_t*
   return d + (size_t)idx * CDIM;
 }
 
+#ifndef LSR_RING_FASTPATH
+#define LSR_RING_FASTPATH 0   // 1: separate predicate-free copy loop for interior chunks (costs code size)
+#endif
 // One KC-row chunk of a streamed B operand -> ring stage (chunk % NSTAGE); always commits a group.
 template <int NCOLS>
 __device__ __forceinline__ void ring_prefetch_chunk(const float* __restrict__ B, int ldb, int Kc, int ncols_valid,
@@ -259,13 +262,25 @@ __device__ __forceinline__ void ring_prefetch_chunk(const float* __restrict__ B,
   if (chunk < nchunks) {
     float* dst = sBuf + (chunk % NSTAGE) * (KC * CLD_);
     const int k0 = chunk * KC;
-    for (int p = threadIdx.x; p < PIECES; p += NT) {
-      const int row = p / PPR, c4 = p % PPR;
-      float* d = dst + row * CLD_ + c4 * 4;
-      if (k0 + row < Kc && c4 * 4 < ncols_valid) {
-        cp_async16(d, B + (size_t)(k0 + row) * ldb + c4 * 4);
-      } else {
-        *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+    static_assert(PIECES % NT == 0 || PIECES < NT, "chunk pieces per thread");
+    constexpr int PER = (PIECES + NT - 1) / NT;           // float4 pieces per thread
+    constexpr int RSTEP = NT / PPR;                       // chunk rows covered by one sweep of the CTA
+    // thread -> (row0 + i * RSTEP, c4): the column is fixed, only the row advances
+    const int row0 = threadIdx.x / PPR, c4 = threadIdx.x % PPR;
+    const bool active = PIECES >= NT || threadIdx.x < PIECES;
+    float* d = dst + row0 * CLD_ + c4 * 4;
+    const float* src = B + (size_t)(k0 + row0) * ldb + c4 * 4;
+    if (LSR_RING_FASTPATH && k0 + KC <= Kc && ncols_valid == NCOLS) {   // interior chunk: no predicates
+      if (active) {
+#pragma unroll
+        for (int i = 0; i < PER; ++i) cp_async16(d + i * RSTEP * CLD_, src + (size_t)i * RSTEP * ldb);
+      }
+    } else if (active) {
+      const bool colok = c4 * 4 < ncols_valid;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        if (colok && k0 + row0 + i * RSTEP < Kc) cp_async16(d + i * RSTEP * CLD_, src + (size_t)i * RSTEP * ldb);
+        else *reinterpret_cast<float4*>(d + i * RSTEP * CLD_) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
   }

@@ -8,6 +8,7 @@
 //   raw2outputs_nerf_color      /root/reference/src/common.py:382-422
 #include <cstdlib>
 // the forward kernel has shared memory to spare: 32-row weight chunks, two stages -> half the barriers per GEMM
+#define LSR_RING_FASTPATH 1
 #define LSR_KC 32
 #define LSR_NSTAGE 2
 #include "lsr_render.cuh"
