@@ -1,45 +1,33 @@
-// Fused forward render kernel: z-sampling -> grid k-NN -> IDW gather -> geometry MLP ->
-// (rel-pos neighbour MLP) -> colour MLP -> alpha compositing, one persistent CTA per SM, one
-// tile of TILE_M sample rows (= floor(128/S) rays) at a time, activations resident in shared memory.
+// Forward render path on sm_100a, two launches per ray batch:
+//
+//   sample_knn_kernel   z-sampling + exact grid k-NN + IDW weights, one warp per pair of sample rows at
+//                       full occupancy (the walk is a chain of dependent global loads: it wants many warps,
+//                       not the few a tensor-core tile kernel can keep resident);
+//   render_fwd_kernel   one persistent CTA per SM, tiles of 128 sample rows (= floor(128/S) rays):
+//                       IDW gather -> geometry MLP -> (rel-pos neighbour MLP) -> colour MLP -> colour head ->
+//                       alpha compositing.  Every dense contraction runs on the 5th-generation tensor cores
+//                       (tcgen05.mma kind::tf32, M = 128, accumulators in TMEM) as an error-compensated
+//                       3xTF32 product; weights are streamed L2 -> shared memory by cp.async.bulk into an
+//                       mbarrier ring, hidden activations never leave TMEM between layers (the epilogue
+//                       warps read the accumulator with tcgen05.ld, apply bias / activation / skip, and write
+//                       the next layer's A operand back with tcgen05.st).  See lsr_umma_prog.cuh for the roles.
 //
 // Reference semantics restated (math only):
 //   Renderer.render_batch_ray   /root/reference/src/utils/Renderer.py:71-201
 //   NICER / MLP_geometry / MLP_color   /root/reference/src/conv_onet/models/decoder.py:106-626
 //   raw2outputs_nerf_color      /root/reference/src/common.py:382-422
 #include <cstdlib>
-// the forward kernel has shared memory to spare: 32-row weight chunks, two stages -> half the barriers per GEMM
-#define LSR_RING_FASTPATH 1
-#define LSR_KC 32
-#define LSR_NSTAGE 2
+#include <cstring>
 #include "lsr_render.cuh"
+#include "lsr_umma_prog.cuh"
 
 namespace lsr {
+
+using namespace umma;
 
 #ifdef LSR_PHASE_TIMING
 __device__ unsigned long long lsr_phase_cycles[2][16];
 #endif
-
-struct FwdArgs {
-  LsrParams prm;
-  const void* grid;
-  const float* cloud;
-  const float *rays_o, *rays_d, *gt_depth;
-  const double* r_query;
-  const float* far_zero;
-  int far_group;
-  int R;
-  const float *geo_feats, *col_feats;
-  const int32_t* remap;
-  const float *geo_leaf, *col_leaf;
-  LsrWeights w;
-  const float* packed;
-  const float* affine;
-  int stage;
-  float *depth, *var, *rgb;
-  uint8_t* valid;
-  float* saved;
-  int rays_per_tile, ntiles;
-};
 
 __global__ void pack_weights_kernel(const float* __restrict__ blob, float* __restrict__ packed, PackJobs jobs) {
   const PackJob jb = jobs.j[blockIdx.y];
@@ -68,462 +56,764 @@ __device__ __forceinline__ float linspace_f32(float start, float end, int S, int
                      : __fsub_rn(end, __fmul_rn(step, (float)(S - 1 - s)));
 }
 
-constexpr int FWD_SMEM_FLOATS = TILE_M * XLD + TILE_M * CLD + SB_FLOATS + TILE_M * KNN * 3 +
-                                TILE_M * 4 + TILE_M * 3 + TILE_M * 4;
+// ------------------------------------------------------------------------------------------------
+// scratch layout (bytes): [legacy packed weights (backward) | UMMA packed weights | k-NN results]
+struct KnnScratch {   // per sample row p = ray * S + s, all planes of Pp rows
+  int32_t* idx;       // [Pp][8] neighbour ids (-1: none)
+  int32_t* rem;       // [Pp][8] leaf row of the neighbour (row_remap), -1 = read the table
+  float* w;           // [Pp][8] normalised IDW weights
+  float4* pos;        // [Pp]    (px, py, pz, z)
+  float2* hw;         // [Pp]    (has_neighbors, sum of weights)
+};
+struct ScratchLayout { size_t legacy, umma, knn_idx, knn_rem, knn_w, knn_pos, knn_hw, total; };
+constexpr int UMMA_PACKED_FLOATS_MAX = 2 * (93 * 32 + 3 * 32 * 32 + 128 * 32 + 5 * 32 * 32 +                  // geometry
+                                            (40 + 128 + 128 + 168 + 128) * 128 + 5 * 32 * 128 + 56 * 128 +   // colour
+                                            128 * 32 + 128 * 16) + 8192;                                     // V2, head, padding
+__host__ __device__ inline ScratchLayout scratch_layout(int64_t n_rays, int S) {
+  ScratchLayout L;
+  const size_t Pp = align_up((size_t)n_rays * S, 128) + 128;
+  size_t o = 0;
+  L.legacy = o;   o = align_up(o + (size_t)Packed::total * sizeof(float), 256);
+  L.umma = o;     o = align_up(o + (size_t)UMMA_PACKED_FLOATS_MAX * sizeof(float), 256);
+  L.knn_idx = o;  o = align_up(o + Pp * KNN * 4, 256);
+  L.knn_rem = o;  o = align_up(o + Pp * KNN * 4, 256);
+  L.knn_w = o;    o = align_up(o + Pp * KNN * 4, 256);
+  L.knn_pos = o;  o = align_up(o + Pp * 16, 256);
+  L.knn_hw = o;   o = align_up(o + Pp * 8, 256);
+  L.total = o + 256;
+  return L;
+}
 
-__global__ void __launch_bounds__(NT, CTAS_PER_SM) render_fwd_kernel(const __grid_constant__ FwdArgs a) {
-  extern __shared__ __align__(16) float smem[];
-  float* sX = smem;
-  float* sC = sX + TILE_M * XLD;
-  float* sB = sC + TILE_M * CLD;
-  int* sIdx = reinterpret_cast<int*>(sB + SB_FLOATS);
-  float* sW = reinterpret_cast<float*>(sIdx + TILE_M * KNN);
-  float* sP = sW + TILE_M * KNN;          // [m][4] = px,py,pz,z
-  float* sOcc = sP + TILE_M * 4;
-  float* sWsum = sOcc + TILE_M;
-  int* sHas = reinterpret_cast<int*>(sWsum + TILE_M);
-  float* sRgb = reinterpret_cast<float*>(sHas + TILE_M);   // [m][4]
-  int* sRem = reinterpret_cast<int*>(sRgb + TILE_M * 4);   // [m][k] leaf row of neighbour k (row_remap), -1 = table
+struct KnnArgs {
+  LsrParams prm;
+  const void* grid;
+  const float *rays_o, *rays_d, *gt_depth;
+  const double* r_query;
+  const float* far_zero;
+  int far_group;
+  int R;
+  const int32_t* remap;
+  KnnScratch ks;
+  float* saved;
+  int stage;
+};
 
-  const int tid = threadIdx.x;
+// ------------------------------------------------------------------------------------------------ kernel 1
+// one warp per PAIR of sample rows, searched in lockstep (lane k < 8 ends up owning the k-th neighbour)
+__global__ void __launch_bounds__(256) sample_knn_kernel(const __grid_constant__ KnnArgs a) {
+  constexpr int NQ = 2;
   const int S = a.prm.n_surface;
-  const float* __restrict__ blob = a.w.blob;
-  const float* __restrict__ packed = a.packed;
-  const bool color = a.stage == LSR_STAGE_COLOR;
-  const bool relpos = (a.prm.flags & LSR_FLAG_REL_POS) != 0;
+  const int P = a.R * S;
   const bool dynr = (a.prm.flags & LSR_FLAG_DYNAMIC_R) != 0;
   const bool save = a.saved != nullptr;
   const SavedLayout SL = saved_layout(a.R, S, a.stage, a.prm.flags);
-  const size_t Pp = SL.Pp;   // row pitch of the per-layer saved planes
   const GridHeader* gh_ = reinterpret_cast<const GridHeader*>(a.grid);
   const GridView gv = grid_view(a.grid, gh_->n_points, gh_->max_cells);
-  const WideMap wm;
-  const NarrowMap nm;
-
-  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-    const int r0 = tile * a.rays_per_tile;
-    const int nr = min(a.rays_per_tile, a.R - r0);
-    const int nrows = nr * S;
-    const size_t p0 = (size_t)r0 * S;
-
-    LSR_PHASE_BEGIN();
-    // ---------------------------------------------------------------- A: sample points + k-NN
-    // one warp per PAIR of sample rows, searched in lockstep (lane k < 8 ends up owning the k-th neighbour)
-    constexpr int NQ = 2;
-    for (int m0 = (tid >> 5) * NQ; m0 < TILE_M; m0 += (NT / 32) * NQ) {
-      const int lane = tid & 31;
-      float px[NQ], py[NQ], pz[NQ], z[NQ], r2f[NQ], rr[NQ];
-      double r2d[NQ];
-      bool rowvalid[NQ];
-      unsigned bD[NQ];
-      int bI[NQ];
+  const int lane = threadIdx.x & 31;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  for (int pair = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pair * NQ < P; pair += warps_total) {
+    const int m0 = pair * NQ;
+    float px[NQ], py[NQ], pz[NQ], z[NQ], r2f[NQ], rr[NQ];
+    double r2d[NQ];
+    bool rowvalid[NQ];
+    unsigned bD[NQ];
+    int bI[NQ];
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        const int m = m0 + q;
-        rowvalid[q] = m < nrows;
-        px[q] = py[q] = pz[q] = z[q] = r2f[q] = rr[q] = 0.f;
-        r2d[q] = 0.0;
-        if (rowvalid[q]) {
-          const int rl = m / S, s = m - rl * S, ray = r0 + rl;
-          const float g = a.gt_depth[ray];
-          if (g > 0.f) {   // Renderer.py:140-150
-            const float t = linspace_f32(0.f, 1.f, S, s);
-            const float zn = __fmul_rn(a.prm.near_end_surface, g), zf = __fmul_rn(a.prm.far_end_surface, g);
-            z[q] = __fadd_rn(__fmul_rn(zn, __fsub_rn(1.f, t)), __fmul_rn(zf, t));
-          } else {         // Renderer.py:162-163
-            const float far = a.far_zero ? a.far_zero[ray / a.far_group] : a.prm.near_end;
-            z[q] = linspace_f32(a.prm.near_end, far, S, s);
-          }
-          px[q] = __fadd_rn(a.rays_o[3 * ray + 0], __fmul_rn(a.rays_d[3 * ray + 0], z[q]));   // Renderer.py:167-168
-          py[q] = __fadd_rn(a.rays_o[3 * ray + 1], __fmul_rn(a.rays_d[3 * ray + 1], z[q]));
-          pz[q] = __fadd_rn(a.rays_o[3 * ray + 2], __fmul_rn(a.rays_d[3 * ray + 2], z[q]));
-          const double r = dynr ? a.r_query[ray] : a.prm.radius_query;
-          r2d[q] = r * r;
-          r2f[q] = (float)r2d[q];
-          rr[q] = (float)r * 1.00001f + 1e-7f;
+    for (int q = 0; q < NQ; ++q) {
+      const int m = m0 + q;
+      rowvalid[q] = m < P;
+      px[q] = py[q] = pz[q] = z[q] = r2f[q] = rr[q] = 0.f;
+      r2d[q] = 0.0;
+      if (rowvalid[q]) {
+        const int ray = m / S, s = m - ray * S;
+        const float g = a.gt_depth[ray];
+        if (g > 0.f) {   // Renderer.py:140-150
+          const float t = linspace_f32(0.f, 1.f, S, s);
+          const float zn = __fmul_rn(a.prm.near_end_surface, g), zf = __fmul_rn(a.prm.far_end_surface, g);
+          z[q] = __fadd_rn(__fmul_rn(zn, __fsub_rn(1.f, t)), __fmul_rn(zf, t));
+        } else {         // Renderer.py:162-163
+          const float far = a.far_zero ? a.far_zero[ray / a.far_group] : a.prm.near_end;
+          z[q] = linspace_f32(a.prm.near_end, far, S, s);
         }
-      }
-      knn_warp_multi<NQ>(gv, px, py, pz, rr, rowvalid, dynr, r2f, r2d, bD, bI);
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        const int m = m0 + q;
-        const bool vk = lane < KNN && bD[q] != KNN_INF;
-        const float Dk = __uint_as_float(bD[q]);
-        const bool strict = vk && (dynr ? ((double)Dk < r2d[q]) : (Dk < r2f[q]));   // neural_point.py:1701-1706
-        const int ns = __popc(__ballot_sync(0xffffffffu, strict));
-        const int cnt = __popc(__ballot_sync(0xffffffffu, vk));
-        const float wraw = vk ? 1.0f / (Dk + 1e-10f) : 0.f;                        // decoder.py:210,217-220
-        float wsum = 0.f;
-#pragma unroll
-        for (int k = 0; k < KNN; ++k) wsum += __shfl_sync(0xffffffffu, wraw, k);
-        const float wn = wraw / fmaxf(wsum, 1e-12f);
-        float wn_sum = 0.f;
-#pragma unroll
-        for (int k = 0; k < KNN; ++k) wn_sum += __shfl_sync(0xffffffffu, wn, k);
-        const int has = (rowvalid[q] && ns >= a.prm.min_nn_num) ? 1 : 0;           // decoder.py:204
-        if (lane < KNN) {
-          sIdx[m * KNN + lane] = vk ? bI[q] : -1;
-          sRem[m * KNN + lane] = (vk && a.remap != nullptr) ? __ldg(a.remap + bI[q]) : -1;
-          sW[m * KNN + lane] = wn;
-          if (save && rowvalid[q]) {
-            reinterpret_cast<int*>(a.saved + SL.idx)[(p0 + m) * KNN + lane] = vk ? bI[q] : -1;
-            a.saved[SL.w + (p0 + m) * KNN + lane] = wn;
-            a.saved[SL.D + (p0 + m) * KNN + lane] = vk ? Dk : FLT_MAX;
-          }
-        }
-        if (lane == 0) {
-          *reinterpret_cast<float4*>(sP + m * 4) = make_float4(px[q], py[q], pz[q], z[q]);
-          sHas[m] = has;
-          sWsum[m] = wn_sum;
-          if (save && rowvalid[q])
-            reinterpret_cast<float4*>(a.saved + SL.misc)[p0 + m] = make_float4(z[q], (float)has, wn_sum, (float)cnt);
-        }
+        px[q] = __fadd_rn(a.rays_o[3 * ray + 0], __fmul_rn(a.rays_d[3 * ray + 0], z[q]));   // Renderer.py:167-168
+        py[q] = __fadd_rn(a.rays_o[3 * ray + 1], __fmul_rn(a.rays_d[3 * ray + 1], z[q]));
+        pz[q] = __fadd_rn(a.rays_o[3 * ray + 2], __fmul_rn(a.rays_d[3 * ray + 2], z[q]));
+        const double r = dynr ? a.r_query[ray] : a.prm.radius_query;
+        r2d[q] = r * r;
+        r2f[q] = (float)r2d[q];
+        rr[q] = (float)r * 1.00001f + 1e-7f;
       }
     }
-    __syncthreads();
+    knn_warp_multi<NQ>(gv, px, py, pz, rr, rowvalid, dynr, r2f, r2d, bD, bI);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int m = m0 + q;
+      if (!rowvalid[q]) continue;   // warp-uniform
+      const bool vk = lane < KNN && bD[q] != KNN_INF;
+      const float Dk = __uint_as_float(bD[q]);
+      const bool strict = vk && (dynr ? ((double)Dk < r2d[q]) : (Dk < r2f[q]));   // neural_point.py:1701-1706
+      const int ns = __popc(__ballot_sync(0xffffffffu, strict));
+      const int cnt = __popc(__ballot_sync(0xffffffffu, vk));
+      const float wraw = vk ? 1.0f / (Dk + 1e-10f) : 0.f;                        // decoder.py:210,217-220
+      float wsum = 0.f;
+#pragma unroll
+      for (int k = 0; k < KNN; ++k) wsum += __shfl_sync(0xffffffffu, wraw, k);
+      const float wn = wraw / fmaxf(wsum, 1e-12f);
+      float wn_sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < KNN; ++k) wn_sum += __shfl_sync(0xffffffffu, wn, k);
+      const int has = (ns >= a.prm.min_nn_num) ? 1 : 0;                          // decoder.py:204
+      if (lane < KNN) {
+        a.ks.idx[(size_t)m * KNN + lane] = vk ? bI[q] : -1;
+        a.ks.rem[(size_t)m * KNN + lane] = (vk && a.remap != nullptr) ? __ldg(a.remap + bI[q]) : -1;
+        a.ks.w[(size_t)m * KNN + lane] = wn;
+        if (save) {
+          reinterpret_cast<int*>(a.saved + SL.idx)[(size_t)m * KNN + lane] = vk ? bI[q] : -1;
+          a.saved[SL.w + (size_t)m * KNN + lane] = wn;
+          a.saved[SL.D + (size_t)m * KNN + lane] = vk ? Dk : FLT_MAX;
+        }
+      }
+      if (lane == 0) {
+        a.ks.pos[m] = make_float4(px[q], py[q], pz[q], z[q]);
+        a.ks.hw[m] = make_float2((float)has, wn_sum);
+        if (save) reinterpret_cast<float4*>(a.saved + SL.misc)[m] = make_float4(z[q], (float)has, wn_sum, (float)cnt);
+      }
+    }
+  }
+}
 
-    LSR_PHASE(0, 0);   // knn
-    // ---------------------------------------------------------------- B: geometry feature (IDW gather)
-    for (int it = tid; it < TILE_M * 8; it += NT) {
-      const int m = it >> 3, q = it & 7;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (sHas[m]) {
-#pragma unroll
-        for (int k = 0; k < KNN; ++k) {
-          const int idx = sIdx[m * KNN + k];
-          if (idx >= 0) {
-            const float w = sW[m * KNN + k];
-            const float4 f = __ldg(reinterpret_cast<const float4*>(feat_row_cached(a.geo_feats, a.geo_leaf, idx, sRem[m * KNN + k])) + q);
-            acc.x = fmaf(w, f.x, acc.x); acc.y = fmaf(w, f.y, acc.y);
-            acc.z = fmaf(w, f.z, acc.z); acc.w = fmaf(w, f.w, acc.w);
-          }
-        }
-      }
-      *reinterpret_cast<float4*>(sC + m * CLD + q * 4) = acc;
-      if (save && m < nrows) reinterpret_cast<float4*>(a.saved + SL.cg)[(p0 + m) * 8 + q] = acc;
-    }
-    // ---------------------------------------------------------------- C: geometry Fourier features
-    for (int it = tid; it < TILE_M * EGP; it += NT) {
-      const int m = it / EGP, j = it - m * EGP;
-      float v = 0.f;
-      if (j < EG) {
-        const float t0 = TWO_PI_F * sP[m * 4 + 0], t1 = TWO_PI_F * sP[m * 4 + 1], t2 = TWO_PI_F * sP[m * 4 + 2];
-        const float arg = fmaf(t2, packed[Packed::gB + 2 * EGP + j],
-                               fmaf(t1, packed[Packed::gB + EGP + j], t0 * packed[Packed::gB + j]));
-        v = sinf(arg);
-      }
-      sX[m * XLD + j] = v;
-    }
-    LSR_PHASE(0, 1);   // gather + fourier
-    // geometry MLP: h = relu(W x + b) + U c + u  (decoder.py:275-283); epilogues work directly on the MMA
-    // accumulator fragments (rows g / g+8, column pairs 2t, 2t+1)
-    {
-      typedef FragTile<TILE_M, HG> FG;
-      FG f;
-#pragma unroll 1
-      for (int li = 0; li < 5; ++li) {
-        const float* A = (li == 0 || li == 3) ? sX : sX + EGP;
-        const int Kc = (li == 0) ? EGP : (li == 3 ? 128 : HG);
-        const int wt = li == 0 ? Packed::gW0t : li == 1 ? Packed::gW1t : li == 2 ? Packed::gW2t
-                     : li == 3 ? Packed::gW3t : Packed::gW4t;
-        f.zero();
-        if (li == 0) mma_core<TILE_M, HG, true, false>(f.c, A, XLD, Kc, packed + wt, HG, HG, sB, nrows);
-        else         mma_core<TILE_M, HG, true, false, true>(f.c, A, XLD, Kc, packed + wt, HG, HG, sB, nrows);
-        gemm_prefetch<HG>(packed + Packed::gUt + li * CDIM * HG, HG, CDIM, HG, sB);   // fc_c weights fly during the epilogue
-#pragma unroll
-        for (int j = 0; j < FG::NJ; ++j) {
-          const int col = FG::col(j);
-          const float2 b = *reinterpret_cast<const float2*>(blob + a.w.g_lin_b[li] + col);
-#pragma unroll
-          for (int i = 0; i < FG::MI; ++i)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int r = FG::row(i, h);
-              const float v0 = fmaxf(f.c[i][j][2 * h] + b.x, 0.f), v1 = fmaxf(f.c[i][j][2 * h + 1] + b.y, 0.f);
-              f.c[i][j][2 * h] = v0; f.c[i][j][2 * h + 1] = v1;
-              if (save && r < nrows)
-                *reinterpret_cast<float2*>(a.saved + SL.gs + ((size_t)li * Pp + p0 + r) * HG + col) = make_float2(v0, v1);
-            }
-        }
-        mma_core<TILE_M, HG, true, false, true>(f.c, sC, CLD, CDIM, packed + Packed::gUt + li * CDIM * HG, HG, HG, sB, nrows);
-        if (li < 4) {   // next layer's weights
-          const int kn = (li + 1 == 3) ? 128 : HG;
-          const int wn_ = li + 1 == 1 ? Packed::gW1t : li + 1 == 2 ? Packed::gW2t : li + 1 == 3 ? Packed::gW3t : Packed::gW4t;
-          gemm_prefetch<HG>(packed + wn_, HG, kn, HG, sB);
-        }
-#pragma unroll
-        for (int j = 0; j < FG::NJ; ++j) {
-          const int col = FG::col(j);
-          const float2 u = *reinterpret_cast<const float2*>(blob + a.w.g_fc_b[li] + col);
-#pragma unroll
-          for (int i = 0; i < FG::MI; ++i)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int r = FG::row(i, h);
-              const float2 hv = make_float2(f.c[i][j][2 * h] + u.x, f.c[i][j][2 * h + 1] + u.y);
-              *reinterpret_cast<float2*>(sX + r * XLD + EGP + col) = hv;
-              if (save && r < nrows)
-                *reinterpret_cast<float2*>(a.saved + SL.gh + ((size_t)li * Pp + p0 + r) * HG + col) = hv;
-            }
-        }
-      }
-      __syncthreads();
-      if (tid < TILE_M) {   // occupancy logit (decoder.py:284)
-        float o = blob[a.w.g_out_b];
-#pragma unroll 8
-        for (int k = 0; k < HG; ++k) o = fmaf(sX[tid * XLD + EGP + k], blob[a.w.g_out_w + k], o);
-        sOcc[tid] = o;
-        if (save && tid < nrows) a.saved[SL.occ + p0 + tid] = o;
-      }
-      __syncthreads();
-    }
+// ------------------------------------------------------------------------------------------------ kernel 2
+constexpr int FNS = 2;                                   // weight ring stages
+constexpr int FT = 320;                                  // threads: 8 compute warps + issuer warp + producer warp
+constexpr int NCT = 256;                                 // compute threads
+// dynamic shared memory carve-up (bytes from the 1024-aligned base)
+constexpr int SM_RING = 0;
+constexpr int SM_UNION = SM_RING + FNS * UM_STAGE_BYTES;
+constexpr int SM_EG_HI = SM_UNION;                       // geometry Fourier features, 96 k = 24 slabs
+constexpr int SM_EG_LO = SM_EG_HI + 24 * UM_A_SLAB;
+constexpr int SM_EC_HI = SM_UNION;                       // colour Fourier features, 40 k = 10 slabs   } alive after the
+constexpr int SM_EC_LO = SM_EC_HI + 10 * UM_A_SLAB;      //                                             } geometry MLP
+constexpr int SM_Q_HI = SM_EC_LO + 10 * UM_A_SLAB;       // rel-pos MLP input Q_k, 56 k = 14 slabs      }
+constexpr int SM_Q_LO = SM_Q_HI + 14 * UM_A_SLAB;
+constexpr int SM_C_HI = SM_UNION + 48 * UM_A_SLAB;       // interpolated feature c, 32 k = 8 slabs
+constexpr int SM_C_LO = SM_C_HI + 8 * UM_A_SLAB;
+constexpr int SM_IDX = SM_C_LO + 8 * UM_A_SLAB;          // [128][8] i32
+constexpr int SM_REM = SM_IDX + 128 * KNN * 4;
+constexpr int SM_W = SM_REM + 128 * KNN * 4;
+constexpr int SM_P = SM_W + 128 * KNN * 4;               // [128] float4 (px, py, pz, z)
+constexpr int SM_OCC = SM_P + 128 * 16;
+constexpr int SM_OCCP = SM_OCC + 128 * 4;                // [2][128] partial occupancy dot products
+constexpr int SM_WSUM = SM_OCCP + 2 * 128 * 4;
+constexpr int SM_HAS = SM_WSUM + 128 * 4;
+constexpr int SM_RGB = SM_HAS + 128 * 4;                 // [128][4]
+constexpr int SM_BIAS = SM_RGB + 128 * 16;               // bias table, see Bias
+constexpr int SM_PIPE = SM_BIAS + 1800 * 4;
+constexpr int FWD_SMEM_BYTES = SM_PIPE + 128;
+static_assert(SM_Q_LO + 14 * UM_A_SLAB <= SM_C_HI && SM_EG_LO + 24 * UM_A_SLAB <= SM_C_HI, "union region");
+static_assert(FWD_SMEM_BYTES <= 232448, "shared memory budget");
+static_assert(8 * 32 * 36 * 4 <= 20 * UM_A_SLAB && 8 * 32 * (36 + 20) * 4 <= 28 * UM_A_SLAB, "store staging fits the dead operand regions");
+struct Bias {   // float offsets inside the shared bias table
+  static constexpr int gb = 0, gu = 160, gow = 320, gob = 352;            // geometry: 5x32, 5x32, 32, 1
+  static constexpr int cb = 356, cu = cb + 640, v1b = cu + 640, v2b = v1b + 128, cob = v2b + 32;   // colour
+  static constexpr int total = cob + 4;
+};
+static_assert(Bias::total <= 1800, "bias table");
+// TMEM columns
+constexpr uint32_t TM_ACC0 = 0, TM_ACC1 = 128, TM_AHI = 256, TM_ALO = 384;
 
-    LSR_PHASE(0, 2);   // geometry MLP
-    if (color) {
-      // -------------------------------------------------------------- D: colour feature
-      if (relpos) {   // decoder.py:477-488
-        typedef FragTile<TILE_M, HC> FW;
-        FW uf, f;
-        uf.zero();
-        for (int m = tid; m < TILE_M; m += NT)
-          *reinterpret_cast<float4*>(sX + m * XLD + QD) = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-        for (int k = 0; k < KNN; ++k) {
-          gemm_prefetch<HC>(packed + Packed::V1t, HC, QDP, HC, sB);   // V1 chunk flies while Q_k is built
-          for (int it = tid; it < TILE_M * ER; it += NT) {
-            const int m = it / ER, j = it - m * ER;
+struct FwdArgs {
+  LsrParams prm;
+  const float* cloud;
+  const float* gt_depth;
+  int R;
+  const float *geo_feats, *col_feats;
+  const float *geo_leaf, *col_leaf;
+  LsrWeights w;
+  const float* packed;     // legacy packed scratch (geometry Fourier matrix)
+  const float* wpk;        // UMMA packed weights
+  const float* affine;
+  int stage;
+  float *depth, *var, *rgb;
+  uint8_t* valid;
+  float* saved;
+  KnnScratch ks;
+  int rays_per_tile, ntiles;
+  int n_ops;
+  UOp ops[UM_MAX_OPS];
+};
+
+#ifdef LSR_PHASE_TIMING
+#define FWD_PHASE(k)                                                                  \
+  do {                                                                                \
+    if (tid == 0) {                                                                   \
+      const long long _n = clock64();                                                 \
+      atomicAdd(&lsr_phase_cycles[0][k], (unsigned long long)(_n - _pt_last));        \
+      _pt_last = _n;                                                                  \
+    }                                                                                 \
+  } while (0)
+#else
+#define FWD_PHASE(k)
+#endif
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;\n" ::"n"(NCT) : "memory"); }
+
+// Saved-activation stores.  An epilogue thread owns ONE ROW (its TMEM lane), so a direct st.global of its
+// values touches 32 different 128-byte lines per warp instruction -- measured at ~2 cycles per line in the
+// LSU, that made the stores (not the MMAs) the bottleneck of the first version of this kernel.  Instead the
+// values go through a per-warp shared-memory staging block [32 rows][NC + 4] and leave as full row segments:
+// NC = 32 -> 8 lanes cover one 128-byte line, 4 lines per instruction.
+template <int LD>
+__device__ __forceinline__ void stage_put(float* stage, int lane, int col, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(stage + lane * LD + col) = make_float4(a, b, c, d);
+}
+// rows [0, nvalid) of the staged block -> g[row * pitch + 0 .. NC)
+template <int NC, int LD>
+__device__ __forceinline__ void stage_flush(const float* stage, int lane, float* g, size_t pitch, int nvalid) {
+  constexpr int LPR = NC / 4, RPI = 32 / LPR;
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < LPR; ++i) {
+    const int r = i * RPI + lane / LPR, c = (lane % LPR) * 4;
+    const float4 x = *reinterpret_cast<const float4*>(stage + r * LD + c);
+    if (r < nvalid) *reinterpret_cast<float4*>(g + (size_t)r * pitch + c) = x;
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant__ FwdArgs a) {
+  // NB: no pointer re-alignment through integer casts here -- it makes the compiler lose the shared address
+  // space and turns every LDS / STS below into a generic LD / ST (measured: 5x slower epilogues)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  UPipe<FNS>* pipe = reinterpret_cast<UPipe<FNS>*>(smem + SM_PIPE);
+  int* sIdx = reinterpret_cast<int*>(smem + SM_IDX);
+  int* sRem = reinterpret_cast<int*>(smem + SM_REM);
+  float* sW = reinterpret_cast<float*>(smem + SM_W);
+  float4* sP = reinterpret_cast<float4*>(smem + SM_P);
+  float* sOcc = reinterpret_cast<float*>(smem + SM_OCC);
+  float* sOccP = reinterpret_cast<float*>(smem + SM_OCCP);
+  float* sWsum = reinterpret_cast<float*>(smem + SM_WSUM);
+  int* sHas = reinterpret_cast<int*>(smem + SM_HAS);
+  float* sRgb = reinterpret_cast<float*>(smem + SM_RGB);
+  float* sBias = reinterpret_cast<float*>(smem + SM_BIAS);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = a.prm.n_surface;
+  const float* __restrict__ blob = a.w.blob;
+  const bool color = a.stage == LSR_STAGE_COLOR;
+  const bool relpos = color && (a.prm.flags & LSR_FLAG_REL_POS) != 0;
+  const bool save = a.saved != nullptr;
+  const SavedLayout SL = saved_layout(a.R, S, a.stage, a.prm.flags);
+  const size_t Pp = SL.Pp;
+
+  // one-time setup: bias table, TMEM, barriers
+  for (int i = tid; i < Bias::total; i += FT) {
+    float v = 0.f;
+    if (i < Bias::gu) v = blob[a.w.g_lin_b[i / 32] + i % 32];
+    else if (i < Bias::gow) v = blob[a.w.g_fc_b[(i - Bias::gu) / 32] + i % 32];
+    else if (i < Bias::gob) v = blob[a.w.g_out_w + (i - Bias::gow)];
+    else if (i == Bias::gob) v = blob[a.w.g_out_b];
+    else if (color && i >= Bias::cb && i < Bias::cu) v = blob[a.w.c_lin_b[(i - Bias::cb) / 128] + (i - Bias::cb) % 128];
+    else if (color && i >= Bias::cu && i < Bias::v1b) v = blob[a.w.c_fc_b[(i - Bias::cu) / 128] + (i - Bias::cu) % 128];
+    else if (relpos && i >= Bias::v1b && i < Bias::v2b) v = blob[a.w.c_nb1_b + (i - Bias::v1b)];
+    else if (relpos && i >= Bias::v2b && i < Bias::cob) v = blob[a.w.c_nb2_b + (i - Bias::v2b)];
+    else if (color && i >= Bias::cob && i < Bias::cob + 3) v = blob[a.w.c_out_b + (i - Bias::cob)];
+    sBias[i] = v;
+  }
+  if (warp == 8) tmem_alloc(&pipe->tmem_base, 512);
+  if (tid == 0) pipe_init<FNS>(pipe, NCT);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = pipe->tmem_base;
+
+  if (warp == 9) {
+    // ================================================================ producer: weight chunks -> ring
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x)
+        producer_tile<FNS>(a.ops, a.n_ops, a.wpk, smem + SM_RING, pipe, it);
+    }
+  } else if (warp == 8) {
+    // ================================================================ issuer: tcgen05.mma
+    uint32_t it = 0, a_par = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x)
+      issuer_tile<FNS>(a.ops, a.n_ops, smem_u32(smem), smem_u32(smem + SM_RING), pipe, tb, it, a_par);
+  } else {
+    // ================================================================ compute / epilogue warps
+    EpiSync es;
+    const int row = 32 * (warp & 3) + lane;       // sample row of the tile = TMEM lane
+    const int half = warp >> 2;                   // which half of the columns this warp handles
+    const uint32_t lane_base = 32u * (warp & 3);
+    const float4* sB4 = reinterpret_cast<const float4*>(sBias);
+
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+      const int r0 = tile * a.rays_per_tile;
+      const int nr = min(a.rays_per_tile, a.R - r0);
+      const int nrows = nr * S;
+      const size_t p0 = (size_t)r0 * S;
+      const bool rv = row < nrows;
+      const size_t prow = p0 + row;
+      const size_t pw0 = p0 + lane_base;                                   // first row of this warp's lane quadrant
+      const int wvalid = save ? min(max(nrows - (int)lane_base, 0), 32) : 0;   // rows of it that are saved
+      LSR_PHASE_BEGIN();
+
+      // ---------------------------------------------------------------- neighbour lists of the tile
+      for (int i = tid; i < 128 * KNN; i += NCT) {
+        const int m = i >> 3;
+        const bool ok = m < nrows;
+        sIdx[i] = ok ? a.ks.idx[p0 * KNN + i] : -1;
+        sRem[i] = ok ? a.ks.rem[p0 * KNN + i] : -1;
+        sW[i] = ok ? a.ks.w[p0 * KNN + i] : 0.f;
+      }
+      if (tid < 128) {
+        const bool ok = tid < nrows;
+        sP[tid] = ok ? a.ks.pos[p0 + tid] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float2 hw = ok ? a.ks.hw[p0 + tid] : make_float2(0.f, 0.f);
+        sHas[tid] = hw.x > 0.5f ? 1 : 0;
+        sWsum[tid] = hw.y;
+      }
+      bar_compute();
+      FWD_PHASE(0);
+
+      // ---------------------------------------------------------------- geometry feature (IDW gather) -> c
+      {
+        const int m = tid & 127, qg = tid >> 7;   // 2 threads per row, 4 float4 each
+        float4 acc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (sHas[m]) {
+#pragma unroll
+          for (int k = 0; k < KNN; ++k) {
             const int idx = sIdx[m * KNN + k];
-            float sn = 0.f, cs = 0.f;
             if (idx >= 0) {
-              const float t0 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 0), sP[m * 4 + 0]);
-              const float t1 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 1), sP[m * 4 + 1]);
-              const float t2 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 2), sP[m * 4 + 2]);
-              const float arg = fmaf(t2, blob[a.w.c_Brel + 2 * ER + j],
-                                     fmaf(t1, blob[a.w.c_Brel + ER + j], t0 * blob[a.w.c_Brel + j]));
-              sincosf(arg, &sn, &cs);
-            }
-            sX[m * XLD + j] = sn;
-            sX[m * XLD + ER + j] = cs;
-          }
-          for (int it = tid; it < TILE_M * 8; it += NT) {
-            const int m = it >> 3, q = it & 7;
-            const int idx = sIdx[m * KNN + k];
-            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (idx >= 0) f = __ldg(reinterpret_cast<const float4*>(feat_row_cached(a.col_feats, a.col_leaf, idx, sRem[m * KNN + k])) + q);
-            *reinterpret_cast<float4*>(sX + m * XLD + 2 * ER + q * 4) = f;
-          }
-          f.zero();
-          mma_core<TILE_M, HC, true, false, true>(f.c, sX, XLD, QDP, packed + Packed::V1t, HC, HC, sB, nrows);
+              const float w = sW[m * KNN + k];
+              const float4* fr = reinterpret_cast<const float4*>(feat_row_cached(a.geo_feats, a.geo_leaf, idx, sRem[m * KNN + k])) + qg * 4;
 #pragma unroll
-          for (int j = 0; j < FW::NJ; ++j) {
-            const int col = FW::col(j);
-            const float2 b = *reinterpret_cast<const float2*>(blob + a.w.c_nb1_b + col);
-#pragma unroll
-            for (int i = 0; i < FW::MI; ++i)
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const int r = FW::row(i, h);
-                const float wk = sW[r * KNN + k];
-                const float s0 = softplus100(f.c[i][j][2 * h] + b.x), s1 = softplus100(f.c[i][j][2 * h + 1] + b.y);
-                uf.c[i][j][2 * h] = fmaf(wk, s0, uf.c[i][j][2 * h]);
-                uf.c[i][j][2 * h + 1] = fmaf(wk, s1, uf.c[i][j][2 * h + 1]);
-                if (save && r < nrows)
-                  *reinterpret_cast<float2*>(a.saved + SL.sp + ((p0 + r) * KNN + k) * HC + col) = make_float2(s0, s1);
+              for (int i = 0; i < 4; ++i) {
+                const float4 f = __ldg(fr + i);
+                acc[i].x = fmaf(w, f.x, acc[i].x); acc[i].y = fmaf(w, f.y, acc[i].y);
+                acc[i].z = fmaf(w, f.z, acc[i].z); acc[i].w = fmaf(w, f.w, acc[i].w);
               }
+            }
           }
         }
-        gemm_prefetch<CDIM>(packed + Packed::V2t, CDIM, HC, CDIM, sB);
 #pragma unroll
-        for (int j = 0; j < FW::NJ; ++j) {
-          const int col = FW::col(j);
-#pragma unroll
-          for (int i = 0; i < FW::MI; ++i)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int r = FW::row(i, h);
-              const float2 u = make_float2(uf.c[i][j][2 * h], uf.c[i][j][2 * h + 1]);
-              *reinterpret_cast<float2*>(sX + r * XLD + col) = u;
-              if (save && r < nrows) *reinterpret_cast<float2*>(a.saved + SL.u + (p0 + r) * HC + col) = u;
-            }
+        for (int i = 0; i < 4; ++i) {
+          store_a_split(smem + SM_C_HI, smem + SM_C_LO, m, (qg * 4 + i) * 4, acc[i]);
+          if (save && m < nrows) reinterpret_cast<float4*>(a.saved + SL.cg)[(p0 + m) * 8 + qg * 4 + i] = acc[i];
         }
-        typedef FragTile<TILE_M, CDIM> FC;
-        FC c4;
-        c4.zero();
-        mma_core<TILE_M, CDIM, true, false, true>(c4.c, sX, XLD, HC, packed + Packed::V2t, CDIM, CDIM, sB, nrows);
+      }
+      // ---------------------------------------------------------------- geometry Fourier features -> e
+      for (int it = tid; it < 128 * (EGP / 4); it += NCT) {
+        const int m = it & 127, g = it >> 7;
+        const float4 p = sP[m];
+        const float t0 = TWO_PI_F * p.x, t1 = TWO_PI_F * p.y, t2 = TWO_PI_F * p.z;
+        float v[4];
 #pragma unroll
-        for (int j = 0; j < FC::NJ; ++j) {
-          const int col = FC::col(j);
-          const float2 v2 = *reinterpret_cast<const float2*>(blob + a.w.c_nb2_b + col);
-#pragma unroll
-          for (int i = 0; i < FC::MI; ++i)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int r = FC::row(i, h);
-              const float ws = sWsum[r];
-              float2 cc = make_float2(0.f, 0.f);
-              if (sHas[r]) cc = make_float2(fmaf(v2.x, ws, c4.c[i][j][2 * h]), fmaf(v2.y, ws, c4.c[i][j][2 * h + 1]));
-              *reinterpret_cast<float2*>(sC + r * CLD + col) = cc;
-              if (save && r < nrows) *reinterpret_cast<float2*>(a.saved + SL.cc + (p0 + r) * CDIM + col) = cc;
-            }
+        for (int t = 0; t < 4; ++t) {
+          const int j = g * 4 + t;
+          v[t] = 0.f;
+          if (j < EG) {
+            const float arg = fmaf(t2, __ldg(a.packed + Packed::gB + 2 * EGP + j),
+                                   fmaf(t1, __ldg(a.packed + Packed::gB + EGP + j), t0 * __ldg(a.packed + Packed::gB + j)));
+            v[t] = sinf(arg);
+          }
         }
-      } else {        // decoder.py:476,487-488
-        for (int it = tid; it < TILE_M * 8; it += NT) {
-          const int m = it >> 3, q = it & 7;
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        store_a_split(smem + SM_EG_HI, smem + SM_EG_LO, m, g * 4, make_float4(v[0], v[1], v[2], v[3]));
+      }
+      es.signal_a(pipe);
+      FWD_PHASE(1);
+
+      // ---------------------------------------------------------------- geometry MLP (decoder.py:275-284)
+      // h = relu(W x + b) + (U c + u); accumulators: W x in columns [0,32), U c in [32,64); this thread: 16 columns
+      {
+        float occ_part = 0.f;
+#pragma unroll 1
+        for (int li = 0; li < 5; ++li) {
+          es.wait_d(pipe, 0);
+          uint32_t x1[16], x2[16];
+          tmem_ld16(tmem_addr(tb, lane_base, TM_ACC0 + 16 * half), x1);
+          tmem_ld16(tmem_addr(tb, lane_base, TM_ACC0 + 32 + 16 * half), x2);
+          tmem_wait_ld();
+          float* gs = a.saved + SL.gs + ((size_t)li * Pp + prow) * HG + 16 * half;
+          float* gh = a.saved + SL.gh + ((size_t)li * Pp + prow) * HG + 16 * half;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 bb = sB4[(Bias::gb + li * 32 + 16 * half + j) >> 2];
+            const float4 uu = sB4[(Bias::gu + li * 32 + 16 * half + j) >> 2];
+            const float bv[4] = {bb.x, bb.y, bb.z, bb.w}, uv[4] = {uu.x, uu.y, uu.z, uu.w};
+            float s[4], h[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              s[t] = fmaxf(__uint_as_float(x1[j + t]) + bv[t], 0.f);
+              h[t] = s[t] + (__uint_as_float(x2[j + t]) + uv[t]);
+              split_hi_lo(h[t], x1[j + t], x2[j + t]);
+            }
+            if (save && rv) {
+              *reinterpret_cast<float4*>(gs + j) = make_float4(s[0], s[1], s[2], s[3]);
+              *reinterpret_cast<float4*>(gh + j) = make_float4(h[0], h[1], h[2], h[3]);
+            }
+            if (li == 4) {
+              const float4 ow = sB4[(Bias::gow + 16 * half + j) >> 2];
+              occ_part = fmaf(h[0], ow.x, occ_part); occ_part = fmaf(h[1], ow.y, occ_part);
+              occ_part = fmaf(h[2], ow.z, occ_part); occ_part = fmaf(h[3], ow.w, occ_part);
+            }
+          }
+          if (li < 4) {
+            tmem_st16(tmem_addr(tb, lane_base, TM_AHI + 16 * half), x1);
+            tmem_st16(tmem_addr(tb, lane_base, TM_ALO + 16 * half), x2);
+            es.signal_a(pipe);
+          }
+        }
+        sOccP[half * 128 + row] = occ_part;
+        bar_compute();
+        if (tid < 128) {   // occupancy logit (decoder.py:284)
+          const float o = (sBias[Bias::gob] + sOccP[tid]) + sOccP[128 + tid];
+          sOcc[tid] = o;
+          if (save && tid < nrows) a.saved[SL.occ + p0 + tid] = o;
+        }
+      }
+
+      FWD_PHASE(2);
+      if (color) {
+        // -------------------------------------------------------------- colour feature
+        if (relpos) {   // decoder.py:477-488: c = V2 . sum_k w_k softplus(V1 q_k + v1) + v2 * sum_k w_k
+          // zero the K padding (columns 52..55) of Q once per tile
+          if (tid < 128) store_a_split(smem + SM_Q_HI, smem + SM_Q_LO, tid, QD, make_float4(0.f, 0.f, 0.f, 0.f));
+          auto build_q = [&](int k) {
+            // relative-position Fourier features: q[0..9] = sin, q[10..19] = cos
+            for (int it = tid; it < 128 * ER; it += NCT) {
+              const int m = it & 127, j = it >> 7;
+              const int idx = sIdx[m * KNN + k];
+              float sn = 0.f, cs = 0.f;
+              if (idx >= 0) {
+                const float4 p = sP[m];
+                const float t0 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 0), p.x);
+                const float t1 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 1), p.y);
+                const float t2 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 2), p.z);
+                const float arg = fmaf(t2, __ldg(blob + a.w.c_Brel + 2 * ER + j),
+                                       fmaf(t1, __ldg(blob + a.w.c_Brel + ER + j), t0 * __ldg(blob + a.w.c_Brel + j)));
+                sincosf(arg, &sn, &cs);
+              }
+              store_a_split1(smem + SM_Q_HI, smem + SM_Q_LO, m, j, sn);
+              store_a_split1(smem + SM_Q_HI, smem + SM_Q_LO, m, ER + j, cs);
+            }
+            // neighbour feature row: q[20..51]
+            {
+              const int m = tid & 127, qg = tid >> 7;
+              const int idx = sIdx[m * KNN + k];
+              float4 f[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) f[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (idx >= 0) {
+                const float4* fr = reinterpret_cast<const float4*>(feat_row_cached(a.col_feats, a.col_leaf, idx, sRem[m * KNN + k])) + qg * 4;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) f[i] = __ldg(fr + i);
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) store_a_split(smem + SM_Q_HI, smem + SM_Q_LO, m, 2 * ER + (qg * 4 + i) * 4, f[i]);
+            }
+          };
+          float uf[64];
+#pragma unroll
+          for (int i = 0; i < 64; ++i) uf[i] = 0.f;
+          build_q(0);
+          es.signal_a(pipe);
+#pragma unroll 1
+          for (int k = 0; k < KNN; ++k) {
+            es.wait_d(pipe, k & 1);               // GEMM k done: Q is free, accumulator (k & 1) is ready
+            if (k + 1 < KNN) { build_q(k + 1); es.signal_a(pipe); }   // GEMM k+1 runs under this epilogue
+            const uint32_t accb = (k & 1) ? TM_ACC1 : TM_ACC0;
+            const float wk = sW[row * KNN + k];
+            float* sp = a.saved + SL.sp + (pw0 * KNN + k) * HC + 64 * half;
+            float* st = reinterpret_cast<float*>(smem + SM_EC_HI) + warp * (32 * 36);   // e' is built after this phase
+            uint32_t x[2][16];
+            tmem_ld16(tmem_addr(tb, lane_base, accb + 64 * half), x[0]);
+            tmem_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if (c < 3) tmem_ld16(tmem_addr(tb, lane_base, accb + 64 * half + 16 * (c + 1)), x[(c + 1) & 1]);
+              uint32_t (&xc)[16] = x[c & 1];
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 bb = sB4[(Bias::v1b + 64 * half + 16 * c + j) >> 2];
+                const float s0 = softplus100(__uint_as_float(xc[j + 0]) + bb.x), s1 = softplus100(__uint_as_float(xc[j + 1]) + bb.y);
+                const float s2 = softplus100(__uint_as_float(xc[j + 2]) + bb.z), s3 = softplus100(__uint_as_float(xc[j + 3]) + bb.w);
+                uf[16 * c + j + 0] = fmaf(wk, s0, uf[16 * c + j + 0]); uf[16 * c + j + 1] = fmaf(wk, s1, uf[16 * c + j + 1]);
+                uf[16 * c + j + 2] = fmaf(wk, s2, uf[16 * c + j + 2]); uf[16 * c + j + 3] = fmaf(wk, s3, uf[16 * c + j + 3]);
+                stage_put<36>(st, lane, 16 * (c & 1) + j, s0, s1, s2, s3);
+              }
+              if (c & 1) stage_flush<32, 36>(st, lane, sp + 16 * (c - 1), (size_t)KNN * HC, wvalid);
+              if (c < 3) tmem_wait_ld();
+            }
+          }
+          // u -> TMEM A operand of the V2 GEMM
+          {
+            float* ug = a.saved + SL.u + pw0 * HC + 64 * half;
+            float* st = reinterpret_cast<float*>(smem + SM_EC_HI) + warp * (32 * 36);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t hi[16], lo[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) split_hi_lo(uf[16 * c + j], hi[j], lo[j]);
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                stage_put<36>(st, lane, 16 * (c & 1) + j, uf[16 * c + j], uf[16 * c + j + 1], uf[16 * c + j + 2], uf[16 * c + j + 3]);
+              if (c & 1) stage_flush<32, 36>(st, lane, ug + 16 * (c - 1), (size_t)HC, wvalid);
+              tmem_st16(tmem_addr(tb, lane_base, TM_AHI + 64 * half + 16 * c), hi);
+              tmem_st16(tmem_addr(tb, lane_base, TM_ALO + 64 * half + 16 * c), lo);
+            }
+          }
+          es.signal_a(pipe);
+          es.wait_d(pipe, 0);
+          {
+            uint32_t x[16];
+            tmem_ld16(tmem_addr(tb, lane_base, TM_ACC0 + 16 * half), x);
+            tmem_wait_ld();
+            const float ws = sWsum[row];
+            const bool has = sHas[row] != 0;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 v2 = sB4[(Bias::v2b + 16 * half + j) >> 2];
+              float4 cc = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (has) cc = make_float4(fmaf(v2.x, ws, __uint_as_float(x[j])), fmaf(v2.y, ws, __uint_as_float(x[j + 1])),
+                                        fmaf(v2.z, ws, __uint_as_float(x[j + 2])), fmaf(v2.w, ws, __uint_as_float(x[j + 3])));
+              store_a_split(smem + SM_C_HI, smem + SM_C_LO, row, 16 * half + j, cc);
+              if (save && rv) *reinterpret_cast<float4*>(a.saved + SL.cc + prow * CDIM + 16 * half + j) = cc;
+            }
+          }
+        } else {        // decoder.py:476,487-488: plain IDW interpolation of the colour features
+          const int m = tid & 127, qg = tid >> 7;
+          float4 acc[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (sHas[m]) {
 #pragma unroll
             for (int k = 0; k < KNN; ++k) {
               const int idx = sIdx[m * KNN + k];
               if (idx >= 0) {
                 const float w = sW[m * KNN + k];
-                const float4 f = __ldg(reinterpret_cast<const float4*>(feat_row_cached(a.col_feats, a.col_leaf, idx, sRem[m * KNN + k])) + q);
-                acc.x = fmaf(w, f.x, acc.x); acc.y = fmaf(w, f.y, acc.y);
-                acc.z = fmaf(w, f.z, acc.z); acc.w = fmaf(w, f.w, acc.w);
+                const float4* fr = reinterpret_cast<const float4*>(feat_row_cached(a.col_feats, a.col_leaf, idx, sRem[m * KNN + k])) + qg * 4;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float4 f = __ldg(fr + i);
+                  acc[i].x = fmaf(w, f.x, acc[i].x); acc[i].y = fmaf(w, f.y, acc[i].y);
+                  acc[i].z = fmaf(w, f.z, acc[i].z); acc[i].w = fmaf(w, f.w, acc[i].w);
+                }
               }
             }
           }
-          *reinterpret_cast<float4*>(sC + m * CLD + q * 4) = acc;
-          if (save && m < nrows) reinterpret_cast<float4*>(a.saved + SL.cc)[(p0 + m) * 8 + q] = acc;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            store_a_split(smem + SM_C_HI, smem + SM_C_LO, m, (qg * 4 + i) * 4, acc[i]);
+            if (save && m < nrows) reinterpret_cast<float4*>(a.saved + SL.cc)[(p0 + m) * 8 + qg * 4 + i] = acc[i];
+          }
         }
-      }
-      __syncthreads();
-      LSR_PHASE(0, 3);   // rel-pos neighbour MLP / colour gather
-      // -------------------------------------------------------------- E: colour trunk (decoder.py:515-533)
-      for (int it = tid; it < TILE_M * EC; it += NT) {
-        const int m = it / EC, j = it - m * EC;
-        const float t0 = TWO_PI_F * sP[m * 4 + 0], t1 = TWO_PI_F * sP[m * 4 + 1], t2 = TWO_PI_F * sP[m * 4 + 2];
-        const float arg = fmaf(t2, blob[a.w.c_B + 2 * EC + j], fmaf(t1, blob[a.w.c_B + EC + j], t0 * blob[a.w.c_B + j]));
-        float sn, cs;
-        sincosf(arg, &sn, &cs);
-        sX[m * XLD + j] = sn;
-        sX[m * XLD + EC + j] = cs;
-      }
-      {
-        typedef FragTile<TILE_M, HC> FW;
-        FW f;
+        FWD_PHASE(3);
+        // -------------------------------------------------------------- colour Fourier features e' = [sin | cos]
+        for (int it = tid; it < 128 * (EC / 4); it += NCT) {
+          const int m = it & 127, g = it >> 7;
+          const float4 p = sP[m];
+          const float t0 = TWO_PI_F * p.x, t1 = TWO_PI_F * p.y, t2 = TWO_PI_F * p.z;
+          float sn[4], cs[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int j = g * 4 + t;
+            const float arg = fmaf(t2, __ldg(blob + a.w.c_B + 2 * EC + j), fmaf(t1, __ldg(blob + a.w.c_B + EC + j), t0 * __ldg(blob + a.w.c_B + j)));
+            sincosf(arg, &sn[t], &cs[t]);
+          }
+          store_a_split(smem + SM_EC_HI, smem + SM_EC_LO, m, g * 4, make_float4(sn[0], sn[1], sn[2], sn[3]));
+          store_a_split(smem + SM_EC_HI, smem + SM_EC_LO, m, EC + g * 4, make_float4(cs[0], cs[1], cs[2], cs[3]));
+        }
+        es.signal_a(pipe);
+
+        // -------------------------------------------------------------- colour trunk (decoder.py:515-533)
+        // h = softplus(W x + b) + (U c + u); W x in ACC0, U c in ACC1; this thread: 64 columns in 4 steps of 16
 #pragma unroll 1
         for (int li = 0; li < 5; ++li) {
-          const float* A = (li == 0 || li == 3) ? sX : sX + ECC;
-          const int Kc = (li == 0) ? ECC : (li == 3 ? ECC + HC : HC);
-          const int wt = li == 0 ? Packed::cW0t : li == 1 ? Packed::cW1t : li == 2 ? Packed::cW2t
-                       : li == 3 ? Packed::cW3t : Packed::cW4t;
-          f.zero();
-          if (li == 0) mma_core<TILE_M, HC, true, false>(f.c, A, XLD, Kc, packed + wt, HC, HC, sB, nrows);
-          else         mma_core<TILE_M, HC, true, false, true>(f.c, A, XLD, Kc, packed + wt, HC, HC, sB, nrows);
-          gemm_prefetch<HC>(packed + Packed::cUt + li * CDIM * HC, HC, CDIM, HC, sB);   // fc_c weights fly during the epilogue
+          es.wait_d(pipe, 0);
+          float* cs_ = a.saved + SL.cs + ((size_t)li * Pp + pw0) * HC + 64 * half;
+          float* ch_ = a.saved + SL.ch + ((size_t)li * Pp + pw0) * HC + 64 * half;
+          float* stS = reinterpret_cast<float*>(smem + SM_Q_HI) + warp * (32 * 36);            // Q is dead by now
+          float* stH = reinterpret_cast<float*>(smem + SM_Q_HI + 8 * 32 * 36 * 4) + warp * (32 * 20);
+          uint32_t v1[2][16], v2[2][16];
+          tmem_ld16(tmem_addr(tb, lane_base, TM_ACC0 + 64 * half), v1[0]);
+          tmem_ld16(tmem_addr(tb, lane_base, TM_ACC1 + 64 * half), v2[0]);
+          tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < FW::NJ; ++j) {
-            const int col = FW::col(j);
-            const float2 b = *reinterpret_cast<const float2*>(blob + a.w.c_lin_b[li] + col);
+          for (int c = 0; c < 4; ++c) {
+            const int col0 = 64 * half + 16 * c;
+            if (c < 3) {   // the next 16 columns fly while these are processed
+              tmem_ld16(tmem_addr(tb, lane_base, TM_ACC0 + col0 + 16), v1[(c + 1) & 1]);
+              tmem_ld16(tmem_addr(tb, lane_base, TM_ACC1 + col0 + 16), v2[(c + 1) & 1]);
+            }
+            uint32_t (&x1)[16] = v1[c & 1];
+            uint32_t (&x2)[16] = v2[c & 1];
 #pragma unroll
-            for (int i = 0; i < FW::MI; ++i)
+            for (int j = 0; j < 16; j += 4) {
+              const float4 bb = sB4[(Bias::cb + li * HC + col0 + j) >> 2], uu = sB4[(Bias::cu + li * HC + col0 + j) >> 2];
+              const float bv[4] = {bb.x, bb.y, bb.z, bb.w}, uv[4] = {uu.x, uu.y, uu.z, uu.w};
+              float s[4], h[4];
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const int r = FW::row(i, h);
-                const float s0 = softplus100(f.c[i][j][2 * h] + b.x), s1 = softplus100(f.c[i][j][2 * h + 1] + b.y);
-                f.c[i][j][2 * h] = s0; f.c[i][j][2 * h + 1] = s1;
-                if (save && r < nrows)
-                  *reinterpret_cast<float2*>(a.saved + SL.cs + ((size_t)li * Pp + p0 + r) * HC + col) = make_float2(s0, s1);
+              for (int t = 0; t < 4; ++t) {
+                s[t] = softplus100(__uint_as_float(x1[j + t]) + bv[t]);
+                h[t] = s[t] + (__uint_as_float(x2[j + t]) + uv[t]);
+                split_hi_lo(h[t], x1[j + t], x2[j + t]);
               }
+              stage_put<36>(stS, lane, 16 * (c & 1) + j, s[0], s[1], s[2], s[3]);
+              stage_put<20>(stH, lane, j, h[0], h[1], h[2], h[3]);
+            }
+            tmem_st16(tmem_addr(tb, lane_base, TM_AHI + col0), x1);
+            tmem_st16(tmem_addr(tb, lane_base, TM_ALO + col0), x2);
+            stage_flush<16, 20>(stH, lane, ch_ + 16 * c, (size_t)HC, wvalid);
+            if (c & 1) stage_flush<32, 36>(stS, lane, cs_ + 16 * (c - 1), (size_t)HC, wvalid);
+            if (c < 3) tmem_wait_ld();
           }
-          mma_core<TILE_M, HC, true, false, true>(f.c, sC, CLD, CDIM, packed + Packed::cUt + li * CDIM * HC, HC, HC, sB, nrows);
-          if (li < 4) {   // next layer's weights
-            const int kn = (li + 1 == 3) ? ECC + HC : HC;
-            const int wn_ = li + 1 == 1 ? Packed::cW1t : li + 1 == 2 ? Packed::cW2t : li + 1 == 3 ? Packed::cW3t : Packed::cW4t;
-            gemm_prefetch<HC>(packed + wn_, HC, kn, HC, sB);
+          es.signal_a(pipe);   // li == 4: feeds the colour head GEMM
+        }
+        FWD_PHASE(4);
+        // -------------------------------------------------------------- colour head (decoder.py:533-546)
+        es.wait_d(pipe, 0);
+        if (half == 0) {
+          uint32_t x[16];
+          tmem_ld16(tmem_addr(tb, lane_base, TM_ACC0), x);
+          tmem_wait_ld();
+          const float o0 = __uint_as_float(x[0]) + sBias[Bias::cob + 0], o1 = __uint_as_float(x[1]) + sBias[Bias::cob + 1],
+                      o2 = __uint_as_float(x[2]) + sBias[Bias::cob + 2];
+          float r0c = o0, r1c = o1, r2c = o2;
+          if (a.prm.rgb_mode == LSR_RGB_SIGMOID) {
+            r0c = sigmoidf_acc(o0); r1c = sigmoidf_acc(o1); r2c = sigmoidf_acc(o2);
+          } else if (a.prm.rgb_mode == LSR_RGB_AFFINE_SIGMOID) {   // out @ A + t  (decoder.py:538-540)
+            const float* Af = a.affine;
+            r0c = sigmoidf_acc(fmaf(o2, Af[6], fmaf(o1, Af[3], o0 * Af[0])) + Af[9]);
+            r1c = sigmoidf_acc(fmaf(o2, Af[7], fmaf(o1, Af[4], o0 * Af[1])) + Af[10]);
+            r2c = sigmoidf_acc(fmaf(o2, Af[8], fmaf(o1, Af[5], o0 * Af[2])) + Af[11]);
           }
-#pragma unroll
-          for (int j = 0; j < FW::NJ; ++j) {
-            const int col = FW::col(j);
-            const float2 u = *reinterpret_cast<const float2*>(blob + a.w.c_fc_b[li] + col);
-#pragma unroll
-            for (int i = 0; i < FW::MI; ++i)
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const int r = FW::row(i, h);
-                const float2 hv = make_float2(f.c[i][j][2 * h] + u.x, f.c[i][j][2 * h + 1] + u.y);
-                *reinterpret_cast<float2*>(sX + r * XLD + ECC + col) = hv;
-                if (save && r < nrows)
-                  *reinterpret_cast<float2*>(a.saved + SL.ch + ((size_t)li * Pp + p0 + r) * HC + col) = hv;
-              }
+          sRgb[row * 4 + 0] = r0c; sRgb[row * 4 + 1] = r1c; sRgb[row * 4 + 2] = r2c;
+          if (save && rv) {
+            reinterpret_cast<float4*>(a.saved + SL.rgbs)[prow] = make_float4(r0c, r1c, r2c, 0.f);
+            reinterpret_cast<float4*>(a.saved + SL.outraw)[prow] = make_float4(o0, o1, o2, 0.f);
           }
         }
+      } else {
+        if (tid < 128) { sRgb[tid * 4 + 0] = 0.f; sRgb[tid * 4 + 1] = 0.f; sRgb[tid * 4 + 2] = 0.f; }
       }
-      __syncthreads();
-      LSR_PHASE(0, 4);   // colour trunk
-      // colour head (decoder.py:533-546)
-      for (int it = tid; it < TILE_M * 3; it += NT) {
-        const int m = it % TILE_M, ch = it / TILE_M;
-        float o = blob[a.w.c_out_b + ch];
-        const float* wrow = blob + a.w.c_out_w + ch * HC;
-        const float* hrow = sX + m * XLD + ECC;
-#pragma unroll 8
-        for (int k = 0; k < HC; ++k) o = fmaf(hrow[k], wrow[k], o);
-        sRgb[m * 4 + ch] = o;
-      }
-      __syncthreads();
-      if (tid < TILE_M) {
-        const float o0 = sRgb[tid * 4 + 0], o1 = sRgb[tid * 4 + 1], o2 = sRgb[tid * 4 + 2];
-        float r0c = o0, r1c = o1, r2c = o2;
-        if (a.prm.rgb_mode == LSR_RGB_SIGMOID) {
-          r0c = sigmoidf_acc(o0); r1c = sigmoidf_acc(o1); r2c = sigmoidf_acc(o2);
-        } else if (a.prm.rgb_mode == LSR_RGB_AFFINE_SIGMOID) {   // out @ A + t  (decoder.py:538-540)
-          const float* Af = a.affine;
-          r0c = sigmoidf_acc(fmaf(o2, Af[6], fmaf(o1, Af[3], o0 * Af[0])) + Af[9]);
-          r1c = sigmoidf_acc(fmaf(o2, Af[7], fmaf(o1, Af[4], o0 * Af[1])) + Af[10]);
-          r2c = sigmoidf_acc(fmaf(o2, Af[8], fmaf(o1, Af[5], o0 * Af[2])) + Af[11]);
-        }
-        sRgb[tid * 4 + 0] = r0c; sRgb[tid * 4 + 1] = r1c; sRgb[tid * 4 + 2] = r2c;
-        if (save && tid < nrows) {
-          reinterpret_cast<float4*>(a.saved + SL.rgbs)[p0 + tid] = make_float4(r0c, r1c, r2c, 0.f);
-          reinterpret_cast<float4*>(a.saved + SL.outraw)[p0 + tid] = make_float4(o0, o1, o2, 0.f);
-        }
-      }
-      __syncthreads();
-    } else {
-      if (tid < TILE_M) { sRgb[tid * 4 + 0] = 0.f; sRgb[tid * 4 + 1] = 0.f; sRgb[tid * 4 + 2] = 0.f; }
-      __syncthreads();
-    }
+      tc_fence_before();
+      bar_compute();
+      FWD_PHASE(5);
 
-    LSR_PHASE(0, 5);   // colour head
-    // ---------------------------------------------------------------- F: compositing (common.py:402-422)
-    if (tid < nr) {
-      const int ray = r0 + tid;
-      const float g = a.gt_depth[ray];
-      const float coef = a.prm.sigmoid_coef;
-      float T = 1.f, sw = 0.f, swz = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
-      float wv[8], zv[8];
-      int nhas = 0;
-      for (int s = 0; s < S; ++s) {
-        const int m = tid * S + s;
-        const int has = sHas[m];
-        nhas += has;
-        const float occ = has ? sOcc[m] : -100.f;            // Renderer.py:184-186
-        const float alpha = sigmoidf_acc(coef * occ);
-        const float w = alpha * T;
-        T = T * ((1.f - alpha) + 1e-10f);
-        const float z = sP[m * 4 + 3];
-        wv[s] = w; zv[s] = z;
-        sw += w;
-        swz += w * z;
-        c0 += w * sRgb[m * 4 + 0]; c1 += w * sRgb[m * 4 + 1]; c2 += w * sRgb[m * 4 + 2];
+      // ---------------------------------------------------------------- compositing (common.py:402-422)
+      if (tid < nr) {
+        const int ray = r0 + tid;
+        const float g = a.gt_depth[ray];
+        const float coef = a.prm.sigmoid_coef;
+        float T = 1.f, sw = 0.f, swz = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        float wv[8], zv[8];
+        int nhas = 0;
+        for (int s = 0; s < S; ++s) {
+          const int m = tid * S + s;
+          const int has = sHas[m];
+          nhas += has;
+          const float occ = has ? sOcc[m] : -100.f;            // Renderer.py:184-186
+          const float alpha = sigmoidf_acc(coef * occ);
+          const float w = alpha * T;
+          T = T * ((1.f - alpha) + 1e-10f);
+          const float z = sP[m].w;
+          wv[s] = w; zv[s] = z;
+          sw += w;
+          swz += w * z;
+          c0 += w * sRgb[m * 4 + 0]; c1 += w * sRgb[m * 4 + 1]; c2 += w * sRgb[m * 4 + 2];
+        }
+        const float wsum = sw + 1e-10f;
+        float depth = swz / wsum;
+        float var = 0.f;
+        for (int s = 0; s < S; ++s) { const float t = zv[s] - depth; var += (wv[s] * t) * t; }
+        float o0 = c0 / wsum, o1 = c1 / wsum, o2 = c2 / wsum;
+        if (!(g > 0.f)) {                                      // Renderer.py:197-200
+          depth = 0.f;
+          if (a.prm.flags & LSR_FLAG_SKIP_ZERO_DEPTH) { o0 = 0.f; o1 = 0.f; o2 = 0.f; }
+        }
+        a.depth[ray] = depth;
+        a.var[ray] = var;
+        a.rgb[3 * ray + 0] = o0; a.rgb[3 * ray + 1] = o1; a.rgb[3 * ray + 2] = o2;
+        a.valid[ray] = (nhas >= S / 2 + 1) ? 1 : 0;            // decoder.py:259-260
       }
-      const float wsum = sw + 1e-10f;
-      float depth = swz / wsum;
-      float var = 0.f;
-      for (int s = 0; s < S; ++s) { const float t = zv[s] - depth; var += (wv[s] * t) * t; }
-      float o0 = c0 / wsum, o1 = c1 / wsum, o2 = c2 / wsum;
-      if (!(g > 0.f)) {                                      // Renderer.py:197-200
-        depth = 0.f;
-        if (a.prm.flags & LSR_FLAG_SKIP_ZERO_DEPTH) { o0 = 0.f; o1 = 0.f; o2 = 0.f; }
-      }
-      a.depth[ray] = depth;
-      a.var[ray] = var;
-      a.rgb[3 * ray + 0] = o0; a.rgb[3 * ray + 1] = o1; a.rgb[3 * ray + 2] = o2;
-      a.valid[ray] = (nhas >= S / 2 + 1) ? 1 : 0;            // decoder.py:259-260
+      bar_compute();
+      FWD_PHASE(6);
     }
-    __syncthreads();
-    LSR_PHASE(0, 6);   // compositing
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tb, 512);
+}
+
+// The GEMM program of one tile (must mirror the order of the epilogue code above) + the weight re-layout jobs.
+static void build_program(const LsrWeights* w, int stage, int flags, UProgram* P) {
+  UBuilder B(P);
+  const bool color = stage == LSR_STAGE_COLOR;
+  const bool relpos = color && (flags & LSR_FLAG_REL_POS);
+  // ---- geometry (hidden 32): accumulators W x -> columns [0,32), U c -> [32,64)
+  const int gW0 = B.weights(w->g_lin_w[0], EG, 0, EG, HG, HG);
+  const int gW1 = B.weights(w->g_lin_w[1], HG, 0, HG, HG, HG);
+  const int gW2 = B.weights(w->g_lin_w[2], HG, 0, HG, HG, HG);
+  const int gW3e = B.weights(w->g_lin_w[3], EG + HG, 0, EG, HG, HG);
+  const int gW3h = B.weights(w->g_lin_w[3], EG + HG, EG, HG, HG, HG);
+  const int gW4 = B.weights(w->g_lin_w[4], HG, 0, HG, HG, HG);
+  int gU[5];
+  for (int i = 0; i < 5; ++i) gU[i] = B.weights(w->g_fc_w[i], CDIM, 0, CDIM, HG, HG);
+  for (int li = 0; li < 5; ++li) {
+    if (li == 0) B.gemm(gW0, false, SM_EG_HI, SM_EG_LO, TM_ACC0, true, true, 0);
+    else if (li == 3) {
+      B.gemm(gW3e, false, SM_EG_HI, SM_EG_LO, TM_ACC0, true, true, 0);
+      B.gemm(gW3h, true, TM_AHI, TM_ALO, TM_ACC0, false, false, 0);
+    } else B.gemm(li == 1 ? gW1 : li == 2 ? gW2 : gW4, true, TM_AHI, TM_ALO, TM_ACC0, true, true, 0);
+    B.gemm(gU[li], false, SM_C_HI, SM_C_LO, TM_ACC0 + 32, true, false, 1);
+  }
+  if (!color) return;
+  if (relpos) {
+    const int V1 = B.weights(w->c_nb1_w, QD, 0, QD, HC, HC);
+    const int V2 = B.weights(w->c_nb2_w, HC, 0, HC, CDIM, CDIM);
+    for (int k = 0; k < KNN; ++k) B.gemm(V1, false, SM_Q_HI, SM_Q_LO, (k & 1) ? TM_ACC1 : TM_ACC0, true, true, 1 + (k & 1));
+    B.gemm(V2, true, TM_AHI, TM_ALO, TM_ACC0, true, true, 1);
+  }
+  const int cW0 = B.weights(w->c_lin_w[0], ECC, 0, ECC, HC, HC);
+  const int cW1 = B.weights(w->c_lin_w[1], HC, 0, HC, HC, HC);
+  const int cW2 = B.weights(w->c_lin_w[2], HC, 0, HC, HC, HC);
+  const int cW3e = B.weights(w->c_lin_w[3], ECC + HC, 0, ECC, HC, HC);
+  const int cW3h = B.weights(w->c_lin_w[3], ECC + HC, ECC, HC, HC, HC);
+  const int cW4 = B.weights(w->c_lin_w[4], HC, 0, HC, HC, HC);
+  int cU[5];
+  for (int i = 0; i < 5; ++i) cU[i] = B.weights(w->c_fc_w[i], CDIM, 0, CDIM, HC, HC);
+  const int cOut = B.weights(w->c_out_w, HC, 0, HC, 16, 3);
+  for (int li = 0; li < 5; ++li) {
+    if (li == 0) B.gemm(cW0, false, SM_EC_HI, SM_EC_LO, TM_ACC0, true, true, 0);
+    else if (li == 3) {
+      B.gemm(cW3e, false, SM_EC_HI, SM_EC_LO, TM_ACC0, true, true, 0);
+      B.gemm(cW3h, true, TM_AHI, TM_ALO, TM_ACC0, false, false, 0);
+    } else B.gemm(li == 1 ? cW1 : li == 2 ? cW2 : cW4, true, TM_AHI, TM_ALO, TM_ACC0, true, true, 0);
+    B.gemm(cU[li], false, SM_C_HI, SM_C_LO, TM_ACC1, true, false, 1);
+  }
+  B.gemm(cOut, true, TM_AHI, TM_ALO, TM_ACC0, true, true, 1);
+}
+
+struct UPackJobs { UPackJob j[UM_MAX_JOBS]; };
+__global__ void pack_umma_jobs_kernel(const float* __restrict__ blob, float* __restrict__ packed, const __grid_constant__ UPackJobs jobs) {
+  const UPackJob jb = jobs.j[blockIdx.y];
+  const int half_total = jb.total / 2;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < half_total; e += gridDim.x * blockDim.x) {
+    const int full = jb.n * UM_KC;
+    const int c = e / full;
+    const int k0 = c * UM_KC;
+    const int kc = (((jb.k_valid - k0 < UM_KC) ? (jb.k_valid - k0) : UM_KC) + 7) / 8 * 8;
+    const int r = e - c * full;
+    const int slab = r / (jb.n * 4), row = (r / 4) % jb.n, kq = r % 4;
+    const int k = k0 + slab * 4 + kq;
+    float v = 0.f;
+    if (row < jb.n_valid && k < jb.k_valid) v = blob[jb.src + (size_t)row * jb.ld + jb.col0 + k];
+    uint32_t hi, lo;
+    split_hi_lo(v, hi, lo);
+    float* chunk = packed + jb.dst + (size_t)c * 2 * full;
+    chunk[r] = __uint_as_float(hi);
+    chunk[jb.n * kc + r] = __uint_as_float(lo);
   }
 }
 
@@ -639,7 +929,7 @@ extern "C" int lsr_render_workspace_bytes(const LsrParams* prm, int64_t n_rays, 
   if (rc) return rc;
   if (n_rays < 0 || n_rays > (1ll << 27)) return LSR_ERR_ARG;
   if (saved_bytes) *saved_bytes = saved_layout(n_rays, prm->n_surface, stage, prm->flags).total * sizeof(float);
-  if (scratch_bytes) *scratch_bytes = align_up((size_t)Packed::total * sizeof(float), 256) + 256;
+  if (scratch_bytes) *scratch_bytes = scratch_layout(n_rays, prm->n_surface).total;
   return LSR_OK;
 }
 
@@ -675,30 +965,68 @@ extern "C" int lsr_render_fwd(const LsrParams* prm, const void* grid_ws, const f
   const int nsm = sm_count();
   if (nsm <= 0) return LSR_ERR_CUDA;
 
-  rc = launch_pack(w, (float*)scratch, stream);
+  const ScratchLayout CL = scratch_layout(n_rays, prm->n_surface);
+  char* sbase = (char*)scratch;
+  rc = launch_pack(w, (float*)(sbase + CL.legacy), stream);   // the backward reads these
   if (rc) return rc;
+
+  // GEMM program of a tile + weights -> chunked (hi, lo) UMMA layout
+  UProgram P;
+  build_program(w, stage, prm->flags, &P);
+  if (P.packed_floats > UMMA_PACKED_FLOATS_MAX || P.n_ops > UM_MAX_OPS || P.n_jobs > UM_MAX_JOBS) return LSR_ERR_UNSUPPORTED;
+  {
+    UPackJobs J;
+    memcpy(J.j, P.jobs, sizeof(UPackJob) * P.n_jobs);
+    pack_umma_jobs_kernel<<<dim3(8, P.n_jobs), 256, 0, stream>>>(w->blob, (float*)(sbase + CL.umma), J);
+    LSR_CUDA_CHECK(cudaGetLastError());
+  }
+
+  KnnScratch ks;
+  ks.idx = (int32_t*)(sbase + CL.knn_idx);
+  ks.rem = (int32_t*)(sbase + CL.knn_rem);
+  ks.w = (float*)(sbase + CL.knn_w);
+  ks.pos = (float4*)(sbase + CL.knn_pos);
+  ks.hw = (float2*)(sbase + CL.knn_hw);
+  {
+    KnnArgs k;
+    k.prm = *prm;
+    k.grid = grid_ws;
+    k.rays_o = rays_o; k.rays_d = rays_d; k.gt_depth = gt_depth; k.r_query = r_query; k.far_zero = far_zero;
+    k.far_group = (int)(far_group > 0 ? (far_group < (1ll << 30) ? far_group : (1ll << 30)) : 1);
+    k.R = (int)n_rays;
+    k.remap = row_remap;
+    k.ks = ks;
+    k.saved = (float*)saved;
+    k.stage = stage;
+    const int64_t pairs = (n_rays * prm->n_surface + 1) / 2;
+    const int64_t blocks = (pairs + 7) / 8;
+    const int kgrid = (int)(blocks < (int64_t)nsm * 8 ? blocks : (int64_t)nsm * 8);
+    sample_knn_kernel<<<kgrid, 256, 0, stream>>>(k);
+    LSR_CUDA_CHECK(cudaGetLastError());
+  }
 
   FwdArgs a;
   a.prm = *prm;
-  a.grid = grid_ws; a.cloud = cloud_pos;
-  a.rays_o = rays_o; a.rays_d = rays_d; a.gt_depth = gt_depth; a.r_query = r_query; a.far_zero = far_zero;
-  a.far_group = (int)(far_group > 0 ? (far_group < (1ll << 30) ? far_group : (1ll << 30)) : 1);
+  a.cloud = cloud_pos;
+  a.gt_depth = gt_depth;
   a.R = (int)n_rays;
   a.geo_feats = geo_feats; a.col_feats = col_feats;
-  a.remap = row_remap; a.geo_leaf = geo_leaf; a.col_leaf = col_leaf;
+  a.geo_leaf = geo_leaf; a.col_leaf = col_leaf;
   a.w = *w;
-  a.packed = (const float*)scratch;
+  a.packed = (const float*)(sbase + CL.legacy);
+  a.wpk = (const float*)(sbase + CL.umma);
   a.affine = exposure_affine;
   a.stage = stage;
   a.depth = depth; a.var = var; a.rgb = rgb; a.valid = valid;
-  a.saved = (float*)saved;
-  a.rays_per_tile = balanced_rays_per_tile(n_rays, prm->n_surface, nsm);
+  a.saved = getenv("LSR_DEBUG_NOSAVE") ? nullptr : (float*)saved;   // timing experiments only
+  a.ks = ks;
+  a.rays_per_tile = UM_M / prm->n_surface;
   a.ntiles = (int)((n_rays + a.rays_per_tile - 1) / a.rays_per_tile);
-  const size_t smem = FWD_SMEM_FLOATS * sizeof(float);
-  LSR_CUDA_CHECK(cudaFuncSetAttribute(render_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int slots = nsm * CTAS_PER_SM;
-  const int grid = a.ntiles < slots ? a.ntiles : slots;
-  render_fwd_kernel<<<grid, NT, smem, stream>>>(a);
+  a.n_ops = P.n_ops;
+  memcpy(a.ops, P.ops, sizeof(UOp) * P.n_ops);
+  LSR_CUDA_CHECK(cudaFuncSetAttribute(render_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES));
+  const int grid = a.ntiles < nsm ? a.ntiles : nsm;
+  render_fwd_kernel<<<grid, FT, FWD_SMEM_BYTES, stream>>>(a);
   LSR_CUDA_CHECK(cudaGetLastError());
   return LSR_OK;
 }

@@ -19,7 +19,7 @@ def build():
 
 
 if __name__ == '__main__':
-    if not os.path.exists(SO) or '--build' in sys.argv:
+    if not os.path.exists(SO) or '--build' in sys.argv or '--build-only' in sys.argv:
         build()
     if '--build-only' in sys.argv:
         sys.exit(0)
@@ -38,7 +38,7 @@ if __name__ == '__main__':
     get = L.lsr_debug_phase_cycles
     get.argtypes = [ctypes.c_void_p]
     get(buf)
-    names = [['knn', 'gather+fourier', 'geo MLP', 'relpos MLP', 'colour trunk', 'colour head', 'compositing'],
+    names = [['load k-NN lists', 'gather+fourier', 'geo MLP', 'relpos MLP', "e'+colour trunk", 'colour head', 'compositing'],
              ['state+composite bwd', 'head bwd+setup', 'colour trunk bwd', 'fourier bwd+dC', 'relpos bwd', 'geo bwd+scatter']]
     for k in range(2):
         tot = sum(buf[k * 16 + i] for i in range(16)) or 1
