@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
         const float t0 = TWO_PI_F * sP[m * 4 + 0], t1 = TWO_PI_F * sP[m * 4 + 1], t2 = TWO_PI_F * sP[m * 4 + 2];
         const float arg = fmaf(t2, blob[a.w.c_B + 2 * EC + j], fmaf(t1, blob[a.w.c_B + EC + j], t0 * blob[a.w.c_B + j]));
         float sn, cs;
-        sincosf(arg, &sn, &cs);
+        sincos_ff(arg, &sn, &cs);
         sE[m * ELD + j] = sn;
         sE[m * ELD + EC + j] = cs;
       }
@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
               const float t2 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 2), sP[m * 4 + 2]);
               const float arg = fmaf(t2, blob[a.w.c_Brel + 2 * ER + j],
                                      fmaf(t1, blob[a.w.c_Brel + ER + j], t0 * blob[a.w.c_Brel + j]));
-              sincosf(arg, &sn, &cs);
+              sincos_ff(arg, &sn, &cs);
             }
             sQ[m * QLD + j] = sn;
             sQ[m * QLD + ER + j] = cs;
@@ -636,7 +636,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
           float v = 0.f;
           if (j < EG) {
             const float t0 = TWO_PI_F * sP[m * 4 + 0], t1 = TWO_PI_F * sP[m * 4 + 1], t2 = TWO_PI_F * sP[m * 4 + 2];
-            v = sinf(fmaf(t2, packed[Packed::gB + 2 * EGP + j], fmaf(t1, packed[Packed::gB + EGP + j], t0 * packed[Packed::gB + j])));
+            v = sin_ff(fmaf(t2, packed[Packed::gB + 2 * EGP + j], fmaf(t1, packed[Packed::gB + EGP + j], t0 * packed[Packed::gB + j])));
           }
           sEg[m * GLD + j] = v;
         }
@@ -767,7 +767,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
                 const int r = wm.row(i);
                 if (r < nrows) {
                   const float t0 = TWO_PI_F * sP[r * 4 + 0], t1 = TWO_PI_F * sP[r * 4 + 1], t2 = TWO_PI_F * sP[r * 4 + 2];
-                  const float dar = dEacc[i][g * 4 + j] * cosf(fmaf(t2, b2, fmaf(t1, b1, t0 * b0)));
+                  const float dar = dEacc[i][g * 4 + j] * cos_ff(fmaf(t2, b2, fmaf(t1, b1, t0 * b0)));
                   s0 = fmaf(t0, dar, s0); s1 = fmaf(t1, dar, s1); s2 = fmaf(t2, dar, s2);
                   dpr[i][0] = fmaf(b0, dar, dpr[i][0]); dpr[i][1] = fmaf(b1, dar, dpr[i][1]);
                   dpr[i][2] = fmaf(b2, dar, dpr[i][2]);

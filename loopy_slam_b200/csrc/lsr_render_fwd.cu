@@ -100,7 +100,7 @@ struct KnnArgs {
 
 // ------------------------------------------------------------------------------------------------ kernel 1
 // one warp per PAIR of sample rows, searched in lockstep (lane k < 8 ends up owning the k-th neighbour)
-__global__ void __launch_bounds__(256) sample_knn_kernel(const __grid_constant__ KnnArgs a) {
+__global__ void __launch_bounds__(256, 4) sample_knn_kernel(const __grid_constant__ KnnArgs a) {
   constexpr int NQ = 2;
   const int S = a.prm.n_surface;
   const int P = a.R * S;
@@ -207,7 +207,7 @@ constexpr int SM_WSUM = SM_OCCP + 2 * 128 * 4;
 constexpr int SM_HAS = SM_WSUM + 128 * 4;
 constexpr int SM_RGB = SM_HAS + 128 * 4;                 // [128][4]
 constexpr int SM_BIAS = SM_RGB + 128 * 16;               // bias table, see Bias
-constexpr int SM_PIPE = SM_BIAS + 1800 * 4;
+constexpr int SM_PIPE = SM_BIAS + 2200 * 4;
 constexpr int FWD_SMEM_BYTES = SM_PIPE + 128;
 static_assert(SM_Q_LO + 14 * UM_A_SLAB <= SM_C_HI && SM_EG_LO + 24 * UM_A_SLAB <= SM_C_HI, "union region");
 static_assert(FWD_SMEM_BYTES <= 232448, "shared memory budget");
@@ -215,9 +215,12 @@ static_assert(8 * 32 * 36 * 4 <= 20 * UM_A_SLAB && 8 * 32 * (36 + 20) * 4 <= 28 
 struct Bias {   // float offsets inside the shared bias table
   static constexpr int gb = 0, gu = 160, gow = 320, gob = 352;            // geometry: 5x32, 5x32, 32, 1
   static constexpr int cb = 356, cu = cb + 640, v1b = cu + 640, v2b = v1b + 128, cob = v2b + 32;   // colour
-  static constexpr int total = cob + 4;
+  static constexpr int gB = cob + 4;            // geometry Fourier matrix [3][96] (padded copy of embedder._B)
+  static constexpr int cB = gB + 3 * EGP;       // colour Fourier matrix [3][20]
+  static constexpr int rB = cB + 3 * EC;        // rel-pos Fourier matrix [3][10] (+2 pad)
+  static constexpr int total = rB + 32;
 };
-static_assert(Bias::total <= 1800, "bias table");
+static_assert(Bias::total <= 2200, "bias table");
 // TMEM columns
 constexpr uint32_t TM_ACC0 = 0, TM_ACC1 = 128, TM_AHI = 256, TM_ALO = 384;
 
@@ -316,6 +319,9 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
     else if (relpos && i >= Bias::v1b && i < Bias::v2b) v = blob[a.w.c_nb1_b + (i - Bias::v1b)];
     else if (relpos && i >= Bias::v2b && i < Bias::cob) v = blob[a.w.c_nb2_b + (i - Bias::v2b)];
     else if (color && i >= Bias::cob && i < Bias::cob + 3) v = blob[a.w.c_out_b + (i - Bias::cob)];
+    else if (i >= Bias::gB && i < Bias::cB) v = a.packed[Packed::gB + (i - Bias::gB)];
+    else if (color && i >= Bias::cB && i < Bias::rB) v = blob[a.w.c_B + (i - Bias::cB)];
+    else if (relpos && i >= Bias::rB && i < Bias::rB + 3 * ER) v = blob[a.w.c_Brel + (i - Bias::rB)];
     sBias[i] = v;
   }
   if (warp == 8) tmem_alloc(&pipe->tmem_base, 512);
@@ -413,9 +419,8 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
           const int j = g * 4 + t;
           v[t] = 0.f;
           if (j < EG) {
-            const float arg = fmaf(t2, __ldg(a.packed + Packed::gB + 2 * EGP + j),
-                                   fmaf(t1, __ldg(a.packed + Packed::gB + EGP + j), t0 * __ldg(a.packed + Packed::gB + j)));
-            v[t] = sinf(arg);
+            const float arg = fmaf(t2, sBias[Bias::gB + 2 * EGP + j], fmaf(t1, sBias[Bias::gB + EGP + j], t0 * sBias[Bias::gB + j]));
+            v[t] = sin_ff(arg);
           }
         }
         store_a_split(smem + SM_EG_HI, smem + SM_EG_LO, m, g * 4, make_float4(v[0], v[1], v[2], v[3]));
@@ -480,37 +485,41 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
           // zero the K padding (columns 52..55) of Q once per tile
           if (tid < 128) store_a_split(smem + SM_Q_HI, smem + SM_Q_LO, tid, QD, make_float4(0.f, 0.f, 0.f, 0.f));
           auto build_q = [&](int k) {
-            // relative-position Fourier features: q[0..9] = sin, q[10..19] = cos
-            for (int it = tid; it < 128 * ER; it += NCT) {
-              const int m = it & 127, j = it >> 7;
+            if (tid < 128) {
+              // relative-position Fourier features of row tid: q[0..9] = sin, q[10..19] = cos
+              const int m = tid;
               const int idx = sIdx[m * KNN + k];
-              float sn = 0.f, cs = 0.f;
+              float q[2 * ER];
+#pragma unroll
+              for (int j = 0; j < 2 * ER; ++j) q[j] = 0.f;
               if (idx >= 0) {
                 const float4 p = sP[m];
                 const float t0 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 0), p.x);
                 const float t1 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 1), p.y);
                 const float t2 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 2), p.z);
-                const float arg = fmaf(t2, __ldg(blob + a.w.c_Brel + 2 * ER + j),
-                                       fmaf(t1, __ldg(blob + a.w.c_Brel + ER + j), t0 * __ldg(blob + a.w.c_Brel + j)));
-                sincosf(arg, &sn, &cs);
+#pragma unroll
+                for (int j = 0; j < ER; ++j) {
+                  const float arg = fmaf(t2, sBias[Bias::rB + 2 * ER + j], fmaf(t1, sBias[Bias::rB + ER + j], t0 * sBias[Bias::rB + j]));
+                  sincos_ff(arg, &q[j], &q[ER + j]);
+                }
               }
-              store_a_split1(smem + SM_Q_HI, smem + SM_Q_LO, m, j, sn);
-              store_a_split1(smem + SM_Q_HI, smem + SM_Q_LO, m, ER + j, cs);
-            }
-            // neighbour feature row: q[20..51]
-            {
-              const int m = tid & 127, qg = tid >> 7;
+#pragma unroll
+              for (int g = 0; g < 5; ++g)
+                store_a_split(smem + SM_Q_HI, smem + SM_Q_LO, m, 4 * g, make_float4(q[4 * g], q[4 * g + 1], q[4 * g + 2], q[4 * g + 3]));
+            } else {
+              // neighbour feature row of row tid - 128: q[20..51]
+              const int m = tid - 128;
               const int idx = sIdx[m * KNN + k];
-              float4 f[4];
+              float4 f[8];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) f[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int i = 0; i < 8; ++i) f[i] = make_float4(0.f, 0.f, 0.f, 0.f);
               if (idx >= 0) {
-                const float4* fr = reinterpret_cast<const float4*>(feat_row_cached(a.col_feats, a.col_leaf, idx, sRem[m * KNN + k])) + qg * 4;
+                const float4* fr = reinterpret_cast<const float4*>(feat_row_cached(a.col_feats, a.col_leaf, idx, sRem[m * KNN + k]));
 #pragma unroll
-                for (int i = 0; i < 4; ++i) f[i] = __ldg(fr + i);
+                for (int i = 0; i < 8; ++i) f[i] = __ldg(fr + i);
               }
 #pragma unroll
-              for (int i = 0; i < 4; ++i) store_a_split(smem + SM_Q_HI, smem + SM_Q_LO, m, 2 * ER + (qg * 4 + i) * 4, f[i]);
+              for (int i = 0; i < 8; ++i) store_a_split(smem + SM_Q_HI, smem + SM_Q_LO, m, 2 * ER + i * 4, f[i]);
             }
           };
           float uf[64];
@@ -618,8 +627,8 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const int j = g * 4 + t;
-            const float arg = fmaf(t2, __ldg(blob + a.w.c_B + 2 * EC + j), fmaf(t1, __ldg(blob + a.w.c_B + EC + j), t0 * __ldg(blob + a.w.c_B + j)));
-            sincosf(arg, &sn[t], &cs[t]);
+            const float arg = fmaf(t2, sBias[Bias::cB + 2 * EC + j], fmaf(t1, sBias[Bias::cB + EC + j], t0 * sBias[Bias::cB + j]));
+            sincos_ff(arg, &sn[t], &cs[t]);
           }
           store_a_split(smem + SM_EC_HI, smem + SM_EC_LO, m, g * 4, make_float4(sn[0], sn[1], sn[2], sn[3]));
           store_a_split(smem + SM_EC_HI, smem + SM_EC_LO, m, EC + g * 4, make_float4(cs[0], cs[1], cs[2], cs[3]));

@@ -21,7 +21,7 @@ constexpr int UM_M = 128;                  // rows (samples) per tile = TMEM lan
 constexpr int UM_KC = 32;                  // contraction values per streamed weight chunk
 constexpr int UM_STAGE_BYTES = 2 * 128 * UM_KC * 4;   // [hi | lo] of a 128 x 32 chunk = 32 KB
 constexpr int UM_A_SLAB = UM_M * 16;       // bytes of one 4-wide K slab of an A operand in shared memory (= LBO of A)
-constexpr int UM_MAX_OPS = 96;
+constexpr int UM_MAX_OPS = 144;
 constexpr int UM_MAX_JOBS = 40;
 
 struct UOp {           // 32 bytes, device-ready (read through the constant bank: kernel parameter)
