@@ -29,25 +29,6 @@ using namespace umma;
 __device__ unsigned long long lsr_phase_cycles[2][16];
 #endif
 
-__global__ void pack_weights_kernel(const float* __restrict__ blob, float* __restrict__ packed, PackJobs jobs) {
-  const PackJob jb = jobs.j[blockIdx.y];
-  const int total = jb.dst_rows * jb.dst_ld;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-    int kp, n;
-    if (jb.transpose) { kp = e / jb.dst_ld; n = e % jb.dst_ld; }
-    else              { n = e / jb.dst_ld; kp = e % jb.dst_ld; }
-    int k = kp;
-    bool ok = true;
-    if (kp >= jb.gap_at) {
-      if (kp < jb.gap_at + jb.gap) ok = false;
-      k = kp - jb.gap;
-    }
-    float v = 0.f;
-    if (ok && k < jb.n_in && n < jb.n_out) v = blob[jb.src + n * jb.n_in + k];
-    packed[jb.dst + e] = v;
-  }
-}
-
 // linspace(start, end, S)[s] exactly as torch computes it in float32
 __device__ __forceinline__ float linspace_f32(float start, float end, int S, int s) {
   if (S <= 1) return start;
@@ -804,8 +785,28 @@ static void build_program(const LsrWeights* w, int stage, int flags, UProgram* P
   B.gemm(cOut, true, TM_AHI, TM_ALO, TM_ACC0, true, true, 1);
 }
 
-struct UPackJobs { UPackJob j[UM_MAX_JOBS]; };
-__global__ void pack_umma_jobs_kernel(const float* __restrict__ blob, float* __restrict__ packed, const __grid_constant__ UPackJobs jobs) {
+// One launch re-lays-out everything: blockIdx.y < n_umma -> UMMA chunk layout (forward), the rest -> the three
+// plain copies the backward still reads (padded geometry Fourier matrix and the two odd-width geometry matrices).
+struct UPackJobs { UPackJob j[UM_MAX_JOBS]; PackJob legacy[3]; int n_umma; };
+__global__ void pack_umma_jobs_kernel(const float* __restrict__ blob, float* __restrict__ packed, float* __restrict__ legacy,
+                                      const __grid_constant__ UPackJobs jobs) {
+  if ((int)blockIdx.y >= jobs.n_umma) {
+    const PackJob jb = jobs.legacy[blockIdx.y - jobs.n_umma];
+    const int total = jb.dst_rows * jb.dst_ld;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+      const int n = e / jb.dst_ld, kp = e % jb.dst_ld;   // never transposed
+      int k = kp;
+      bool ok = true;
+      if (kp >= jb.gap_at) {
+        if (kp < jb.gap_at + jb.gap) ok = false;
+        k = kp - jb.gap;
+      }
+      float v = 0.f;
+      if (ok && k < jb.n_in && n < jb.n_out) v = blob[jb.src + n * jb.n_in + k];
+      legacy[jb.dst + e] = v;
+    }
+    return;
+  }
   const UPackJob jb = jobs.j[blockIdx.y];
   const int half_total = jb.total / 2;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < half_total; e += gridDim.x * blockDim.x) {
@@ -867,30 +868,6 @@ int check_weights(const LsrWeights* w) {
   for (int i = 0; i < n; ++i)
     if (offs[i] < 0 || (offs[i] & 3) || offs[i] >= w->n_elems) return LSR_ERR_ARG;
   return LSR_OK;
-}
-
-int launch_pack(const LsrWeights* w, float* packed, cudaStream_t st) {
-  PackJobs J;
-  J.n = 0;
-  add_job(J, w->g_B, 3, EG, Packed::gB, 3, EGP, 0);
-  add_job(J, w->g_lin_w[0], HG, EG, Packed::gW0t, EGP, HG, 1);
-  add_job(J, w->g_lin_w[1], HG, HG, Packed::gW1t, HG, HG, 1);
-  add_job(J, w->g_lin_w[2], HG, HG, Packed::gW2t, HG, HG, 1);
-  add_job(J, w->g_lin_w[3], HG, EG + HG, Packed::gW3t, 128, HG, 1, EG, EGP - EG);
-  add_job(J, w->g_lin_w[4], HG, HG, Packed::gW4t, HG, HG, 1);
-  for (int i = 0; i < 5; ++i) add_job(J, w->g_fc_w[i], HG, CDIM, Packed::gUt + i * CDIM * HG, CDIM, HG, 1);
-  add_job(J, w->g_lin_w[0], HG, EG, Packed::gW0n, HG, EGP, 0);
-  add_job(J, w->g_lin_w[3], HG, EG + HG, Packed::gW3n, HG, 128, 0, EG, EGP - EG);
-  add_job(J, w->c_lin_w[0], HC, ECC, Packed::cW0t, ECC, HC, 1);
-  add_job(J, w->c_lin_w[1], HC, HC, Packed::cW1t, HC, HC, 1);
-  add_job(J, w->c_lin_w[2], HC, HC, Packed::cW2t, HC, HC, 1);
-  add_job(J, w->c_lin_w[3], HC, ECC + HC, Packed::cW3t, ECC + HC, HC, 1);
-  add_job(J, w->c_lin_w[4], HC, HC, Packed::cW4t, HC, HC, 1);
-  for (int i = 0; i < 5; ++i) add_job(J, w->c_fc_w[i], HC, CDIM, Packed::cUt + i * CDIM * HC, CDIM, HC, 1);
-  add_job(J, w->c_nb1_w, HC, QD, Packed::V1t, QDP, HC, 1);
-  add_job(J, w->c_nb2_w, CDIM, HC, Packed::V2t, HC, CDIM, 1);
-  pack_weights_kernel<<<dim3(8, J.n), 256, 0, st>>>(w->blob, packed, J);
-  return cudaGetLastError() == cudaSuccess ? LSR_OK : LSR_ERR_CUDA;
 }
 
 int check_params(const LsrParams* p) {
@@ -976,9 +953,6 @@ extern "C" int lsr_render_fwd(const LsrParams* prm, const void* grid_ws, const f
 
   const ScratchLayout CL = scratch_layout(n_rays, prm->n_surface);
   char* sbase = (char*)scratch;
-  rc = launch_pack(w, (float*)(sbase + CL.legacy), stream);   // the backward reads these
-  if (rc) return rc;
-
   // GEMM program of a tile + weights -> chunked (hi, lo) UMMA layout
   UProgram P;
   build_program(w, stage, prm->flags, &P);
@@ -986,7 +960,15 @@ extern "C" int lsr_render_fwd(const LsrParams* prm, const void* grid_ws, const f
   {
     UPackJobs J;
     memcpy(J.j, P.jobs, sizeof(UPackJob) * P.n_jobs);
-    pack_umma_jobs_kernel<<<dim3(8, P.n_jobs), 256, 0, stream>>>(w->blob, (float*)(sbase + CL.umma), J);
+    J.n_umma = P.n_jobs;
+    PackJobs L;   // what the backward (and the bias table above) reads from the legacy scratch
+    L.n = 0;
+    add_job(L, w->g_B, 3, EG, Packed::gB, 3, EGP, 0);
+    add_job(L, w->g_lin_w[0], HG, EG, Packed::gW0n, HG, EGP, 0);
+    add_job(L, w->g_lin_w[3], HG, EG + HG, Packed::gW3n, HG, 128, 0, EG, EGP - EG);
+    memcpy(J.legacy, L.j, sizeof(PackJob) * 3);
+    pack_umma_jobs_kernel<<<dim3(8, P.n_jobs + 3), 256, 0, stream>>>(w->blob, (float*)(sbase + CL.umma),
+                                                                      (float*)(sbase + CL.legacy), J);
     LSR_CUDA_CHECK(cudaGetLastError());
   }
 

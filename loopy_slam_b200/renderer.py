@@ -182,18 +182,29 @@ class _RenderFn(torch.autograd.Function):
             flags |= _lib.GRAD_RAYS
             d_o = torch.empty(R, 3, dtype=torch.float32, device=dev)
             d_d = torch.empty(R, 3, dtype=torch.float32, device=dev)
-        if (need[8] if sub else need[4]):
-            flags |= _lib.GRAD_GEO_FEATS
-            d_geo = torch.zeros_like(geo_leaf if sub else geo_feats)
-        if (need[9] if sub else need[5]) and rc.stage == 1:
-            flags |= _lib.GRAD_COL_FEATS
-            d_col = torch.zeros_like(col_leaf if sub else col_feats)
-        if need[6] and affine is not None:
-            flags |= _lib.GRAD_AFFINE
-            d_aff = torch.zeros(12, dtype=torch.float32, device=dev)
+        # every accumulated gradient sink lives in ONE zero-filled buffer (one fill launch instead of four)
+        want_geo = need[8] if sub else need[4]
+        want_col = (need[9] if sub else need[5]) and rc.stage == 1
+        want_aff = need[6] and affine is not None
         pneed = need[10:]
+        geo_like = geo_leaf if sub else geo_feats
+        col_like = col_leaf if sub else col_feats
+        sizes = [geo_like.numel() if want_geo else 0, col_like.numel() if want_col else 0,
+                 blob.n_elems if any(pneed) else 0, 12 if want_aff else 0]
+        sizes = [(n + 3) // 4 * 4 for n in sizes]     # keep every view 16-byte aligned
+        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev) if sum(sizes) else None
+        o0, o1, o2 = sizes[0], sizes[0] + sizes[1], sizes[0] + sizes[1] + sizes[2]
+        if want_geo:
+            flags |= _lib.GRAD_GEO_FEATS
+            d_geo = flat[:geo_like.numel()].view(geo_like.shape)
+        if want_col:
+            flags |= _lib.GRAD_COL_FEATS
+            d_col = flat[o0:o0 + col_like.numel()].view(col_like.shape)
+        if want_aff:
+            flags |= _lib.GRAD_AFFINE
+            d_aff = flat[o2:o2 + 12]
         if any(pneed):
-            d_w = torch.zeros(blob.n_elems, dtype=torch.float32, device=dev)
+            d_w = flat[o1:o1 + blob.n_elems]
             if any(pneed[k] for k in blob.geo_w_idx):
                 flags |= _lib.GRAD_GEO_W
             if any(pneed[k] for k in blob.geo_b_idx):
