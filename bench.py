@@ -187,7 +187,7 @@ def run_lsr(args, rank, world, local):
         rend._timing = None
         if world > 1:
             reducer.allreduce_()
-        launches[0] += 5            # far_bound + pack + render_fwd + mapper_loss + render_bwd (ours); torch ops not counted
+        launches[0] += 6            # far_bound + weight re-layout + sample_knn + render_fwd + mapper_loss + render_bwd (ours); torch ops not counted
         return loss
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
@@ -307,17 +307,21 @@ def run_lsr(args, rank, world, local):
         'gpu_launches': n_launch,
         'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
                      'frac': ach / peak,
-                     'traffic': (331.4e6 if t_b >= t_f else 254.1e6) if stage == 'color' and R == 4936 else None, 'peak_source': peak_src,
+                     'traffic': (304.7e6 if t_b >= t_f else 254.5e6) if stage == 'color' and R == 4936 else None, 'peak_source': peak_src,
                      'algorithmic_bytes_per_launch': bytes_dom,
-                     'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_ncu_final_summary.md '
+                     'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_ncu_v10_summary.md '
                                        '(same command; the excess over the algorithmic bytes is the saved-activation round trip)',
                      'note': 'HBM fraction as defined in BASELINE.md section 3; arithmetic intensity ~190 FLOP/B puts both '
                              'fused kernels on the tensor/issue side of the roofline, see "tensor"'},
         'tensor': {'algorithmic_tflops': flops_step / ((t_f + t_b) * 1e-3) / 1e12 if t_f + t_b > 0 else 0,
                    'executed_tflops_3xtf32': 3 * flops_step / ((t_f + t_b) * 1e-3) / 1e12 if t_f + t_b > 0 else 0,
                    'peak_tf32_mma_sync_tflops_measured': 278.0, 'peak_bf16_tflops_measured': peaks.get('bf16_tflops'),
-                   'note': 'MLP contractions run as error-compensated 3xTF32 mma.sync (HMMA.1688.F32.TF32); 278 TFLOP/s '
-                           'is this path\'s measured issue peak on B200 (tools/mma_rate.cu)'},
+                   'forward': 'tcgen05.mma kind::tf32 (M=128, accumulators + hidden activations in TMEM, weights by '
+                              'cp.async.bulk), error-compensated 3xTF32',
+                   'backward': 'mma.sync m16n8k8 tf32 (HMMA.1688.F32.TF32), error-compensated 3xTF32',
+                   'note': '3 tensor-core passes per fp32 product (hi*hi + lo*hi + hi*lo) keep the 1e-4 parity contract; 278 '
+                           'TFLOP/s is the measured mma.sync TF32 issue peak on this B200 (tools/mma_rate.cu), the tcgen05 '
+                           'tf32 rate measured in tools/umma_probe.cu is 92 cycles per 128x128x8 MMA per SM'},
         'kernels': {'render_fwd_ms': t_f, 'render_bwd_ms': t_b,
                     'fwd_bwd_GBps': R * BYTES_RAY_ALL[stage] / ((t_f + t_b) * 1e-3) / 1e9 if t_f + t_b > 0 else 0},
         'fp32_fma_peak_tflops_at_clock': fp32_peak,
