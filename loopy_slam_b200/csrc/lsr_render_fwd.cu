@@ -810,10 +810,11 @@ __global__ void pack_umma_jobs_kernel(const float* __restrict__ blob, float* __r
   const UPackJob jb = jobs.j[blockIdx.y];
   const int half_total = jb.total / 2;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < half_total; e += gridDim.x * blockDim.x) {
-    const int full = jb.n * UM_KC;
+    const int KC = um_kc(jb.n);
+    const int full = jb.n * KC;
     const int c = e / full;
-    const int k0 = c * UM_KC;
-    const int kc = (((jb.k_valid - k0 < UM_KC) ? (jb.k_valid - k0) : UM_KC) + 7) / 8 * 8;
+    const int k0 = c * KC;
+    const int kc = (((jb.k_valid - k0 < KC) ? (jb.k_valid - k0) : KC) + 7) / 8 * 8;
     const int r = e - c * full;
     const int slab = r / (jb.n * 4), row = (r / 4) % jb.n, kq = r % 4;
     const int k = k0 + slab * 4 + kq;

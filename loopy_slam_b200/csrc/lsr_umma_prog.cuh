@@ -18,8 +18,10 @@ namespace lsr {
 namespace umma {
 
 constexpr int UM_M = 128;                  // rows (samples) per tile = TMEM lanes
-constexpr int UM_KC = 32;                  // contraction values per streamed weight chunk
+constexpr int UM_KC = 32;                  // contraction values per streamed weight chunk of a 128-row matrix
 constexpr int UM_STAGE_BYTES = 2 * 128 * UM_KC * 4;   // [hi | lo] of a 128 x 32 chunk = 32 KB
+// Narrow matrices get proportionally deeper chunks (N = 32 -> K = 128): the same stage bytes, fewer L2 round trips.
+__host__ __device__ constexpr int um_kc(int n) { return (UM_STAGE_BYTES / 8) / n < 128 ? (UM_STAGE_BYTES / 8) / n : 128; }
 constexpr int UM_A_SLAB = UM_M * 16;       // bytes of one 4-wide K slab of an A operand in shared memory (= LBO of A)
 constexpr int UM_MAX_OPS = 144;
 constexpr int UM_MAX_JOBS = 40;
@@ -32,7 +34,7 @@ struct UOp {           // 32 bytes, device-ready (read through the constant bank
   uint32_t b_lbo_word; // (LBO >> 4) << 16 of the B descriptors, LBO = n * 16
   uint16_t b_k8_step;  // descriptor start-address increment per K = 8 step = (2 * LBO) >> 4
   uint16_t d_col;      // first accumulator column
-  uint8_t nk8;         // K/8 steps in this chunk (1..4)
+  uint8_t nk8;         // K/8 steps in this chunk (1..16)
   uint8_t flags;       // UOP_*
   uint8_t commit_d;    // 0: none, 1 / 2: commit d_ready[0 / 1] after this chunk
   uint8_t pad;
@@ -67,8 +69,9 @@ struct UBuilder {
     j.src = src; j.ld = ld; j.col0 = col0; j.k_valid = k_valid; j.n = n; j.n_valid = n_valid;
     j.dst = P->packed_floats;
     int total = 0;
-    for (int k0 = 0; k0 < k_valid; k0 += UM_KC) {
-      const int kc = (((k_valid - k0 < UM_KC) ? (k_valid - k0) : UM_KC) + 7) / 8 * 8;
+    const int KC = um_kc(n);
+    for (int k0 = 0; k0 < k_valid; k0 += KC) {
+      const int kc = (((k_valid - k0 < KC) ? (k_valid - k0) : KC) + 7) / 8 * 8;
       total += 2 * n * kc;
     }
     j.total = total;
@@ -81,9 +84,10 @@ struct UBuilder {
     const UPackJob& j = P->jobs[job];
     int off = j.dst;
     int c = 0;
-    const int nchunks = (j.k_valid + UM_KC - 1) / UM_KC;
-    for (int k0 = 0; k0 < j.k_valid; k0 += UM_KC, ++c) {
-      const int kc = (((j.k_valid - k0 < UM_KC) ? (j.k_valid - k0) : UM_KC) + 7) / 8 * 8;
+    const int KC = um_kc(j.n);
+    const int nchunks = (j.k_valid + KC - 1) / KC;
+    for (int k0 = 0; k0 < j.k_valid; k0 += KC, ++c) {
+      const int kc = (((j.k_valid - k0 < KC) ? (j.k_valid - k0) : KC) + 7) / 8 * 8;
       UOp& o = P->ops[P->n_ops++];
       o.src = (uint32_t)off;
       o.half_bytes = (uint32_t)(j.n * kc * 4);
@@ -111,10 +115,11 @@ __global__ void pack_umma_kernel(const float* __restrict__ blob, float* __restri
   const int half_total = jb.total / 2;   // one element per (chunk, row, k) pair
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < half_total; e += gridDim.x * blockDim.x) {
     // locate the chunk: all chunks but the last hold UM_KC k-values
-    const int full = jb.n * UM_KC;
+    const int KC = um_kc(jb.n);
+    const int full = jb.n * KC;
     const int c = e / full;
-    const int k0 = c * UM_KC;
-    const int kc = (((jb.k_valid - k0 < UM_KC) ? (jb.k_valid - k0) : UM_KC) + 7) / 8 * 8;
+    const int k0 = c * KC;
+    const int kc = (((jb.k_valid - k0 < KC) ? (jb.k_valid - k0) : KC) + 7) / 8 * 8;
     const int r = e - c * full;            // index inside the chunk's hi block: (slab, row, k%4)
     const int slab = r / (jb.n * 4), row = (r / 4) % jb.n, kq = r % 4;
     const int k = k0 + slab * 4 + kq;

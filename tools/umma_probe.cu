@@ -111,6 +111,68 @@ __global__ void __launch_bounds__(128) probe_gemm(const float* A, const float* B
   if (warp == 0) tmem_dealloc(tb, 512);
 }
 
+// ------------------------------------------------------------------------------------------- test 3
+// Weight-gradient shaped GEMM: D[m][n] = sum_r A[r][m] * B[r][n] (contraction over the 128 ROWS), A (128 x 128) and
+// B (128 x N) stored exactly like the forward's activation tiles (row-thread float4 stores: (f/4) * 2048 + r * 16 +
+// (f % 4) * 4), but described to the tensor core as MN-major operands.  swap: exchange the LBO / SBO fields.
+__global__ void __launch_bounds__(128) probe_gemm_mn(const float* A, const float* B, float* D, int N, int swap, int three) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tslot;
+  uint8_t* sAhi = smem;
+  uint8_t* sAlo = sAhi + 128 * 128 * 4;
+  uint8_t* sBhi = sAlo + 128 * 128 * 4;
+  uint8_t* sBlo = sBhi + 128 * N * 4;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc(&tslot, 512);
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tslot;
+  for (int f = 0; f < 128; f += 4) {   // thread = row
+    float4 v = *reinterpret_cast<const float4*>(A + tid * 128 + f);
+    if (!three) { store_a_split(sAhi, sAlo, tid, f, v); *reinterpret_cast<float4*>(sAhi + (f >> 2) * 2048 + tid * 16) = v; }
+    else store_a_split(sAhi, sAlo, tid, f, v);
+  }
+  for (int f = 0; f < N; f += 4) {
+    float4 v = *reinterpret_cast<const float4*>(B + tid * N + f);
+    if (!three) { store_a_split(sBhi, sBlo, tid, f, v); *reinterpret_cast<float4*>(sBhi + (f >> 2) * 2048 + tid * 16) = v; }
+    else store_a_split(sBhi, sBlo, tid, f, v);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+    const uint32_t idesc = idesc_tf32(128, N) | (1u << 15) | (1u << 16);   // A and B MN-major
+    uint32_t acc = 0;
+    for (int k8 = 0; k8 < 16; ++k8) {   // 8 rows per MMA: one 128-byte core matrix along K
+      const uint32_t off = k8 * 128;
+      const uint64_t dah = swap ? smem_desc(smem_u32(sAhi) + off, 2048, 128) : smem_desc(smem_u32(sAhi) + off, 128, 2048);
+      const uint64_t dal = swap ? smem_desc(smem_u32(sAlo) + off, 2048, 128) : smem_desc(smem_u32(sAlo) + off, 128, 2048);
+      const uint64_t dbh = swap ? smem_desc(smem_u32(sBhi) + off, 2048, 128) : smem_desc(smem_u32(sBhi) + off, 128, 2048);
+      const uint64_t dbl = swap ? smem_desc(smem_u32(sBlo) + off, 2048, 128) : smem_desc(smem_u32(sBlo) + off, 128, 2048);
+      if (three) { mma_ss(tb, dal, dbh, idesc, acc); mma_ss(tb, dah, dbl, idesc, 1u); acc = 1u; }
+      mma_ss(tb, dah, dbh, idesc, acc);
+      acc = 1u;
+    }
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem_addr(tb, 32 * warp, c0), v);
+    tmem_wait_ld();
+    for (int j = 0; j < 32; ++j)
+      if (c0 + j < N) D[tid * N + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
 // ------------------------------------------------------------------------------------------- test 2
 #ifndef PROBE_NS
 #define PROBE_NS 2
@@ -302,6 +364,46 @@ static int test_gemm(int K, int N, int swap, int ts, int three, bool exact_input
   return rel < (three || exact_inputs ? 2e-6 : 2e-3) ? 1 : 0;
 }
 
+static int test_gemm_mn(int N, int swap, int three, bool exact_inputs, int pattern = 0) {
+  std::vector<float> A(128 * 128), B(128 * N), D(128 * N);
+  for (auto& v : A) v = exact_inputs ? (float)((rand() % 17) - 8) * 0.125f : frand();
+  for (auto& v : B) v = exact_inputs ? (float)((rand() % 17) - 8) * 0.25f : frand();
+  if (pattern == 1) { for (auto& v : A) v = 1.f; for (auto& v : B) v = 1.f; }
+  if (pattern == 2) {   // A[r][m] = 1 iff r == 3 and m == 5; B[r][n] = n + 1 iff r == 3  ->  D[5][n] = n + 1
+    for (auto& v : A) v = 0.f; for (auto& v : B) v = 0.f;
+    A[3 * 128 + 5] = 1.f;
+    for (int n = 0; n < N; ++n) B[3 * N + n] = (float)(n + 1);
+  }
+  std::vector<double> ref(128 * N);
+  for (int m = 0; m < 128; ++m)
+    for (int n = 0; n < N; ++n) {
+      double s = 0;
+      for (int r = 0; r < 128; ++r) s += (double)A[r * 128 + m] * (double)B[r * N + n];
+      ref[m * N + n] = s;
+    }
+  float *dA, *dB, *dD;
+  CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dB, B.size() * 4)); CK(cudaMalloc(&dD, D.size() * 4));
+  CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dD, 0, D.size() * 4));
+  const int smem = (2 * 128 * 128 + 2 * 128 * N) * 4 + 1024;
+  CK(cudaFuncSetAttribute(probe_gemm_mn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  probe_gemm_mn<<<1, 128, smem>>>(dA, dB, dD, N, swap, three);
+  cudaError_t e = cudaDeviceSynchronize();
+  char name[128];
+  snprintf(name, sizeof name, "A^T.B (MN-major) N=%d %s %s", N, swap ? "LBO=MN SBO=K" : "LBO=K(128B) SBO=MN(2048B)", three ? "3xTF32" : "1xTF32");
+  if (e != cudaSuccess) { printf("  %-44s CUDA error: %s\n", name, cudaGetErrorString(e)); return -1; }
+  CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+  const double rel = check(name, D, ref);
+  if (pattern) {
+    int nz = 0; double sum = 0;
+    for (size_t i = 0; i < D.size(); ++i) { if (D[i] != 0.f) { if (nz < 12) printf("    D[%zu][%zu] = %g\n", i / N, i % N, D[i]); ++nz; } sum += D[i]; }
+    printf("    pattern %d: %d non-zeros, sum %g\n", pattern, nz, sum);
+  }
+  cudaFree(dA); cudaFree(dB); cudaFree(dD);
+  return rel < (three || exact_inputs ? 2e-6 : 2e-3) ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
   srand(1219);
   int only = argc > 1 ? atoi(argv[1]) : 0;
@@ -319,6 +421,14 @@ int main(int argc, char** argv) {
     test_gemm(56, 128, 0, 0, 1, false);
     printf("  1xTF32, random inputs (expected ~5e-4):\n");
     test_gemm(128, 128, 0, 0, 0, false);
+  }
+  if (only == 3) {
+    printf("test 3: weight-gradient shaped GEMMs, operands MN-major (contraction over the rows)\n");
+    for (int swap = 0; swap < 2; ++swap)
+      if (test_gemm_mn(64, swap, 0, true) < 0) { printf("  (context lost, stopping)\n"); return 1; }
+    test_gemm_mn(64, 0, 0, true, 1);
+    test_gemm_mn(64, 0, 0, true, 2);
+    test_gemm_mn(64, 1, 0, true, 2);
   }
   if (only == 0 || only == 2) {
     printf("test 2: streamed-weight engine on a colour-trunk-shaped MLP\n");
