@@ -186,7 +186,7 @@ def run_lsr(args, rank, world, local):
         loss.backward()
         rend._timing = None
         if world > 1:
-            reducer.allreduce_()
+            reducer.allreduce_(getattr(rend, 'last_grad_buffer', None))
         launches[0] += 6            # far_bound + weight re-layout + sample_knn + render_fwd + mapper_loss + render_bwd (ours); torch ops not counted
         return loss
 

@@ -68,14 +68,37 @@ class GradAllReducer:
             self.flat = torch.zeros(max(self.numel, 1), dtype=torch.float32, device=device)
         return self.flat
 
-    def allreduce_(self):
+    @staticmethod
+    def _inside(t, buf):
+        """True when tensor t is a view into buf's memory."""
+        if t is None or buf is None or t.device != buf.device or not t.is_contiguous():
+            return False
+        lo = buf.data_ptr()
+        return lo <= t.data_ptr() and t.data_ptr() + t.numel() * t.element_size() <= lo + buf.numel() * buf.element_size()
+
+    def allreduce_(self, grad_buffer=None):
         """Sum .grad of all params across ranks in place (missing grads count as zero).  Returns the
-        number of bytes exchanged per rank."""
+        number of bytes exchanged per rank.
+        grad_buffer: the flat buffer the last fused backward accumulated into (Renderer.last_grad_buffer).
+        Every .grad that is a view of it (autograd keeps the views the backward returned) is covered by ONE
+        all-reduce of that buffer -- no per-parameter staging copies; the others take the generic path."""
         if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
             return 0
         dev = next((p.grad.device for p in self.params if p.grad is not None), self.params[0].device)
         works, nbytes = [], 0
-        for p in self.big:
+        covered = set()
+        if grad_buffer is not None and grad_buffer.numel() > 0:
+            covered = {id(p) for p in self.params if self._inside(p.grad, grad_buffer)}
+            if covered:
+                works.append(dist.all_reduce(grad_buffer, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+                nbytes += grad_buffer.numel() * 4
+        if len(covered) == len(self.params):
+            for w in works:
+                w.wait()
+            return nbytes
+        big = [p for p in self.big if id(p) not in covered]
+        small = [p for p in self.small if id(p) not in covered]
+        for p in big:
             if p.grad is None:
                 p.grad = torch.zeros_like(p)
             g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
@@ -85,7 +108,7 @@ class GradAllReducer:
             nbytes += g.numel() * 4
         flat = self._ensure(dev)
         off, views = 0, []
-        for p in self.small:
+        for p in small:
             n = p.numel()
             v = flat[off:off + n]
             if p.grad is None:
@@ -94,12 +117,12 @@ class GradAllReducer:
                 v.copy_(p.grad.reshape(-1))
             views.append(v)
             off += n
-        if self.small:
-            works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
-            nbytes += self.numel * 4
+        if small:
+            works.append(dist.all_reduce(flat[:max(off, 1)], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            nbytes += off * 4
         for w in works:
             w.wait()
-        for p, v in zip(self.small, views):
+        for p, v in zip(small, views):
             if p.grad is None:
                 p.grad = v.view(p.shape).clone()
             else:

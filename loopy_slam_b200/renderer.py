@@ -87,7 +87,7 @@ def _grid_for(npc, cloud_pos, cell, cache):
 class _RenderCtx:
     """Per-call constants shared by forward and backward."""
     __slots__ = ('prm', 'grid', 'stage', 'is_tracker', 'blob', 'wstruct', 'flat', 'saved', 'scratch', 'R',
-                 'r_query', 'device', 'far_group', 'force_save', 'timing', 'remap')
+                 'r_query', 'device', 'far_group', 'force_save', 'timing', 'remap', 'renderer')
 
 
 def _tick(timing):
@@ -193,6 +193,9 @@ class _RenderFn(torch.autograd.Function):
                  blob.n_elems if any(pneed) else 0, 12 if want_aff else 0]
         sizes = [(n + 3) // 4 * 4 for n in sizes]     # keep every view 16-byte aligned
         flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev) if sum(sizes) else None
+        if rc.renderer is not None:
+            # parallel.GradAllReducer can exchange this ONE buffer instead of every parameter's .grad
+            rc.renderer.last_grad_buffer = flat
         o0, o1, o2 = sizes[0], sizes[0] + sizes[1], sizes[0] + sizes[1] + sizes[2]
         if want_geo:
             flags |= _lib.GRAD_GEO_FEATS
@@ -279,6 +282,7 @@ def fused_render(renderer, npc, decoders, rays_d, rays_o, stage, gt_depth, npc_g
     prm.radius_query = float(radius)
     rc = _RenderCtx()
     rc.prm = prm
+    rc.renderer = renderer
     rc.stage = _lib.LSR_STAGE[stage]
     rc.is_tracker = bool(is_tracker)
     rc.r_query = None

@@ -38,6 +38,21 @@ def _worker(rank, world, port, out):
         ((rays @ w2).sum(0) * f2).sum().backward()
         ok = torch.allclose(w.grad, w2.grad, rtol=1e-5, atol=1e-5) and torch.allclose(feats.grad, f2.grad, rtol=1e-5, atol=1e-5)
         ok = ok and unused.grad is not None and float(unused.grad.abs().sum()) == 0 and nbytes == (12 + 40 + 5) * 4
+        # fast path: gradients that are views of ONE flat buffer (what the fused backward returns) travel in a
+        # single all-reduce of that buffer; a parameter outside it still takes the generic path
+        flat = torch.zeros(16 + 40)
+        a = torch.nn.Parameter(torch.randn(3, 4))
+        b = torch.nn.Parameter(torch.randn(10, 4))
+        c = torch.nn.Parameter(torch.randn(7))
+        a.grad = flat[:12].view(3, 4)
+        b.grad = flat[16:56].view(10, 4)
+        a.grad.fill_(rank + 1.0)
+        b.grad.fill_(10.0 * (rank + 1))
+        c.grad = torch.full((7,), float(rank + 1))
+        nb = GradAllReducer([a, b, c]).allreduce_(flat)
+        tot = world * (world + 1) / 2
+        ok = ok and bool((a.grad == tot).all()) and bool((b.grad == 10 * tot).all()) and bool((c.grad == tot).all())
+        ok = ok and a.grad.data_ptr() == flat.data_ptr() and nb == (56 + 7) * 4
         out[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
