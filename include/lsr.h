@@ -160,15 +160,17 @@ int lsr_dynamic_radius(const float* color_f32, const double* color_f64, int32_t 
 
 /* ---------------------------------------------------------------- fused render
  * Workspace sizes: `saved` holds the activations the backward needs (0 rows -> forward only),
- * `scratch` the re-laid-out weights (+ a tile counter). */
+ * `scratch` the re-laid-out weights (tcgen05 chunk layout for the forward, three plain copies for the backward)
+ * and the per-sample k-NN results the forward's two kernels hand over (120 B per sample row).  The SAME scratch
+ * must be passed to lsr_render_bwd of that forward. */
 int lsr_render_workspace_bytes(const LsrParams* prm, int64_t n_rays, int stage, size_t* saved_bytes,
                                size_t* scratch_bytes);
 
 /* far[g] = min(5*mean(d), 1.2*max(d)) over rays [g*group, (g+1)*group)  (Renderer.py:104-121) */
 int lsr_far_bound(const float* gt_depth, int64_t n_rays, int64_t group, float* far_out, lsr_stream_t stream);
 
-/* One fused launch: z-sampling, grid k-NN, IDW gather, geometry MLP, (rel-pos neighbour MLP,)
- * colour MLP, alpha compositing.  r_query: per-ray float64 radii when LSR_FLAG_DYNAMIC_R.
+/* The forward: weight re-layout, then z-sampling + grid k-NN (sample_knn_kernel), then IDW gather, geometry MLP,
+ * (rel-pos neighbour MLP,) colour MLP, alpha compositing on tcgen05 / TMEM (render_fwd_kernel); three launches.  r_query: per-ray float64 radii when LSR_FLAG_DYNAMIC_R.
  * far_zero: far bound of the z-range used for rays with gt_depth <= 0, one value per group of
  *   far_group consecutive rays (Renderer.py:102-121 batch statistic; see lsr_far_bound); nullable.
  * exposure_affine: 12 floats [A row-major 3x3 | t] for LSR_RGB_AFFINE_SIGMOID.
