@@ -175,7 +175,12 @@ class WeightBlob:
         self.col_w_idx = [k for k, e in enumerate(ent) if e[0].startswith('c_') and e[0] != 'c_B']
 
     def tensors(self):
-        return [getattr(owner, attr) for (_, _, owner, attr) in self.entries]
+        # nn.Module.__getattr__ is a slow path (called per step for ~45 tensors): look parameters up directly
+        out = []
+        for (_, _, owner, attr) in self.entries:
+            t = owner._parameters.get(attr)
+            out.append(t if t is not None else getattr(owner, attr))
+        return out
 
     def _aliased(self, device):
         if self.flat is None or self.flat.device != device:
