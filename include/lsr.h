@@ -187,6 +187,12 @@ int lsr_render_fwd(const LsrParams* prm, const void* grid_ws, const float* cloud
                    const float* exposure_affine, int stage, float* depth, float* var, float* rgb,
                    uint8_t* valid, void* saved, void* scratch, lsr_stream_t stream);
 
+/* Host-logic introspection (no GPU needed; used by the CPU test-suite): statistics of the per-tile tensor-core
+ * GEMM program lsr_render_fwd builds for (stage, flags): out[0..7] = {weight chunks (= bulk copies = mbarrier ring
+ * steps) per tile, weight matrices, packed floats, chunks that wait for an operand hand-over, completions signalled on
+ * accumulator barrier 0, on barrier 1, largest chunk in bytes, capacity of the packed-weight scratch in floats}. */
+int lsr_debug_program_stats(const LsrWeights* w, int stage, int flags, int64_t* out);
+
 /* Backward of lsr_render_fwd for upstream gradients g_depth (R), g_var (R, nullable), g_rgb (R,3).
  * is_tracker: neighbour weights depend on the sample position (decoder.py:191-198).
  * Gradient buffers must be ZEROED by the caller; they are accumulated into with atomics:

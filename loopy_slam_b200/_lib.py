@@ -21,7 +21,7 @@ EXPORTS = [
     'lsr_version', 'lsr_strerror', 'lsr_device_sm_count', 'lsr_grid_workspace_bytes', 'lsr_grid_build',
     'lsr_knn_query', 'lsr_sample_rays', 'lsr_sample_rays_bwd', 'lsr_pose_fwd', 'lsr_pose_bwd',
     'lsr_render_workspace_bytes', 'lsr_far_bound', 'lsr_render_fwd', 'lsr_render_bwd', 'lsr_dynamic_radius',
-    'lsr_loss_scratch_bytes', 'lsr_mapper_loss', 'lsr_tracker_resid', 'lsr_tracker_loss',
+    'lsr_loss_scratch_bytes', 'lsr_mapper_loss', 'lsr_tracker_resid', 'lsr_tracker_loss', 'lsr_debug_program_stats',
 ]
 
 

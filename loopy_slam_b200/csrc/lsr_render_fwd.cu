@@ -808,24 +808,8 @@ __global__ void pack_umma_jobs_kernel(const float* __restrict__ blob, float* __r
     return;
   }
   const UPackJob jb = jobs.j[blockIdx.y];
-  const int half_total = jb.total / 2;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < half_total; e += gridDim.x * blockDim.x) {
-    const int KC = um_kc(jb.n);
-    const int full = jb.n * KC;
-    const int c = e / full;
-    const int k0 = c * KC;
-    const int kc = (((jb.k_valid - k0 < KC) ? (jb.k_valid - k0) : KC) + 7) / 8 * 8;
-    const int r = e - c * full;
-    const int slab = r / (jb.n * 4), row = (r / 4) % jb.n, kq = r % 4;
-    const int k = k0 + slab * 4 + kq;
-    float v = 0.f;
-    if (row < jb.n_valid && k < jb.k_valid) v = blob[jb.src + (size_t)row * jb.ld + jb.col0 + k];
-    uint32_t hi, lo;
-    split_hi_lo(v, hi, lo);
-    float* chunk = packed + jb.dst + (size_t)c * 2 * full;
-    chunk[r] = __uint_as_float(hi);
-    chunk[jb.n * kc + r] = __uint_as_float(lo);
-  }
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < jb.total / 2; e += gridDim.x * blockDim.x)
+    pack_umma_element(jb, e, blob, packed);
 }
 
 // far bound of the z-range of zero-depth rays: min(5*mean, 1.2*max) per group of rays
@@ -909,6 +893,26 @@ int sm_count() {
 }  // namespace lsr
 
 using namespace lsr;
+
+// Host-logic introspection for the CPU test-suite: the GEMM program a (stage, flags) pair compiles to.
+// out[0..7] = {n_ops, n_jobs, packed_floats, ops that wait for a_ready, commits to d_ready[0], commits to d_ready[1],
+//              largest chunk bytes (hi + lo), capacity of the packed buffer in floats}
+extern "C" int lsr_debug_program_stats(const LsrWeights* w, int stage, int flags, int64_t* out) {
+  if (!w || !out) return LSR_ERR_ARG;
+  UProgram P;
+  build_program(w, stage, flags, &P);
+  int waits = 0, c0 = 0, c1 = 0;
+  int64_t maxb = 0;
+  for (int i = 0; i < P.n_ops; ++i) {
+    waits += (P.ops[i].flags & UOP_WAIT_A) ? 1 : 0;
+    c0 += P.ops[i].commit_d == 1;
+    c1 += P.ops[i].commit_d == 2;
+    if (2 * (int64_t)P.ops[i].half_bytes > maxb) maxb = 2 * (int64_t)P.ops[i].half_bytes;
+  }
+  out[0] = P.n_ops; out[1] = P.n_jobs; out[2] = P.packed_floats; out[3] = waits; out[4] = c0; out[5] = c1;
+  out[6] = maxb; out[7] = UMMA_PACKED_FLOATS_MAX;
+  return LSR_OK;
+}
 
 extern "C" int lsr_render_workspace_bytes(const LsrParams* prm, int64_t n_rays, int stage, size_t* saved_bytes,
                                           size_t* scratch_bytes) {
@@ -1010,7 +1014,7 @@ extern "C" int lsr_render_fwd(const LsrParams* prm, const void* grid_ws, const f
   a.affine = exposure_affine;
   a.stage = stage;
   a.depth = depth; a.var = var; a.rgb = rgb; a.valid = valid;
-  a.saved = getenv("LSR_DEBUG_NOSAVE") ? nullptr : (float*)saved;   // timing experiments only
+  a.saved = (float*)saved;
   a.ks = ks;
   a.rays_per_tile = UM_M / prm->n_surface;
   a.ntiles = (int)((n_rays + a.rays_per_tile - 1) / a.rays_per_tile);

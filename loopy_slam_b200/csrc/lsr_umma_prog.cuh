@@ -108,29 +108,31 @@ struct UBuilder {
 
 #ifdef __CUDACC__
 // ---- weight re-layout ----------------------------------------------------------------------------
-// grid (blocks, n_jobs): every thread produces elements of one job.  Destination element order inside a
-// chunk: [hi block | lo block], each slab-major: ((k/4) * n + row) * 4 + k % 4.
+// Element e of job jb -> its (hi, lo) words in the chunked layout.  Destination element order inside a chunk:
+// [hi block | lo block], each slab-major: ((k/4) * n + row) * 4 + k % 4; all chunks but the last hold um_kc(n) k-values.
+__device__ __forceinline__ void pack_umma_element(const UPackJob& jb, int e, const float* __restrict__ blob,
+                                                  float* __restrict__ packed) {
+  const int KC = um_kc(jb.n);
+  const int full = jb.n * KC;
+  const int c = e / full;
+  const int k0 = c * KC;
+  const int kc = (((jb.k_valid - k0 < KC) ? (jb.k_valid - k0) : KC) + 7) / 8 * 8;
+  const int r = e - c * full;            // index inside the chunk's hi block: (slab, row, k%4)
+  const int slab = r / (jb.n * 4), row = (r / 4) % jb.n, kq = r % 4;
+  const int k = k0 + slab * 4 + kq;
+  float v = 0.f;
+  if (row < jb.n_valid && k < jb.k_valid) v = blob[jb.src + (size_t)row * jb.ld + jb.col0 + k];
+  uint32_t hi, lo;
+  split_hi_lo(v, hi, lo);
+  float* chunk = packed + jb.dst + (size_t)c * 2 * full;
+  chunk[r] = __uint_as_float(hi);
+  chunk[jb.n * kc + r] = __uint_as_float(lo);
+}
+// grid (blocks, n_jobs): job list in global memory (bring-up probe; the library passes its jobs by value)
 __global__ void pack_umma_kernel(const float* __restrict__ blob, float* __restrict__ packed, const UPackJob* __restrict__ jobs) {
   const UPackJob jb = jobs[blockIdx.y];
-  const int half_total = jb.total / 2;   // one element per (chunk, row, k) pair
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < half_total; e += gridDim.x * blockDim.x) {
-    // locate the chunk: all chunks but the last hold UM_KC k-values
-    const int KC = um_kc(jb.n);
-    const int full = jb.n * KC;
-    const int c = e / full;
-    const int k0 = c * KC;
-    const int kc = (((jb.k_valid - k0 < KC) ? (jb.k_valid - k0) : KC) + 7) / 8 * 8;
-    const int r = e - c * full;            // index inside the chunk's hi block: (slab, row, k%4)
-    const int slab = r / (jb.n * 4), row = (r / 4) % jb.n, kq = r % 4;
-    const int k = k0 + slab * 4 + kq;
-    float v = 0.f;
-    if (row < jb.n_valid && k < jb.k_valid) v = blob[jb.src + (size_t)row * jb.ld + jb.col0 + k];
-    uint32_t hi, lo;
-    split_hi_lo(v, hi, lo);
-    float* chunk = packed + jb.dst + (size_t)c * 2 * full;
-    chunk[r] = __uint_as_float(hi);
-    chunk[jb.n * kc + r] = __uint_as_float(lo);
-  }
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < jb.total / 2; e += gridDim.x * blockDim.x)
+    pack_umma_element(jb, e, blob, packed);
 }
 
 // ---- pipeline state (shared memory) ----------------------------------------------------------------

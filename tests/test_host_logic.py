@@ -95,3 +95,47 @@ def test_frustum_selection_cpu():
     assert sel[:surf.shape[0]].float().mean() > 0.9
     assert not sel[surf.shape[0]:2 * surf.shape[0]].any()
     assert sel[2 * surf.shape[0]:].float().mean() < 0.1
+
+
+def test_forward_gemm_program_invariants():
+    """The static tensor-core program of a forward tile (csrc/lsr_render_fwd.cu:build_program) must match what the
+    epilogue warps of render_fwd_kernel expect: one operand hand-over per GEMM group, one completion per epilogue
+    wait, chunks that fit a ring stage, packed weights that fit the scratch."""
+    import ctypes
+    import numpy as np
+    import __graft_entry__ as entry
+    entry.build()
+    from loopy_slam_b200 import _lib
+    L = _lib.lib()
+    W = _lib.LsrWeights()
+    # realistic offsets (state_dict order, every tensor 16-byte aligned); the blob itself is never dereferenced here
+    W.blob = 16
+    W.n_elems = 1 << 20
+    off = 0
+    sizes = {'g_fc_w': [1024] * 5, 'g_fc_b': [32] * 5, 'g_B': 279, 'g_lin_w': [2976, 1024, 1024, 4000, 1024], 'g_lin_b': [32] * 5,
+             'g_out_w': 32, 'g_out_b': 1, 'c_fc_w': [4096] * 5, 'c_fc_b': [128] * 5, 'c_B': 60, 'c_Brel': 30,
+             'c_nb1_w': 6656, 'c_nb1_b': 128, 'c_nb2_w': 4096, 'c_nb2_b': 32,
+             'c_lin_w': [5120, 16384, 16384, 21504, 16384], 'c_lin_b': [128] * 5, 'c_out_w': 384, 'c_out_b': 3}
+    for name, sz in sizes.items():
+        if isinstance(sz, list):
+            for i, n in enumerate(sz):
+                getattr(W, name)[i] = off
+                off += (n + 3) // 4 * 4
+        else:
+            setattr(W, name, off)
+            off += (sz + 3) // 4 * 4
+    out = (ctypes.c_int64 * 8)()
+    L.lsr_debug_program_stats.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    expect = {  # (stage, flags) -> (operand hand-overs, completions on barrier 0, on barrier 1)
+        (0, 0): (5, 5, 0),              # geometry: 5 layers
+        (1, 0): (5 + 6, 5 + 6, 0),      # + colour trunk (5 layers) + head
+        (1, 1): (5 + 9 + 6, 5 + 4 + 1 + 6, 4),   # + rel-pos MLP: 8 neighbour passes on ping-pong accumulators + V2
+    }
+    for (stage, flags), (waits, c0, c1) in expect.items():
+        assert L.lsr_debug_program_stats(ctypes.byref(W), stage, flags, out) == 0
+        n_ops, n_jobs, packed, w_, a_, b_, maxb, cap = list(out)
+        assert (w_, a_, b_) == (waits, c0, c1), (stage, flags, list(out))
+        assert 0 < n_ops <= 96 and 0 < n_jobs <= 40
+        assert maxb <= 32768 and maxb % 32 == 0          # a chunk (hi + lo) fits one ring stage, 16-byte halves
+        assert packed <= cap
+    assert L.lsr_debug_program_stats(None, 1, 1, out) == 1

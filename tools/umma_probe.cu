@@ -1,8 +1,9 @@
 // Bring-up probe of the tcgen05 building blocks (lsr_umma.cuh / lsr_umma_prog.cuh) on a real B200:
-//   1. one 128 x N x K GEMM, operands laid out by hand, A from shared memory (SS) or from TMEM (TS),
-//      both assignments of the descriptor LBO / SBO fields -> tells which convention the hardware uses;
+//   1. one 128 x N x K GEMM, operands laid out by hand, A from shared memory (SS) or from TMEM (TS), exact on
+//      tf32-representable inputs (mode 4: the other assignment of the descriptor LBO / SBO fields, which faults);
 //   2. the streamed-weight engine (producer / issuer / epilogue warps) on a colour-trunk-shaped 5-layer MLP,
-//      checked against an fp64 host evaluation, then timed over many tiles on all SMs.
+//      checked against an fp64 host evaluation, then timed over many tiles on all SMs;
+//   3. (open) weight-gradient shaped GEMMs with MN-major operands: kind::tf32 + SWIZZLE_NONE yields zeros so far.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o tools/umma_probe tools/umma_probe.cu
 #include <cmath>
 #include <cstdio>
@@ -409,18 +410,22 @@ int main(int argc, char** argv) {
   int only = argc > 1 ? atoi(argv[1]) : 0;
   if (only == 0 || only == 1) {
     printf("test 1: single GEMMs (exact-in-tf32 inputs: any layout error shows as O(1) mismatch)\n");
-    for (int swap = 0; swap < 2; ++swap)
-      for (int ts = 0; ts < 2; ++ts) {
-        if (test_gemm(32, 128, swap, ts, 0, true) < 0) { printf("  (context lost, stopping)\n"); return 1; }
-      }
+    for (int ts = 0; ts < 2; ++ts)
+      if (test_gemm(32, 128, 0, ts, 0, true) < 0) { printf("  (context lost, stopping)\n"); return 1; }
     printf("  3xTF32, random inputs:\n");
     test_gemm(40, 128, 0, 0, 1, false);
-    test_gemm(128, 128, 0, 1, 1, false);
+    test_gemm(64, 128, 0, 1, 1, false);
     test_gemm(128, 32, 0, 1, 1, false);
     test_gemm(128, 16, 0, 1, 1, false);
     test_gemm(56, 128, 0, 0, 1, false);
     printf("  1xTF32, random inputs (expected ~5e-4):\n");
-    test_gemm(128, 128, 0, 0, 0, false);
+    test_gemm(64, 128, 0, 0, 0, false);
+  }
+  if (only == 4) {
+    printf("test 4: the OTHER assignment of the descriptor LBO / SBO fields (how the convention was found; on B200 this\n"
+           "        faults with an illegal memory access, i.e. LBO = K direction, SBO = row direction is the right one)\n");
+    for (int ts = 0; ts < 2; ++ts)
+      if (test_gemm(32, 128, 1, ts, 0, true) < 0) { printf("  (context lost, stopping)\n"); return 1; }
   }
   if (only == 3) {
     printf("test 3: weight-gradient shaped GEMMs, operands MN-major (contraction over the rows)\n");
