@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(128) probe_gemm(const float* A, const float* B
 // Weight-gradient shaped GEMM: D[m][n] = sum_r A[r][m] * B[r][n] (contraction over the 128 ROWS), A (128 x 128) and
 // B (128 x N) stored exactly like the forward's activation tiles (row-thread float4 stores: (f/4) * 2048 + r * 16 +
 // (f % 4) * 4), but described to the tensor core as MN-major operands.  swap: exchange the LBO / SBO fields.
-__global__ void __launch_bounds__(128) probe_gemm_mn(const float* A, const float* B, float* D, int N, int swap, int three) {
+__global__ void __launch_bounds__(128) probe_gemm_mn(const float* A, const float* B, float* D, int N, int swap, int three, int which) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tslot;
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(128) probe_gemm_mn(const float* A, const float
   __syncthreads();
   if (tid == 0) {
     tc_fence_after();
-    const uint32_t idesc = idesc_tf32(128, N) | (1u << 15) | (1u << 16);   // A and B MN-major
+    const uint32_t idesc = idesc_tf32(128, N) | ((which & 1) ? (1u << 15) : 0u) | ((which & 2) ? (1u << 16) : 0u);   // A / B MN-major
     uint32_t acc = 0;
     for (int k8 = 0; k8 < 16; ++k8) {   // 8 rows per MMA: one 128-byte core matrix along K
       const uint32_t off = k8 * 128;
@@ -365,7 +365,7 @@ static int test_gemm(int K, int N, int swap, int ts, int three, bool exact_input
   return rel < (three || exact_inputs ? 2e-6 : 2e-3) ? 1 : 0;
 }
 
-static int test_gemm_mn(int N, int swap, int three, bool exact_inputs, int pattern = 0) {
+static int test_gemm_mn(int N, int swap, int three, bool exact_inputs, int pattern = 0, int which = 3) {
   std::vector<float> A(128 * 128), B(128 * N), D(128 * N);
   for (auto& v : A) v = exact_inputs ? (float)((rand() % 17) - 8) * 0.125f : frand();
   for (auto& v : B) v = exact_inputs ? (float)((rand() % 17) - 8) * 0.25f : frand();
@@ -389,10 +389,10 @@ static int test_gemm_mn(int N, int swap, int three, bool exact_inputs, int patte
   CK(cudaMemset(dD, 0, D.size() * 4));
   const int smem = (2 * 128 * 128 + 2 * 128 * N) * 4 + 1024;
   CK(cudaFuncSetAttribute(probe_gemm_mn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  probe_gemm_mn<<<1, 128, smem>>>(dA, dB, dD, N, swap, three);
+  probe_gemm_mn<<<1, 128, smem>>>(dA, dB, dD, N, swap, three, which);
   cudaError_t e = cudaDeviceSynchronize();
   char name[128];
-  snprintf(name, sizeof name, "A^T.B (MN-major) N=%d %s %s", N, swap ? "LBO=MN SBO=K" : "LBO=K(128B) SBO=MN(2048B)", three ? "3xTF32" : "1xTF32");
+  snprintf(name, sizeof name, "A^T.B (MN-major %s%s) N=%d %s %s", (which & 1) ? "A" : "", (which & 2) ? "B" : "", N, swap ? "LBO=MN SBO=K" : "LBO=K(128B) SBO=MN(2048B)", three ? "3xTF32" : "1xTF32");
   if (e != cudaSuccess) { printf("  %-44s CUDA error: %s\n", name, cudaGetErrorString(e)); return -1; }
   CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
   const double rel = check(name, D, ref);
@@ -431,9 +431,8 @@ int main(int argc, char** argv) {
     printf("test 3: weight-gradient shaped GEMMs, operands MN-major (contraction over the rows)\n");
     for (int swap = 0; swap < 2; ++swap)
       if (test_gemm_mn(64, swap, 0, true) < 0) { printf("  (context lost, stopping)\n"); return 1; }
-    test_gemm_mn(64, 0, 0, true, 1);
-    test_gemm_mn(64, 0, 0, true, 2);
-    test_gemm_mn(64, 1, 0, true, 2);
+    for (int which = 0; which < 4; ++which)
+      for (int swap = 0; swap < 2; ++swap) test_gemm_mn(64, swap, 0, true, 1, which);
   }
   if (only == 0 || only == 2) {
     printf("test 2: streamed-weight engine on a colour-trunk-shaped MLP\n");
