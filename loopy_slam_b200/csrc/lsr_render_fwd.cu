@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
           if (li < 4) {
             tmem_st16(tmem_addr(tb, lane_base, TM_AHI + 16 * half), x1);
             tmem_st16(tmem_addr(tb, lane_base, TM_ALO + 16 * half), x2);
-            es.signal_a(pipe);
+            es.signal_a_tmem(pipe);
           }
         }
         sOccP[half * 128 + row] = occ_part;
@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
               tmem_st16(tmem_addr(tb, lane_base, TM_ALO + 64 * half + 16 * c), lo);
             }
           }
-          es.signal_a(pipe);
+          es.signal_a_tmem(pipe);
           es.wait_d(pipe, 0);
           {
             uint32_t x[16];
@@ -658,7 +658,7 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
             if (c & 1) stage_flush<32, 36>(stS, lane, cs_ + 16 * (c - 1), (size_t)HC, wvalid);
             if (c < 3) tmem_wait_ld();
           }
-          es.signal_a(pipe);   // li == 4: feeds the colour head GEMM
+          es.signal_a_tmem(pipe);   // li == 4: feeds the colour head GEMM
         }
         FWD_PHASE(4);
         // -------------------------------------------------------------- colour head (decoder.py:533-546)

@@ -268,6 +268,14 @@ struct EpiSync {
     fence_proxy_async();
     mbar_arrive(&p->a_ready);
   }
+  // same, when the hand-over is TMEM only (no shared-memory operand was written since the last signal): skips
+  // the generic->async proxy fence, which is a MEMBAR that also waits for this thread's global stores in flight
+  template <int NS>
+  __device__ __forceinline__ void signal_a_tmem(UPipe<NS>* p) {
+    tmem_wait_st();
+    tc_fence_before();
+    mbar_arrive(&p->a_ready);
+  }
 };
 
 // float4 of 4 consecutive k (k % 4 == 0) of row r -> shared-memory A operand (hi and lo tiles)
