@@ -354,7 +354,15 @@ def run_lsr(args, rank, world, local):
         'clocks': clocks, 'loss': loss_host,
     }
     if world == 1 and not args.no_cpu_baseline:
-        out['cpu_baseline'] = cpu_baseline(sc, stage, budget_s=args.cpu_budget)
+        for p in model.parameters():
+            p.requires_grad_(False)
+        o0, d0, g0, _ = dev_batches[0]
+        with torch.no_grad():
+            dep, _, colr, val = rend.render_batch_ray(npc, model, d0, o0, dev, stage, gt_depth=g0, npc_geo_feats=npc_geo,
+                                                      npc_col_feats=npc_col, is_tracker=False, cloud_pos=cloud)
+        torch.cuda.synchronize(dev)
+        out['cpu_baseline'] = cpu_baseline(sc, stage, budget_s=args.cpu_budget, cuda_render=(dep, colr, val))
+        out['depth_l1_vs_reference_m'] = out['cpu_baseline']['parity']['depth_l1_vs_oracle_m']
     print(json.dumps(out))
 
 
@@ -373,7 +381,7 @@ def _oracle_setup(sc, stage):
     return orc, ocfg, W, grid
 
 
-def _oracle_step(orc, ocfg, W, grid, sc, batch, stage):
+def _oracle_step(orc, ocfg, W, grid, sc, batch, stage, outputs=None):
     """The reference's step restated on the CPU: exact 8-NN + decoders + compositing + loss + backward."""
     o, d, g, c = batch
     t0 = time.perf_counter()
@@ -387,10 +395,12 @@ def _oracle_step(orc, ocfg, W, grid, sc, batch, stage):
     depth, var, rgb, valid, _ = orc.render_rays(Wl, ocfg, o, d, g, geo, col, sc['cloud'], stage, knn=knn)
     loss = mapper_loss_eager(depth, rgb, valid, g, c, stage)
     loss.backward()
+    if outputs is not None:
+        outputs.update(depth=depth.detach(), rgb=rgb.detach(), valid=valid.detach())
     return time.perf_counter() - t0
 
 
-def cpu_baseline(sc, stage, budget_s=20.0, rays=None):
+def cpu_baseline(sc, stage, budget_s=20.0, rays=None, cuda_render=None):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     orc, ocfg, W, grid = _oracle_setup(sc, stage)
@@ -398,15 +408,29 @@ def cpu_baseline(sc, stage, budget_s=20.0, rays=None):
     if rays:
         batch = [t[:rays] for t in batch]
     R = batch[0].shape[0]
-    _oracle_step(orc, ocfg, W, grid, sc, batch, stage)                  # warm-up
+    ref = {}
+    _oracle_step(orc, ocfg, W, grid, sc, batch, stage, outputs=ref)     # warm-up; its render is the parity reference
     ts = []
     t_start = time.perf_counter()
     while len(ts) < 3 or (time.perf_counter() - t_start < budget_s and len(ts) < 20):
         ts.append(_oracle_step(orc, ocfg, W, grid, sc, batch, stage))
     t = sum(ts) / len(ts)
-    return {'value': R / t, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
-            'sample': f'{len(ts)} iterations of the same step ({R} rays x 5 samples, N={sc["cloud"].shape[0]}) on the '
-                      f'oracle torch-CPU restatement + C grid k-NN, {cores} threads', 'ms_per_step': t * 1e3}
+    out = {'value': R / t, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
+           'sample': f'{len(ts)} iterations of the same step ({R} rays x 5 samples, N={sc["cloud"].shape[0]}) on the '
+                     f'oracle torch-CPU restatement + C grid k-NN, {cores} threads', 'ms_per_step': t * 1e3}
+    if cuda_render is not None:
+        # second half of BASELINE's metric: depth-L1 of the CUDA render against the reference (oracle) render of the
+        # same rays (the reference's depth_l1_render, src/Mapper.py:1146-1147, restricted to this batch)
+        d_cu, c_cu, v_cu = [t.detach().cpu() for t in cuda_render]
+        ok = ref['valid'].bool() & (batch[2] > 0)
+        same_mask = bool((v_cu.bool() == ref['valid'].bool()).all())
+        dl1 = float((d_cu - ref['depth']).abs()[ok].mean()) if ok.any() else 0.0
+        cl1 = float((c_cu - ref['rgb']).abs()[ok].mean()) if ok.any() else 0.0
+        out['parity'] = {'depth_l1_vs_oracle_m': dl1, 'rgb_l1_vs_oracle': cl1, 'valid_mask_identical': same_mask,
+                         'rays': int(ok.sum()), 'mean_depth_m': float(ref['depth'][ok].mean()) if ok.any() else 0.0,
+                         'depth_l1_vs_sensor_m_cuda': float((d_cu - batch[2]).abs()[ok].mean()) if ok.any() else 0.0,
+                         'depth_l1_vs_sensor_m_oracle': float((ref['depth'] - batch[2]).abs()[ok].mean()) if ok.any() else 0.0}
+    return out
 
 
 def run_reference(args, rank, world):

@@ -89,3 +89,31 @@ def test_fullsize_backward_linearity(scene):
     _, g3, c3 = _render(sc, grads=True, up=(2 * u1[0] - u2[0], 2 * u1[1] - u2[1]))
     assert (g3 - (2 * g1 - g2)).norm() / g3.norm() < 1e-5
     assert (c3 - (2 * c1 - c2)).norm() / c3.norm() < 1e-5
+
+
+def test_fullsize_depth_l1_vs_oracle(scene):
+    """BASELINE.json's quality half: depth-L1 between the CUDA render and the reference (oracle) render of the same
+    4 992-ray mapper batch (the reference's depth_l1_render, src/Mapper.py:1146-1147, on this batch).  The oracle
+    runs at full size here because its neighbour search goes through the C grid k-NN (oracle/c/knn_grid.c)."""
+    from oracle import render as orc
+    from oracle.knn_c import GridKNN
+    sc = scene
+    with torch.no_grad():
+        depth, var, rgb, valid = [t.cpu() for t in _render(sc)]
+    W = {k: v.detach().cpu().clone() for k, v in sc['model'].state_dict().items()}
+    W['color_decoder.embedder._B'] = sc['model'].color_decoder.embedder._B.detach().cpu().clone()
+    ocfg = orc.OracleCfg.from_cfg(sc['cfg'])
+    o, d, g = sc['o'].cpu(), sc['d'].cpu(), sc['g'].cpu()
+    cloud = sc['cloud'].cpu()
+    z = orc.sample_z(g, ocfg)
+    p = (o[:, None, :] + d[:, None, :] * z[:, :, None]).reshape(-1, 3)
+    knn = GridKNN(cloud, 0.08).query(p, ocfg.radius_query)
+    with torch.no_grad():
+        dr, vr, cr, validr, _ = orc.render_rays(W, ocfg, o, d, g, sc['geo'].cpu(), sc['col'].cpu(), cloud, 'color', knn=knn)
+    assert torch.equal(valid.bool(), validr.bool())
+    m = validr.bool() & (g > 0)
+    assert m.float().mean() > 0.9
+    depth_l1 = (depth - dr).abs()[m].mean().item()
+    rgb_l1 = (rgb - cr).abs()[m].mean().item()
+    assert depth_l1 < 2e-5 and rgb_l1 < 2e-5, (depth_l1, rgb_l1)      # metres / colour units; sensor depth is 1-5 m
+    assert torch.allclose(depth[m], dr[m], rtol=1e-4, atol=1e-6) and torch.allclose(rgb[m], cr[m], rtol=1e-4, atol=2e-5)
