@@ -23,7 +23,7 @@ constexpr int UM_STAGE_BYTES = 2 * 128 * UM_KC * 4;   // [hi | lo] of a 128 x 32
 // Narrow matrices get proportionally deeper chunks (N = 32 -> K = 128): the same stage bytes, fewer L2 round trips.
 __host__ __device__ constexpr int um_kc(int n) { return (UM_STAGE_BYTES / 8) / n < 128 ? (UM_STAGE_BYTES / 8) / n : 128; }
 constexpr int UM_A_SLAB = UM_M * 16;       // bytes of one 4-wide K slab of an A operand in shared memory (= LBO of A)
-constexpr int UM_MAX_OPS = 144;
+constexpr int UM_MAX_OPS = 96;
 constexpr int UM_MAX_JOBS = 40;
 
 struct UOp {           // 32 bytes, device-ready (read through the constant bank: kernel parameter)
