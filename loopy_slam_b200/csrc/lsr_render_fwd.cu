@@ -165,8 +165,18 @@ __global__ void __launch_bounds__(256, 4) sample_knn_kernel(const __grid_constan
 
 // ------------------------------------------------------------------------------------------------ kernel 2
 constexpr int FNS = 2;                                   // weight ring stages
-constexpr int FT = 320;                                  // threads: 8 compute warps + issuer warp + producer warp
-constexpr int NCT = 256;                                 // compute threads
+#ifndef LSR_FWD_CW
+#define LSR_FWD_CW 16
+#endif
+constexpr int CW = LSR_FWD_CW;                           // compute / epilogue warps: 8 or 16 (4 lane quadrants x NCG column groups)
+constexpr int NCG = CW / 4;                              // column groups of the 128-wide layers
+constexpr int CPT = HC / NCG;                            // columns per thread in the 128-wide epilogues (64 / 32)
+constexpr int STEPS = CPT / 16;                          // 16-column TMEM steps per thread
+constexpr int TPR = CW / 4;                              // threads per row in the gather / operand-build phases
+constexpr int F4T = 8 / TPR;                             // float4 of a 32-float feature row per thread
+constexpr int NCT = CW * 32;                             // compute threads
+constexpr int FT = NCT + 64;                             // + issuer warp + producer warp
+static_assert(CW == 8 || CW == 16, "compute warps");
 // dynamic shared memory carve-up (bytes from the 1024-aligned base)
 constexpr int SM_RING = 0;
 constexpr int SM_UNION = SM_RING + FNS * UM_STAGE_BYTES;
@@ -192,7 +202,7 @@ constexpr int SM_PIPE = SM_BIAS + 2200 * 4;
 constexpr int FWD_SMEM_BYTES = SM_PIPE + 128;
 static_assert(SM_Q_LO + 14 * UM_A_SLAB <= SM_C_HI && SM_EG_LO + 24 * UM_A_SLAB <= SM_C_HI, "union region");
 static_assert(FWD_SMEM_BYTES <= 232448, "shared memory budget");
-static_assert(8 * 32 * 36 * 4 <= 20 * UM_A_SLAB && 8 * 32 * (36 + 20) * 4 <= 28 * UM_A_SLAB, "store staging fits the dead operand regions");
+static_assert(CW * 32 * 20 * 4 <= 20 * UM_A_SLAB, "store staging ([32][20] floats per warp) fits the dead e' / Q operand regions");
 struct Bias {   // float offsets inside the shared bias table
   static constexpr int gb = 0, gu = 160, gow = 320, gob = 352;            // geometry: 5x32, 5x32, 32, 1
   static constexpr int cb = 356, cu = cb + 640, v1b = cu + 640, v2b = v1b + 128, cob = v2b + 32;   // colour
@@ -305,21 +315,21 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
     else if (relpos && i >= Bias::rB && i < Bias::rB + 3 * ER) v = blob[a.w.c_Brel + (i - Bias::rB)];
     sBias[i] = v;
   }
-  if (warp == 8) tmem_alloc(&pipe->tmem_base, 512);
+  if (warp == CW) tmem_alloc(&pipe->tmem_base, 512);
   if (tid == 0) pipe_init<FNS>(pipe, NCT);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tb = pipe->tmem_base;
 
-  if (warp == 9) {
+  if (warp == CW + 1) {
     // ================================================================ producer: weight chunks -> ring
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x)
         producer_tile<FNS>(a.ops, a.n_ops, a.wpk, smem + SM_RING, pipe, it);
     }
-  } else if (warp == 8) {
+  } else if (warp == CW) {
     // ================================================================ issuer: tcgen05.mma
     uint32_t it = 0, a_par = 0;
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x)
@@ -328,7 +338,8 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
     // ================================================================ compute / epilogue warps
     EpiSync es;
     const int row = 32 * (warp & 3) + lane;       // sample row of the tile = TMEM lane
-    const int half = warp >> 2;                   // which half of the columns this warp handles
+    const int cg = warp >> 2;                     // column group of this warp: columns [CPT * cg, +CPT) of a 128-wide layer
+    const bool narrow = cg < 2;                   // the 32-wide layers (geometry, V2) are handled by column groups 0, 1 (16 each)
     const uint32_t lane_base = 32u * (warp & 3);
     const float4* sB4 = reinterpret_cast<const float4*>(sBias);
 
@@ -363,19 +374,19 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
 
       // ---------------------------------------------------------------- geometry feature (IDW gather) -> c
       {
-        const int m = tid & 127, qg = tid >> 7;   // 2 threads per row, 4 float4 each
-        float4 acc[4];
+        const int m = tid & 127, qg = tid >> 7;   // TPR threads per row, F4T float4 each
+        float4 acc[F4T];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < F4T; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (sHas[m]) {
 #pragma unroll
           for (int k = 0; k < KNN; ++k) {
             const int idx = sIdx[m * KNN + k];
             if (idx >= 0) {
               const float w = sW[m * KNN + k];
-              const float4* fr = reinterpret_cast<const float4*>(feat_row_cached(a.geo_feats, a.geo_leaf, idx, sRem[m * KNN + k])) + qg * 4;
+              const float4* fr = reinterpret_cast<const float4*>(feat_row_cached(a.geo_feats, a.geo_leaf, idx, sRem[m * KNN + k])) + qg * F4T;
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
+              for (int i = 0; i < F4T; ++i) {
                 const float4 f = __ldg(fr + i);
                 acc[i].x = fmaf(w, f.x, acc[i].x); acc[i].y = fmaf(w, f.y, acc[i].y);
                 acc[i].z = fmaf(w, f.z, acc[i].z); acc[i].w = fmaf(w, f.w, acc[i].w);
@@ -384,9 +395,9 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
           }
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          store_a_split(smem + SM_C_HI, smem + SM_C_LO, m, (qg * 4 + i) * 4, acc[i]);
-          if (save && m < nrows) reinterpret_cast<float4*>(a.saved + SL.cg)[(p0 + m) * 8 + qg * 4 + i] = acc[i];
+        for (int i = 0; i < F4T; ++i) {
+          store_a_split(smem + SM_C_HI, smem + SM_C_LO, m, (qg * F4T + i) * 4, acc[i]);
+          if (save && m < nrows) reinterpret_cast<float4*>(a.saved + SL.cg)[(p0 + m) * 8 + qg * F4T + i] = acc[i];
         }
       }
       // ---------------------------------------------------------------- geometry Fourier features -> e
@@ -416,16 +427,20 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
 #pragma unroll 1
         for (int li = 0; li < 5; ++li) {
           es.wait_d(pipe, 0);
+          if (!narrow) {                       // warp-uniform: the other column groups only keep the handshake counts
+            if (li < 4) es.signal_a_tmem(pipe);
+            continue;
+          }
           uint32_t x1[16], x2[16];
-          tmem_ld16(tmem_addr(tb, lane_base, TM_ACC0 + 16 * half), x1);
-          tmem_ld16(tmem_addr(tb, lane_base, TM_ACC0 + 32 + 16 * half), x2);
+          tmem_ld16(tmem_addr(tb, lane_base, TM_ACC0 + 16 * cg), x1);
+          tmem_ld16(tmem_addr(tb, lane_base, TM_ACC0 + 32 + 16 * cg), x2);
           tmem_wait_ld();
-          float* gs = a.saved + SL.gs + ((size_t)li * Pp + prow) * HG + 16 * half;
-          float* gh = a.saved + SL.gh + ((size_t)li * Pp + prow) * HG + 16 * half;
+          float* gs = a.saved + SL.gs + ((size_t)li * Pp + prow) * HG + 16 * cg;
+          float* gh = a.saved + SL.gh + ((size_t)li * Pp + prow) * HG + 16 * cg;
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
-            const float4 bb = sB4[(Bias::gb + li * 32 + 16 * half + j) >> 2];
-            const float4 uu = sB4[(Bias::gu + li * 32 + 16 * half + j) >> 2];
+            const float4 bb = sB4[(Bias::gb + li * 32 + 16 * cg + j) >> 2];
+            const float4 uu = sB4[(Bias::gu + li * 32 + 16 * cg + j) >> 2];
             const float bv[4] = {bb.x, bb.y, bb.z, bb.w}, uv[4] = {uu.x, uu.y, uu.z, uu.w};
             float s[4], h[4];
 #pragma unroll
@@ -439,18 +454,18 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
               *reinterpret_cast<float4*>(gh + j) = make_float4(h[0], h[1], h[2], h[3]);
             }
             if (li == 4) {
-              const float4 ow = sB4[(Bias::gow + 16 * half + j) >> 2];
+              const float4 ow = sB4[(Bias::gow + 16 * cg + j) >> 2];
               occ_part = fmaf(h[0], ow.x, occ_part); occ_part = fmaf(h[1], ow.y, occ_part);
               occ_part = fmaf(h[2], ow.z, occ_part); occ_part = fmaf(h[3], ow.w, occ_part);
             }
           }
           if (li < 4) {
-            tmem_st16(tmem_addr(tb, lane_base, TM_AHI + 16 * half), x1);
-            tmem_st16(tmem_addr(tb, lane_base, TM_ALO + 16 * half), x2);
+            tmem_st16(tmem_addr(tb, lane_base, TM_AHI + 16 * cg), x1);
+            tmem_st16(tmem_addr(tb, lane_base, TM_ALO + 16 * cg), x2);
             es.signal_a_tmem(pipe);
           }
         }
-        sOccP[half * 128 + row] = occ_part;
+        if (narrow) sOccP[cg * 128 + row] = occ_part;
         bar_compute();
         if (tid < 128) {   // occupancy logit (decoder.py:284)
           const float o = (sBias[Bias::gob] + sOccP[tid]) + sOccP[128 + tid];
@@ -466,46 +481,53 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
           // zero the K padding (columns 52..55) of Q once per tile
           if (tid < 128) store_a_split(smem + SM_Q_HI, smem + SM_Q_LO, tid, QD, make_float4(0.f, 0.f, 0.f, 0.f));
           auto build_q = [&](int k) {
-            if (tid < 128) {
-              // relative-position Fourier features of row tid: q[0..9] = sin, q[10..19] = cos
-              const int m = tid;
-              const int idx = sIdx[m * KNN + k];
-              float q[2 * ER];
+            constexpr int HG2 = TPR / 2;                 // thread groups (of 128) per half of the work
+            const int m = tid & 127, grp = tid >> 7;
+            const int idx = sIdx[m * KNN + k];
+            if (grp < HG2) {
+              // relative-position Fourier features of row m: q[0..9] = sin, q[10..19] = cos; this thread: ER / HG2 frequencies
+              constexpr int NJ = ER / HG2;
+              float sn[NJ], cs[NJ];
 #pragma unroll
-              for (int j = 0; j < 2 * ER; ++j) q[j] = 0.f;
+              for (int j = 0; j < NJ; ++j) { sn[j] = 0.f; cs[j] = 0.f; }
               if (idx >= 0) {
                 const float4 p = sP[m];
                 const float t0 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 0), p.x);
                 const float t1 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 1), p.y);
                 const float t2 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 2), p.z);
 #pragma unroll
-                for (int j = 0; j < ER; ++j) {
-                  const float arg = fmaf(t2, sBias[Bias::rB + 2 * ER + j], fmaf(t1, sBias[Bias::rB + ER + j], t0 * sBias[Bias::rB + j]));
-                  sincos_ff(arg, &q[j], &q[ER + j]);
+                for (int j = 0; j < NJ; ++j) {
+                  const int jj = grp * NJ + j;
+                  const float arg = fmaf(t2, sBias[Bias::rB + 2 * ER + jj], fmaf(t1, sBias[Bias::rB + ER + jj], t0 * sBias[Bias::rB + jj]));
+                  sincos_ff(arg, &sn[j], &cs[j]);
                 }
               }
 #pragma unroll
-              for (int g = 0; g < 5; ++g)
-                store_a_split(smem + SM_Q_HI, smem + SM_Q_LO, m, 4 * g, make_float4(q[4 * g], q[4 * g + 1], q[4 * g + 2], q[4 * g + 3]));
+              for (int j = 0; j < NJ; ++j) {
+                store_a_split1(smem + SM_Q_HI, smem + SM_Q_LO, m, grp * NJ + j, sn[j]);
+                store_a_split1(smem + SM_Q_HI, smem + SM_Q_LO, m, ER + grp * NJ + j, cs[j]);
+              }
             } else {
-              // neighbour feature row of row tid - 128: q[20..51]
-              const int m = tid - 128;
-              const int idx = sIdx[m * KNN + k];
-              float4 f[8];
+              // neighbour feature row of row m: q[20..51]; this thread: 8 / HG2 float4
+              constexpr int NF = 8 / HG2;
+              const int f0 = (grp - HG2) * NF;
+              float4 f[NF];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int i = 0; i < NF; ++i) f[i] = make_float4(0.f, 0.f, 0.f, 0.f);
               if (idx >= 0) {
-                const float4* fr = reinterpret_cast<const float4*>(feat_row_cached(a.col_feats, a.col_leaf, idx, sRem[m * KNN + k]));
+                const float4* fr = reinterpret_cast<const float4*>(feat_row_cached(a.col_feats, a.col_leaf, idx, sRem[m * KNN + k])) + f0;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = __ldg(fr + i);
+                for (int i = 0; i < NF; ++i) f[i] = __ldg(fr + i);
               }
 #pragma unroll
-              for (int i = 0; i < 8; ++i) store_a_split(smem + SM_Q_HI, smem + SM_Q_LO, m, 2 * ER + i * 4, f[i]);
+              for (int i = 0; i < NF; ++i) store_a_split(smem + SM_Q_HI, smem + SM_Q_LO, m, 2 * ER + (f0 + i) * 4, f[i]);
             }
           };
-          float uf[64];
+          float uf[CPT];
 #pragma unroll
-          for (int i = 0; i < 64; ++i) uf[i] = 0.f;
+          for (int i = 0; i < CPT; ++i) uf[i] = 0.f;
+          // saved-activation staging of this warp: [32][20] floats inside the (still unused) e' region
+          float* st = reinterpret_cast<float*>(smem + SM_EC_HI) + warp * (32 * 20);
           build_q(0);
           es.signal_a(pipe);
 #pragma unroll 1
@@ -514,77 +536,75 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
             if (k + 1 < KNN) { build_q(k + 1); es.signal_a(pipe); }   // GEMM k+1 runs under this epilogue
             const uint32_t accb = (k & 1) ? TM_ACC1 : TM_ACC0;
             const float wk = sW[row * KNN + k];
-            float* sp = a.saved + SL.sp + (pw0 * KNN + k) * HC + 64 * half;
-            float* st = reinterpret_cast<float*>(smem + SM_EC_HI) + warp * (32 * 36);   // e' is built after this phase
+            float* sp = a.saved + SL.sp + (pw0 * KNN + k) * HC + CPT * cg;
             uint32_t x[2][16];
-            tmem_ld16(tmem_addr(tb, lane_base, accb + 64 * half), x[0]);
+            tmem_ld16(tmem_addr(tb, lane_base, accb + CPT * cg), x[0]);
             tmem_wait_ld();
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              if (c < 3) tmem_ld16(tmem_addr(tb, lane_base, accb + 64 * half + 16 * (c + 1)), x[(c + 1) & 1]);
+            for (int c = 0; c < STEPS; ++c) {
+              if (c + 1 < STEPS) tmem_ld16(tmem_addr(tb, lane_base, accb + CPT * cg + 16 * (c + 1)), x[(c + 1) & 1]);
               uint32_t (&xc)[16] = x[c & 1];
 #pragma unroll
               for (int j = 0; j < 16; j += 4) {
-                const float4 bb = sB4[(Bias::v1b + 64 * half + 16 * c + j) >> 2];
+                const float4 bb = sB4[(Bias::v1b + CPT * cg + 16 * c + j) >> 2];
                 const float s0 = softplus100(__uint_as_float(xc[j + 0]) + bb.x), s1 = softplus100(__uint_as_float(xc[j + 1]) + bb.y);
                 const float s2 = softplus100(__uint_as_float(xc[j + 2]) + bb.z), s3 = softplus100(__uint_as_float(xc[j + 3]) + bb.w);
                 uf[16 * c + j + 0] = fmaf(wk, s0, uf[16 * c + j + 0]); uf[16 * c + j + 1] = fmaf(wk, s1, uf[16 * c + j + 1]);
                 uf[16 * c + j + 2] = fmaf(wk, s2, uf[16 * c + j + 2]); uf[16 * c + j + 3] = fmaf(wk, s3, uf[16 * c + j + 3]);
-                stage_put<36>(st, lane, 16 * (c & 1) + j, s0, s1, s2, s3);
+                stage_put<20>(st, lane, j, s0, s1, s2, s3);
               }
-              if (c & 1) stage_flush<32, 36>(st, lane, sp + 16 * (c - 1), (size_t)KNN * HC, wvalid);
-              if (c < 3) tmem_wait_ld();
+              stage_flush<16, 20>(st, lane, sp + 16 * c, (size_t)KNN * HC, wvalid);
+              if (c + 1 < STEPS) tmem_wait_ld();
             }
           }
           // u -> TMEM A operand of the V2 GEMM
           {
-            float* ug = a.saved + SL.u + pw0 * HC + 64 * half;
-            float* st = reinterpret_cast<float*>(smem + SM_EC_HI) + warp * (32 * 36);
+            float* ug = a.saved + SL.u + pw0 * HC + CPT * cg;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < STEPS; ++c) {
               uint32_t hi[16], lo[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) split_hi_lo(uf[16 * c + j], hi[j], lo[j]);
 #pragma unroll
               for (int j = 0; j < 16; j += 4)
-                stage_put<36>(st, lane, 16 * (c & 1) + j, uf[16 * c + j], uf[16 * c + j + 1], uf[16 * c + j + 2], uf[16 * c + j + 3]);
-              if (c & 1) stage_flush<32, 36>(st, lane, ug + 16 * (c - 1), (size_t)HC, wvalid);
-              tmem_st16(tmem_addr(tb, lane_base, TM_AHI + 64 * half + 16 * c), hi);
-              tmem_st16(tmem_addr(tb, lane_base, TM_ALO + 64 * half + 16 * c), lo);
+                stage_put<20>(st, lane, j, uf[16 * c + j], uf[16 * c + j + 1], uf[16 * c + j + 2], uf[16 * c + j + 3]);
+              stage_flush<16, 20>(st, lane, ug + 16 * c, (size_t)HC, wvalid);
+              tmem_st16(tmem_addr(tb, lane_base, TM_AHI + CPT * cg + 16 * c), hi);
+              tmem_st16(tmem_addr(tb, lane_base, TM_ALO + CPT * cg + 16 * c), lo);
             }
           }
           es.signal_a_tmem(pipe);
           es.wait_d(pipe, 0);
-          {
+          if (narrow) {
             uint32_t x[16];
-            tmem_ld16(tmem_addr(tb, lane_base, TM_ACC0 + 16 * half), x);
+            tmem_ld16(tmem_addr(tb, lane_base, TM_ACC0 + 16 * cg), x);
             tmem_wait_ld();
             const float ws = sWsum[row];
             const bool has = sHas[row] != 0;
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
-              const float4 v2 = sB4[(Bias::v2b + 16 * half + j) >> 2];
+              const float4 v2 = sB4[(Bias::v2b + 16 * cg + j) >> 2];
               float4 cc = make_float4(0.f, 0.f, 0.f, 0.f);
               if (has) cc = make_float4(fmaf(v2.x, ws, __uint_as_float(x[j])), fmaf(v2.y, ws, __uint_as_float(x[j + 1])),
                                         fmaf(v2.z, ws, __uint_as_float(x[j + 2])), fmaf(v2.w, ws, __uint_as_float(x[j + 3])));
-              store_a_split(smem + SM_C_HI, smem + SM_C_LO, row, 16 * half + j, cc);
-              if (save && rv) *reinterpret_cast<float4*>(a.saved + SL.cc + prow * CDIM + 16 * half + j) = cc;
+              store_a_split(smem + SM_C_HI, smem + SM_C_LO, row, 16 * cg + j, cc);
+              if (save && rv) *reinterpret_cast<float4*>(a.saved + SL.cc + prow * CDIM + 16 * cg + j) = cc;
             }
           }
         } else {        // decoder.py:476,487-488: plain IDW interpolation of the colour features
           const int m = tid & 127, qg = tid >> 7;
-          float4 acc[4];
+          float4 acc[F4T];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int i = 0; i < F4T; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (sHas[m]) {
 #pragma unroll
             for (int k = 0; k < KNN; ++k) {
               const int idx = sIdx[m * KNN + k];
               if (idx >= 0) {
                 const float w = sW[m * KNN + k];
-                const float4* fr = reinterpret_cast<const float4*>(feat_row_cached(a.col_feats, a.col_leaf, idx, sRem[m * KNN + k])) + qg * 4;
+                const float4* fr = reinterpret_cast<const float4*>(feat_row_cached(a.col_feats, a.col_leaf, idx, sRem[m * KNN + k])) + qg * F4T;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < F4T; ++i) {
                   const float4 f = __ldg(fr + i);
                   acc[i].x = fmaf(w, f.x, acc[i].x); acc[i].y = fmaf(w, f.y, acc[i].y);
                   acc[i].z = fmaf(w, f.z, acc[i].z); acc[i].w = fmaf(w, f.w, acc[i].w);
@@ -593,9 +613,9 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
             }
           }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            store_a_split(smem + SM_C_HI, smem + SM_C_LO, m, (qg * 4 + i) * 4, acc[i]);
-            if (save && m < nrows) reinterpret_cast<float4*>(a.saved + SL.cc)[(p0 + m) * 8 + qg * 4 + i] = acc[i];
+          for (int i = 0; i < F4T; ++i) {
+            store_a_split(smem + SM_C_HI, smem + SM_C_LO, m, (qg * F4T + i) * 4, acc[i]);
+            if (save && m < nrows) reinterpret_cast<float4*>(a.saved + SL.cc)[(p0 + m) * 8 + qg * F4T + i] = acc[i];
           }
         }
         FWD_PHASE(3);
@@ -621,49 +641,50 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
 #pragma unroll 1
         for (int li = 0; li < 5; ++li) {
           es.wait_d(pipe, 0);
-          float* cs_ = a.saved + SL.cs + ((size_t)li * Pp + pw0) * HC + 64 * half;
-          float* ch_ = a.saved + SL.ch + ((size_t)li * Pp + pw0) * HC + 64 * half;
-          float* stS = reinterpret_cast<float*>(smem + SM_Q_HI) + warp * (32 * 36);            // Q is dead by now
-          float* stH = reinterpret_cast<float*>(smem + SM_Q_HI + 8 * 32 * 36 * 4) + warp * (32 * 20);
+          float* cs_ = a.saved + SL.cs + ((size_t)li * Pp + pw0) * HC + CPT * cg;
+          float* ch_ = a.saved + SL.ch + ((size_t)li * Pp + pw0) * HC + CPT * cg;
+          float* stg = reinterpret_cast<float*>(smem + SM_Q_HI) + warp * (32 * 20);            // Q is dead by now
           uint32_t v1[2][16], v2[2][16];
-          tmem_ld16(tmem_addr(tb, lane_base, TM_ACC0 + 64 * half), v1[0]);
-          tmem_ld16(tmem_addr(tb, lane_base, TM_ACC1 + 64 * half), v2[0]);
+          tmem_ld16(tmem_addr(tb, lane_base, TM_ACC0 + CPT * cg), v1[0]);
+          tmem_ld16(tmem_addr(tb, lane_base, TM_ACC1 + CPT * cg), v2[0]);
           tmem_wait_ld();
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int col0 = 64 * half + 16 * c;
-            if (c < 3) {   // the next 16 columns fly while these are processed
+          for (int c = 0; c < STEPS; ++c) {
+            const int col0 = CPT * cg + 16 * c;
+            if (c + 1 < STEPS) {   // the next 16 columns fly while these are processed
               tmem_ld16(tmem_addr(tb, lane_base, TM_ACC0 + col0 + 16), v1[(c + 1) & 1]);
               tmem_ld16(tmem_addr(tb, lane_base, TM_ACC1 + col0 + 16), v2[(c + 1) & 1]);
             }
             uint32_t (&x1)[16] = v1[c & 1];
             uint32_t (&x2)[16] = v2[c & 1];
+            float hk[16];
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
               const float4 bb = sB4[(Bias::cb + li * HC + col0 + j) >> 2], uu = sB4[(Bias::cu + li * HC + col0 + j) >> 2];
               const float bv[4] = {bb.x, bb.y, bb.z, bb.w}, uv[4] = {uu.x, uu.y, uu.z, uu.w};
-              float s[4], h[4];
+              float s[4];
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
                 s[t] = softplus100(__uint_as_float(x1[j + t]) + bv[t]);
-                h[t] = s[t] + (__uint_as_float(x2[j + t]) + uv[t]);
-                split_hi_lo(h[t], x1[j + t], x2[j + t]);
+                hk[j + t] = s[t] + (__uint_as_float(x2[j + t]) + uv[t]);
+                split_hi_lo(hk[j + t], x1[j + t], x2[j + t]);
               }
-              stage_put<36>(stS, lane, 16 * (c & 1) + j, s[0], s[1], s[2], s[3]);
-              stage_put<20>(stH, lane, j, h[0], h[1], h[2], h[3]);
+              stage_put<20>(stg, lane, j, s[0], s[1], s[2], s[3]);
             }
             tmem_st16(tmem_addr(tb, lane_base, TM_AHI + col0), x1);
             tmem_st16(tmem_addr(tb, lane_base, TM_ALO + col0), x2);
-            stage_flush<16, 20>(stH, lane, ch_ + 16 * c, (size_t)HC, wvalid);
-            if (c & 1) stage_flush<32, 36>(stS, lane, cs_ + 16 * (c - 1), (size_t)HC, wvalid);
-            if (c < 3) tmem_wait_ld();
+            stage_flush<16, 20>(stg, lane, cs_ + 16 * c, (size_t)HC, wvalid);   // softplus outputs, then h through the same block
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) stage_put<20>(stg, lane, j, hk[j], hk[j + 1], hk[j + 2], hk[j + 3]);
+            stage_flush<16, 20>(stg, lane, ch_ + 16 * c, (size_t)HC, wvalid);
+            if (c + 1 < STEPS) tmem_wait_ld();
           }
           es.signal_a_tmem(pipe);   // li == 4: feeds the colour head GEMM
         }
         FWD_PHASE(4);
         // -------------------------------------------------------------- colour head (decoder.py:533-546)
         es.wait_d(pipe, 0);
-        if (half == 0) {
+        if (cg == 0) {
           uint32_t x[16];
           tmem_ld16(tmem_addr(tb, lane_base, TM_ACC0), x);
           tmem_wait_ld();
@@ -733,7 +754,7 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tb, 512);
+  if (warp == CW) tmem_dealloc(tb, 512);
 }
 
 // The GEMM program of one tile (must mirror the order of the epilogue code above) + the weight re-layout jobs.
