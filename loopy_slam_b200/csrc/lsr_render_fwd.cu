@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
     sBias[i] = v;
   }
   if (warp == CW) tmem_alloc(&pipe->tmem_base, 512);
-  if (tid == 0) pipe_init<FNS>(pipe, NCT);
+  if (tid == 0) pipe_init<FNS>(pipe, CW);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();

@@ -145,9 +145,9 @@ struct UPipe {
 };
 
 template <int NS>
-__device__ __forceinline__ void pipe_init(UPipe<NS>* p, uint32_t n_epilogue_threads) {
+__device__ __forceinline__ void pipe_init(UPipe<NS>* p, uint32_t n_epilogue_warps) {
   for (int s = 0; s < NS; ++s) { mbar_init(&p->full[s], 1); mbar_init(&p->empty[s], 1); }
-  mbar_init(&p->a_ready, n_epilogue_threads);
+  mbar_init(&p->a_ready, n_epilogue_warps);
   mbar_init(&p->d_ready[0], 1);
   mbar_init(&p->d_ready[1], 1);
   fence_barrier_init();
@@ -171,7 +171,8 @@ __device__ __forceinline__ void producer_tile(const UOp* __restrict__ ops, int n
   }
 }
 
-// three MMAs of one K = 8 step: D (+)= A_lo.B_hi ; D += A_hi.B_lo ; D += A_hi.B_hi  (small terms first)
+// three MMAs of one K = 8 step: D (+)= A_hi.B_lo ; D += A_lo.B_hi ; D += A_hi.B_hi  (small terms first; the two
+// that read the B_hi tile back to back)
 __device__ __forceinline__ void mma3_ts(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t bh_lo, uint32_t bl_lo,
                                         uint32_t b_hiword, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -180,8 +181,8 @@ __device__ __forceinline__ void mma3_ts(uint32_t d, uint32_t a_hi, uint32_t a_lo
       "setp.eq.b32 q, 0, 0;\n\t"
       "mov.b64 bh, {%3, %5};\n\t"
       "mov.b64 bl, {%4, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%2], bh, %6, p;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bl, %6, q;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bl, %6, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%2], bh, %6, q;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bh, %6, q;\n\t}\n" ::"r"(d),
       "r"(a_hi), "r"(a_lo), "r"(bh_lo), "r"(bl_lo), "r"(b_hiword), "r"(idesc), "r"(acc)
       : "memory");
@@ -196,8 +197,8 @@ __device__ __forceinline__ void mma3_ss(uint32_t d, uint32_t ah_lo, uint32_t al_
       "mov.b64 al, {%2, %3};\n\t"
       "mov.b64 bh, {%4, %6};\n\t"
       "mov.b64 bl, {%5, %6};\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], al, bh, %7, p;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bl, %7, q;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bl, %7, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], al, bh, %7, q;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], ah, bh, %7, q;\n\t}\n" ::"r"(d),
       "r"(ah_lo), "r"(al_lo), "r"(a_hiword), "r"(bh_lo), "r"(bl_lo), "r"(b_hiword), "r"(idesc), "r"(acc)
       : "memory");
@@ -261,12 +262,15 @@ struct EpiSync {
     tc_fence_after();
   }
   // this thread's TMEM loads / stores and shared-memory operand writes are done -> the issuer may go on
+  // (a_ready counts WARPS: every lane fences its own writes, the warp converges, one lane arrives -- 512 per-thread
+  //  arrivals on one shared-memory word cost ~0.5 k cycles per hand-over)
   template <int NS>
   __device__ __forceinline__ void signal_a(UPipe<NS>* p) {
     tmem_wait_st();
     tc_fence_before();
     fence_proxy_async();
-    mbar_arrive(&p->a_ready);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&p->a_ready);
   }
   // same, when the hand-over is TMEM only (no shared-memory operand was written since the last signal): skips
   // the generic->async proxy fence, which is a MEMBAR that also waits for this thread's global stores in flight
@@ -274,7 +278,8 @@ struct EpiSync {
   __device__ __forceinline__ void signal_a_tmem(UPipe<NS>* p) {
     tmem_wait_st();
     tc_fence_before();
-    mbar_arrive(&p->a_ready);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&p->a_ready);
   }
 };
 

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(320, 1) trunk_kernel(const __grid_constant__ T
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < 10 * 128; i += blockDim.x) sBias[i] = a.bias[i];
   if (warp == 8) tmem_alloc(&pipe->tmem_base, 512);
-  if (tid == 0) pipe_init<NS>(pipe, 256);
+  if (tid == 0) pipe_init<NS>(pipe, 8);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
