@@ -53,7 +53,9 @@ enum { LSR_STAGE_GEOMETRY = 0, LSR_STAGE_COLOR = 1 };
 enum {
   LSR_FLAG_REL_POS = 1,          /* model.encode_rel_pos_in_col   (decoder.py:477-485)          */
   LSR_FLAG_DYNAMIC_R = 2,        /* use_dynamic_radius: per-ray float64 radii (Appendix D)      */
-  LSR_FLAG_SKIP_ZERO_DEPTH = 4   /* rendering.skip_zero_depth_pixel (Renderer.py:199-200)       */
+  LSR_FLAG_SKIP_ZERO_DEPTH = 4,  /* rendering.skip_zero_depth_pixel (Renderer.py:199-200)       */
+  LSR_FLAG_SAMPLE_NEAR_PCL = 8   /* rendering.sample_near_pcl: zero-depth rays take their z from  */
+                                 /*   z_zero_depth and keep their rendered depth (Renderer.py:150-158,197-198) */
 };
 
 /* LsrParams.rgb_mode: what happens to the colour head output (decoder.py:534-546) */
@@ -171,6 +173,8 @@ int lsr_far_bound(const float* gt_depth, int64_t n_rays, int64_t group, float* f
 
 /* The forward: weight re-layout, then z-sampling + grid k-NN (sample_knn_kernel), then IDW gather, geometry MLP,
  * (rel-pos neighbour MLP,) colour MLP, alpha compositing on tcgen05 / TMEM (render_fwd_kernel); three launches.  r_query: per-ray float64 radii when LSR_FLAG_DYNAMIC_R.
+ * z_zero_depth (nullable; required with LSR_FLAG_SAMPLE_NEAR_PCL): (R, S) sample depths; row r is used when
+ *   gt_depth[r] <= 0 (NeuralPointCloud.sample_near_pcl, src/neural_point.py:1734-1786), the other rows are ignored.
  * far_zero: far bound of the z-range used for rays with gt_depth <= 0, one value per group of
  *   far_group consecutive rays (Renderer.py:102-121 batch statistic; see lsr_far_bound); nullable.
  * exposure_affine: 12 floats [A row-major 3x3 | t] for LSR_RGB_AFFINE_SIGMOID.
@@ -181,8 +185,8 @@ int lsr_far_bound(const float* gt_depth, int64_t n_rays, int64_t group, float* f
  *   src/Mapper.py:581-582 (and without the (N,C) gradient tables + gather of its backward). */
 int lsr_render_fwd(const LsrParams* prm, const void* grid_ws, const float* cloud_pos, int64_t n_points,
                    const float* rays_o, const float* rays_d, const float* gt_depth,
-                   const double* r_query, const float* far_zero, int64_t far_group, int64_t n_rays,
-                   const float* geo_feats, const float* col_feats, const int32_t* row_remap,
+                   const double* r_query, const float* far_zero, int64_t far_group, const float* z_zero_depth,
+                   int64_t n_rays, const float* geo_feats, const float* col_feats, const int32_t* row_remap,
                    const float* geo_leaf, const float* col_leaf, const LsrWeights* w,
                    const float* exposure_affine, int stage, float* depth, float* var, float* rgb,
                    uint8_t* valid, void* saved, void* scratch, lsr_stream_t stream);

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('LSR_LIB', os.path.join(_HERE, 'liblsr.so'))   # LSR_LIB: A/B experiments only
 
 LSR_STAGE = {'geometry': 0, 'color': 1}
-FLAG_REL_POS, FLAG_DYNAMIC_R, FLAG_SKIP_ZERO_DEPTH = 1, 2, 4
+FLAG_REL_POS, FLAG_DYNAMIC_R, FLAG_SKIP_ZERO_DEPTH, FLAG_SAMPLE_NEAR_PCL = 1, 2, 4, 8
 RGB_SIGMOID, RGB_RAW, RGB_AFFINE_SIGMOID = 0, 1, 2
 GRAD_GEO_FEATS, GRAD_COL_FEATS, GRAD_GEO_W, GRAD_GEO_B, GRAD_COL_W, GRAD_RAYS, GRAD_AFFINE = 1, 2, 4, 8, 16, 32, 64
 
@@ -73,7 +73,7 @@ def lib():
                                                  ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]
         L.lsr_far_bound.argtypes = [vp, i64, i64, vp, vp]
         L.lsr_dynamic_radius.argtypes = [vp, vp, i32, i32, f64, f64, f64, f64, vp, vp, vp]
-        L.lsr_render_fwd.argtypes = [ctypes.POINTER(LsrParams), vp, vp, i64, vp, vp, vp, vp, vp, i64, i64, vp, vp,
+        L.lsr_render_fwd.argtypes = [ctypes.POINTER(LsrParams), vp, vp, i64, vp, vp, vp, vp, vp, i64, vp, i64, vp, vp,
                                      vp, vp, vp,
                                      ctypes.POINTER(LsrWeights), vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp]
         L.lsr_render_bwd.argtypes = [ctypes.POINTER(LsrParams), vp, vp, i64, vp, vp, vp, vp, i64, vp, vp,

@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
       const float g = a.gt_depth[ray];
       const float coef = a.prm.sigmoid_coef;
       const bool nz = g > 0.f;
-      const float gD = nz ? a.g_depth[ray] : 0.f;
+      const float gD = (nz || (a.prm.flags & LSR_FLAG_SAMPLE_NEAR_PCL)) ? a.g_depth[ray] : 0.f;   // Renderer.py:197-198
       const float gV = a.g_var ? a.g_var[ray] : 0.f;
       float gC[3] = {0.f, 0.f, 0.f};
       if (color && a.g_rgb && (nz || !(a.prm.flags & LSR_FLAG_SKIP_ZERO_DEPTH))) {

@@ -71,6 +71,7 @@ struct KnnArgs {
   const float *rays_o, *rays_d, *gt_depth;
   const double* r_query;
   const float* far_zero;
+  const float* z_override;   // (R, S) z of zero-depth rays (sample_near_pcl), nullable
   int far_group;
   int R;
   const int32_t* remap;
@@ -112,6 +113,8 @@ __global__ void __launch_bounds__(256, 4) sample_knn_kernel(const __grid_constan
           const float t = linspace_f32(0.f, 1.f, S, s);
           const float zn = __fmul_rn(a.prm.near_end_surface, g), zf = __fmul_rn(a.prm.far_end_surface, g);
           z[q] = __fadd_rn(__fmul_rn(zn, __fsub_rn(1.f, t)), __fmul_rn(zf, t));
+        } else if (a.z_override) {   // Renderer.py:151-158: npc-guided z-range (sample_near_pcl)
+          z[q] = a.z_override[m];
         } else {         // Renderer.py:162-163
           const float far = a.far_zero ? a.far_zero[ray / a.far_group] : a.prm.near_end;
           z[q] = linspace_f32(a.prm.near_end, far, S, s);
@@ -740,7 +743,7 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
         for (int s = 0; s < S; ++s) { const float t = zv[s] - depth; var += (wv[s] * t) * t; }
         float o0 = c0 / wsum, o1 = c1 / wsum, o2 = c2 / wsum;
         if (!(g > 0.f)) {                                      // Renderer.py:197-200
-          depth = 0.f;
+          if (!(a.prm.flags & LSR_FLAG_SAMPLE_NEAR_PCL)) depth = 0.f;
           if (a.prm.flags & LSR_FLAG_SKIP_ZERO_DEPTH) { o0 = 0.f; o1 = 0.f; o2 = 0.f; }
         }
         a.depth[ray] = depth;
@@ -956,7 +959,8 @@ extern "C" int lsr_far_bound(const float* gt_depth, int64_t n_rays, int64_t grou
 
 extern "C" int lsr_render_fwd(const LsrParams* prm, const void* grid_ws, const float* cloud_pos, int64_t n_points,
                               const float* rays_o, const float* rays_d, const float* gt_depth,
-                              const double* r_query, const float* far_zero, int64_t far_group, int64_t n_rays,
+                              const double* r_query, const float* far_zero, int64_t far_group,
+                              const float* z_zero_depth, int64_t n_rays,
                               const float* geo_feats, const float* col_feats, const int32_t* row_remap,
                               const float* geo_leaf, const float* col_leaf, const LsrWeights* w,
                               const float* exposure_affine, int stage, float* depth, float* var, float* rgb,
@@ -973,6 +977,7 @@ extern "C" int lsr_render_fwd(const LsrParams* prm, const void* grid_ws, const f
   if (n_points > 0 && stage == LSR_STAGE_COLOR && !col_feats) return LSR_ERR_ARG;
   if (row_remap && (!geo_leaf || (stage == LSR_STAGE_COLOR && !col_leaf))) return LSR_ERR_ARG;
   if ((prm->flags & LSR_FLAG_DYNAMIC_R) && !r_query) return LSR_ERR_ARG;
+  if ((prm->flags & LSR_FLAG_SAMPLE_NEAR_PCL) && !z_zero_depth) return LSR_ERR_ARG;
   if (prm->rgb_mode == LSR_RGB_AFFINE_SIGMOID && !exposure_affine) return LSR_ERR_ARG;
   const int nsm = sm_count();
   if (nsm <= 0) return LSR_ERR_CUDA;
@@ -1009,6 +1014,7 @@ extern "C" int lsr_render_fwd(const LsrParams* prm, const void* grid_ws, const f
     k.prm = *prm;
     k.grid = grid_ws;
     k.rays_o = rays_o; k.rays_d = rays_d; k.gt_depth = gt_depth; k.r_query = r_query; k.far_zero = far_zero;
+    k.z_override = (prm->flags & LSR_FLAG_SAMPLE_NEAR_PCL) ? z_zero_depth : nullptr;
     k.far_group = (int)(far_group > 0 ? (far_group < (1ll << 30) ? far_group : (1ll << 30)) : 1);
     k.R = (int)n_rays;
     k.remap = row_remap;

@@ -196,7 +196,8 @@ class NeuralPointCloud(object):
     # ------------------------------------------------------------------ zero-depth ray sampling
     def sample_near_pcl(self, rays_o, rays_d, near, far, num):
         """neural_point.py:1734-1786: for rays without sensor depth, place the `num` samples between the
-        first and last of 25 coarse steps that have any neighbour; rays with < 2 such steps are invalid."""
+        first TWO of 25 coarse steps that have any neighbour (`item[0]`, `item[1]`, :1781-1782); rays with < 2 such
+        steps are invalid and keep linspace(near, far, num)."""
         rays_o, rays_d = rays_o.reshape(-1, 3), rays_d.reshape(-1, 3)
         n_rays = rays_d.shape[0]
         intervals = 25
@@ -209,8 +210,11 @@ class NeuralPointCloud(object):
         z_sec = torch.from_numpy(np.linspace(near, far_f, intervals)).to(rays_o.device)
         first = torch.argmax(hit.int(), dim=1)
         second = torch.argmax((hit & (torch.arange(intervals, device=hit.device)[None, :] > first[:, None])).int(), dim=1)
-        t = torch.linspace(0.0, 1.0, num, device=rays_o.device, dtype=torch.float64)
-        z_valid = z_sec[first][:, None] * (1 - t) + z_sec[second][:, None] * t
+        # np.linspace(a, b, num) in float64: a + arange(num) * ((b - a) / (num - 1)), last element = b exactly
+        za, zb = z_sec[first], z_sec[second]
+        steps = torch.arange(num, device=rays_o.device, dtype=torch.float64)
+        z_valid = za[:, None] + steps[None, :] * ((zb - za) / max(num - 1, 1))[:, None]
+        z_valid[:, -1] = zb
         z_def = torch.from_numpy(np.linspace(near, far_f, num)).to(rays_o.device)[None, :].repeat(n_rays, 1)
         z = torch.where(invalid[:, None], z_def, z_valid)
         return z.float(), invalid

@@ -87,7 +87,7 @@ def _grid_for(npc, cloud_pos, cell, cache):
 class _RenderCtx:
     """Per-call constants shared by forward and backward."""
     __slots__ = ('prm', 'grid', 'stage', 'is_tracker', 'blob', 'wstruct', 'flat', 'saved', 'scratch', 'R',
-                 'r_query', 'device', 'far_group', 'force_save', 'timing', 'remap', 'renderer')
+                 'r_query', 'device', 'far_group', 'force_save', 'timing', 'remap', 'renderer', 'z_zero')
 
 
 def _tick(timing):
@@ -156,7 +156,7 @@ class _RenderFn(torch.autograd.Function):
         ev = _tick(rc.timing)
         check(lib().lsr_render_fwd(ctypes.byref(rc.prm), ptr(rc.grid.ws), ptr(rc.grid.cloud), rc.grid.n,
                                    ptr(rays_o), ptr(rays_d), ptr(gt_depth), ptr(rc.r_query), ptr(far_zero),
-                                   rc.far_group, R, ptr(geo_feats), ptr(col_feats), ptr(rc.remap), ptr(geo_leaf),
+                                   rc.far_group, ptr(rc.z_zero), R, ptr(geo_feats), ptr(col_feats), ptr(rc.remap), ptr(geo_leaf),
                                    ptr(col_leaf), ctypes.byref(rc.wstruct),
                                    ptr(affine), rc.stage, ptr(depth), ptr(var), ptr(rgb), ptr(valid),
                                    ptr(rc.saved), ptr(rc.scratch), stream_ptr(dev)), 'lsr_render_fwd')
@@ -266,7 +266,7 @@ def _make_params(renderer, decoders, stage, coef):
 
 def fused_render(renderer, npc, decoders, rays_d, rays_o, stage, gt_depth, npc_geo_feats, npc_col_feats,
                  is_tracker, cloud_pos, dynamic_r_query, exposure_feat, far_group=None, n_surface=None,
-                 force_save=False, return_ctx=False, feat_subset=None):
+                 force_save=False, return_ctx=False, feat_subset=None, z_zero_depth=None):
     """The one place that marshals a render call into lsr_render_fwd / lsr_render_bwd."""
     _lib.require_cuda(rays_o, 'rays_o')
     dev = rays_o.device
@@ -329,6 +329,12 @@ def fused_render(renderer, npc, decoders, rays_d, rays_o, stage, gt_depth, npc_g
         rc.remap = subset.remap
         geo_leaf = _f32c(geo_leaf)
         col_leaf = _f32c(col_leaf) if col_leaf is not None else None
+    rc.z_zero = None
+    if z_zero_depth is not None:   # rendering.sample_near_pcl: (R, S) sample depths, rows of zero-depth rays are used
+        rc.z_zero = _f32c(z_zero_depth.detach())
+        if rc.z_zero.shape != (R, prm.n_surface):
+            raise ValueError('z_zero_depth must be (n_rays, N_surface)')
+        prm.flags |= _lib.FLAG_SAMPLE_NEAR_PCL
     rc.R = R
     rc.device = dev
     rc.far_group = fgroup
@@ -414,9 +420,6 @@ class Renderer(object):
         self.max_query_radius = float(pc.get('radius_add_max', 0.08)) * float(pc.get('radius_query_ratio', 2))
         self.sigmoid_coefficient = cfg['rendering'].get('sigmoid_coef_mapper', 0.1)   # callers overwrite it
         self._grid_cache = _GridCache()
-        if self.sample_near_pcl:
-            warnings.warn('rendering.sample_near_pcl=True: zero-depth rays use the npc-guided z-range only if the '
-                          'npc provides sample_near_pcl(); every shipped dataset config turns it off')
 
     # -- Renderer.py:24-69
     def eval_points(self, p, decoders, npc, stage='color', device=None, npc_geo_feats=None, npc_col_feats=None,
@@ -440,15 +443,41 @@ class Renderer(object):
             gt_depth = None
         if self.sample_near_pcl and gt_depth is not None and hasattr(npc, 'sample_near_pcl'):
             return self._render_with_near_pcl(npc, decoders, rays_d, rays_o, stage, gt_depth, npc_geo_feats,
-                                              npc_col_feats, is_tracker, cloud_pos, dynamic_r_query, exposure_feat)
+                                              npc_col_feats, is_tracker, cloud_pos, dynamic_r_query, exposure_feat,
+                                              feat_subset)
         depth, var, rgb, valid = fused_render(self, npc, decoders, rays_d, rays_o, stage, gt_depth, npc_geo_feats,
                                               npc_col_feats, is_tracker, cloud_pos, dynamic_r_query, exposure_feat,
                                               feat_subset=feat_subset)
         return depth, var, rgb, valid.bool()
 
-    def _render_with_near_pcl(self, *a):
-        raise NotImplementedError('rendering.sample_near_pcl=True is not on the fused path yet '
-                                  '(off in configs/Replica, TUM_RGBD, ScanNet)')
+    def _render_with_near_pcl(self, npc, decoders, rays_d, rays_o, stage, gt_depth, npc_geo_feats, npc_col_feats,
+                              is_tracker, cloud_pos, dynamic_r_query, exposure_feat, feat_subset):
+        """Renderer.py:150-158,191-198 with rendering.sample_near_pcl: rays without sensor depth take their samples
+        from npc.sample_near_pcl (between the first two of 25 coarse steps that have a neighbour), keep their
+        rendered depth, and are invalid when fewer than two such steps exist."""
+        g = gt_depth.detach().reshape(-1)
+        zero = ~(g > 0)
+        z_zero = None
+        not_near_rays = None
+        if bool(zero.any()):
+            from . import _lib as lb
+            R = g.shape[0]
+            g32 = _f32c(g)
+            far = torch.empty(1, dtype=torch.float32, device=g32.device)
+            check(lib().lsr_far_bound(ptr(g32), R, max(R, 1), ptr(far), stream_ptr(g32.device)), 'lsr_far_bound')
+            z0, not_near = npc.sample_near_pcl(rays_o[zero].clone().detach(), rays_d[zero].clone().detach(),
+                                               self.near_end, float(far.item()), self.N_surface)   # Renderer.py:151-153
+            z_zero = torch.zeros(R, self.N_surface, dtype=torch.float32, device=g32.device)
+            z_zero[zero] = z0.to(device=g32.device, dtype=torch.float32)
+            not_near_rays = torch.nonzero(zero, as_tuple=True)[0][not_near.to(g32.device)]
+        depth, var, rgb, valid = fused_render(self, npc, decoders, rays_d, rays_o, stage, gt_depth, npc_geo_feats,
+                                              npc_col_feats, is_tracker, cloud_pos, dynamic_r_query, exposure_feat,
+                                              feat_subset=feat_subset, z_zero_depth=z_zero)
+        valid = valid.bool()
+        if not_near_rays is not None and not_near_rays.numel():
+            valid = valid.clone()
+            valid[not_near_rays] = False                                                        # Renderer.py:154-157,194
+        return depth, var, rgb, valid
 
     # -- Renderer.py:203-276
     def render_img(self, npc, decoders, c2w, device, stage, gt_depth=None, npc_geo_feats=None, npc_col_feats=None,

@@ -22,6 +22,7 @@ Weights are a flat dict keyed like ``NICER.state_dict()`` plus the non-persisten
 import math
 from dataclasses import dataclass
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -76,6 +77,29 @@ def sample_z(gt_depth, ocfg, far_zero=None):
         z = z.clone()
         z[zero] = torch.linspace(ocfg.near_end, float(far_zero), steps=S, dtype=torch.float32)
     return z
+
+
+def sample_near_pcl(rays_o, rays_d, near, far, num, cloud_pos, radius_query, nn_num=8):
+    """NeuralPointCloud.sample_near_pcl (src/neural_point.py:1734-1786) on the exact k-NN: 25 coarse steps in
+    [near, far] per ray; a ray with >= 2 steps that have a neighbour within radius_query takes its `num` samples
+    between the FIRST TWO such steps (np.linspace in float64, cast to float32), the others keep
+    linspace(near, far, num) and are reported invalid.  -> (z (n,num) f32, invalid (n,) bool)"""
+    o, d = rays_o.reshape(-1, 3).float(), rays_d.reshape(-1, 3).float()
+    n_rays = d.shape[0]
+    intervals = 25
+    z_vals = torch.linspace(near, far, steps=intervals)                              # :1748
+    pts = (o[..., None, :] + d[..., None, :] * z_vals[..., :, None]).reshape(-1, 3)  # :1749-1751
+    z_sec = np.linspace(near, far, intervals)                                        # :1755
+    z_total = np.tile(np.linspace(near, far, num), (n_rays, 1))                      # :1756-1757
+    D, _ = exact_knn(pts, cloud_pos, nn_num)
+    nn = neighbor_num(D, radius_sq(radius_query, None)).numpy().reshape(n_rays, -1)  # :1762-1772
+    invalid = nn.astype(bool).sum(axis=-1) < 2                                       # :1773-1774
+    if invalid.sum() < n_rays:
+        r, c = np.where(nn[~invalid].astype(bool))
+        idx = np.concatenate(([0], np.flatnonzero(r[1:] != r[:-1]) + 1, [r.size]))
+        out = [c[idx[i]:idx[i + 1]] for i in range(len(idx) - 1)]
+        z_total[~invalid] = np.asarray([np.linspace(z_sec[it[0]], z_sec[it[1]], num=num) for it in out])   # :1781-1783
+    return torch.from_numpy(z_total).float(), torch.from_numpy(invalid)
 
 
 def far_for_zero_depth(gt_depth):
@@ -230,8 +254,10 @@ def composite(raw, z, coef):
 
 def render_rays(W, ocfg, rays_o, rays_d, gt_depth, geo_feats, col_feats, cloud_pos, stage,
                 is_tracker=False, dynamic_r=None, exposure_feat=None, dtype=torch.float32,
-                knn=None):
-    """Renderer.render_batch_ray (Renderer.py:71-201) for gt_depth given, sample_near_pcl off.
+                knn=None, z_zero=None):
+    """Renderer.render_batch_ray (Renderer.py:71-201) for gt_depth given.  sample_near_pcl: pass
+    ``z_zero`` = (R,S) sample depths whose zero-depth rows come from sample_near_pcl() (:150-158); those rays
+    then keep their rendered depth (:197-198) -- the caller clears their valid bit where sample_near_pcl said so.
 
     Returns (depth, var, rgb, valid_mask, aux).  ``knn`` = optional precomputed
     (D, I, n) from a previous call (to share neighbour sets between fp32 / fp64 runs)."""
@@ -240,6 +266,8 @@ def render_rays(W, ocfg, rays_o, rays_d, gt_depth, geo_feats, col_feats, cloud_p
     g32 = gt_depth.reshape(-1).to(torch.float32)
     far_zero = far_for_zero_depth(g32) if (g32 <= 0).any() else None
     z32 = sample_z(g32, ocfg, far_zero)                        # (R,S) fp32, exact op order
+    if z_zero is not None:
+        z32 = torch.where((g32 <= 0)[:, None], z_zero.to(torch.float32), z32)
     o32, d32 = rays_o.detach().to(torch.float32), rays_d.detach().to(torch.float32)
     p32 = (o32[:, None, :] + d32[:, None, :] * z32[:, :, None]).reshape(-1, 3)
 
@@ -267,7 +295,8 @@ def render_rays(W, ocfg, rays_o, rays_d, gt_depth, geo_feats, col_feats, cloud_p
     depth, var, rgb, wts = composite(raw, z, ocfg.sigmoid_coef)
     valid = has.view(R, S).sum(1) >= int(S / 2 + 1)            # decoder.py:259-260
     nz = g32 > 0
-    depth = torch.where(nz, depth, torch.zeros_like(depth))    # Renderer.py:197-198
+    if z_zero is None:
+        depth = torch.where(nz, depth, torch.zeros_like(depth))    # Renderer.py:197-198 (not with sample_near_pcl)
     if ocfg.skip_zero_depth_pixel:
         rgb = torch.where(nz[:, None], rgb, torch.zeros_like(rgb))
     aux.update({'knn': knn, 'z': z32, 'p': p32, 'raw': raw, 'weights': wts})

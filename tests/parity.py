@@ -38,9 +38,10 @@ def build_model(cfg, weights, device):
     return model.to(device)
 
 
-def run_cuda(g, device='cuda:0', param_grads=True, loss_fn=None):
+def run_cuda(g, device='cuda:0', param_grads=True, loss_fn=None, near_pcl=False):
     """Run our fused path on a golden scene -> dict of outputs and gradients (CPU tensors)."""
     cfg = cfg_from_ocfg(g.ocfg)
+    cfg['rendering']['sample_near_pcl'] = bool(near_pcl)
     H, W, fx, fy, cx, cy = g.raw['intrinsics']
     model = build_model(cfg, g.weights, device)
     for p in model.parameters():
@@ -58,8 +59,12 @@ def run_cuda(g, device='cuda:0', param_grads=True, loss_fn=None):
     class NPC:   # the reference passes its npc proxy; only get_radius_query is needed here
         def get_radius_query(self_inner):
             return g.ocfg.radius_query
+    npc = NPC()
+    if near_pcl:   # the real mirror class: its sample_near_pcl runs on the CUDA k-NN
+        npc = L.NeuralPointCloud(cfg, device=device)
+        npc.set_cloud(cloud, geo.detach(), col.detach())
     depth, var, rgb, valid = renderer.render_batch_ray(
-        NPC(), model, d, o, device, g.stage, gt_depth=g.t('gt_depth').to(device), npc_geo_feats=geo,
+        npc, model, d, o, device, g.stage, gt_depth=g.t('gt_depth').to(device), npc_geo_feats=geo,
         npc_col_feats=col, is_tracker=g.is_tracker, cloud_pos=cloud, dynamic_r_query=dyn, exposure_feat=ef)
     if loss_fn is None:
         loss = (g.t('up_depth').to(device) * depth).sum() + (g.t('up_rgb').to(device) * rgb).sum()
@@ -78,7 +83,7 @@ def run_cuda(g, device='cuda:0', param_grads=True, loss_fn=None):
     return out
 
 
-def run_oracle(g, dtype):
+def run_oracle(g, dtype, z_zero=None):
     geo = g.t('geo_feats').clone().requires_grad_(True)
     col = g.t('col_feats').clone().requires_grad_(True)
     o = g.t('rays_o').clone().requires_grad_(g.is_tracker)
@@ -87,7 +92,8 @@ def run_oracle(g, dtype):
     ef = g.t('exposure_feat').clone().requires_grad_(True) if g.has('exposure_feat') else None
     dyn = g.t('dynamic_r') if g.has('dynamic_r') else None
     depth, var, rgb, valid, aux = orc.render_rays(W, g.ocfg, o, d, g.t('gt_depth'), geo, col, g.t('cloud'), g.stage,
-                                                  is_tracker=g.is_tracker, dynamic_r=dyn, exposure_feat=ef, dtype=dtype)
+                                                  is_tracker=g.is_tracker, dynamic_r=dyn, exposure_feat=ef, dtype=dtype,
+                                                  z_zero=z_zero)
     loss = (g.t('up_depth').to(dtype) * depth).sum() + (g.t('up_rgb').to(dtype) * rgb).sum()
     loss.backward()
     return dict(depth=depth.detach(), var=var.detach(), rgb=rgb.detach(), valid=valid, g_geo=geo.grad, g_col=col.grad,

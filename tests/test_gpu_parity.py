@@ -342,3 +342,35 @@ def test_feature_subset_equals_index_put_flow(name):
     assert a[6].keys() == b[6].keys()
     for k in a[6]:
         assert rel_l2(b[6][k].cpu(), a[6][k].cpu()) < 1e-4, k
+
+
+def test_sample_near_pcl_on_the_fused_path():
+    """rendering.sample_near_pcl=True (configs/point_slam.yaml:127; Renderer.py:150-158,191-198): zero-depth rays take
+    their samples from NeuralPointCloud.sample_near_pcl, keep their rendered depth, and are invalid when the cloud is
+    not near.  CUDA (mirror npc on the grid k-NN + z override in the fused kernels) vs the oracle restatement."""
+    import torch
+    from helpers import Golden, rel_l2
+    from oracle import render as orc
+    from parity import run_cuda, run_oracle, grad_ok
+    g = Golden('replica_color_sparse_zero_depth')
+    gt = g.t('gt_depth').reshape(-1)
+    zero = ~(gt > 0)
+    assert zero.any() and (~zero).any()
+    S = g.ocfg.N_surface
+    far = float(orc.far_for_zero_depth(gt))
+    z0, invalid = orc.sample_near_pcl(g.t('rays_o')[zero], g.t('rays_d')[zero], g.ocfg.near_end, far, S, g.t('cloud'),
+                                      g.ocfg.radius_query)
+    z_zero = torch.zeros(gt.shape[0], S)
+    z_zero[zero] = z0
+    o32, o64 = run_oracle(g, torch.float32, z_zero=z_zero), run_oracle(g, torch.float64, z_zero=z_zero)
+    valid_ref = o32['valid'].clone()
+    valid_ref[torch.nonzero(zero, as_tuple=True)[0][invalid]] = False
+    ours = run_cuda(g, near_pcl=True)
+    assert torch.equal(ours['valid'].bool(), valid_ref)
+    assert rel_l2(ours['depth'], o32['depth']) < 1e-4 and rel_l2(ours['rgb'], o32['rgb']) < 1e-4
+    assert rel_l2(ours['var'], o32['var']) < 1e-4
+    # zero-depth rays keep a (non-zero) rendered depth on this path, and its gradient flows
+    assert (ours['depth'][zero] != 0).any()
+    for key in ('g_geo', 'g_col'):
+        ok, e, eo = grad_ok(ours[key], o64[key], o32[key])
+        assert ok, (key, e, eo)

@@ -79,3 +79,23 @@ def test_exact_knn_properties():
     assert I[0, 0] == 3 and I[0, 1] == 10
     D2, I2 = exact_knn(q, cloud[:5], 8)       # N < K -> padded
     assert (I2[:, 5:] == -1).all() and (D2[:, 5:] > 1e38).all()
+
+
+def test_oracle_sample_near_pcl_restatement():
+    """oracle.render.sample_near_pcl (neural_point.py:1734-1786): first-two-hits rule, invalid rays, float64 linspace."""
+    import numpy as np
+    import torch
+    from oracle import render as orc
+    # a wall of points at x = 1.0, rays along +x from the origin; near 0.2, far 2.2 -> coarse step 2.0 / 24
+    ys, zs = torch.meshgrid(torch.linspace(-0.05, 0.05, 5), torch.linspace(-0.05, 0.05, 5), indexing='ij')
+    cloud = torch.stack([torch.full_like(ys, 1.0), ys, zs], -1).reshape(-1, 3)
+    o = torch.zeros(3, 3)
+    d = torch.tensor([[1.0, 0, 0], [0, 1.0, 0], [1.0, 0, 0]])
+    z, invalid = orc.sample_near_pcl(o, d, 0.2, 2.2, 5, cloud, 0.08)
+    assert invalid.tolist() == [False, True, False]
+    sec = np.linspace(0.2, 2.2, 25)
+    hits = [i for i, zc in enumerate(sec) if abs(zc - 1.0) < 0.08 - 1e-6]
+    assert len(hits) >= 2
+    expect = np.linspace(sec[hits[0]], sec[hits[1]], 5).astype(np.float32)
+    assert np.array_equal(z[0].numpy(), expect) and np.array_equal(z[2].numpy(), expect)
+    assert np.array_equal(z[1].numpy(), np.linspace(0.2, 2.2, 5).astype(np.float32))
