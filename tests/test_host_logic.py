@@ -139,3 +139,62 @@ def test_forward_gemm_program_invariants():
         assert maxb <= 32768 and maxb % 32 == 0          # a chunk (hi + lo) fits one ring stage, 16-byte halves
         assert packed <= cap
     assert L.lsr_debug_program_stats(None, 1, 1, out) == 1
+
+
+def test_frustum_helpers_match_numpy_restatement():
+    """frustum.filter_point_before_add / keyframe_overlap_percent vs a line-by-line numpy restatement of
+    /root/reference/src/Mapper.py:137-163 and :252-274 (pure projection logic, runs on any device)."""
+    import numpy as np
+    import torch
+    from loopy_slam_b200.frustum import filter_point_before_add, keyframe_overlap_percent
+    rng = np.random.default_rng(3)
+    H, W, fx, fy, cx, cy = 68, 120, 60.0, 60.0, 59.5, 33.5
+
+    def pose(yaw, t):
+        c, s = np.cos(yaw), np.sin(yaw)
+        m = np.eye(4, dtype=np.float32)
+        m[:3, :3] = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]], dtype=np.float32)
+        m[:3, 3] = t
+        return m
+    n = 400
+    o = np.tile(np.array([[0.1, -0.05, 0.2]], dtype=np.float32), (n, 1))
+    d = np.concatenate([rng.uniform(-1.2, 1.2, (n, 2)), -np.ones((n, 1))], 1).astype(np.float32)
+    g = rng.uniform(0.5, 4.0, n).astype(np.float32)
+    prev = pose(0.35, [0.3, 0.0, 0.1])
+
+    def ref_filter(o, d, g, prev_c2w):        # Mapper.py:139-163
+        points = (o[..., None, :] + d[..., None, :] * g[..., None, None]).reshape(-1, 3)
+        w2c = np.linalg.inv(prev_c2w)
+        homo = np.concatenate([points, np.ones_like(points[:, 0]).reshape(-1, 1)], axis=1).reshape(-1, 4, 1)
+        cam = (w2c @ homo)[:, :3]
+        K = np.array([[fx, .0, cx], [.0, fy, cy], [.0, .0, 1.0]]).reshape(3, 3)
+        cam[:, 0] *= -1
+        uv = K @ cam
+        z = uv[:, -1:] + 1e-5
+        uv = (uv[:, :2] / z).astype(np.float32)
+        mask = (uv[:, 0] < W) * (uv[:, 0] > 0) * (uv[:, 1] < H) * (uv[:, 1] > 0)
+        return ~mask.reshape(-1)
+    ours = filter_point_before_add(torch.from_numpy(o), torch.from_numpy(d), torch.from_numpy(g), torch.from_numpy(prev),
+                                   H, W, fx, fy, cx, cy)
+    ref = ref_filter(o, d, g, prev)
+    assert ours.dtype == torch.bool and 0 < ref.sum() < n
+    assert np.array_equal(ours.numpy(), ref)
+
+    verts = (o[:, None, :] + d[:, None, :] * np.linspace(0.8, 1.2, 4, dtype=np.float32)[None, :, None] * g[:, None, None]).reshape(-1, 3)
+    kfs = [pose(0.0, [0, 0, 0]), pose(0.6, [0.5, 0, 0]), pose(3.0, [0, 0, 1.0]), prev]
+
+    def ref_percent(vertices, c2w, edge=20):  # Mapper.py:253-272
+        w2c = np.linalg.inv(c2w)
+        homo = np.concatenate([vertices, np.ones_like(vertices[:, 0]).reshape(-1, 1)], axis=1).reshape(-1, 4, 1)
+        cam = (w2c @ homo)[:, :3]
+        K = np.array([[fx, .0, cx], [.0, fy, cy], [.0, .0, 1.0]]).reshape(3, 3)
+        uv = K @ cam
+        z = uv[:, -1:] + 1e-5
+        uv = (uv[:, :2] / z).astype(np.float32)
+        mask = (uv[:, 0] < W - edge) * (uv[:, 0] > edge) * (uv[:, 1] < H - edge) * (uv[:, 1] > edge)
+        mask = mask & (z[:, :, 0] < 0)
+        return mask.reshape(-1).sum() / uv.shape[0]
+    pct = keyframe_overlap_percent(torch.from_numpy(verts), [torch.from_numpy(k) for k in kfs], H, W, fx, fy, cx, cy)
+    refp = np.array([ref_percent(verts, k) for k in kfs])
+    assert pct.shape == (4,) and refp.max() > 0.05 and refp.min() == 0.0
+    assert np.allclose(pct.numpy(), refp, atol=2.0 / verts.shape[0])      # at most a borderline vertex or two
