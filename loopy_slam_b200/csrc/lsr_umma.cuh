@@ -45,7 +45,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) __trap();   // ~2 s: far beyond any legitimate wait
+    if (clock64() - t0 > 20000000000ll) __trap();   // ~10 s of SM clock (it also runs while another process holds the
+                                                    // GPU's time slice): far beyond any legitimate wait
   }
 }
 
