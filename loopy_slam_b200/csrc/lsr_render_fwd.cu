@@ -81,9 +81,15 @@ struct KnnArgs {
 };
 
 // ------------------------------------------------------------------------------------------------ kernel 1
-// one warp per PAIR of sample rows, searched in lockstep (lane k < 8 ends up owning the k-th neighbour)
-__global__ void __launch_bounds__(256, 4) sample_knn_kernel(const __grid_constant__ KnnArgs a) {
-  constexpr int NQ = 2;
+// one warp per sample row (LSR_KNN_NQ rows in lockstep; lane k < 8 ends up owning the k-th neighbour)
+#ifndef LSR_KNN_NQ
+#define LSR_KNN_NQ 1          // sample rows searched in lockstep by one warp (1 beats 2 and 4 at 32 warps/SM: 0.281 / 0.288 / 0.308 ms forward)
+#endif
+#ifndef LSR_KNN_BLOCKS
+#define LSR_KNN_BLOCKS 4      // resident 256-thread blocks per SM the register budget is set for
+#endif
+__global__ void __launch_bounds__(256, LSR_KNN_BLOCKS) sample_knn_kernel(const __grid_constant__ KnnArgs a) {
+  constexpr int NQ = LSR_KNN_NQ;
   const int S = a.prm.n_surface;
   const int P = a.R * S;
   const bool dynr = (a.prm.flags & LSR_FLAG_DYNAMIC_R) != 0;
@@ -1021,7 +1027,7 @@ extern "C" int lsr_render_fwd(const LsrParams* prm, const void* grid_ws, const f
     k.ks = ks;
     k.saved = (float*)saved;
     k.stage = stage;
-    const int64_t pairs = (n_rays * prm->n_surface + 1) / 2;
+    const int64_t pairs = (n_rays * prm->n_surface + LSR_KNN_NQ - 1) / LSR_KNN_NQ;
     const int64_t blocks = (pairs + 7) / 8;
     const int kgrid = (int)(blocks < (int64_t)nsm * 8 ? blocks : (int64_t)nsm * 8);
     sample_knn_kernel<<<kgrid, 256, 0, stream>>>(k);
