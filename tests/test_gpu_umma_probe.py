@@ -44,3 +44,15 @@ def test_streamed_weight_engine_on_trunk_shaped_mlp():
     assert m and float(m.group(1)) < 1e-5, out
     tiles = re.findall(r'tile \d h \(all layers\)\s+rel-L2 ([0-9.e+-]+)', out)
     assert len(tiles) == 3 and max(float(t) for t in tiles) < 1e-5, out     # tiles 2+ reuse ring / barriers / TMEM
+
+
+@pytest.mark.gpu
+def test_row_contraction_gemm_on_kmajor_operands():
+    """Weight-gradient shaped GEMMs (contraction over the 128 rows) with operands transposed by the row-owning
+    threads into the K-major layout (padded LBO): the primitive the tcgen05 backward needs."""
+    out = _run(5)
+    rows = re.findall(r'rows-as-K, K-major padded LBO N=(\d+) (\dxTF32)\s+rel-L2 ([0-9.e+-]+)', out)
+    assert len(rows) == 4, out
+    exact = [float(r[2]) for r in rows if r[1] == '1xTF32']
+    three = [float(r[2]) for r in rows if r[1] == '3xTF32']
+    assert exact == [0.0] and len(three) == 3 and max(three) < 2e-6, out

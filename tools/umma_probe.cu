@@ -3,7 +3,8 @@
 //      tf32-representable inputs (mode 4: the other assignment of the descriptor LBO / SBO fields, which faults);
 //   2. the streamed-weight engine (producer / issuer / epilogue warps) on a colour-trunk-shaped 5-layer MLP,
 //      checked against an fp64 host evaluation, then timed over many tiles on all SMs;
-//   3. (open) weight-gradient shaped GEMMs with MN-major operands: kind::tf32 + SWIZZLE_NONE yields zeros so far.
+//   3. (open) weight-gradient shaped GEMMs with MN-major operands: kind::tf32 + SWIZZLE_NONE yields zeros so far;
+//   5. the same GEMMs on the verified K-major path: operands transposed by the row-owning threads, padded LBO.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o tools/umma_probe tools/umma_probe.cu
 #include <cmath>
 #include <cstdio>
@@ -155,6 +156,74 @@ __global__ void __launch_bounds__(128) probe_gemm_mn(const float* A, const float
       const uint64_t dbh = swap ? smem_desc(smem_u32(sBhi) + off, 2048, 128) : smem_desc(smem_u32(sBhi) + off, 128, 2048);
       const uint64_t dbl = swap ? smem_desc(smem_u32(sBlo) + off, 2048, 128) : smem_desc(smem_u32(sBlo) + off, 128, 2048);
       if (three) { mma_ss(tb, dal, dbh, idesc, acc); mma_ss(tb, dah, dbl, idesc, 1u); acc = 1u; }
+      mma_ss(tb, dah, dbh, idesc, acc);
+      acc = 1u;
+    }
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem_addr(tb, 32 * warp, c0), v);
+    tmem_wait_ld();
+    for (int j = 0; j < 32; ++j)
+      if (c0 + j < N) D[tid * N + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
+// ------------------------------------------------------------------------------------------- test 5
+// Row-contraction (weight-gradient shaped) GEMM with K-MAJOR operands only: D[m][n] = sum_r X[r][m] * Y[r][n].
+// The row-owning threads write X^T and Y^T themselves: element (feature f, row r) goes to slab r / 4 at
+// (r / 4) * LBO + f * 16 + (r % 4) * 4 with LBO = F * 16 + 16 -- the 16 bytes of padding make the 32 lanes of a
+// warp (32 consecutive rows, same f) hit 32 different banks, so the transposing 4-byte stores are conflict-free.
+__global__ void __launch_bounds__(128) probe_gemm_rows(const float* X, const float* Y, float* D, int N, int three) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tslot;
+  const uint32_t lbo_a = 128 * 16 + 16, lbo_b = N * 16 + 16;
+  uint8_t* sAhi = smem;
+  uint8_t* sAlo = sAhi + 32 * lbo_a;
+  uint8_t* sBhi = sAlo + 32 * lbo_a;
+  uint8_t* sBlo = sBhi + 32 * lbo_b;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc(&tslot, 512);
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tslot;
+  const int r = tid;   // thread = row
+  for (int f = 0; f < 128; ++f) {
+    uint32_t hi, lo;
+    const float x = X[r * 128 + f];
+    split_hi_lo(x, hi, lo);
+    const uint32_t off = (r >> 2) * lbo_a + f * 16 + (r & 3) * 4;
+    *reinterpret_cast<uint32_t*>(sAhi + off) = three ? hi : __float_as_uint(x);
+    *reinterpret_cast<uint32_t*>(sAlo + off) = lo;
+  }
+  for (int f = 0; f < N; ++f) {
+    uint32_t hi, lo;
+    const float y = Y[r * N + f];
+    split_hi_lo(y, hi, lo);
+    const uint32_t off = (r >> 2) * lbo_b + f * 16 + (r & 3) * 4;
+    *reinterpret_cast<uint32_t*>(sBhi + off) = three ? hi : __float_as_uint(y);
+    *reinterpret_cast<uint32_t*>(sBlo + off) = lo;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+    const uint32_t idesc = idesc_tf32(128, N);
+    uint32_t acc = 0;
+    for (int k8 = 0; k8 < 16; ++k8) {   // 8 rows per MMA = two slabs
+      const uint64_t dah = smem_desc(smem_u32(sAhi) + k8 * 2 * lbo_a, lbo_a, 128), dal = smem_desc(smem_u32(sAlo) + k8 * 2 * lbo_a, lbo_a, 128);
+      const uint64_t dbh = smem_desc(smem_u32(sBhi) + k8 * 2 * lbo_b, lbo_b, 128), dbl = smem_desc(smem_u32(sBlo) + k8 * 2 * lbo_b, lbo_b, 128);
+      if (three) { mma_ss(tb, dah, dbl, idesc, acc); mma_ss(tb, dal, dbh, idesc, 1u); acc = 1u; }
       mma_ss(tb, dah, dbh, idesc, acc);
       acc = 1u;
     }
@@ -405,6 +474,35 @@ static int test_gemm_mn(int N, int swap, int three, bool exact_inputs, int patte
   return rel < (three || exact_inputs ? 2e-6 : 2e-3) ? 1 : 0;
 }
 
+static int test_gemm_rows(int N, int three, bool exact_inputs) {
+  std::vector<float> A(128 * 128), B(128 * N), D(128 * N);
+  for (auto& v : A) v = exact_inputs ? (float)((rand() % 17) - 8) * 0.125f : frand();
+  for (auto& v : B) v = exact_inputs ? (float)((rand() % 17) - 8) * 0.25f : frand();
+  std::vector<double> ref(128 * N);
+  for (int m = 0; m < 128; ++m)
+    for (int n = 0; n < N; ++n) {
+      double s = 0;
+      for (int r = 0; r < 128; ++r) s += (double)A[r * 128 + m] * (double)B[r * N + n];
+      ref[m * N + n] = s;
+    }
+  float *dA, *dB, *dD;
+  CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dB, B.size() * 4)); CK(cudaMalloc(&dD, D.size() * 4));
+  CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dD, 0, D.size() * 4));
+  const int smem = 2 * 32 * (128 * 16 + 16) + 2 * 32 * (N * 16 + 16) + 1024;
+  CK(cudaFuncSetAttribute(probe_gemm_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  probe_gemm_rows<<<1, 128, smem>>>(dA, dB, dD, N, three);
+  cudaError_t e = cudaDeviceSynchronize();
+  char name[128];
+  snprintf(name, sizeof name, "X^T.Y rows-as-K, K-major padded LBO N=%d %s", N, three ? "3xTF32" : "1xTF32");
+  if (e != cudaSuccess) { printf("  %-44s CUDA error: %s\n", name, cudaGetErrorString(e)); return -1; }
+  CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+  const double rel = check(name, D, ref);
+  cudaFree(dA); cudaFree(dB); cudaFree(dD);
+  return rel < (three || exact_inputs ? 2e-6 : 2e-3) ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
   srand(1219);
   int only = argc > 1 ? atoi(argv[1]) : 0;
@@ -420,6 +518,13 @@ int main(int argc, char** argv) {
     test_gemm(56, 128, 0, 0, 1, false);
     printf("  1xTF32, random inputs (expected ~5e-4):\n");
     test_gemm(64, 128, 0, 0, 0, false);
+  }
+  if (only == 0 || only == 5) {
+    printf("test 5: weight-gradient shaped GEMMs on the verified K-major path (transposed operands, padded LBO)\n");
+    if (test_gemm_rows(64, 0, true) < 0) { printf("  (context lost, stopping)\n"); return 1; }
+    test_gemm_rows(64, 1, false);
+    test_gemm_rows(48, 1, false);
+    test_gemm_rows(32, 1, false);
   }
   if (only == 4) {
     printf("test 4: the OTHER assignment of the descriptor LBO / SBO fields (how the convention was found; on B200 this\n"
