@@ -80,18 +80,42 @@ struct PackJob {
 constexpr int MAX_PACK_JOBS = 32;
 struct PackJobs { PackJob j[MAX_PACK_JOBS]; int n; };
 
+__host__ __device__ inline size_t scratch_legacy_floats() { return (size_t)Packed::total; }
+
 // ------------------------------------------------------------------ saved activations (global)
 // Row p = ray*S + s.  Offsets in floats from the saved base.
+//
+// Two kinds of planes:
+//  * row-major planes [Pp][width] (k-NN results, geometry activations, rel-pos activations);
+//  * "T-planes" (colour trunk): tile-blocked and TRANSPOSED, tile = the forward's 128-row tile
+//    (rows_per_tile = floor(128 / S) * S valid rows).  A T-plane of F features holds per tile
+//    [4 atom columns q = row / 32][F features][32 rows] floats, the 16-byte chunks of each 128-byte feature
+//    line XOR-swizzled with (f % 8): element (row, f) at  q * F * 32 + f * 32 + ((((row % 32) / 4) ^ (f % 8)) * 4) + row % 4.
+//    This is byte-for-byte the UMMA SWIZZLE_128B K-major operand image with K = rows, so
+//      - a row-owning thread (lane = row) reads / writes one feature of 32 rows as ONE coalesced 128-byte line,
+//      - the backward bulk-copies an atom column (F * 128 bytes, contiguous) into shared memory and the tensor
+//        core contracts over the ROWS directly (weight-gradient GEMMs), tools/umma_sw128_probe.cu test 1.
 struct SavedLayout {
-  size_t idx, w, D, misc, cg, cc, gs, gh, occ, cs, ch, u, sp, rgbs, outraw, total;
+  size_t idx, w, D, misc, cg, gs, gh, occ, cst, cht, cc1t, ect, u, sp, rgbs, outraw, total;
   size_t P, Pp;
+  int ntiles, rays_per_tile;
 };
+constexpr int TP_ROWS = 128;          // rows of a T-plane tile
+constexpr int TP_C1 = 40;             // features of the [c (32) | 1 | 0 x 7] plane
+__host__ __device__ inline size_t tplane_tile_floats(int F) { return (size_t)F * TP_ROWS; }
+__host__ __device__ inline int tplane_off(int F, int row, int f) {
+  const int q = row >> 5, j = row & 31;
+  return q * (F * 32) + f * 32 + ((((j >> 2) ^ (f & 7)) << 2) | (j & 3));
+}
 __host__ __device__ inline SavedLayout saved_layout(int64_t R, int S, int stage, int flags) {
   SavedLayout L;
   const size_t P = (size_t)R * S;
-  const size_t Pp = align_up(P, 128) + 128;   // row pitch of every plane (independent of the tile height)
+  const size_t Pp = align_up(P, 128) + 128;   // row pitch of every row-major plane (independent of the tile height)
   L.P = P;
   L.Pp = Pp;
+  L.rays_per_tile = TP_ROWS / S;
+  L.ntiles = (int)((R + L.rays_per_tile - 1) / L.rays_per_tile);
+  const size_t nt = (size_t)(L.ntiles > 0 ? L.ntiles : 1);
   size_t o = 0;
   L.idx = o;   o += Pp * KNN;
   L.w = o;     o += Pp * KNN;
@@ -101,19 +125,49 @@ __host__ __device__ inline SavedLayout saved_layout(int64_t R, int S, int stage,
   L.gs = o;    o += 5 * Pp * HG;
   L.gh = o;    o += 5 * Pp * HG;
   L.occ = o;   o += Pp;
-  L.cc = o; L.cs = o; L.ch = o; L.u = o; L.sp = o; L.rgbs = o; L.outraw = o;
+  L.cst = o; L.cht = o; L.cc1t = o; L.ect = o; L.u = o; L.sp = o; L.rgbs = o; L.outraw = o;
   if (stage == LSR_STAGE_COLOR) {
-    L.cc = o;      o += Pp * CDIM;
-    L.cs = o;      o += 5 * Pp * HC;
-    L.ch = o;      o += 5 * Pp * HC;
     L.rgbs = o;    o += Pp * 4;
     L.outraw = o;  o += Pp * 4;
+    L.cst = o;     o += 5 * nt * tplane_tile_floats(HC);    // softplus outputs s_l          [layer][tile]
+    L.cht = o;     o += 5 * nt * tplane_tile_floats(HC);    // layer outputs h_l             [layer][tile]
+    L.cc1t = o;    o += nt * tplane_tile_floats(TP_C1);     // [c | 1 | 0]
+    L.ect = o;     o += nt * tplane_tile_floats(ECC);       // colour Fourier features e' = [sin | cos]
     if (flags & LSR_FLAG_REL_POS) {
       L.u = o;     o += Pp * HC;
       L.sp = o;    o += Pp * KNN * HC;
     }
   }
   L.total = o;
+  return L;
+}
+
+// ------------------------------------------------------------------ scratch (global, caller-sized)
+// [legacy packed weights | UMMA packed weights (forward) | k-NN results | backward: packed transposed weights,
+//  per-call accumulators of the row-contracted extras, per-row hand-over planes]
+constexpr int UMMA_PACKED_FLOATS_MAX = 2 * (93 * 32 + 3 * 32 * 32 + 128 * 32 + 5 * 32 * 32 +                  // geometry
+                                            (40 + 128 + 128 + 168 + 128) * 128 + 5 * 32 * 128 + 56 * 128 +   // colour
+                                            128 * 32 + 128 * 16) + 8192;                                     // V2, head, padding
+constexpr int BWD_PACK_FLOATS_MAX = 4 * 128 * 128 + (32 + 80 + 32 + 32 + 48) * 128 + 128 + 4096;   // W^hT x 4, extras, P_out
+constexpr int BWD_ACC_SLOTS = 80;                 // per colour layer: [e' (40) | c (32) | 1 | pad (7)] x 128 outputs
+constexpr int BWD_ACC_FLOATS = 5 * BWD_ACC_SLOTS * 128 + 3 * TP_C1;   // + M_out [3][40]
+struct ScratchLayout { size_t legacy, umma, knn_idx, knn_rem, knn_w, knn_pos, knn_hw, bwd_pack, bwd_acc, bwd_dc, bwd_dp, total; };
+__host__ __device__ inline ScratchLayout scratch_layout(int64_t n_rays, int S) {
+  ScratchLayout L;
+  const size_t Pp = align_up((size_t)n_rays * S, 128) + 128;
+  size_t o = 0;
+  L.legacy = o;   o = align_up(o + (size_t)Packed::total * sizeof(float), 256);
+  L.umma = o;     o = align_up(o + (size_t)UMMA_PACKED_FLOATS_MAX * sizeof(float), 256);
+  L.knn_idx = o;  o = align_up(o + Pp * KNN * 4, 256);
+  L.knn_rem = o;  o = align_up(o + Pp * KNN * 4, 256);
+  L.knn_w = o;    o = align_up(o + Pp * KNN * 4, 256);
+  L.knn_pos = o;  o = align_up(o + Pp * 16, 256);
+  L.knn_hw = o;   o = align_up(o + Pp * 8, 256);
+  L.bwd_pack = o; o = align_up(o + (size_t)BWD_PACK_FLOATS_MAX * sizeof(float), 256);
+  L.bwd_acc = o;  o = align_up(o + (size_t)BWD_ACC_FLOATS * sizeof(float), 256);
+  L.bwd_dc = o;   o = align_up(o + Pp * CDIM * 4, 256);     // dL/dc (colour feature) per sample row
+  L.bwd_dp = o;   o = align_up(o + Pp * 16, 256);           // dL/dp contribution of the colour Fourier features
+  L.total = o + 256;
   return L;
 }
 

@@ -28,6 +28,7 @@ struct BwdArgs {
   const float *g_depth, *g_var, *g_rgb;
   int gflags;
   float *d_geo, *d_col, *d_w, *d_affine, *d_ro, *d_rd;
+  const float *ext_dc, *ext_dp;   // colour trunk hand-over (scratch planes)
   int rays_per_tile, ntiles;
 };
 
@@ -223,216 +224,17 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
 
     LSR_PHASE(1, 0);   // load state + compositing backward
     if (color) {
-      // ---------------------------------------------------------- colour head activation backward
-      if (tid < TILE_M) {
-        const int m = tid;
-        float d0 = sDOut[m * 4 + 0], d1 = sDOut[m * 4 + 1], d2 = sDOut[m * 4 + 2];
-        float da[12];
-#pragma unroll
-        for (int k = 0; k < 12; ++k) da[k] = 0.f;
-        if (m < nrows && a.prm.rgb_mode != LSR_RGB_RAW) {
-          const float4 rs = reinterpret_cast<const float4*>(sv + SL.rgbs)[p0 + m];
-          d0 *= rs.x * (1.f - rs.x); d1 *= rs.y * (1.f - rs.y); d2 *= rs.z * (1.f - rs.z);
-          if (a.prm.rgb_mode == LSR_RGB_AFFINE_SIGMOID) {
-            const float4 o = reinterpret_cast<const float4*>(sv + SL.outraw)[p0 + m];
-            const float* Af = a.affine;
-            const float y0 = d0, y1 = d1, y2 = d2;
-            da[0] = o.x * y0; da[1] = o.x * y1; da[2] = o.x * y2;
-            da[3] = o.y * y0; da[4] = o.y * y1; da[5] = o.y * y2;
-            da[6] = o.z * y0; da[7] = o.z * y1; da[8] = o.z * y2;
-            da[9] = y0; da[10] = y1; da[11] = y2;
-            d0 = Af[0] * y0 + Af[1] * y1 + Af[2] * y2;
-            d1 = Af[3] * y0 + Af[4] * y1 + Af[5] * y2;
-            d2 = Af[6] * y0 + Af[7] * y1 + Af[8] * y2;
-          }
-        }
-        sDOut[m * 4 + 0] = d0; sDOut[m * 4 + 1] = d1; sDOut[m * 4 + 2] = d2;
-        if (g_af) {
-#pragma unroll
-          for (int k = 0; k < 12; ++k) {
-            float v = da[k];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if ((tid & 31) == 0) atomicAdd(a.d_affine + k, v);
-          }
-        }
-      }
-      // sC <- cc, sE <- e', sDE <- 0
+      // The colour head + trunk backward ran on the tensor cores (lsr_render_bwd_umma.cu); it left dL/dc and the
+      // colour-Fourier part of dL/dp per sample row.
       for (int it = tid; it < TILE_M * 8; it += NT) {
         const int m = it >> 3, q = it & 7;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m < nrows) v = reinterpret_cast<const float4*>(sv + SL.cc)[(p0 + m) * 8 + q];
-        *reinterpret_cast<float4*>(sC + m * CLD + q * 4) = v;
+        if (m < nrows && sHas[m]) v = reinterpret_cast<const float4*>(a.ext_dc)[(p0 + m) * 8 + q];
+        *reinterpret_cast<float4*>(sDC + m * CLD + q * 4) = v;
       }
-      for (int it = tid; it < TILE_M * EC; it += NT) {
-        const int m = it / EC, j = it - m * EC;
-        const float t0 = TWO_PI_F * sP[m * 4 + 0], t1 = TWO_PI_F * sP[m * 4 + 1], t2 = TWO_PI_F * sP[m * 4 + 2];
-        const float arg = fmaf(t2, blob[a.w.c_B + 2 * EC + j], fmaf(t1, blob[a.w.c_B + EC + j], t0 * blob[a.w.c_B + j]));
-        float sn, cs;
-        sincos_ff(arg, &sn, &cs);
-        sE[m * ELD + j] = sn;
-        sE[m * ELD + EC + j] = cs;
-      }
-      for (int it = tid; it < TILE_M * ELD; it += NT) sDE[it] = 0.f;
-      __syncthreads();
-
-      if (g_cw) {   // output_linear gradients
-        for (int c = tid; c < HC; c += NT) {
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-          for (int m = 0; m < nrows; ++m) {
-            const float h = sv[SL.ch + ((size_t)4 * Pp + p0 + m) * HC + c];
-            s0 = fmaf(sDOut[m * 4 + 0], h, s0); s1 = fmaf(sDOut[m * 4 + 1], h, s1); s2 = fmaf(sDOut[m * 4 + 2], h, s2);
-          }
-          atomicAdd(dW + a.w.c_out_w + c, s0);
-          atomicAdd(dW + a.w.c_out_w + HC + c, s1);
-          atomicAdd(dW + a.w.c_out_w + 2 * HC + c, s2);
-        }
-        if (tid < 3) {
-          float s = 0.f;
-          for (int m = 0; m < nrows; ++m) s += sDOut[m * 4 + tid];
-          atomicAdd(dW + a.w.c_out_b + tid, s);
-        }
-      }
-      float dH[TMA][8];
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        const int col = wm.col(g);
-        const float4 w0 = *reinterpret_cast<const float4*>(blob + a.w.c_out_w + col);
-        const float4 w1 = *reinterpret_cast<const float4*>(blob + a.w.c_out_w + HC + col);
-        const float4 w2 = *reinterpret_cast<const float4*>(blob + a.w.c_out_w + 2 * HC + col);
-#pragma unroll
-        for (int i = 0; i < TMA; ++i) {
-          const int r = wm.row(i);
-          const float d0 = sDOut[r * 4 + 0], d1 = sDOut[r * 4 + 1], d2 = sDOut[r * 4 + 2];
-          dH[i][g * 4 + 0] = d0 * w0.x + d1 * w1.x + d2 * w2.x;
-          dH[i][g * 4 + 1] = d0 * w0.y + d1 * w1.y + d2 * w2.y;
-          dH[i][g * 4 + 2] = d0 * w0.z + d1 * w1.z + d2 * w2.z;
-          dH[i][g * 4 + 3] = d0 * w0.w + d1 * w1.w + d2 * w2.w;
-        }
-      }
-      LSR_PHASE(1, 1);   // head backward + setup
-      float dCacc[TMNA][4];
-      zero_acc(dCacc);
-#pragma unroll 1
-      for (int li = 4; li >= 0; --li) {
-        // DRAM -> L2 prefetch of the saved tiles this layer will read (softplus outputs now, the
-        // previous layer's h as the dW operand later)
-        prefetch_rows_l2(sv + SL.cs + ((size_t)li * Pp + p0) * HC, nrows, HC);
-        if (g_cw && li > 0) prefetch_rows_l2(sv + SL.ch + ((size_t)(li - 1) * Pp + p0) * HC, nrows, HC);
-#pragma unroll
-        for (int g = 0; g < 2; ++g)
-#pragma unroll
-          for (int i = 0; i < TMA; ++i)
-            *reinterpret_cast<float4*>(sD + wm.row(i) * DLD + wm.col(g)) =
-                make_float4(dH[i][g * 4 + 0], dH[i][g * 4 + 1], dH[i][g * 4 + 2], dH[i][g * 4 + 3]);
-        __syncthreads();
-        if (g_cw) {
-          for (int c = tid; c < HC; c += NT) {
-            float s = 0.f;
-            for (int m = 0; m < nrows; ++m) s += sD[m * DLD + c];
-            atomicAdd(dW + a.w.c_fc_b[li] + c, s);
-          }
-          float au[TMN128][4];
-          zero_acc(au);
-          tile_gemm<TMN128, 8, 1, false, true>(au, sD, DLD, nrows, sC, CLD, CDIM, sB);
-#pragma unroll
-          for (int i = 0; i < TMN128; ++i)
-            red_add_v4(dW + a.w.c_fc_w[li] + nm.row(i) * CDIM + nm.col(), au[i][0], au[i][1], au[i][2], au[i][3]);
-        }
-        tile_gemm<TMNA, 8, 1, true, false>(dCacc, sD, DLD, HC, blob + a.w.c_fc_w[li], CDIM, CDIM, sB, nrows);
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const int col = wm.col(g);
-          float4 s4[TMA];
-#pragma unroll
-          for (int i = 0; i < TMA; ++i) {      // all loads first: 8 independent 16 B requests in flight
-            const int r = wm.row(i);
-            s4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < nrows) s4[i] = __ldcs(reinterpret_cast<const float4*>(sv + SL.cs + ((size_t)li * Pp + p0 + r) * HC + col));
-          }
-#pragma unroll
-          for (int i = 0; i < TMA; ++i) {
-            const int r = wm.row(i);
-            float4 dA = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < nrows)
-              dA = make_float4(dH[i][g * 4 + 0] * softplus100_grad_from_out(s4[i].x),
-                               dH[i][g * 4 + 1] * softplus100_grad_from_out(s4[i].y),
-                               dH[i][g * 4 + 2] * softplus100_grad_from_out(s4[i].z),
-                               dH[i][g * 4 + 3] * softplus100_grad_from_out(s4[i].w));
-            *reinterpret_cast<float4*>(sD + r * DLD + col) = dA;
-          }
-        }
-        __syncthreads();
-        if (g_cw) {
-          for (int c = tid; c < HC; c += NT) {
-            float s = 0.f;
-            for (int m = 0; m < nrows; ++m) s += sD[m * DLD + c];
-            atomicAdd(dW + a.w.c_lin_b[li] + c, s);
-          }
-          if (li == 0 || li == 3) {   // embedding columns of W0 / W3
-            float aw[TMW][4];
-            zero_acc(aw);
-            tile_gemm<TMW, 16, 1, false, true>(aw, sD, DLD, nrows, sE, ELD, ECC, sB);
-            const int ldw = li == 0 ? ECC : ECC + HC;
-            if (wm.tx * 4 < ECC) {
-#pragma unroll
-              for (int i = 0; i < TMW; ++i)
-                red_add_v4(dW + a.w.c_lin_w[li] + wm.row(i) * ldw + wm.tx * 4, aw[i][0], aw[i][1], aw[i][2], aw[i][3]);
-            }
-          }
-          if (li > 0) {
-            float aw[TMW][8];
-            zero_acc(aw);
-            tile_gemm<TMW, 16, 2, false, false>(aw, sD, DLD, nrows, sv + SL.ch + ((size_t)(li - 1) * Pp + p0) * HC, HC, HC, sB);
-            const int ldw = li == 3 ? ECC + HC : HC;
-            const int off = li == 3 ? ECC : 0;
-#pragma unroll
-            for (int g = 0; g < 2; ++g)
-#pragma unroll
-              for (int i = 0; i < TMW; ++i)
-                red_add_v4(dW + a.w.c_lin_w[li] + wm.row(i) * ldw + off + wm.col(g), aw[i][g * 4 + 0], aw[i][g * 4 + 1],
-                           aw[i][g * 4 + 2], aw[i][g * 4 + 3]);
-          }
-        }
-        if (li == 0 || li == 3) {     // d e'
-          float ae[TMA][4];
-          zero_acc(ae);
-          tile_gemm<TMA, 16, 1, true, false>(ae, sD, DLD, HC, blob + a.w.c_lin_w[li], li == 3 ? ECC + HC : ECC, ECC, sB, nrows);
-          if (wm.tx * 4 < ECC) {
-#pragma unroll
-            for (int i = 0; i < TMA; ++i) {
-              float* d = sDE + wm.row(i) * ELD + wm.tx * 4;
-              d[0] += ae[i][0]; d[1] += ae[i][1]; d[2] += ae[i][2]; d[3] += ae[i][3];
-            }
-          }
-        }
-        if (li > 0) {
-          zero_acc(dH);
-          tile_gemm<TMA, 16, 2, true, false>(dH, sD, DLD, HC, blob + a.w.c_lin_w[li] + (li == 3 ? ECC : 0),
-                                           li == 3 ? ECC + HC : HC, HC, sB, nrows);
-        }
-      }
-      LSR_PHASE(1, 2);   // colour trunk backward
-      __syncthreads();
-      // colour Fourier backward -> dp
-      if (g_ry && tid < TILE_M) {
-        const int m = tid;
-        float q0 = 0.f, q1 = 0.f, q2 = 0.f;
-        for (int j = 0; j < EC; ++j) {
-          const float sn = sE[m * ELD + j], cs = sE[m * ELD + EC + j];
-          const float dar = sDE[m * ELD + j] * cs - sDE[m * ELD + EC + j] * sn;
-          q0 = fmaf(blob[a.w.c_B + j], dar, q0);
-          q1 = fmaf(blob[a.w.c_B + EC + j], dar, q1);
-          q2 = fmaf(blob[a.w.c_B + 2 * EC + j], dar, q2);
-        }
-        sDP[m * 4 + 0] += TWO_PI_F * q0; sDP[m * 4 + 1] += TWO_PI_F * q1; sDP[m * 4 + 2] += TWO_PI_F * q2;
-      }
-#pragma unroll
-      for (int i = 0; i < TMNA; ++i) {
-        const int r = nm.row(i);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (sHas[r]) v = make_float4(dCacc[i][0], dCacc[i][1], dCacc[i][2], dCacc[i][3]);
-        *reinterpret_cast<float4*>(sDC + r * CLD + nm.col()) = v;
+      if (g_ry && tid < nrows) {
+        const float4 v = reinterpret_cast<const float4*>(a.ext_dp)[p0 + tid];
+        sDP[tid * 4 + 0] += v.x; sDP[tid * 4 + 1] += v.y; sDP[tid * 4 + 2] += v.z;
       }
       __syncthreads();
 
@@ -859,6 +661,9 @@ int check_weights(const LsrWeights* w);
 int check_params(const LsrParams* p);
 int sm_count();
 int balanced_rays_per_tile(int64_t n_rays, int n_surface, int nsm);
+int launch_trunk_bwd(const LsrParams* prm, const LsrWeights* w, const float* gt_depth, int64_t n_rays, const float* affine,
+                     const void* saved, void* scratch, const float* g_depth, const float* g_var, const float* g_rgb, int grad_flags,
+                     float* d_weights, float* d_affine, cudaStream_t stream);
 
 }  // namespace lsr
 
@@ -901,7 +706,15 @@ extern "C" int lsr_render_bwd(const LsrParams* prm, const void* grid_ws, const f
   const int nsm = sm_count();
   if (nsm <= 0) return LSR_ERR_CUDA;
 
+  const ScratchLayout CL = scratch_layout(n_rays, prm->n_surface);
+  if (stage == LSR_STAGE_COLOR) {
+    rc = launch_trunk_bwd(prm, w, gt_depth, n_rays, exposure_affine, saved, scratch, g_depth, g_var, g_rgb, grad_flags, d_weights,
+                          d_exposure_affine, stream);
+    if (rc) return rc;
+  }
   BwdArgs a;
+  a.ext_dc = (const float*)((const char*)scratch + CL.bwd_dc);
+  a.ext_dp = (const float*)((const char*)scratch + CL.bwd_dp);
   a.prm = *prm;
   a.cloud = cloud_pos;
   a.rays_o = rays_o; a.rays_d = rays_d; a.gt_depth = gt_depth;

@@ -46,24 +46,7 @@ struct KnnScratch {   // per sample row p = ray * S + s, all planes of Pp rows
   float4* pos;        // [Pp]    (px, py, pz, z)
   float2* hw;         // [Pp]    (has_neighbors, sum of weights)
 };
-struct ScratchLayout { size_t legacy, umma, knn_idx, knn_rem, knn_w, knn_pos, knn_hw, total; };
-constexpr int UMMA_PACKED_FLOATS_MAX = 2 * (93 * 32 + 3 * 32 * 32 + 128 * 32 + 5 * 32 * 32 +                  // geometry
-                                            (40 + 128 + 128 + 168 + 128) * 128 + 5 * 32 * 128 + 56 * 128 +   // colour
-                                            128 * 32 + 128 * 16) + 8192;                                     // V2, head, padding
-__host__ __device__ inline ScratchLayout scratch_layout(int64_t n_rays, int S) {
-  ScratchLayout L;
-  const size_t Pp = align_up((size_t)n_rays * S, 128) + 128;
-  size_t o = 0;
-  L.legacy = o;   o = align_up(o + (size_t)Packed::total * sizeof(float), 256);
-  L.umma = o;     o = align_up(o + (size_t)UMMA_PACKED_FLOATS_MAX * sizeof(float), 256);
-  L.knn_idx = o;  o = align_up(o + Pp * KNN * 4, 256);
-  L.knn_rem = o;  o = align_up(o + Pp * KNN * 4, 256);
-  L.knn_w = o;    o = align_up(o + Pp * KNN * 4, 256);
-  L.knn_pos = o;  o = align_up(o + Pp * 16, 256);
-  L.knn_hw = o;   o = align_up(o + Pp * 8, 256);
-  L.total = o + 256;
-  return L;
-}
+// (ScratchLayout / scratch_layout: lsr_render.cuh)
 
 struct KnnArgs {
   LsrParams prm;
@@ -485,6 +468,9 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
 
       FWD_PHASE(2);
       if (color) {
+        // T-planes of this tile (lsr_render.cuh): read back by the tcgen05 backward as row-contraction operands
+        float* tp_c1 = a.saved + SL.cc1t + (size_t)tile * tplane_tile_floats(TP_C1);
+        float* tp_ec = a.saved + SL.ect + (size_t)tile * tplane_tile_floats(ECC);
         // -------------------------------------------------------------- colour feature
         if (relpos) {   // decoder.py:477-488: c = V2 . sum_k w_k softplus(V1 q_k + v1) + v2 * sum_k w_k
           // zero the K padding (columns 52..55) of Q once per tile
@@ -597,8 +583,15 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
               if (has) cc = make_float4(fmaf(v2.x, ws, __uint_as_float(x[j])), fmaf(v2.y, ws, __uint_as_float(x[j + 1])),
                                         fmaf(v2.z, ws, __uint_as_float(x[j + 2])), fmaf(v2.w, ws, __uint_as_float(x[j + 3])));
               store_a_split(smem + SM_C_HI, smem + SM_C_LO, row, 16 * cg + j, cc);
-              if (save && rv) *reinterpret_cast<float4*>(a.saved + SL.cc + prow * CDIM + 16 * cg + j) = cc;
+              if (save) {   // [c | 1 | 0] T-plane: lane = row, one 128-byte line per feature
+                const float cv[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) tp_c1[tplane_off(TP_C1, row, 16 * cg + j + t)] = rv ? cv[t] : 0.f;
+              }
             }
+          } else if (cg == 2 && save) {
+#pragma unroll
+            for (int f = CDIM; f < TP_C1; ++f) tp_c1[tplane_off(TP_C1, row, f)] = (rv && f == CDIM) ? 1.f : 0.f;
           }
         } else {        // decoder.py:476,487-488: plain IDW interpolation of the colour features
           const int m = tid & 127, qg = tid >> 7;
@@ -624,7 +617,15 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
 #pragma unroll
           for (int i = 0; i < F4T; ++i) {
             store_a_split(smem + SM_C_HI, smem + SM_C_LO, m, (qg * F4T + i) * 4, acc[i]);
-            if (save && m < nrows) reinterpret_cast<float4*>(a.saved + SL.cc)[(p0 + m) * 8 + qg * F4T + i] = acc[i];
+            if (save) {
+              const float cv[4] = {acc[i].x, acc[i].y, acc[i].z, acc[i].w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) tp_c1[tplane_off(TP_C1, m, (qg * F4T + i) * 4 + t)] = m < nrows ? cv[t] : 0.f;
+            }
+          }
+          if (save && qg == 0) {
+#pragma unroll
+            for (int f = CDIM; f < TP_C1; ++f) tp_c1[tplane_off(TP_C1, m, f)] = (m < nrows && f == CDIM) ? 1.f : 0.f;
           }
         }
         FWD_PHASE(3);
@@ -642,6 +643,13 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
           }
           store_a_split(smem + SM_EC_HI, smem + SM_EC_LO, m, g * 4, make_float4(sn[0], sn[1], sn[2], sn[3]));
           store_a_split(smem + SM_EC_HI, smem + SM_EC_LO, m, EC + g * 4, make_float4(cs[0], cs[1], cs[2], cs[3]));
+          if (save) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              tp_ec[tplane_off(ECC, m, g * 4 + t)] = m < nrows ? sn[t] : 0.f;
+              tp_ec[tplane_off(ECC, m, EC + g * 4 + t)] = m < nrows ? cs[t] : 0.f;
+            }
+          }
         }
         es.signal_a(pipe);
 
@@ -650,9 +658,10 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
 #pragma unroll 1
         for (int li = 0; li < 5; ++li) {
           es.wait_d(pipe, 0);
-          float* cs_ = a.saved + SL.cs + ((size_t)li * Pp + pw0) * HC + CPT * cg;
-          float* ch_ = a.saved + SL.ch + ((size_t)li * Pp + pw0) * HC + CPT * cg;
-          float* stg = reinterpret_cast<float*>(smem + SM_Q_HI) + warp * (32 * 20);            // Q is dead by now
+          // s_l / h_l T-planes: this thread's row inside the tile's atom column, chunk swizzle folded per feature
+          float* tps = a.saved + SL.cst + ((size_t)li * SL.ntiles + tile) * tplane_tile_floats(HC) + (row >> 5) * (HC * 32) + (row & 3);
+          float* tph = a.saved + SL.cht + ((size_t)li * SL.ntiles + tile) * tplane_tile_floats(HC) + (row >> 5) * (HC * 32) + (row & 3);
+          const int tchunk = (row & 31) >> 2;
           uint32_t v1[2][16], v2[2][16];
           tmem_ld16(tmem_addr(tb, lane_base, TM_ACC0 + CPT * cg), v1[0]);
           tmem_ld16(tmem_addr(tb, lane_base, TM_ACC1 + CPT * cg), v2[0]);
@@ -678,14 +687,18 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
                 hk[j + t] = s[t] + (__uint_as_float(x2[j + t]) + uv[t]);
                 split_hi_lo(hk[j + t], x1[j + t], x2[j + t]);
               }
-              stage_put<20>(stg, lane, j, s[0], s[1], s[2], s[3]);
+              if (save) {   // lane = row: every store instruction of the warp fills one 128-byte line
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const int f = col0 + j + t;
+                  const int off = f * 32 + ((tchunk ^ ((j + t) & 7)) << 2);
+                  tps[off] = rv ? s[t] : 0.f;
+                  tph[off] = rv ? hk[j + t] : 0.f;
+                }
+              }
             }
             tmem_st16(tmem_addr(tb, lane_base, TM_AHI + col0), x1);
             tmem_st16(tmem_addr(tb, lane_base, TM_ALO + col0), x2);
-            stage_flush<16, 20>(stg, lane, cs_ + 16 * c, (size_t)HC, wvalid);   // softplus outputs, then h through the same block
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) stage_put<20>(stg, lane, j, hk[j], hk[j + 1], hk[j + 2], hk[j + 3]);
-            stage_flush<16, 20>(stg, lane, ch_ + 16 * c, (size_t)HC, wvalid);
             if (c + 1 < STEPS) tmem_wait_ld();
           }
           es.signal_a_tmem(pipe);   // li == 4: feeds the colour head GEMM

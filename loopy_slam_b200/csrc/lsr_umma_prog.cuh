@@ -129,7 +129,7 @@ __device__ __forceinline__ void pack_umma_element(const UPackJob& jb, int e, con
   chunk[jb.n * kc + r] = __uint_as_float(lo);
 }
 // grid (blocks, n_jobs): job list in global memory (bring-up probe; the library passes its jobs by value)
-__global__ void pack_umma_kernel(const float* __restrict__ blob, float* __restrict__ packed, const UPackJob* __restrict__ jobs) {
+static __global__ void pack_umma_kernel(const float* __restrict__ blob, float* __restrict__ packed, const UPackJob* __restrict__ jobs) {
   const UPackJob jb = jobs[blockIdx.y];
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < jb.total / 2; e += gridDim.x * blockDim.x)
     pack_umma_element(jb, e, blob, packed);

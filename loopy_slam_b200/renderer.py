@@ -362,11 +362,8 @@ def _saved_views(rc):
     take('idx', Pp * 8, (Pp, 8)); take('w', Pp * 8, (Pp, 8)); take('D', Pp * 8, (Pp, 8)); take('misc', Pp * 4, (Pp, 4))
     take('cg', Pp * 32, (Pp, 32)); take('gs', 5 * Pp * 32, (5, Pp, 32)); take('gh', 5 * Pp * 32, (5, Pp, 32))
     take('occ', Pp, (Pp,))
-    if rc.stage == 1:
-        take('cc', Pp * 32, (Pp, 32)); take('cs', 5 * Pp * 128, (5, Pp, 128)); take('ch', 5 * Pp * 128, (5, Pp, 128))
+    if rc.stage == 1:   # the colour-trunk planes behind these two are tile-blocked (csrc/lsr_render.cuh) and not viewed here
         take('rgbs', Pp * 4, (Pp, 4)); take('outraw', Pp * 4, (Pp, 4))
-        if rc.prm.flags & _lib.FLAG_REL_POS:
-            take('u', Pp * 128, (Pp, 128)); take('sp', Pp * 8 * 128, (Pp, 8, 128))
     return v, P
 
 
