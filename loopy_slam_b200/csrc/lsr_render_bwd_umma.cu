@@ -54,18 +54,37 @@ __global__ void bwd_prep_kernel(const float* __restrict__ blob, float* __restric
     return;
   }
   const BJob jb = jobs.j[blockIdx.y];
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < jb.n_valid * jb.k_total; e += gridDim.x * blockDim.x) {
-    const int n = e % jb.n_valid, k = e / jb.n_valid;
-    float v;
-    if (jb.type == 0) {
-      v = blob[jb.w + (size_t)k * jb.ld + jb.col0 + n];
-    } else {
-      v = 0.f;
-      const float* wr = blob + jb.w + (size_t)k * jb.ld + jb.col0;
-      for (int i = 0; i < HC; ++i) v = fmaf(wr[i], blob[jb.u + i * CDIM + n], v);
-    }
+  auto put = [&](int n, int k, float v) {
     const int c = k / jb.kc, kl = k - c * jb.kc;
     pack[jb.dst + (size_t)c * jb.n_pad * jb.kc + ((kl >> 2) * jb.n_pad + jb.n0 + n) * 4 + (kl & 3)] = v;
+  };
+  if (jb.type == 0) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < jb.n_valid * jb.k_total; e += gridDim.x * blockDim.x) {
+      const int n = e % jb.n_valid, k = e / jb.n_valid;
+      put(n, k, blob[jb.w + (size_t)k * jb.ld + jb.col0 + n]);
+    }
+  } else {
+    // P[n = c][k = o] = sum_i W[o][col0 + i] U[i][c]: block handles output features k = blockIdx.x, +gridDim.x, ...;
+    // 256 threads = 32 c x 8 slices of i, the W row staged in shared memory
+    __shared__ float wrow[HC];
+    __shared__ float part[8][CDIM];
+    const int c = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    for (int k = blockIdx.x; k < jb.k_total; k += gridDim.x) {
+      if (threadIdx.x < HC) wrow[threadIdx.x] = blob[jb.w + (size_t)k * jb.ld + jb.col0 + threadIdx.x];
+      __syncthreads();
+      float v = 0.f;
+#pragma unroll
+      for (int i = sl * 16; i < sl * 16 + 16; ++i) v = fmaf(wrow[i], blob[jb.u + i * CDIM + c], v);
+      part[sl][c] = v;
+      __syncthreads();
+      if (sl == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t += part[j][c];
+        put(c, k, t);
+      }
+      __syncthreads();
+    }
   }
 }
 
@@ -104,6 +123,7 @@ constexpr int SB_PIPE = SB_TAB + TAB_TOTAL * 4;
 constexpr int BWD_UMMA_SMEM = SB_PIPE + 256;
 static_assert(BWD_UMMA_SMEM <= 232448, "shared memory budget");
 static_assert(SB_ZT % 1024 == 0 && ZT_ATOM % 1024 == 0, "swizzle atoms need 1024-byte alignment");
+static_assert(HC * (HC + 4) * 4 + 80 * HC * 4 <= 2 * ZT_LO, "weight-gradient staging image fits the Z^T region");
 constexpr uint32_t TMB_ZHI = 0, TMB_ZLO = 128, TMB_G = 256, TMB_EX = 384;
 constexpr uint32_t SW128_HIWORD = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
 
@@ -134,9 +154,40 @@ struct TrunkArgs {
   ROp ops[MAX_ROPS];
 };
 
+#ifdef LSR_TRACE
+// bring-up only (tools/trace_bwd.py builds a separate .so with -DLSR_TRACE): clock64 stamps of CTA 0, first tile
+__device__ long long lsr_trace[3][512];
+#define TRC(role, k) do { if (blockIdx.x == 0 && tile == (int)blockIdx.x && (threadIdx.x & 31) == 0) lsr_trace[role][k] = clock64(); } while (0)
+#else
+#define TRC(role, k)
+#endif
 __device__ __forceinline__ void bar_compute_b() { asm volatile("bar.sync 1, %0;\n" ::"n"(BNCT) : "memory"); }
 __device__ __forceinline__ void red_add_f32(float* addr, float v) {
   asm volatile("red.global.add.f32 [%0], %1;\n" ::"l"(addr), "f"(v) : "memory");
+}
+// single tcgen05.mma with descriptors assembled from 32-bit halves inside the asm (keeps them in the uniform datapath)
+__device__ __forceinline__ void mma_ts2(uint32_t d, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hiword, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 bd, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, p;\n\t}\n" ::"r"(d),
+      "r"(a_tmem), "r"(b_lo), "r"(b_hiword), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ss2(uint32_t d, uint32_t a_lo, uint32_t a_hiword, uint32_t b_lo, uint32_t b_hiword, uint32_t idesc,
+                                        uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 ad, bd;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 ad, {%1, %2};\n\t"
+      "mov.b64 bd, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], ad, bd, %5, p;\n\t}\n" ::"r"(d),
+      "r"(a_lo), "r"(a_hiword), "r"(b_lo), "r"(b_hiword), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gmem), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
@@ -216,12 +267,37 @@ __global__ void __launch_bounds__(BT, 1) trunk_bwd_umma_kernel(const __grid_cons
           const float4 v = *reinterpret_cast<const float4*>(base + 16 * e);
           uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
           split_hi_lo(v.x, h0, l0); split_hi_lo(v.y, h1, l1); split_hi_lo(v.z, h2, l2); split_hi_lo(v.w, h3, l3);
-          *reinterpret_cast<uint4*>(base + 16 * e) = make_uint4(h0, h1, h2, h3);
+          // the tensor core reads only the top 19 bits of an fp32 word (tools/umma_sw128_probe.cu test 4): the raw image IS
+          // the hi operand, only the residuals have to be produced
+          (void)h0; (void)h1; (void)h2; (void)h3;
           *reinterpret_cast<uint4*>(base + UM_STAGE_BYTES / 2 + 16 * e) = make_uint4(l0, l1, l2, l3);
         }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&pipe->conv[stage]);
+        // DRAM -> L2 prefetch (LSU path: the TMA queue stays free for the ring) of what the NEXT tile of this CTA reads
+        // from the saved planes -- s_l and h_l T-planes, [c|1], e' -- one request per 128-byte line, spread over the ops
+        const int tt = tile + (int)gridDim.x;
+        if (tt < a.ntiles) {
+          constexpr int LINES = 10 * HC * 4 + (TP_C1 + ECC) * 4;
+          const int per = (LINES + a.n_ops - 1) / a.n_ops;
+          for (int e = i * per + cw * 32 + lane; e < min((i + 1) * per, LINES); e += 32 * BCONV) {
+            const float* base;
+            int ln = e;
+            if (ln < 10 * HC * 4) {
+              const int pl = ln / (HC * 4);
+              ln -= pl * HC * 4;
+              base = sv + (pl < 5 ? SL.cst : SL.cht) + ((size_t)(pl % 5) * SL.ntiles + tt) * tplane_tile_floats(HC);
+            } else if (ln < 10 * HC * 4 + TP_C1 * 4) {
+              ln -= 10 * HC * 4;
+              base = sv + SL.cc1t + (size_t)tt * tplane_tile_floats(TP_C1);
+            } else {
+              ln -= 10 * HC * 4 + TP_C1 * 4;
+              base = sv + SL.ect + (size_t)tt * tplane_tile_floats(ECC);
+            }
+            prefetch_l2(base + (size_t)ln * 32);
+          }
+        }
       }
     }
   } else if (warp == W_ISSUER) {
@@ -234,49 +310,78 @@ __global__ void __launch_bounds__(BT, 1) trunk_bwd_umma_kernel(const __grid_cons
         const uint32_t flags = a.ops[i].flags;
         if (flags & RF_WAIT_A) { mbar_wait(&pipe->a_ready, a_par); a_par ^= 1; }
         if (flags & RF_WAIT_B) { mbar_wait(&pipe->b_ready, b_par); b_par ^= 1; }
-        mbar_wait(&pipe->conv[stage], use & 1);
+        TRC(0, 3 * i);
+        // Two-phase issue: the products that only need the RAW chunk (= its hi part) go out as soon as the bulk copy has
+        // landed; the one product per K step that needs the residual image waits for the converters.
+        const uint32_t kind = a.ops[i].kind, n = a.ops[i].n, q = a.ops[i].q;
+        const int nk8 = a.ops[i].nk8;
+        const uint32_t idesc = idesc_tf32(128, (int)n);
+        const uint32_t st_hi = ring_addr + stage * UM_STAGE_BYTES, st_lo = st_hi + UM_STAGE_BYTES / 2;
+        const uint32_t acc0 = (flags & RF_FIRST) ? 0u : 1u;
+        mbar_wait(&pipe->full[stage], use & 1);
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t kind = a.ops[i].kind, n = a.ops[i].n, q = a.ops[i].q;
-          const int nk8 = a.ops[i].nk8;
-          const uint32_t idesc = idesc_tf32(128, (int)n);
-          const uint32_t st_hi = ring_addr + stage * UM_STAGE_BYTES, st_lo = st_hi + UM_STAGE_BYTES / 2;
-          uint32_t acc = (flags & RF_FIRST) ? 0u : 1u;
-          if (kind <= K_DXE) {
-            // D[rows][n] (+)= Z[rows][K chunk] . B[n][K chunk]^T ; A from TMEM, B = ring chunk (no swizzle, LBO = n * 16)
-            const uint32_t lbo_word = ((n * 16u) >> 4) << 16, step = (2u * n * 16u) >> 4;
-            uint32_t bh = lbo_word | ((st_hi >> 4) & 0x3fffu), bl = lbo_word | ((st_lo >> 4) & 0x3fffu);
+        TRC(0, 3 * i + 1);
+        if (kind <= K_DXE) {
+          // D[rows][n] (+)= Z[rows][K chunk] . B[n][K chunk]^T ; A from TMEM, B = ring chunk (no swizzle, LBO = n * 16)
+          const uint32_t lbo_word = ((n * 16u) >> 4) << 16, step = (2u * n * 16u) >> 4;
+          const uint32_t d = tb + (kind == K_DXW ? TMB_G : TMB_EX);
+          if (elect_one()) {
+            uint32_t bh = lbo_word | ((st_hi >> 4) & 0x3fffu);
             uint32_t ah = tb + TMB_ZHI + q * 8u, al = tb + TMB_ZLO + q * 8u;
-            const uint32_t d = tb + (kind == K_DXW ? TMB_G : TMB_EX);
+            uint32_t acc = acc0;
 #pragma unroll 4
             for (int k8 = 0; k8 < nk8; ++k8) {
-              mma3_ts(d, ah, al, bh, bl, UM_DESC_HIWORD, idesc, acc);
-              acc = 1u; ah += 8; al += 8; bh += step; bl += step;
-            }
-          } else {
-            // row-contracted: both operands 128-byte-swizzled K-major with K = rows; one operand is the ring chunk,
-            // the other atom column q of Z^T.  K = 8 rows = 32 bytes inside the 128-byte line.
-            uint32_t rh = (st_hi >> 4) & 0x3fffu, rl = (st_lo >> 4) & 0x3fffu;
-            uint32_t zh = ((zt_addr + q * ZT_ATOM) >> 4) & 0x3fffu, zl = ((zt_addr + ZT_LO + q * ZT_ATOM) >> 4) & 0x3fffu;
-            if (kind == K_DWH) {      // D[h_{l-1} feature][out] (+)= h^T (ring) . Z^T
-#pragma unroll
-              for (int k8 = 0; k8 < 4; ++k8) {
-                mma3_ss(tb + TMB_G, rh, rl, SW128_HIWORD, zh, zl, SW128_HIWORD, idesc, acc);
-                acc = 1u; rh += 2; rl += 2; zh += 2; zl += 2;
-              }
-            } else {                  // D[out][extra feature] (+)= Z^T . [e' | c | 1]^T (ring)
-#pragma unroll
-              for (int k8 = 0; k8 < 4; ++k8) {
-                mma3_ss(tb + TMB_EX, zh, zl, SW128_HIWORD, rh, rl, SW128_HIWORD, idesc, acc);
-                acc = 1u; rh += 2; rl += 2; zh += 2; zl += 2;
-              }
+              mma_ts2(d, al, bh, UM_DESC_HIWORD, idesc, acc);
+              mma_ts2(d, ah, bh, UM_DESC_HIWORD, idesc, 1u);
+              acc = 1u; ah += 8; al += 8; bh += step;
             }
           }
+          __syncwarp();
+          mbar_wait(&pipe->conv[stage], use & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            uint32_t bl = lbo_word | ((st_lo >> 4) & 0x3fffu);
+            uint32_t ah = tb + TMB_ZHI + q * 8u;
+#pragma unroll 4
+            for (int k8 = 0; k8 < nk8; ++k8) {
+              mma_ts2(d, ah, bl, UM_DESC_HIWORD, idesc, 1u);
+              ah += 8; bl += step;
+            }
+          }
+        } else {
+          // row-contracted: D[out][feature] (+)= Z^T (atom column q, resident) . X^T (ring chunk); both operands
+          // 128-byte-swizzled K-major with K = rows; K = 8 rows = 32 bytes inside the 128-byte line.
+          const uint32_t d = tb + (kind == K_DWH ? TMB_G : TMB_EX);
+          const uint32_t zh0 = ((zt_addr + q * ZT_ATOM) >> 4) & 0x3fffu, zl0 = ((zt_addr + ZT_LO + q * ZT_ATOM) >> 4) & 0x3fffu;
+          if (elect_one()) {
+            uint32_t rh = (st_hi >> 4) & 0x3fffu, zh = zh0, zl = zl0;
+            uint32_t acc = acc0;
+#pragma unroll
+            for (int k8 = 0; k8 < 4; ++k8) {
+              mma_ss2(d, zl, SW128_HIWORD, rh, SW128_HIWORD, idesc, acc);
+              mma_ss2(d, zh, SW128_HIWORD, rh, SW128_HIWORD, idesc, 1u);
+              acc = 1u; rh += 2; zh += 2; zl += 2;
+            }
+          }
+          __syncwarp();
+          mbar_wait(&pipe->conv[stage], use & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            uint32_t rl = (st_lo >> 4) & 0x3fffu, zh = zh0;
+#pragma unroll
+            for (int k8 = 0; k8 < 4; ++k8) {
+              mma_ss2(d, zh, SW128_HIWORD, rl, SW128_HIWORD, idesc, 1u);
+              rl += 2; zh += 2;
+            }
+          }
+        }
+        if (elect_one()) {
           mma_commit(&pipe->empty[stage]);
           if (flags & RF_COMMIT_D0) mma_commit(&pipe->d_ready[0]);
           if (flags & RF_COMMIT_D1) mma_commit(&pipe->d_ready[1]);
         }
         __syncwarp();
+        TRC(0, 3 * i + 2);
       }
     }
   } else {
@@ -308,14 +413,25 @@ __global__ void __launch_bounds__(BT, 1) trunk_bwd_umma_kernel(const __grid_cons
       const bool rv = row < nrows;
 
       // ---------------------------------------------------------------- per-row state + compositing backward
-      if (tid < 128) {
+      if (warp == 0) TRC(2, 0);
+      float4 h_rgbs = make_float4(0.f, 0.f, 0.f, 0.f), h_raw = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (tid < 128) {   // all per-row loads of the head in flight together (one DRAM round trip)
         float4 mi = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (tid < nrows) mi = reinterpret_cast<const float4*>(sv + SL.misc)[p0 + tid];
-        sHas[tid] = (tid < nrows && mi.y > 0.5f) ? 1 : 0;
-        sDOut[tid * 4 + 0] = 0.f; sDOut[tid * 4 + 1] = 0.f; sDOut[tid * 4 + 2] = 0.f; sDOut[tid * 4 + 3] = 0.f;
+        float occ = 0.f;
+        if (tid < nrows) {
+          mi = reinterpret_cast<const float4*>(sv + SL.misc)[p0 + tid];
+          occ = sv[SL.occ + p0 + tid];
+          h_rgbs = reinterpret_cast<const float4*>(sv + SL.rgbs)[p0 + tid];
+          if (a.prm.rgb_mode == LSR_RGB_AFFINE_SIGMOID) h_raw = reinterpret_cast<const float4*>(sv + SL.outraw)[p0 + tid];
+        }
+        const int has = (tid < nrows && mi.y > 0.5f) ? 1 : 0;
+        sHas[tid] = has;
+        sDOut[tid * 4 + 0] = 0.f; sDOut[tid * 4 + 1] = 0.f; sDOut[tid * 4 + 2] = 0.f;
+        sDOut[tid * 4 + 3] = has ? occ : -100.f;            // Renderer.py:184-186 (slot 3: occupancy logit for the compositing pass)
         sDP[tid * 4 + 0] = 0.f; sDP[tid * 4 + 1] = 0.f; sDP[tid * 4 + 2] = 0.f; sDP[tid * 4 + 3] = 0.f;
       }
       bar_compute_b();
+      if (warp == 0) TRC(2, 4);
       if (tid < nr) {   // common.py:410-421 backward: only d(rgb_s) is needed here
         const int ray = r0 + tid;
         const float g = a.gt_depth[ray];
@@ -331,8 +447,7 @@ __global__ void __launch_bounds__(BT, 1) trunk_bwd_umma_kernel(const __grid_cons
         for (int s = 0; s < 8; ++s) {
           if (s < S) {
             const int m = tid * S + s;
-            const float occ = sHas[m] ? sv[SL.occ + p0 + m] : -100.f;
-            const float alpha = sigmoidf_acc(coef * occ);
+            const float alpha = sigmoidf_acc(coef * sDOut[m * 4 + 3]);
             wv[s] = alpha * T;
             T = T * ((1.f - alpha) + 1e-10f);
             sw += wv[s];
@@ -349,6 +464,7 @@ __global__ void __launch_bounds__(BT, 1) trunk_bwd_umma_kernel(const __grid_cons
         }
       }
       bar_compute_b();
+      if (warp == 0) TRC(2, 5);
       // ---------------------------------------------------------------- colour head activation backward (decoder.py:533-546)
       if (tid < 128) {
         const int m = tid;
@@ -357,10 +473,10 @@ __global__ void __launch_bounds__(BT, 1) trunk_bwd_umma_kernel(const __grid_cons
 #pragma unroll
         for (int k = 0; k < 12; ++k) da[k] = 0.f;
         if (m < nrows && a.prm.rgb_mode != LSR_RGB_RAW) {
-          const float4 rs = reinterpret_cast<const float4*>(sv + SL.rgbs)[p0 + m];
+          const float4 rs = h_rgbs;
           d0 *= rs.x * (1.f - rs.x); d1 *= rs.y * (1.f - rs.y); d2 *= rs.z * (1.f - rs.z);
           if (a.prm.rgb_mode == LSR_RGB_AFFINE_SIGMOID) {
-            const float4 o = reinterpret_cast<const float4*>(sv + SL.outraw)[p0 + m];
+            const float4 o = h_raw;
             const float* Af = a.affine;
             const float y0 = d0, y1 = d1, y2 = d2;
             da[0] = o.x * y0; da[1] = o.x * y1; da[2] = o.x * y2;
@@ -384,19 +500,33 @@ __global__ void __launch_bounds__(BT, 1) trunk_bwd_umma_kernel(const __grid_cons
         }
       }
       bar_compute_b();
+      if (warp == 0) TRC(2, 6);
 
       // ---------------------------------------------------------------- output_linear gradients + M_out = dOut^T [c | 1]
       // thread-per-feature-line FMAs: lane l reads 4 rows of the (swizzled) 128-byte lines of feature f
       if (g_cw) {
         const float* tph4 = sv + SL.cht + ((size_t)4 * SL.ntiles + tile) * tplane_tile_floats(HC);
         const float* tpc1 = sv + SL.cc1t + (size_t)tile * tplane_tile_floats(TP_C1);
-        for (int f = warp; f < HC + CDIM + 1; f += BCW) {
+        constexpr int NL = (HC + CDIM + 1 + BCW - 1) / BCW;   // feature lines per warp (11)
+        float4 xs[NL];
+#pragma unroll
+        for (int it = 0; it < NL; ++it) {     // every load of this warp in flight before the first use
+          const int f = warp + BCW * it;
+          xs[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (f < HC + CDIM + 1) {
+            const bool isc = f >= HC;
+            const int ff = isc ? f - HC : f, F = isc ? TP_C1 : HC;
+            xs[it] = __ldcs(reinterpret_cast<const float4*>((isc ? tpc1 : tph4) + (lane >> 3) * (F * 32) + ff * 32 + (lane & 7) * 4));
+          }
+        }
+#pragma unroll
+        for (int it = 0; it < NL; ++it) {
+          const int f = warp + BCW * it;
+          if (f >= HC + CDIM + 1) break;
           const bool isc = f >= HC;
-          const int ff = isc ? f - HC : f, F = isc ? TP_C1 : HC;
-          const float* line = (isc ? tpc1 : tph4) + (lane >> 3) * (F * 32) + ff * 32 + (lane & 7) * 4;
-          const float4 x = *reinterpret_cast<const float4*>(line);
+          const int ff = isc ? f - HC : f;
           const int rbase = (lane >> 3) * 32 + (((lane & 7) ^ (ff & 7)) << 2);
-          const float xv[4] = {x.x, x.y, x.z, x.w};
+          const float xv[4] = {xs[it].x, xs[it].y, xs[it].z, xs[it].w};
           float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
@@ -418,6 +548,7 @@ __global__ void __launch_bounds__(BT, 1) trunk_bwd_umma_kernel(const __grid_cons
         }
       }
 
+      if (warp == 0) TRC(2, 1);
       // ---------------------------------------------------------------- G_4 = dOut . W_out, dC = dOut . (W_out U_4)
       float g[32];
       float dCacc[8], dEacc[16];
@@ -437,9 +568,61 @@ __global__ void __launch_bounds__(BT, 1) trunk_bwd_umma_kernel(const __grid_cons
         for (int j = 0; j < 16; ++j) dEacc[j] = 0.f;
       }
 
+      // Weight-gradient flush of layer lw, in two steps so that only a register/shared-memory copy sits on the critical
+      // path: (1) flush_load: TMEM accumulators -> staging image in the (idle) Z^T region, then the accumulator columns
+      // go back to the issuer; (2) flush_store: staging -> global with coalesced red.global (one 128-byte line per
+      // instruction) WHILE the dX MMAs of the next layer run.  (Measured: the atomics cost 5-8 k cycles per layer and
+      // tile whichever way they are issued -- LSU scalar, LSU v4 or cp.reduce.async.bulk, the latter also delaying the
+      // ring's bulk copies in the shared TMA queue.)
+      constexpr int STP = HC + 4;                                        // staging row pitch (floats): conflict-free 16-byte row stores
+      float* st_h = reinterpret_cast<float*>(smem + SB_ZT);              // [128 o][STP]  (i contiguous)
+      float* st_e = st_h + HC * STP;                                     // [80 slots][128 o]
+      auto flush_load = [&](int lw) {
+        const bool has_e = lw == 0 || lw == 3;
+        const int ncol = has_e ? 80 : 48;
+        if (lw >= 1) {   // dW^h: lane = output o of layer lw, columns = features i of h_{lw-1}
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t x[16];
+            tmem_ld16(tmem_addr(tb, lane_base, TMB_G + 32 * cg + 16 * h), x);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<uint4*>(st_h + row * STP + 32 * cg + 16 * h + j) = make_uint4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+          }
+        }
+        // extras: lane = output o, columns = [e' (40) |] c (32) | 1 | pad;  16-column groups cg, cg + 4
+        for (int c0 = 16 * cg; c0 < ncol; c0 += 64) {
+          uint32_t x[16];
+          tmem_ld16(tmem_addr(tb, lane_base, TMB_EX + c0), x);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) st_e[(c0 + j + (has_e ? 0 : 40)) * HC + row] = __uint_as_float(x[j]);
+        }
+      };
+      auto flush_store = [&](int lw) {
+        const bool has_e = lw == 0 || lw == 3;
+        bar_compute_b();                                   // staging image complete
+        if (lw >= 1) {   // lane = feature i (= row index of this thread), this thread's 32 outputs o
+          const int ldw = lw == 3 ? ECC + HC : HC;
+          float* dst = a.d_w + a.w.c_lin_w[lw] + (lw == 3 ? ECC : 0) + row;
+#pragma unroll 8
+          for (int j = 0; j < 32; ++j) {
+            const int o = 32 * cg + j;
+            red_add_f32(dst + (size_t)o * ldw, st_h[o * STP + row]);
+          }
+        }
+        {
+          float* dse = a.acc + (size_t)lw * BWD_ACC_SLOTS * 128 + row;
+          const int s0 = has_e ? 0 : 40, s1 = 40 + CDIM + 1;
+          for (int slot = s0 + cg; slot < s1; slot += 4) red_add_f32(dse + (size_t)slot * HC, st_e[slot * HC + row]);
+        }
+        bar_compute_b();                                   // staging image read: Z^T may be rewritten
+      };
 #pragma unroll 1
       for (int l = 4; l >= 0; --l) {
         // ---- A: Z_l = G_l * softplus'(s_l) -> TMEM (hi, lo); kept in g[] for the transposed copy
+        if (warp == 0) TRC(1, (4 - l) * 10 + 0);
         {
           const float* tps = sv + SL.cst + ((size_t)l * SL.ntiles + tile) * tplane_tile_floats(HC) + tq * (HC * 32) + (tj & 3);
 #pragma unroll
@@ -461,40 +644,19 @@ __global__ void __launch_bounds__(BT, 1) trunk_bwd_umma_kernel(const __grid_cons
             tmem_st16(tmem_addr(tb, lane_base, TMB_ZLO + 32 * cg + 16 * h), lo);
           }
         }
-        // ---- B: weight-gradient accumulators of layer l + 1 -> global (their MMAs also read Z^T: it is free afterwards)
+        // ---- B: weight-gradient accumulators of layer l + 1 (their MMAs also read Z^T: it is free afterwards)
+        if (warp == 0) TRC(1, (4 - l) * 10 + 1);
         if (g_cw && l < 4) {
           wait_d(1);
-          const int lw = l + 1;
-          {   // dW^h^T: lane = feature i of h_{lw-1}, columns = outputs o of layer lw
-            const int ldw = lw == 3 ? ECC + HC : HC, off = lw == 3 ? ECC : 0;
-            float* dst = a.d_w + a.w.c_lin_w[lw] + off + row;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              uint32_t x[16];
-              tmem_ld16(tmem_addr(tb, lane_base, TMB_G + 32 * cg + 16 * h), x);
-              tmem_wait_ld();
-#pragma unroll
-              for (int j = 0; j < 16; ++j) red_add_f32(dst + (size_t)(32 * cg + 16 * h + j) * ldw, __uint_as_float(x[j]));
-            }
-          }
-          {   // extras: lane = output o, columns = [e' (40) |] c (32) | 1 | pad
-            const bool has_e = lw == 3;
-            const int ncol = has_e ? 80 : 48;
-            float* dst = a.acc + (size_t)lw * BWD_ACC_SLOTS * 128 + row;
-            for (int c0 = 16 * cg; c0 < ncol; c0 += 64) {
-              uint32_t x[16];
-              tmem_ld16(tmem_addr(tb, lane_base, TMB_EX + c0), x);
-              tmem_wait_ld();
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int e = c0 + j, slot = has_e ? e : 40 + e;
-                if (slot < 40 + CDIM + 1) red_add_f32(dst + (size_t)slot * 128, __uint_as_float(x[j]));
-              }
-            }
-          }
+          if (warp == 0) TRC(1, (4 - l) * 10 + 2);
+          flush_load(l + 1);
         }
+        if (warp == 0) TRC(1, (4 - l) * 10 + 3);
         // ---- C: Z_l is in TMEM, the accumulator columns are free -> dX MMAs of layer l
         signal(&pipe->a_ready);
+        if (warp == 0) TRC(1, (4 - l) * 10 + 4);
+        if (g_cw && l < 4) flush_store(l + 1);
+        if (warp == 0) TRC(1, (4 - l) * 10 + 5);
         // ---- D: Z_l^T -> shared memory (row-contraction operand), lane = row: one 128-byte line per store instruction
         if (g_cw) {
 #pragma unroll
@@ -503,12 +665,14 @@ __global__ void __launch_bounds__(BT, 1) trunk_bwd_umma_kernel(const __grid_cons
             uint32_t hi, lo;
             split_hi_lo(g[j], hi, lo);
             uint8_t* p = zt_row + f * 128 + ((tchunk ^ (j & 7)) << 4);
-            *reinterpret_cast<uint32_t*>(p) = hi;
+            *reinterpret_cast<uint32_t*>(p) = __float_as_uint(g[j]);   // raw word == hi operand (the tensor core truncates)
             *reinterpret_cast<uint32_t*>(p + ZT_LO) = lo;
           }
         }
         // ---- E: results of the dX GEMMs
+        if (warp == 0) TRC(1, (4 - l) * 10 + 6);
         wait_d(0);
+        if (warp == 0) TRC(1, (4 - l) * 10 + 7);
         if (l >= 1) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -542,21 +706,17 @@ __global__ void __launch_bounds__(BT, 1) trunk_bwd_umma_kernel(const __grid_cons
           }
         }
         // ---- F: Z^T written, accumulator columns read -> weight-gradient MMAs of layer l
+        if (warp == 0) TRC(1, (4 - l) * 10 + 8);
         if (g_cw) signal(&pipe->b_ready);
         else { tc_fence_before(); }
+        if (warp == 0) TRC(1, (4 - l) * 10 + 9);
       }
       if (g_cw) {   // layer 0: extras only ([E_0 | M_0])
         wait_d(1);
-        float* dst = a.acc + row;
-        for (int c0 = 16 * cg; c0 < 80; c0 += 64) {
-          uint32_t x[16];
-          tmem_ld16(tmem_addr(tb, lane_base, TMB_EX + c0), x);
-          tmem_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (c0 + j < 40 + CDIM + 1) red_add_f32(dst + (size_t)(c0 + j) * 128, __uint_as_float(x[j]));
-        }
+        flush_load(0);
+        flush_store(0);
       }
+      if (warp == 0) TRC(2, 2);
       // ---------------------------------------------------------------- hand-over: dL/dc and the Fourier part of dL/dp
       if (rv) {
         float4* o = reinterpret_cast<float4*>(a.out_dc + (p0 + row) * CDIM + 8 * cg);
@@ -584,6 +744,7 @@ __global__ void __launch_bounds__(BT, 1) trunk_bwd_umma_kernel(const __grid_cons
       }
       tc_fence_before();
       bar_compute_b();
+      if (warp == 0) TRC(2, 3);
       if (g_ry && tid < nrows)
         reinterpret_cast<float4*>(a.out_dp)[p0 + tid] = make_float4(sDP[tid * 4 + 0], sDP[tid * 4 + 1], sDP[tid * 4 + 2], 0.f);
       bar_compute_b();
@@ -600,32 +761,43 @@ __global__ void __launch_bounds__(BT, 1) trunk_bwd_umma_kernel(const __grid_cons
 //   d c_lin_w[l][o][e]   += E_l[e][o]                          (l = 0, 3)
 //   d c_fc_w[l-1][i][c]   = sum_o W_l[o][hoff + i] M_l[c][o]   (l = 1..4);  d c_fc_b[l-1][i] = sum_o W_l[o][hoff + i] M_l[ones][o]
 //   d c_fc_w[4][i][c]     = sum_o W_out[o][i] M_out[o][c];     d c_fc_b[4][i] = sum_o W_out[o][i] M_out[o][ones];  d c_out_b = M_out[:, ones]
-__global__ void trunk_bwd_finalize_kernel(const float* __restrict__ blob, const float* __restrict__ acc, float* __restrict__ dW,
-                                          const __grid_constant__ LsrWeights w) {
-  const int l = blockIdx.y;   // 0..4: produces fc_c[l] from layer l + 1 (or the head), and the layer-l bias / e' terms
+__global__ void __launch_bounds__(HC) trunk_bwd_finalize_kernel(const float* __restrict__ blob, const float* __restrict__ acc,
+                                                                float* __restrict__ dW, const __grid_constant__ LsrWeights w) {
+  // grid (33 + 2, 5): blockIdx.x = c < 33 -> column c of fc_c[l] (32: bias) for all 128 i (threadIdx.x);
+  //                   33 -> lin bias of layer l; 34 -> e' columns of c_lin_w[l] (l = 0, 3) and the head bias
+  const int l = blockIdx.y, c = blockIdx.x, i = threadIdx.x;
   const float* mo = acc + 5 * BWD_ACC_SLOTS * 128;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < HC * (CDIM + 1); e += gridDim.x * blockDim.x) {
-    const int i = e % HC, c = e / HC;   // c == 32: bias
+  __shared__ float sm[HC];
+  if (c <= CDIM) {
     float s = 0.f;
     if (l == 4) {
       for (int o = 0; o < 3; ++o) s = fmaf(blob[w.c_out_w + o * HC + i], mo[o * TP_C1 + c], s);
     } else {
       const int lw = l + 1, ldw = lw == 3 ? ECC + HC : HC, off = lw == 3 ? ECC : 0;
-      const float* m = acc + ((size_t)lw * BWD_ACC_SLOTS + 40 + c) * 128;
+      sm[i] = acc[((size_t)lw * BWD_ACC_SLOTS + 40 + c) * 128 + i];
+      __syncthreads();
       const float* wr = blob + w.c_lin_w[lw] + off + i;
-      for (int o = 0; o < HC; ++o) s = fmaf(wr[(size_t)o * ldw], m[o], s);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 8
+      for (int o = 0; o < HC; o += 4) {
+        s0 = fmaf(wr[(size_t)(o + 0) * ldw], sm[o + 0], s0);
+        s1 = fmaf(wr[(size_t)(o + 1) * ldw], sm[o + 1], s1);
+        s2 = fmaf(wr[(size_t)(o + 2) * ldw], sm[o + 2], s2);
+        s3 = fmaf(wr[(size_t)(o + 3) * ldw], sm[o + 3], s3);
+      }
+      s = (s0 + s1) + (s2 + s3);
     }
     if (c < CDIM) dW[w.c_fc_w[l] + i * CDIM + c] += s;
     else dW[w.c_fc_b[l] + i] += s;
-  }
-  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < HC; o += gridDim.x * blockDim.x) {
-    dW[w.c_lin_b[l] + o] += acc[((size_t)l * BWD_ACC_SLOTS + 40 + CDIM) * 128 + o];
+  } else if (c == CDIM + 1) {
+    dW[w.c_lin_b[l] + i] += acc[((size_t)l * BWD_ACC_SLOTS + 40 + CDIM) * 128 + i];
+  } else {
     if (l == 0 || l == 3) {
       const int ldw = l == 3 ? ECC + HC : ECC;
-      for (int e = 0; e < ECC; ++e) dW[w.c_lin_w[l] + (size_t)o * ldw + e] += acc[((size_t)l * BWD_ACC_SLOTS + e) * 128 + o];
+      for (int e = 0; e < ECC; ++e) dW[w.c_lin_w[l] + (size_t)i * ldw + e] += acc[((size_t)l * BWD_ACC_SLOTS + e) * 128 + i];
     }
+    if (l == 4 && i < 3) dW[w.c_out_b + i] += mo[i * TP_C1 + CDIM];
   }
-  if (l == 4 && blockIdx.x == 0 && threadIdx.x < 3) dW[w.c_out_b + threadIdx.x] += mo[threadIdx.x * TP_C1 + CDIM];
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -686,7 +858,7 @@ static void build_trunk_program(const LsrWeights* w, const SavedLayout& SL, bool
       pk += n_pad * HC;
     }
     if (!g_cw) continue;
-    // ---- dW: h_{l-1}^T . Z_l^T per atom column, then Z_l^T . [e' | c | 1]^T
+    // ---- dW: Z_l^T . h_{l-1}^T per atom column, then Z_l^T . [e' | c | 1]^T
     bool first_dw = true;
     if (l >= 1) {
       for (int q = 0; q < 4; ++q) {
@@ -730,7 +902,7 @@ int launch_trunk_bwd(const LsrParams* prm, const LsrWeights* w, const float* gt_
   float* acc = (float*)(sbase + CL.bwd_acc);
   LSR_CUDA_CHECK(cudaMemsetAsync(pack, 0, (size_t)BWD_PACK_FLOATS_MAX * sizeof(float), stream));
   if (g_cw) LSR_CUDA_CHECK(cudaMemsetAsync(acc, 0, (size_t)BWD_ACC_FLOATS * sizeof(float), stream));
-  bwd_prep_kernel<<<dim3(16, P.jobs.n + 1), 256, 0, stream>>>(w->blob, pack, P.jobs);
+  bwd_prep_kernel<<<dim3(32, P.jobs.n + 1), 256, 0, stream>>>(w->blob, pack, P.jobs);
   LSR_CUDA_CHECK(cudaGetLastError());
 
   static TrunkArgs a;
@@ -759,10 +931,23 @@ int launch_trunk_bwd(const LsrParams* prm, const LsrWeights* w, const float* gt_
   trunk_bwd_umma_kernel<<<grid, BT, BWD_UMMA_SMEM, stream>>>(a);
   LSR_CUDA_CHECK(cudaGetLastError());
   if (g_cw) {
-    trunk_bwd_finalize_kernel<<<dim3(8, 5), 256, 0, stream>>>(w->blob, acc, d_weights, *w);
+    trunk_bwd_finalize_kernel<<<dim3(CDIM + 3, 5), HC, 0, stream>>>(w->blob, acc, d_weights, *w);
     LSR_CUDA_CHECK(cudaGetLastError());
   }
   return LSR_OK;
 }
 
 }  // namespace lsr
+
+#ifdef LSR_TRACE
+extern "C" int lsr_debug_trace(long long* out) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out, lsr::lsr_trace, sizeof(long long) * 3 * 512) == cudaSuccess ? 0 : 3;
+}
+extern "C" int lsr_debug_trace_ops(const LsrWeights* w, int64_t n_rays, int S, int flags, int g_cw, unsigned char* kinds) {
+  static lsr::TrunkProgram P;
+  lsr::build_trunk_program(w, lsr::saved_layout(n_rays, S, LSR_STAGE_COLOR, flags), g_cw != 0, &P);
+  for (int i = 0; i < P.n_ops; ++i) { kinds[2 * i] = P.ops[i].kind; kinds[2 * i + 1] = P.ops[i].flags; }
+  return P.n_ops;
+}
+#endif

@@ -15,6 +15,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o tools/umma_sw128_probe tools/umma_sw128_probe.cu
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 #include "../loopy_slam_b200/csrc/lsr_umma.cuh"
 
@@ -211,6 +212,27 @@ int main() {
   run(Cfg{2, 1, 0, 16384, 1024, 0, 0, 0, 0}, "T2 A MN-major SW128_BASE32B swz<3,4,3> (LBO 16K, SBO 1K)");
   run(Cfg{2, 2, 0, 16384, 1024, 1, 0, 0, 0}, "T2 A and B MN-major SW128 (LBO 16K/8K, SBO 1K)");
   run(Cfg{2, 2, 0, 1024, 16384, 1, 0, 0, 0}, "T2 A and B MN-major SW128 (LBO 1K/512, SBO 16K)");
+  // test 4: does the tensor core TRUNCATE fp32 operands to tf32 (ignore the low 13 mantissa bits)?  If so the raw fp32 image
+  // can serve as the "hi" operand of the 3xTF32 split and only the "lo" image has to be produced.
+  {
+    std::vector<float> Zr(Z.size()), Xr(X.size()), Zm(Z.size()), Xm(X.size());
+    srand(7);
+    for (size_t i = 0; i < Z.size(); ++i) { Zr[i] = ((float)rand() / RAND_MAX - 0.5f) * 3.f; uint32_t u; memcpy(&u, &Zr[i], 4); u &= 0xffffe000u; memcpy(&Zm[i], &u, 4); }
+    for (size_t i = 0; i < X.size(); ++i) { Xr[i] = ((float)rand() / RAND_MAX - 0.5f) * 3.f; uint32_t u; memcpy(&u, &Xr[i], 4); u &= 0xffffe000u; memcpy(&Xm[i], &u, 4); }
+    std::vector<float> D1(128 * 64), D2(128 * 64);
+    Cfg c{1, 2, 0, 0, 1024, 0, 0, 0, 0};
+    CK(cudaMemcpy(dZ, Zr.data(), Z.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dX, Xr.data(), X.size() * 4, cudaMemcpyHostToDevice));
+    probe<<<1, 128, SMEM_TOTAL>>>(dZ, dX, dW, dD, dC, c); CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(D1.data(), dD, D1.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(dZ, Zm.data(), Z.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dX, Xm.data(), X.size() * 4, cudaMemcpyHostToDevice));
+    probe<<<1, 128, SMEM_TOTAL>>>(dZ, dX, dW, dD, dC, c); CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(D2.data(), dD, D2.size() * 4, cudaMemcpyDeviceToHost));
+    int diff = 0;
+    for (size_t i = 0; i < D1.size(); ++i) diff += memcmp(&D1[i], &D2[i], 4) != 0;
+    printf("T4 raw fp32 operands vs operands masked to 19 bits: %d / %zu results differ  -> %s\n", diff, D1.size(),
+           diff ? "the hardware ROUNDS (or uses) the low bits" : "the hardware TRUNCATES: raw image == hi image");
+    CK(cudaMemcpy(dZ, Z.data(), Z.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dX, X.data(), X.size() * 4, cudaMemcpyHostToDevice));
+  }
   // test 3: issue cost
   for (int n : {32, 64, 128, 208, 256})
     for (int nacc : {1, 2}) {
