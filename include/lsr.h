@@ -120,6 +120,8 @@ int lsr_version(void);
 const char* lsr_strerror(int code);
 /* number of SMs of the current device (grid sizing is done inside; exposed for benches) */
 int lsr_device_sm_count(int* out);
+/* Number of CUDA kernels this library has launched since the last reset (host-side counter; bench.py: gpu_launches). */
+long long lsr_launch_count(int reset);
 
 /* ---------------------------------------------------------------- neighbour index (hash grid)
  * Uniform grid over the cloud's bounding box, cell edge >= `cell` (doubled until the grid has
@@ -145,6 +147,14 @@ int lsr_sample_rays(const float* depth_img, const float* color_img, int32_t H, i
                     int64_t n, int32_t H0, int32_t H1, int32_t W0, int32_t W1, float* rays_o,
                     float* rays_d, float* depth, float* color, int64_t* i_out, int64_t* j_out,
                     lsr_stream_t stream);
+/* get_samples(..., depth_filter=True, depth_limit) (src/common.py:249-255) in one launch: as lsr_sample_rays, but only the
+ * picks with depth > 0 (and < depth_limit when depth_limit > 0) are written, compacted in their original order; *count
+ * (device int32) receives how many.  Output buffers must hold n entries. */
+int lsr_sample_rays_filtered(const float* depth_img, const float* color_img, int32_t H, int32_t W, float fx,
+                             float fy, float cx, float cy, const float* c2w, int32_t c2w_ld, const int64_t* pix,
+                             int64_t n, int32_t H0, int32_t H1, int32_t W0, int32_t W1, float depth_limit,
+                             float* rays_o, float* rays_d, float* depth, float* color, int64_t* i_out,
+                             int64_t* j_out, int32_t* count, lsr_stream_t stream);
 /* d_c2w (3x4 row-major, 12 floats, overwritten) from d_rays_o/d_rays_d and the pixel coords */
 int lsr_sample_rays_bwd(const float* d_rays_o, const float* d_rays_d, const int64_t* i_pix,
                         const int64_t* j_pix, int64_t n, float fx, float fy, float cx, float cy,

@@ -18,8 +18,8 @@ GRAD_GEO_FEATS, GRAD_COL_FEATS, GRAD_GEO_W, GRAD_GEO_B, GRAD_COL_W, GRAD_RAYS, G
 
 # every exported symbol declared in include/lsr.h (checked by tests/test_abi.py)
 EXPORTS = [
-    'lsr_version', 'lsr_strerror', 'lsr_device_sm_count', 'lsr_grid_workspace_bytes', 'lsr_grid_build',
-    'lsr_knn_query', 'lsr_sample_rays', 'lsr_sample_rays_bwd', 'lsr_pose_fwd', 'lsr_pose_bwd',
+    'lsr_version', 'lsr_strerror', 'lsr_device_sm_count', 'lsr_launch_count', 'lsr_grid_workspace_bytes', 'lsr_grid_build',
+    'lsr_knn_query', 'lsr_sample_rays', 'lsr_sample_rays_filtered', 'lsr_sample_rays_bwd', 'lsr_pose_fwd', 'lsr_pose_bwd',
     'lsr_render_workspace_bytes', 'lsr_far_bound', 'lsr_render_fwd', 'lsr_render_bwd', 'lsr_dynamic_radius',
     'lsr_loss_scratch_bytes', 'lsr_mapper_loss', 'lsr_tracker_resid', 'lsr_tracker_loss', 'lsr_debug_program_stats',
 ]
@@ -61,11 +61,14 @@ def lib():
         L.lsr_strerror.argtypes = [ctypes.c_int]
         vp, i64, i32, f32, f64 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_double
         L.lsr_device_sm_count.argtypes = [ctypes.POINTER(ctypes.c_int)]
+        L.lsr_launch_count.argtypes = [ctypes.c_int]
         L.lsr_grid_workspace_bytes.argtypes = [i64, i64, ctypes.POINTER(ctypes.c_size_t)]
         L.lsr_grid_build.argtypes = [vp, i64, f32, i64, vp, ctypes.c_size_t, vp]
         L.lsr_knn_query.argtypes = [vp, vp, vp, f64, i64, vp, vp, vp, vp]
         L.lsr_sample_rays.argtypes = [vp, vp, i32, i32, f32, f32, f32, f32, vp, i32, vp, i64, i32, i32, i32, i32,
                                       vp, vp, vp, vp, vp, vp, vp]
+        L.lsr_sample_rays_filtered.argtypes = [vp, vp, i32, i32, f32, f32, f32, f32, vp, i32, vp, i64, i32, i32, i32, i32, f32,
+                                               vp, vp, vp, vp, vp, vp, vp, vp]
         L.lsr_sample_rays_bwd.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, vp]
         L.lsr_pose_fwd.argtypes = [vp, vp, vp]
         L.lsr_pose_bwd.argtypes = [vp, vp, vp, vp]
@@ -85,8 +88,9 @@ def lib():
         L.lsr_tracker_resid.argtypes = [vp, vp, vp, i64, ctypes.c_int, vp, vp, vp]
         L.lsr_tracker_loss.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp, ctypes.c_int, f32, vp, vp, vp, vp, vp, vp]
         for name in EXPORTS:
-            if name not in ('lsr_strerror',):
+            if name not in ('lsr_strerror', 'lsr_launch_count'):
                 getattr(L, name).restype = ctypes.c_int
+        L.lsr_launch_count.restype = ctypes.c_longlong
         _lib = L
     return _lib
 

@@ -59,6 +59,58 @@ class _SampleRaysFn(torch.autograd.Function):
         return g.to(ctx.c2w_dtype), None, None, None, None
 
 
+def _sample_rays_filtered(c2w_f, depth_img, color_img, pix, geom, depth_limit):
+    """lsr_sample_rays_filtered + ONE count readback.  One allocation for all outputs, one launch, one host sync."""
+    H, W, fx, fy, cx, cy, H0, H1, W0, W1 = geom
+    dev = pix.device
+    n = pix.shape[0]
+    # [rays_o 3n | rays_d 3n | depth n | colour 3n] f32 and [i n | j n | count] i64 in two buffers
+    fbuf = torch.empty(10 * n, dtype=torch.float32, device=dev)
+    ibuf = torch.empty(2 * n + 1, dtype=torch.int64, device=dev)
+    base_f, base_i = fbuf.data_ptr(), ibuf.data_ptr()
+    check(lib().lsr_sample_rays_filtered(depth_img.data_ptr(), color_img.data_ptr(), H, W, fx, fy, cx, cy, c2w_f.data_ptr(),
+                                         c2w_f.shape[-1], pix.data_ptr(), n, H0, H1, W0, W1,
+                                         float(depth_limit) if depth_limit is not None else 0.0, base_f, base_f + 12 * n,
+                                         base_f + 24 * n, base_f + 28 * n, base_i, base_i + 8 * n, base_i + 16 * n,
+                                         stream_ptr(dev)), 'lsr_sample_rays_filtered')
+    m = int(ibuf[2 * n:].view(torch.int32)[0].item())    # the one host sync of the call: the size of the returned tensors
+    return (fbuf[:3 * m].view(m, 3), fbuf[3 * n:3 * n + 3 * m].view(m, 3), fbuf[6 * n:6 * n + m],
+            fbuf[7 * n:7 * n + 3 * m].view(m, 3), ibuf[:m], ibuf[n:n + m])
+
+
+class _SampleRaysFilteredFn(torch.autograd.Function):
+    """get_samples with depth_filter=True in one launch, differentiable w.r.t. the camera matrix."""
+
+    @staticmethod
+    def forward(ctx, c2w, depth_img, color_img, pix, geom, depth_limit):
+        c2w_f = c2w.to(torch.float32)
+        if not c2w_f.is_contiguous():
+            c2w_f = c2w_f.contiguous()
+        with torch.cuda.device(pix.device):
+            rays_o, rays_d, depth, color, i, j = _sample_rays_filtered(c2w_f, depth_img, color_img, pix, geom, depth_limit)
+        ctx.geom = geom
+        ctx.c2w_shape = c2w.shape
+        ctx.c2w_dtype = c2w.dtype
+        ctx.save_for_backward(i, j)
+        ctx.mark_non_differentiable(depth, color, i, j)
+        return rays_o, rays_d, depth, color, i, j
+
+    @staticmethod
+    def backward(ctx, g_o, g_d, *_):
+        i, j = ctx.saved_tensors
+        H, W, fx, fy, cx, cy, H0, H1, W0, W1 = ctx.geom
+        dev = i.device
+        d12 = torch.empty(12, dtype=torch.float32, device=dev)
+        g_o = g_o.contiguous().float() if g_o is not None else None
+        g_d = g_d.contiguous().float() if g_d is not None else None
+        with torch.cuda.device(dev):
+            check(lib().lsr_sample_rays_bwd(ptr(g_o), ptr(g_d), ptr(i), ptr(j), i.shape[0], fx, fy, cx, cy, ptr(d12),
+                                            stream_ptr(dev)), 'lsr_sample_rays_bwd')
+        g = torch.zeros(ctx.c2w_shape, dtype=torch.float32, device=dev)
+        g[:3, :4] = d12.view(3, 4)
+        return g.to(ctx.c2w_dtype), None, None, None, None, None
+
+
 def _as_c2w_tensor(c2w, device):
     if isinstance(c2w, np.ndarray):
         c2w = torch.from_numpy(c2w).to(device)
@@ -75,6 +127,20 @@ def get_samples(H0, H1, W0, W1, n, H, W, fx, fy, cx, cy, c2w, depth, color, devi
     depth_f = depth if (depth.dtype == torch.float32 and depth.is_contiguous()) else depth.float().contiguous()
     fused_color = color.dtype == torch.float32 and color.is_contiguous()
     geom = (int(H), int(W), float(fx), float(fy), float(cx), float(cy), int(H0), int(H1), int(W0), int(W1))
+    if not c2w.is_cuda:
+        c2w = c2w.to(device)
+    if depth_filter and fused_color and depth.dtype == torch.float32:
+        # the common case of both callers (src/Mapper.py:652-655, src/Tracker.py:138-141): sampling, depth filter and
+        # order-preserving compaction in one kernel, one host sync for the output size
+        if c2w.requires_grad and torch.is_grad_enabled():
+            out = _SampleRaysFilteredFn.apply(c2w, depth_f, color, pix, geom, depth_limit)
+        else:   # mapper without BA: constant poses, no autograd node
+            c2w_f = c2w.detach()
+            if c2w_f.dtype != torch.float32 or not c2w_f.is_contiguous():
+                c2w_f = c2w_f.to(torch.float32).contiguous()
+            with torch.cuda.device(pix.device):
+                out = _sample_rays_filtered(c2w_f, depth_f, color, pix, geom, depth_limit)
+        return out if return_index else out[:4]
     out = _SampleRaysFn.apply(c2w, depth_f, color if fused_color else None, pix, geom)
     if fused_color:
         rays_o, rays_d, sample_depth, sample_color, i, j = out
@@ -87,8 +153,10 @@ def get_samples(H0, H1, W0, W1, n, H, W, fx, fy, cx, cy, c2w, depth, color, devi
         mask = sample_depth > 0
         if depth_limit is not None:
             mask = mask & (sample_depth < depth_limit)
-        rays_o, rays_d, sample_depth, sample_color = rays_o[mask], rays_d[mask], sample_depth[mask], sample_color[mask]
-        i, j = i[mask], j[mask]
+        keep = torch.nonzero(mask, as_tuple=True)[0]      # ONE host sync for the output size instead of one per masked gather
+        rays_o, rays_d = rays_o.index_select(0, keep), rays_d.index_select(0, keep)
+        sample_depth, sample_color = sample_depth.index_select(0, keep), sample_color.index_select(0, keep)
+        i, j = i.index_select(0, keep), j.index_select(0, keep)
     if return_index:
         return rays_o, rays_d, sample_depth, sample_color, i, j
     return rays_o, rays_d, sample_depth, sample_color

@@ -5,6 +5,10 @@
 #include <float.h>
 #include "../../include/lsr.h"
 
+// every kernel launch of the library bumps this counter (lsr_launch_count; bench.py reports it as gpu_launches)
+namespace lsr { extern long long g_launch_count; }
+#define LSR_LAUNCHED(n) (__atomic_fetch_add(&lsr::g_launch_count, (long long)(n), __ATOMIC_RELAXED))
+
 #define LSR_CUDA_CHECK(expr)                          \
   do {                                                \
     cudaError_t _e = (expr);                          \

@@ -256,18 +256,30 @@ extern "C" int lsr_grid_build(const float* cloud_pos, int64_t n, float cell, int
   const int nb = (nscan + SCAN_TILE - 1) / SCAN_TILE;
 
   grid_init_kernel<<<1, 32, 0, stream>>>(h, (int32_t)n, (int32_t)max_cells);
+  LSR_LAUNCHED(1);
   if (n > 0) {
     int blocks = (int)((n + 255) / 256);
     if (blocks > 1184) blocks = 1184;
     grid_bbox_kernel<<<blocks, 256, 0, stream>>>(cloud_pos, (int)n, h);
+    LSR_LAUNCHED(1);
   }
   grid_setup_kernel<<<1, 32, 0, stream>>>(h, cell);
+  LSR_LAUNCHED(1);
   LSR_CUDA_CHECK(cudaMemsetAsync(cell_start, 0, sizeof(int32_t) * (size_t)nscan, stream));
-  if (n > 0) grid_count_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(cloud_pos, (int)n, h, cell_start, cop);
+  if (n > 0) {
+    grid_count_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(cloud_pos, (int)n, h, cell_start, cop);
+    LSR_LAUNCHED(1);
+  }
   scan_pass1<<<nb, SCAN_BLOCK, 0, stream>>>(cell_start, nscan, bsum);
+  LSR_LAUNCHED(1);
   scan_pass2<<<1, SCAN_BLOCK, 0, stream>>>(bsum, nb);
+  LSR_LAUNCHED(1);
   scan_pass3<<<nb, SCAN_BLOCK, 0, stream>>>(cell_start, nscan, bsum, cursor);
-  if (n > 0) grid_scatter_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(cloud_pos, (int)n, cop, cursor, sorted);
+  LSR_LAUNCHED(1);
+  if (n > 0) {
+    grid_scatter_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(cloud_pos, (int)n, cop, cursor, sorted);
+    LSR_LAUNCHED(1);
+  }
   LSR_CUDA_CHECK(cudaGetLastError());
   return LSR_OK;
 }
@@ -278,6 +290,7 @@ extern "C" int lsr_knn_query(const void* grid_ws, const float* q, const double* 
   if (P == 0) return LSR_OK;
   const int64_t per_block = (KQ_NT / 32) * KQ_NQ;
   knn_query_kernel<<<(unsigned)((P + per_block - 1) / per_block), KQ_NT, 0, stream>>>(grid_ws, q, r_dyn, r_fixed, P, D, I, nnum);
+  LSR_LAUNCHED(1);
   LSR_CUDA_CHECK(cudaGetLastError());
   return LSR_OK;
 }

@@ -164,6 +164,7 @@ int lsr_mapper_loss(const float* depth, const float* rgb, const uint8_t* valid, 
   LSR_CUDA_CHECK(cudaMemsetAsync(scratch, 0, sizeof(LossScratch), st));
   mapper_loss_kernel<<<loss_grid(n_rays), LOSS_NT, 0, st>>>(depth, rgb, valid, gt_depth, gt_rgb, n_rays, use_color,
                                                             w_color, (LossScratch*)scratch, loss3, d_depth, d_rgb);
+  LSR_LAUNCHED(1);
   LSR_CUDA_CHECK(cudaGetLastError());
   return LSR_OK;
 }
@@ -176,6 +177,7 @@ int lsr_tracker_resid(const float* depth, const float* var, const float* gt_dept
   LSR_CUDA_CHECK(cudaMemsetAsync(scratch, 0, sizeof(LossScratch), st));
   tracker_resid_kernel<<<loss_grid(n_rays), LOSS_NT, 0, st>>>(depth, var, gt_depth, n_rays, handle_dynamic,
                                                               (LossScratch*)scratch, tmp);
+  LSR_LAUNCHED(1);
   LSR_CUDA_CHECK(cudaGetLastError());
   return LSR_OK;
 }
@@ -190,6 +192,7 @@ int lsr_tracker_loss(const float* depth, const float* var, const float* rgb, con
   tracker_loss_kernel<<<loss_grid(n_rays), LOSS_NT, 0, st>>>(depth, var, rgb, gt_depth, gt_rgb, tmp, n_rays, thr,
                                                              use_color, w_color, (LossScratch*)scratch, loss3, d_depth,
                                                              d_rgb, mask_out);
+  LSR_LAUNCHED(1);
   LSR_CUDA_CHECK(cudaGetLastError());
   return LSR_OK;
 }

@@ -737,6 +737,7 @@ extern "C" int lsr_render_bwd(const LsrParams* prm, const void* grid_ws, const f
   const int slots = nsm * CTAS_PER_SM;
   const int grid = a.ntiles < slots ? a.ntiles : slots;
   render_bwd_kernel<<<grid, NT, smem, stream>>>(a);
+  LSR_LAUNCHED(1);
   LSR_CUDA_CHECK(cudaGetLastError());
   return LSR_OK;
 }

@@ -903,6 +903,7 @@ int launch_trunk_bwd(const LsrParams* prm, const LsrWeights* w, const float* gt_
   LSR_CUDA_CHECK(cudaMemsetAsync(pack, 0, (size_t)BWD_PACK_FLOATS_MAX * sizeof(float), stream));
   if (g_cw) LSR_CUDA_CHECK(cudaMemsetAsync(acc, 0, (size_t)BWD_ACC_FLOATS * sizeof(float), stream));
   bwd_prep_kernel<<<dim3(32, P.jobs.n + 1), 256, 0, stream>>>(w->blob, pack, P.jobs);
+  LSR_LAUNCHED(1);
   LSR_CUDA_CHECK(cudaGetLastError());
 
   static TrunkArgs a;
@@ -929,9 +930,11 @@ int launch_trunk_bwd(const LsrParams* prm, const LsrWeights* w, const float* gt_
   LSR_CUDA_CHECK(cudaFuncSetAttribute(trunk_bwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_UMMA_SMEM));
   const int grid = a.ntiles < nsm ? a.ntiles : nsm;
   trunk_bwd_umma_kernel<<<grid, BT, BWD_UMMA_SMEM, stream>>>(a);
+  LSR_LAUNCHED(1);
   LSR_CUDA_CHECK(cudaGetLastError());
   if (g_cw) {
     trunk_bwd_finalize_kernel<<<dim3(CDIM + 3, 5), HC, 0, stream>>>(w->blob, acc, d_weights, *w);
+    LSR_LAUNCHED(1);
     LSR_CUDA_CHECK(cudaGetLastError());
   }
   return LSR_OK;

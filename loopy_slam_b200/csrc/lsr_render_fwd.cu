@@ -972,6 +972,7 @@ extern "C" int lsr_far_bound(const float* gt_depth, int64_t n_rays, int64_t grou
   if (n_rays == 0) return LSR_OK;
   const int64_t ng = (n_rays + group - 1) / group;
   far_bound_kernel<<<(unsigned)ng, 256, 0, stream>>>(gt_depth, n_rays, group, far_out);
+  LSR_LAUNCHED(1);
   LSR_CUDA_CHECK(cudaGetLastError());
   return LSR_OK;
 }
@@ -1019,6 +1020,7 @@ extern "C" int lsr_render_fwd(const LsrParams* prm, const void* grid_ws, const f
     memcpy(J.legacy, L.j, sizeof(PackJob) * 3);
     pack_umma_jobs_kernel<<<dim3(8, P.n_jobs + 3), 256, 0, stream>>>(w->blob, (float*)(sbase + CL.umma),
                                                                       (float*)(sbase + CL.legacy), J);
+    LSR_LAUNCHED(1);
     LSR_CUDA_CHECK(cudaGetLastError());
   }
 
@@ -1044,6 +1046,7 @@ extern "C" int lsr_render_fwd(const LsrParams* prm, const void* grid_ws, const f
     const int64_t blocks = (pairs + 7) / 8;
     const int kgrid = (int)(blocks < (int64_t)nsm * 8 ? blocks : (int64_t)nsm * 8);
     sample_knn_kernel<<<kgrid, 256, 0, stream>>>(k);
+    LSR_LAUNCHED(1);
     LSR_CUDA_CHECK(cudaGetLastError());
   }
 
@@ -1069,6 +1072,7 @@ extern "C" int lsr_render_fwd(const LsrParams* prm, const void* grid_ws, const f
   LSR_CUDA_CHECK(cudaFuncSetAttribute(render_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES));
   const int grid = a.ntiles < nsm ? a.ntiles : nsm;
   render_fwd_kernel<<<grid, FT, FWD_SMEM_BYTES, stream>>>(a);
+  LSR_LAUNCHED(1);
   LSR_CUDA_CHECK(cudaGetLastError());
   return LSR_OK;
 }

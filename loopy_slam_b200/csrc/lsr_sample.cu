@@ -43,6 +43,70 @@ __global__ void sample_rays_kernel(const float* __restrict__ depth_img, const fl
   if (j_out) j_out[t] = row;
 }
 
+// get_samples(..., depth_filter=True[, depth_limit]) in ONE launch: the n picks are sampled as above and the ones with
+// depth > 0 (and < depth_limit) are COMPACTED in their original order (common.py:249-255 keeps the order: boolean-mask
+// indexing).  One block walks the picks in chunks of its size with an order-preserving ballot / prefix scan; the number
+// of kept samples goes to *count (the host reads it once to size the returned views instead of syncing on six
+// boolean-mask gathers).
+__global__ void __launch_bounds__(1024) sample_rays_filtered_kernel(
+    const float* __restrict__ depth_img, const float* __restrict__ color_img, int H, int W, float fx, float fy, float cx, float cy,
+    const float* __restrict__ c2w, int ld, const int64_t* __restrict__ pix, int64_t n, int H0, int H1, int W0, int W1,
+    float depth_limit, float* __restrict__ rays_o, float* __restrict__ rays_d, float* __restrict__ depth,
+    float* __restrict__ color, int64_t* __restrict__ i_out, int64_t* __restrict__ j_out, int32_t* __restrict__ count) {
+  __shared__ int warp_cnt[32];
+  __shared__ int base_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (threadIdx.x == 0) base_s = 0;
+  __syncthreads();
+  const int ww = W1 - W0;
+  const int64_t tot = (int64_t)ww * (H1 - H0);
+  float R[12];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) { R[4 * a] = c2w[a * ld]; R[4 * a + 1] = c2w[a * ld + 1]; R[4 * a + 2] = c2w[a * ld + 2]; R[4 * a + 3] = c2w[a * ld + 3]; }
+  for (int64_t t0 = 0; t0 < n; t0 += blockDim.x) {
+    const int64_t t = t0 + threadIdx.x;
+    bool keep = false;
+    int col = 0, row = 0;
+    float dv = 0.f;
+    size_t lin = 0;
+    if (t < n) {
+      int64_t p = pix[t];
+      p = p < 0 ? 0 : (p >= tot ? tot - 1 : p);
+      const int h = (int)(p / ww), w = (int)(p - (int64_t)h * ww);
+      col = W0 + w; row = H0 + h;
+      lin = (size_t)row * W + col;
+      dv = depth_img[lin];
+      keep = dv > 0.f && (!(depth_limit > 0.f) || dv < depth_limit);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int k = 0; k < nw; ++k) { const int c = warp_cnt[k]; if (k < warp) before += c; total += c; }
+    const int base = base_s;
+    if (keep) {
+      const int64_t o = base + before + __popc(bal & ((1u << lane) - 1u));
+      const float d0 = __fdiv_rn(__fsub_rn((float)col, cx), fx);
+      const float d1 = -__fdiv_rn(__fsub_rn((float)row, cy), fy);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        rays_d[3 * o + a] = __fadd_rn(__fadd_rn(__fmul_rn(d0, R[4 * a]), __fmul_rn(d1, R[4 * a + 1])), __fmul_rn(-1.0f, R[4 * a + 2]));
+        rays_o[3 * o + a] = R[4 * a + 3];
+      }
+      depth[o] = dv;
+      if (color && color_img) {
+        color[3 * o + 0] = color_img[3 * lin + 0]; color[3 * o + 1] = color_img[3 * lin + 1]; color[3 * o + 2] = color_img[3 * lin + 2];
+      }
+      i_out[o] = col;
+      j_out[o] = row;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) base_s = base + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = base_s;
+}
+
 __global__ void sample_rays_bwd_kernel(const float* __restrict__ g_o, const float* __restrict__ g_d,
                                        const int64_t* __restrict__ ip, const int64_t* __restrict__ jp, int64_t n,
                                        float fx, float fy, float cx, float cy, float* __restrict__ d_c2w) {
@@ -158,6 +222,7 @@ extern "C" int lsr_dynamic_radius(const float* color_f32, const double* color_f6
     dynamic_radius_kernel<double><<<grd, blk, 0, stream>>>(color_f64, H, W, thr, r_add_max, r_add_min, ratio, r_add, r_query);
   else
     dynamic_radius_kernel<float><<<grd, blk, 0, stream>>>(color_f32, H, W, thr, r_add_max, r_add_min, ratio, r_add, r_query);
+  LSR_LAUNCHED(1);
   LSR_CUDA_CHECK(cudaGetLastError());
   return LSR_OK;
 }
@@ -174,6 +239,23 @@ extern "C" int lsr_sample_rays(const float* depth_img, const float* color_img, i
   sample_rays_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(depth_img, color_img, H, W, fx, fy, cx, cy, c2w,
                                                                      c2w_ld, pix, n, H0, H1, W0, W1, rays_o, rays_d,
                                                                      depth, color, i_out, j_out);
+  LSR_LAUNCHED(1);
+  LSR_CUDA_CHECK(cudaGetLastError());
+  return LSR_OK;
+}
+
+extern "C" int lsr_sample_rays_filtered(const float* depth_img, const float* color_img, int32_t H, int32_t W, float fx,
+                                        float fy, float cx, float cy, const float* c2w, int32_t c2w_ld, const int64_t* pix,
+                                        int64_t n, int32_t H0, int32_t H1, int32_t W0, int32_t W1, float depth_limit,
+                                        float* rays_o, float* rays_d, float* depth, float* color, int64_t* i_out,
+                                        int64_t* j_out, int32_t* count, lsr_stream_t stream) {
+  if (n < 0 || H <= 0 || W <= 0 || H0 < 0 || W0 < 0 || H1 > H || W1 > W || H0 >= H1 || W0 >= W1 || c2w_ld < 4 || !count)
+    return LSR_ERR_ARG;
+  if (n == 0) { LSR_CUDA_CHECK(cudaMemsetAsync(count, 0, sizeof(int32_t), stream)); return LSR_OK; }
+  if (!depth_img || !c2w || !pix || !rays_o || !rays_d || !depth || !i_out || !j_out) return LSR_ERR_ARG;
+  sample_rays_filtered_kernel<<<1, 1024, 0, stream>>>(depth_img, color_img, H, W, fx, fy, cx, cy, c2w, c2w_ld, pix, n, H0, H1,
+                                                      W0, W1, depth_limit, rays_o, rays_d, depth, color, i_out, j_out, count);
+  LSR_LAUNCHED(1);
   LSR_CUDA_CHECK(cudaGetLastError());
   return LSR_OK;
 }
@@ -188,6 +270,7 @@ extern "C" int lsr_sample_rays_bwd(const float* d_rays_o, const float* d_rays_d,
   int blocks = (int)((n + 255) / 256);
   if (blocks > 296) blocks = 296;
   sample_rays_bwd_kernel<<<blocks, 256, 0, stream>>>(d_rays_o, d_rays_d, i_pix, j_pix, n, fx, fy, cx, cy, d_c2w);
+  LSR_LAUNCHED(1);
   LSR_CUDA_CHECK(cudaGetLastError());
   return LSR_OK;
 }
@@ -195,6 +278,7 @@ extern "C" int lsr_sample_rays_bwd(const float* d_rays_o, const float* d_rays_d,
 extern "C" int lsr_pose_fwd(const float* cam7, float* c2w12, lsr_stream_t stream) {
   if (!cam7 || !c2w12) return LSR_ERR_ARG;
   pose_fwd_kernel<<<1, 32, 0, stream>>>(cam7, c2w12);
+  LSR_LAUNCHED(1);
   LSR_CUDA_CHECK(cudaGetLastError());
   return LSR_OK;
 }
@@ -202,11 +286,17 @@ extern "C" int lsr_pose_fwd(const float* cam7, float* c2w12, lsr_stream_t stream
 extern "C" int lsr_pose_bwd(const float* cam7, const float* d_c2w12, float* d_cam7, lsr_stream_t stream) {
   if (!cam7 || !d_c2w12 || !d_cam7) return LSR_ERR_ARG;
   pose_bwd_kernel<<<1, 32, 0, stream>>>(cam7, d_c2w12, d_cam7);
+  LSR_LAUNCHED(1);
   LSR_CUDA_CHECK(cudaGetLastError());
   return LSR_OK;
 }
 
-extern "C" int lsr_version(void) { return 100; }
+namespace lsr { long long g_launch_count = 0; }
+extern "C" int lsr_version(void) { return 200; }
+// kernels launched by this library since the last reset (host-side counter; reset != 0 zeroes it after reading)
+extern "C" long long lsr_launch_count(int reset) {
+  return reset ? __atomic_exchange_n(&lsr::g_launch_count, 0ll, __ATOMIC_RELAXED) : __atomic_load_n(&lsr::g_launch_count, __ATOMIC_RELAXED);
+}
 
 extern "C" const char* lsr_strerror(int code) {
   switch (code) {

@@ -122,6 +122,42 @@ def test_sample_rays_and_pose_match_torch():
     assert rel_l2(cam_g.grad, cam.grad) < 1e-5
 
 
+def test_get_samples_matches_reference_golden():
+    """L.get_samples / get_camera_from_tensor through the C ABI vs the vectors of the REAL reference
+    (tests/golden/sampling.npz): same pixel picks (global CUDA generator replaced by the stored indices through
+    torch.randint monkeypatching is not possible -- the CUDA generator differs from the CPU one -- so the picks are
+    injected: the kernel consumes `pix`), rays within 1e-6, gathered depth / colour and (i, j) exact."""
+    import os
+    from loopy_slam_b200.common import _SampleRaysFn
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'sampling.npz'))
+    depth, color = torch.from_numpy(z['depth']).to(DEV), torch.from_numpy(z['color']).to(DEV)
+    H, W, fx, fy, cx, cy = z['intr']
+    c2w = L.get_camera_from_tensor(torch.from_numpy(z['cam']).to(DEV))
+    torch.testing.assert_close(c2w.cpu(), torch.from_numpy(z['c2w']), rtol=1e-6, atol=1e-7)
+    for k in range(3):
+        H0, H1, W0, W1, n, filt, lim = z[f'case{k}']
+        pix = torch.from_numpy(z[f'idx{k}']).to(DEV)
+        geom = (int(H), int(W), float(fx), float(fy), float(cx), float(cy), int(H0), int(H1), int(W0), int(W1))
+        o, d, sd, sc, i, j = _SampleRaysFn.apply(torch.from_numpy(z['c2w']).to(DEV), depth, color, pix, geom)
+        mask = torch.ones_like(sd, dtype=torch.bool)
+        if filt:
+            mask = sd > 0
+            if lim > 0:
+                mask = mask & (sd < lim)
+        for got, name, tol in ((o[mask], 'o', 1e-6), (d[mask], 'd', 1e-6)):
+            torch.testing.assert_close(got.cpu(), torch.from_numpy(z[f'{name}{k}']), rtol=tol, atol=tol)
+        assert torch.equal(sd[mask].cpu(), torch.from_numpy(z[f'sd{k}']))
+        assert torch.equal(sc[mask].cpu(), torch.from_numpy(z[f'sc{k}']))
+        assert torch.equal(i[mask].cpu(), torch.from_numpy(z[f'i{k}']))
+        assert torch.equal(j[mask].cpu(), torch.from_numpy(z[f'j{k}']))
+        if filt:   # the one-launch filter + order-preserving compaction the public get_samples uses
+            from loopy_slam_b200.common import _SampleRaysFilteredFn
+            o2, d2, sd2, sc2, i2, j2 = _SampleRaysFilteredFn.apply(torch.from_numpy(z['c2w']).to(DEV), depth, color, pix, geom,
+                                                                  None if lim < 0 else float(lim))
+            for got, ref in ((o2, o[mask]), (d2, d[mask]), (sd2, sd[mask]), (sc2, sc[mask]), (i2, i[mask]), (j2, j[mask])):
+                assert torch.equal(got, ref)
+
+
 def test_render_img_matches_tiled_oracle():
     """render_img (one fused launch, per-3000-ray far statistics) vs the oracle run tile by tile."""
     from oracle import render as orc

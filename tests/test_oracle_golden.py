@@ -99,3 +99,23 @@ def test_oracle_sample_near_pcl_restatement():
     expect = np.linspace(sec[hits[0]], sec[hits[1]], 5).astype(np.float32)
     assert np.array_equal(z[0].numpy(), expect) and np.array_equal(z[2].numpy(), expect)
     assert np.array_equal(z[1].numpy(), np.linspace(0.2, 2.2, 5).astype(np.float32))
+
+
+def test_oracle_sampling_matches_reference_golden():
+    """oracle/sampling.py vs the vectors the REAL reference produced (tests/golden/make_golden_sampling.py):
+    get_samples with / without the depth filter and depth_limit, get_camera_from_tensor."""
+    import os
+    import numpy as np
+    from oracle import sampling as osm
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'sampling.npz'))
+    depth, color = torch.from_numpy(z['depth']), torch.from_numpy(z['color'])
+    H, W, fx, fy, cx, cy = z['intr']
+    c2w = osm.get_camera_from_tensor(torch.from_numpy(z['cam']))
+    assert torch.equal(c2w, torch.from_numpy(z['c2w']))
+    for k in range(3):
+        H0, H1, W0, W1, n, filt, lim = z[f'case{k}']
+        torch.manual_seed(100 + k)   # the picks come from the global generator, exactly as in the reference
+        o, d, sd, sc, i, j = osm.get_samples(int(H0), int(H1), int(W0), int(W1), int(n), int(H), int(W), fx, fy, cx, cy,
+                                             c2w, depth, color, depth_filter=bool(filt), depth_limit=None if lim < 0 else lim)
+        for got, name in ((o, 'o'), (d, 'd'), (sd, 'sd'), (sc, 'sc'), (i, 'i'), (j, 'j')):
+            assert torch.equal(got, torch.from_numpy(z[f'{name}{k}'])), (k, name)
