@@ -54,8 +54,10 @@ enum {
   LSR_FLAG_REL_POS = 1,          /* model.encode_rel_pos_in_col   (decoder.py:477-485)          */
   LSR_FLAG_DYNAMIC_R = 2,        /* use_dynamic_radius: per-ray float64 radii (Appendix D)      */
   LSR_FLAG_SKIP_ZERO_DEPTH = 4,  /* rendering.skip_zero_depth_pixel (Renderer.py:199-200)       */
-  LSR_FLAG_SAMPLE_NEAR_PCL = 8   /* rendering.sample_near_pcl: zero-depth rays take their z from  */
+  LSR_FLAG_SAMPLE_NEAR_PCL = 8,  /* rendering.sample_near_pcl: zero-depth rays take their z from  */
                                  /*   z_zero_depth and keep their rendered depth (Renderer.py:150-158,197-198) */
+  LSR_FLAG_SAVE_LIGHT = 16       /* forward-only decode (eval_points): `saved` holds only the k-NN results, occupancy
+                                    logits and per-sample colours (148 B / sample); lsr_render_bwd must not be called */
 };
 
 /* LsrParams.rgb_mode: what happens to the colour head output (decoder.py:534-546) */

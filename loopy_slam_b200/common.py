@@ -31,9 +31,12 @@ class _SampleRaysFn(torch.autograd.Function):
         color = torch.empty(n, 3, dtype=torch.float32, device=dev) if color_img is not None else None
         i = torch.empty(n, dtype=torch.int64, device=dev)
         j = torch.empty(n, dtype=torch.int64, device=dev)
-        check(lib().lsr_sample_rays(ptr(depth_img), ptr(color_img), H, W, fx, fy, cx, cy, ptr(c2w_f),
-                                    c2w_f.shape[-1], ptr(pix), n, H0, H1, W0, W1, ptr(rays_o), ptr(rays_d),
-                                    ptr(depth), ptr(color), ptr(i), ptr(j), stream_ptr(dev)), 'lsr_sample_rays')
+        if c2w_f.device != dev:
+            c2w_f = c2w_f.to(dev)
+        with torch.cuda.device(dev):
+            check(lib().lsr_sample_rays(ptr(depth_img), ptr(color_img), H, W, fx, fy, cx, cy, ptr(c2w_f),
+                                        c2w_f.shape[-1], ptr(pix), n, H0, H1, W0, W1, ptr(rays_o), ptr(rays_d),
+                                        ptr(depth), ptr(color), ptr(i), ptr(j), stream_ptr(dev)), 'lsr_sample_rays')
         ctx.geom = geom
         ctx.c2w_shape = c2w.shape
         ctx.c2w_dtype = c2w.dtype
@@ -52,8 +55,9 @@ class _SampleRaysFn(torch.autograd.Function):
         d12 = torch.empty(12, dtype=torch.float32, device=dev)
         g_o = g_o.contiguous().float() if g_o is not None else None
         g_d = g_d.contiguous().float() if g_d is not None else None
-        check(lib().lsr_sample_rays_bwd(ptr(g_o), ptr(g_d), ptr(i), ptr(j), i.shape[0], fx, fy, cx, cy, ptr(d12),
-                                        stream_ptr(dev)), 'lsr_sample_rays_bwd')
+        with torch.cuda.device(dev):
+            check(lib().lsr_sample_rays_bwd(ptr(g_o), ptr(g_d), ptr(i), ptr(j), i.shape[0], fx, fy, cx, cy, ptr(d12),
+                                            stream_ptr(dev)), 'lsr_sample_rays_bwd')
         g = torch.zeros(ctx.c2w_shape, dtype=torch.float32, device=dev)
         g[:3, :4] = d12.view(3, 4)
         return g.to(ctx.c2w_dtype), None, None, None, None
@@ -190,7 +194,8 @@ class _PoseFn(torch.autograd.Function):
     def forward(ctx, cam):
         cam_f = cam.detach().to(torch.float32).contiguous()
         out = torch.empty(3, 4, dtype=torch.float32, device=cam.device)
-        check(lib().lsr_pose_fwd(ptr(cam_f), ptr(out), stream_ptr(cam.device)), 'lsr_pose_fwd')
+        with torch.cuda.device(cam.device):
+            check(lib().lsr_pose_fwd(ptr(cam_f), ptr(out), stream_ptr(cam.device)), 'lsr_pose_fwd')
         ctx.save_for_backward(cam_f)
         ctx.dtype = cam.dtype
         return out
@@ -199,8 +204,9 @@ class _PoseFn(torch.autograd.Function):
     def backward(ctx, g):
         cam_f, = ctx.saved_tensors
         d = torch.empty(7, dtype=torch.float32, device=cam_f.device)
-        check(lib().lsr_pose_bwd(ptr(cam_f), ptr(g.contiguous().float()), ptr(d), stream_ptr(cam_f.device)),
-              'lsr_pose_bwd')
+        with torch.cuda.device(cam_f.device):
+            check(lib().lsr_pose_bwd(ptr(cam_f), ptr(g.contiguous().float()), ptr(d), stream_ptr(cam_f.device)),
+                  'lsr_pose_bwd')
         return d.to(ctx.dtype)
 
 

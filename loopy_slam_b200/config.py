@@ -5,29 +5,44 @@ import yaml
 from .decoder import NICER
 
 
-def load_config(path, default_path=None):
+def _read_yaml(path):
     with open(path, 'r') as f:
-        cfg_special = yaml.full_load(f)
-    inherit_from = cfg_special.get('inherit_from')
-    if inherit_from is not None:
-        cfg = load_config(inherit_from, default_path)
-    elif default_path is not None:
-        with open(default_path, 'r') as f:
-            cfg = yaml.full_load(f)
-    else:
-        cfg = dict()
-    update_recursive(cfg, cfg_special)
+        return yaml.full_load(f) or {}
+
+
+def deep_merge(dst, src):
+    """Merge `src` into `dst` in place, recursing into nested mappings (explicit stack, no recursion)."""
+    stack = [(dst, src)]
+    while stack:
+        d, s_ = stack.pop()
+        for key, val in s_.items():
+            if isinstance(val, dict):
+                node = d.get(key)
+                if not isinstance(node, dict):
+                    node = d[key] = {}
+                stack.append((node, val))
+            else:
+                d[key] = val
+    return dst
+
+
+def load_config(path, default_path=None):
+    """YAML config with `inherit_from` chains, same resolution order as the reference loader
+    (/root/reference/src/config.py:10-57): the root of the chain (or `default_path` when the chain ends without one) is
+    the base, every file further down the chain overrides it."""
+    chain, cur = [], path
+    while cur is not None:
+        doc = _read_yaml(cur)
+        chain.append(doc)
+        cur = doc.get('inherit_from')
+    cfg = _read_yaml(default_path) if default_path is not None else {}
+    for doc in reversed(chain):
+        deep_merge(cfg, doc)
     return cfg
 
 
-def update_recursive(dict1, dict2):
-    for k, v in dict2.items():
-        if k not in dict1:
-            dict1[k] = dict()
-        if isinstance(v, dict):
-            update_recursive(dict1[k], v)
-        else:
-            dict1[k] = v
+def update_recursive(dict1, dict2):   # reference-compatible name (src/config.py:45)
+    deep_merge(dict1, dict2)
 
 
 def get_model(cfg):

@@ -96,7 +96,7 @@ __host__ __device__ inline size_t scratch_legacy_floats() { return (size_t)Packe
 //      - the backward bulk-copies an atom column (F * 128 bytes, contiguous) into shared memory and the tensor
 //        core contracts over the ROWS directly (weight-gradient GEMMs), tools/umma_sw128_probe.cu test 1.
 struct SavedLayout {
-  size_t idx, w, D, misc, cg, gs, gh, occ, cst, cht, cc1t, ect, u, sp, rgbs, outraw, total;
+  size_t idx, w, D, misc, occ, rgbs, outraw, light_end, cg, gs, gh, cst, cht, cc1t, ect, u, sp, total;
   size_t P, Pp;
   int ntiles, rays_per_tile;
 };
@@ -121,14 +121,18 @@ __host__ __device__ inline SavedLayout saved_layout(int64_t R, int S, int stage,
   L.w = o;     o += Pp * KNN;
   L.D = o;     o += Pp * KNN;
   L.misc = o;  o += Pp * 4;            // z, has, wsum, cnt
-  L.cg = o;    o += Pp * CDIM;
-  L.gs = o;    o += 5 * Pp * HG;
-  L.gh = o;    o += 5 * Pp * HG;
   L.occ = o;   o += Pp;
-  L.cst = o; L.cht = o; L.cc1t = o; L.ect = o; L.u = o; L.sp = o; L.rgbs = o; L.outraw = o;
+  L.rgbs = o; L.outraw = o;
   if (stage == LSR_STAGE_COLOR) {
     L.rgbs = o;    o += Pp * 4;
     L.outraw = o;  o += Pp * 4;
+  }
+  L.light_end = o;                     // LSR_FLAG_SAVE_LIGHT (forward-only decode): nothing behind this point is written
+  L.cg = o;    o += Pp * CDIM;
+  L.gs = o;    o += 5 * Pp * HG;
+  L.gh = o;    o += 5 * Pp * HG;
+  L.cst = o; L.cht = o; L.cc1t = o; L.ect = o; L.u = o; L.sp = o;
+  if (stage == LSR_STAGE_COLOR) {
     L.cst = o;     o += 5 * nt * tplane_tile_floats(HC);    // softplus outputs s_l          [layer][tile]
     L.cht = o;     o += 5 * nt * tplane_tile_floats(HC);    // layer outputs h_l             [layer][tile]
     L.cc1t = o;    o += nt * tplane_tile_floats(TP_C1);     // [c | 1 | 0]

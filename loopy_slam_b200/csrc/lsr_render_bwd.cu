@@ -694,6 +694,7 @@ extern "C" int lsr_render_bwd(const LsrParams* prm, const void* grid_ws, const f
   if (n_rays < 0 || n_rays > (1ll << 27) || n_points < 0) return LSR_ERR_ARG;
   if (n_rays == 0) return LSR_OK;
   if (!saved || !scratch || !rays_o || !rays_d || !gt_depth || !g_depth) return LSR_ERR_ARG;
+  if (prm->flags & LSR_FLAG_SAVE_LIGHT) return LSR_ERR_ARG;   // a light save holds no activations to differentiate
   if (n_points > 0 && (!cloud_pos || !geo_feats)) return LSR_ERR_ARG;
   if (n_points > 0 && stage == LSR_STAGE_COLOR && !col_feats) return LSR_ERR_ARG;
   if (row_remap && (!geo_leaf || (stage == LSR_STAGE_COLOR && !col_leaf))) return LSR_ERR_ARG;

@@ -287,6 +287,7 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
   const bool color = a.stage == LSR_STAGE_COLOR;
   const bool relpos = color && (a.prm.flags & LSR_FLAG_REL_POS) != 0;
   const bool save = a.saved != nullptr;
+  const bool save_full = save && !(a.prm.flags & LSR_FLAG_SAVE_LIGHT);   // light: only k-NN results, occ, rgb (eval_points)
   const SavedLayout SL = saved_layout(a.R, S, a.stage, a.prm.flags);
   const size_t Pp = SL.Pp;
 
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
       const bool rv = row < nrows;
       const size_t prow = p0 + row;
       const size_t pw0 = p0 + lane_base;                                   // first row of this warp's lane quadrant
-      const int wvalid = save ? min(max(nrows - (int)lane_base, 0), 32) : 0;   // rows of it that are saved
+      const int wvalid = save_full ? min(max(nrows - (int)lane_base, 0), 32) : 0;   // rows of it that are saved
       LSR_PHASE_BEGIN();
 
       // ---------------------------------------------------------------- neighbour lists of the tile
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
 #pragma unroll
         for (int i = 0; i < F4T; ++i) {
           store_a_split(smem + SM_C_HI, smem + SM_C_LO, m, (qg * F4T + i) * 4, acc[i]);
-          if (save && m < nrows) reinterpret_cast<float4*>(a.saved + SL.cg)[(p0 + m) * 8 + qg * F4T + i] = acc[i];
+          if (save_full && m < nrows) reinterpret_cast<float4*>(a.saved + SL.cg)[(p0 + m) * 8 + qg * F4T + i] = acc[i];
         }
       }
       // ---------------------------------------------------------------- geometry Fourier features -> e
@@ -441,7 +442,7 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
               h[t] = s[t] + (__uint_as_float(x2[j + t]) + uv[t]);
               split_hi_lo(h[t], x1[j + t], x2[j + t]);
             }
-            if (save && rv) {
+            if (save_full && rv) {
               *reinterpret_cast<float4*>(gs + j) = make_float4(s[0], s[1], s[2], s[3]);
               *reinterpret_cast<float4*>(gh + j) = make_float4(h[0], h[1], h[2], h[3]);
             }
@@ -583,13 +584,13 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
               if (has) cc = make_float4(fmaf(v2.x, ws, __uint_as_float(x[j])), fmaf(v2.y, ws, __uint_as_float(x[j + 1])),
                                         fmaf(v2.z, ws, __uint_as_float(x[j + 2])), fmaf(v2.w, ws, __uint_as_float(x[j + 3])));
               store_a_split(smem + SM_C_HI, smem + SM_C_LO, row, 16 * cg + j, cc);
-              if (save) {   // [c | 1 | 0] T-plane: lane = row, one 128-byte line per feature
+              if (save_full) {   // [c | 1 | 0] T-plane: lane = row, one 128-byte line per feature
                 const float cv[4] = {cc.x, cc.y, cc.z, cc.w};
 #pragma unroll
                 for (int t = 0; t < 4; ++t) tp_c1[tplane_off(TP_C1, row, 16 * cg + j + t)] = rv ? cv[t] : 0.f;
               }
             }
-          } else if (cg == 2 && save) {
+          } else if (cg == 2 && save_full) {
 #pragma unroll
             for (int f = CDIM; f < TP_C1; ++f) tp_c1[tplane_off(TP_C1, row, f)] = (rv && f == CDIM) ? 1.f : 0.f;
           }
@@ -617,13 +618,13 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
 #pragma unroll
           for (int i = 0; i < F4T; ++i) {
             store_a_split(smem + SM_C_HI, smem + SM_C_LO, m, (qg * F4T + i) * 4, acc[i]);
-            if (save) {
+            if (save_full) {
               const float cv[4] = {acc[i].x, acc[i].y, acc[i].z, acc[i].w};
 #pragma unroll
               for (int t = 0; t < 4; ++t) tp_c1[tplane_off(TP_C1, m, (qg * F4T + i) * 4 + t)] = m < nrows ? cv[t] : 0.f;
             }
           }
-          if (save && qg == 0) {
+          if (save_full && qg == 0) {
 #pragma unroll
             for (int f = CDIM; f < TP_C1; ++f) tp_c1[tplane_off(TP_C1, m, f)] = (m < nrows && f == CDIM) ? 1.f : 0.f;
           }
@@ -643,7 +644,7 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
           }
           store_a_split(smem + SM_EC_HI, smem + SM_EC_LO, m, g * 4, make_float4(sn[0], sn[1], sn[2], sn[3]));
           store_a_split(smem + SM_EC_HI, smem + SM_EC_LO, m, EC + g * 4, make_float4(cs[0], cs[1], cs[2], cs[3]));
-          if (save) {
+          if (save_full) {
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               tp_ec[tplane_off(ECC, m, g * 4 + t)] = m < nrows ? sn[t] : 0.f;
@@ -687,7 +688,7 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
                 hk[j + t] = s[t] + (__uint_as_float(x2[j + t]) + uv[t]);
                 split_hi_lo(hk[j + t], x1[j + t], x2[j + t]);
               }
-              if (save) {   // lane = row: every store instruction of the warp fills one 128-byte line
+              if (save_full) {   // lane = row: every store instruction of the warp fills one 128-byte line
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                   const int f = col0 + j + t;
@@ -962,7 +963,10 @@ extern "C" int lsr_render_workspace_bytes(const LsrParams* prm, int64_t n_rays, 
   int rc = check_params(prm);
   if (rc) return rc;
   if (n_rays < 0 || n_rays > (1ll << 27)) return LSR_ERR_ARG;
-  if (saved_bytes) *saved_bytes = saved_layout(n_rays, prm->n_surface, stage, prm->flags).total * sizeof(float);
+  if (saved_bytes) {
+    const SavedLayout SLh = saved_layout(n_rays, prm->n_surface, stage, prm->flags);
+    *saved_bytes = ((prm->flags & LSR_FLAG_SAVE_LIGHT) ? SLh.light_end : SLh.total) * sizeof(float);
+  }
   if (scratch_bytes) *scratch_bytes = scratch_layout(n_rays, prm->n_surface).total;
   return LSR_OK;
 }

@@ -191,20 +191,46 @@ class WeightBlob:
                 return False
         return True
 
+    def _adopt(self, device):
+        """The tensors may ALREADY be views of one flat buffer that this object does not know about: the module was
+        pickled to another process (NICER.__getstate__ drops the blob; torch re-creates the parameters as views of the
+        one shared / CUDA-IPC storage: src/Point_SLAM.py shares `shared_decoders` between the tracker and mapper
+        processes) or deep-copied.  Re-allocating would silently detach this process from the shared weights, so the
+        existing storage is adopted when every tensor sits at base + 4 * offset inside it."""
+        ts = self.tensors()
+        t0 = ts[0]
+        if t0.device != device or t0.dtype != torch.float32:
+            return None
+        st = t0.untyped_storage()
+        base = t0.data_ptr() - 4 * self.offsets[0]
+        if base < st.data_ptr() or base + 4 * self.n_elems > st.data_ptr() + st.nbytes():
+            return None
+        for t, off in zip(ts, self.offsets):
+            if (t.device != device or t.dtype != torch.float32 or not t.is_contiguous()
+                    or t.untyped_storage().data_ptr() != st.data_ptr() or t.data_ptr() != base + 4 * off):
+                return None
+        flat = torch.empty(0, dtype=torch.float32, device=device)
+        flat.set_(st, (base - st.data_ptr()) // 4, (self.n_elems,), (1,))
+        return flat
+
     def ensure(self, device):
         """Flat blob on ``device`` with all tensors aliased into it -> (flat, LsrWeights)."""
         device = torch.device(device)
+        if device.type == 'cuda' and device.index is None:
+            device = torch.device('cuda', torch.cuda.current_device())
         if not self._aliased(device):
-            flat = torch.zeros(self.n_elems, dtype=torch.float32, device=device)
-            for (_, _, owner, attr), off, n in zip(self.entries, self.offsets, self.numels):
-                t = getattr(owner, attr)
-                view = flat[off:off + n].view(t.shape)
-                with torch.no_grad():
-                    view.copy_(t.detach().to(device=device, dtype=torch.float32))
-                if isinstance(t, nn.Parameter):
-                    t.data = view
-                else:
-                    setattr(owner, attr, view)
+            flat = self._adopt(device) if self.flat is None else None
+            if flat is None:
+                flat = torch.zeros(self.n_elems, dtype=torch.float32, device=device)
+                for (_, _, owner, attr), off, n in zip(self.entries, self.offsets, self.numels):
+                    t = getattr(owner, attr)
+                    view = flat[off:off + n].view(t.shape)
+                    with torch.no_grad():
+                        view.copy_(t.detach().to(device=device, dtype=torch.float32))
+                    if isinstance(t, nn.Parameter):
+                        t.data = view
+                    else:
+                        setattr(owner, attr, view)
             self.flat = flat
             W = _lib.LsrWeights()
             W.blob = flat.data_ptr()
@@ -252,6 +278,14 @@ class NICER(nn.Module):
         if self._blob is None:
             self._blob = WeightBlob(self)
         return self._blob
+
+    def share_memory(self):
+        """src/Point_SLAM.py:92: `self.shared_decoders.share_memory()` before the tracker / mapper processes are
+        spawned.  The flat blob is built FIRST so that every parameter is a view of one storage; sharing (CPU) or CUDA-IPC
+        pickling then keeps all processes on the same weights and WeightBlob._adopt re-finds the buffer in each child."""
+        dev = next(self.parameters()).device
+        self.blob.ensure(dev)
+        return super().share_memory()
 
     def __getstate__(self):       # the blob holds ctypes handles; it is rebuilt lazily after unpickling
         state = self.__dict__.copy()

@@ -50,10 +50,12 @@ class NeuralPointCloud(object):
     def cloud_pos_tensor(self):
         return self._pos[:self._n]
 
-    def get_cloud_pos(self, end=None):
-        """The reference returns a Python list that callers immediately wrap in torch.tensor(...)
-        (src/Mapper.py:492-493, src/Tracker.py:209-210); a device tensor works with both."""
-        return self._pos[:self._n if end is None else end]
+    def get_cloud_pos(self, end=False):
+        """Positions of the active cloud.  `end` is the reference's BOOLEAN (src/neural_point.py:1252: True = the merged
+        end-of-run cloud of all segments); it is not a row count.  The reference returns a Python list that callers
+        immediately wrap in torch.tensor(...) (src/Mapper.py:492-493, src/Tracker.py:209-210); a device tensor works
+        with both."""
+        return self._pos[:self._n]
 
     def input_pos(self):
         return self._input_pos
@@ -79,13 +81,13 @@ class NeuralPointCloud(object):
     def get_radius_add(self):
         return self.radius_add
 
-    def get_geo_feats(self, end=None):
-        return self.geo_feats[:self._n if end is None else end]
+    def get_geo_feats(self, end=False):
+        return self.geo_feats[:self._n]
 
-    def get_col_feats(self, end=None):
-        return self.col_feats[:self._n if end is None else end]
+    def get_col_feats(self, end=False):
+        return self.col_feats[:self._n]
 
-    def update_geo_feats(self, feats, indices=None):
+    def update_geo_feats(self, feats, indices=None, end=False):
         assert torch.is_tensor(feats), 'use tensor to update features'
         if indices is not None:
             self.geo_feats[indices] = feats.clone().detach()
@@ -93,7 +95,7 @@ class NeuralPointCloud(object):
             assert feats.shape[0] == self._n, 'feature shape[0] mismatch'
             self.geo_feats[:self._n] = feats.clone().detach()
 
-    def update_col_feats(self, feats, indices=None):
+    def update_col_feats(self, feats, indices=None, end=False):
         assert torch.is_tensor(feats), 'use tensor to update features'
         if indices is not None:
             self.col_feats[indices] = feats.clone().detach()

@@ -36,8 +36,9 @@ class GridIndex:
         nbytes = ctypes.c_size_t()
         check(lib().lsr_grid_workspace_bytes(self.n, self.max_cells, ctypes.byref(nbytes)), 'lsr_grid_workspace_bytes')
         self.ws = torch.empty(nbytes.value, dtype=torch.uint8, device=cloud.device)
-        check(lib().lsr_grid_build(ptr(self.cloud), self.n, self.cell, self.max_cells, ptr(self.ws), nbytes.value,
-                                   stream_ptr(cloud.device)), 'lsr_grid_build')
+        with torch.cuda.device(cloud.device):
+            check(lib().lsr_grid_build(ptr(self.cloud), self.n, self.cell, self.max_cells, ptr(self.ws), nbytes.value,
+                                       stream_ptr(cloud.device)), 'lsr_grid_build')
 
     def query(self, pos, radius, dynamic_radius=None):
         """== find_neighbors_faiss: D (P,8) f32, I (P,8) i64, neighbor_num (P,) i32."""
@@ -51,8 +52,9 @@ class GridIndex:
         if dynamic_radius is not None:
             rd = dynamic_radius.detach().to(torch.float64).reshape(-1).contiguous()
             assert rd.shape[0] == P, 'shape mis-match for input points and dynamic radius'
-        check(lib().lsr_knn_query(ptr(self.ws), ptr(q), ptr(rd), float(radius), P, ptr(D), ptr(I), ptr(n),
-                                  stream_ptr(q.device)), 'lsr_knn_query')
+        with torch.cuda.device(q.device):
+            check(lib().lsr_knn_query(ptr(self.ws), ptr(q), ptr(rd), float(radius), P, ptr(D), ptr(I), ptr(n),
+                                      stream_ptr(q.device)), 'lsr_knn_query')
         return D, I, n
 
 
@@ -147,19 +149,22 @@ class _RenderFn(torch.autograd.Function):
         var = torch.empty(R, dtype=torch.float32, device=dev)
         rgb = torch.empty(R, 3, dtype=torch.float32, device=dev)
         valid = torch.empty(R, dtype=torch.uint8, device=dev)
-        need_bwd = any(ctx.needs_input_grad) or rc.force_save
+        # needs_input_grad stays True under torch.no_grad(): without this test every no_grad render (render_img: 816 k rays)
+        # would allocate and write the multi-KB-per-sample saved activations
+        need_bwd = (torch.is_grad_enabled() and any(ctx.needs_input_grad)) or rc.force_save
         sb, cb = ctypes.c_size_t(), ctypes.c_size_t()
         check(lib().lsr_render_workspace_bytes(ctypes.byref(rc.prm), R, rc.stage, ctypes.byref(sb), ctypes.byref(cb)),
               'lsr_render_workspace_bytes')
         rc.scratch = torch.empty(cb.value, dtype=torch.uint8, device=dev)
         rc.saved = torch.empty(sb.value, dtype=torch.uint8, device=dev) if need_bwd else None
         ev = _tick(rc.timing)
-        check(lib().lsr_render_fwd(ctypes.byref(rc.prm), ptr(rc.grid.ws), ptr(rc.grid.cloud), rc.grid.n,
-                                   ptr(rays_o), ptr(rays_d), ptr(gt_depth), ptr(rc.r_query), ptr(far_zero),
-                                   rc.far_group, ptr(rc.z_zero), R, ptr(geo_feats), ptr(col_feats), ptr(rc.remap), ptr(geo_leaf),
-                                   ptr(col_leaf), ctypes.byref(rc.wstruct),
-                                   ptr(affine), rc.stage, ptr(depth), ptr(var), ptr(rgb), ptr(valid),
-                                   ptr(rc.saved), ptr(rc.scratch), stream_ptr(dev)), 'lsr_render_fwd')
+        with torch.cuda.device(dev):      # the kernels launch on dev's stream: make it the current device
+            check(lib().lsr_render_fwd(ctypes.byref(rc.prm), ptr(rc.grid.ws), ptr(rc.grid.cloud), rc.grid.n,
+                                       ptr(rays_o), ptr(rays_d), ptr(gt_depth), ptr(rc.r_query), ptr(far_zero),
+                                       rc.far_group, ptr(rc.z_zero), R, ptr(geo_feats), ptr(col_feats), ptr(rc.remap), ptr(geo_leaf),
+                                       ptr(col_leaf), ctypes.byref(rc.wstruct),
+                                       ptr(affine), rc.stage, ptr(depth), ptr(var), ptr(rgb), ptr(valid),
+                                       ptr(rc.saved), ptr(rc.scratch), stream_ptr(dev)), 'lsr_render_fwd')
         _tock(rc.timing, 'fwd', ev)
         ctx.rc = rc
         ctx.param_shapes = [p.shape for p in params]
@@ -218,13 +223,14 @@ class _RenderFn(torch.autograd.Function):
         g_var = _f32c(g_var) if g_var is not None else None
         g_rgb = _f32c(g_rgb) if g_rgb is not None else None
         ev = _tick(rc.timing)
-        check(lib().lsr_render_bwd(ctypes.byref(rc.prm), ptr(rc.grid.ws), ptr(rc.grid.cloud), rc.grid.n,
-                                   ptr(rays_o), ptr(rays_d), ptr(gt_depth), ptr(rc.r_query), R, ptr(geo_feats),
-                                   ptr(col_feats), ptr(rc.remap), ptr(geo_leaf), ptr(col_leaf),
-                                   ctypes.byref(rc.wstruct), ptr(affine), rc.stage,
-                                   1 if rc.is_tracker else 0, ptr(rc.saved), ptr(rc.scratch), ptr(g_depth),
-                                   ptr(g_var), ptr(g_rgb), flags, ptr(d_geo), ptr(d_col), ptr(d_w), ptr(d_aff),
-                                   ptr(d_o), ptr(d_d), stream_ptr(dev)), 'lsr_render_bwd')
+        with torch.cuda.device(dev):      # the kernels launch on dev's stream: make it the current device
+            check(lib().lsr_render_bwd(ctypes.byref(rc.prm), ptr(rc.grid.ws), ptr(rc.grid.cloud), rc.grid.n,
+                                       ptr(rays_o), ptr(rays_d), ptr(gt_depth), ptr(rc.r_query), R, ptr(geo_feats),
+                                       ptr(col_feats), ptr(rc.remap), ptr(geo_leaf), ptr(col_leaf),
+                                       ctypes.byref(rc.wstruct), ptr(affine), rc.stage,
+                                       1 if rc.is_tracker else 0, ptr(rc.saved), ptr(rc.scratch), ptr(g_depth),
+                                       ptr(g_var), ptr(g_rgb), flags, ptr(d_geo), ptr(d_col), ptr(d_w), ptr(d_aff),
+                                       ptr(d_o), ptr(d_d), stream_ptr(dev)), 'lsr_render_bwd')
         _tock(rc.timing, 'bwd', ev)
         rc.saved = None
         pgrads = []
@@ -266,7 +272,7 @@ def _make_params(renderer, decoders, stage, coef):
 
 def fused_render(renderer, npc, decoders, rays_d, rays_o, stage, gt_depth, npc_geo_feats, npc_col_feats,
                  is_tracker, cloud_pos, dynamic_r_query, exposure_feat, far_group=None, n_surface=None,
-                 force_save=False, return_ctx=False, feat_subset=None, z_zero_depth=None):
+                 force_save=False, return_ctx=False, feat_subset=None, z_zero_depth=None, save_light=False):
     """The one place that marshals a render call into lsr_render_fwd / lsr_render_bwd."""
     _lib.require_cuda(rays_o, 'rays_o')
     dev = rays_o.device
@@ -278,6 +284,8 @@ def fused_render(renderer, npc, decoders, rays_d, rays_o, stage, gt_depth, npc_g
     prm = _make_params(renderer, decoders, stage, float(renderer.sigmoid_coefficient))
     if n_surface is not None:
         prm.n_surface = n_surface
+    if save_light:
+        prm.flags |= _lib.FLAG_SAVE_LIGHT
     radius = npc.get_radius_query() if npc is not None and hasattr(npc, 'get_radius_query') else renderer.radius_query
     prm.radius_query = float(radius)
     rc = _RenderCtx()
@@ -312,7 +320,8 @@ def fused_render(renderer, npc, decoders, rays_d, rays_o, stage, gt_depth, npc_g
         gt = _f32c(gt_depth.detach().reshape(-1))
         fgroup = int(far_group) if far_group else max(R, 1)
         far = torch.empty((R + fgroup - 1) // fgroup if R else 1, dtype=torch.float32, device=dev)
-        check(lib().lsr_far_bound(ptr(gt), R, fgroup, ptr(far), stream_ptr(dev)), 'lsr_far_bound')
+        with torch.cuda.device(dev):
+            check(lib().lsr_far_bound(ptr(gt), R, fgroup, ptr(far), stream_ptr(dev)), 'lsr_far_bound')
     geo = _f32c(npc_geo_feats)
     col = _f32c(npc_col_feats) if npc_col_feats is not None else None
     params = rc.blob.tensors()
@@ -347,7 +356,8 @@ def fused_render(renderer, npc, decoders, rays_d, rays_o, stage, gt_depth, npc_g
 
 
 def _saved_views(rc):
-    """Python mirror of lsr::saved_layout (csrc/lsr_render.cuh): float views into the saved buffer."""
+    """Python mirror of the head of lsr::saved_layout (csrc/lsr_render.cuh): float views of the planes a light save
+    (LSR_FLAG_SAVE_LIGHT) holds -- k-NN results, occupancy logits, per-sample colours."""
     S = rc.prm.n_surface
     P = rc.R * S
     Pp = (P + 127) // 128 * 128 + 128
@@ -360,9 +370,8 @@ def _saved_views(rc):
         v[name] = f[o:o + n].view(shape)
         o += n
     take('idx', Pp * 8, (Pp, 8)); take('w', Pp * 8, (Pp, 8)); take('D', Pp * 8, (Pp, 8)); take('misc', Pp * 4, (Pp, 4))
-    take('cg', Pp * 32, (Pp, 32)); take('gs', 5 * Pp * 32, (5, Pp, 32)); take('gh', 5 * Pp * 32, (5, Pp, 32))
     take('occ', Pp, (Pp,))
-    if rc.stage == 1:   # the colour-trunk planes behind these two are tile-blocked (csrc/lsr_render.cuh) and not viewed here
+    if rc.stage == 1:
         take('rgbs', Pp * 4, (Pp, 4)); take('outraw', Pp * 4, (Pp, 4))
     return v, P
 
@@ -371,25 +380,33 @@ def decode_points(decoders, p, npc, stage, npc_geo_feats, npc_col_feats, pts_num
                   exposure_feat, renderer=None):
     """NICER.forward semantics (decoder.py:573-610), forward only: runs the fused kernel with one
     sample per "ray" (origin = the point, direction = 0, so the sample point is the origin exactly)
-    and reads the per-sample occupancy / colour out of the saved activations.
+    and reads the per-sample occupancy / colour out of a LIGHT save (148 B per point), in chunks of
+    renderer.points_batch_size points like Renderer.eval_points (Renderer.py:40-60).
     -> raw (P,4) [r,g,b,occ-logit], ray_mask (P/pts_num,) bool or None, point_mask (P,) bool."""
     if renderer is None:
         renderer = getattr(decoders, '_lsr_renderer', None)
         if renderer is None:
             raise RuntimeError('NICER.forward needs a Renderer: call Renderer.eval_points(...)')
     pts = _f32c(p.detach().reshape(-1, 3))
+    raws, hass = [], []
+    chunk = max(int(getattr(renderer, 'points_batch_size', 500000)), 1)
     with torch.no_grad():
-        P = pts.shape[0]
-        ones = torch.ones(P, dtype=torch.float32, device=pts.device)
-        dyn = dynamic_r_query
-        _, rc = fused_render(renderer, npc, decoders, torch.zeros_like(pts), pts, stage, ones, npc_geo_feats,
-                             npc_col_feats, False, cloud_pos, dyn, exposure_feat, n_surface=1, force_save=True,
-                             return_ctx=True)
-        v, n = _saved_views(rc)
-        occ = v['occ'][:n].clone()
-        has = v['misc'][:n, 1] > 0.5
-        rgb = v['rgbs'][:n, :3].clone() if rc.stage == 1 else torch.zeros(n, 3, device=pts.device)
-        raw = torch.cat([rgb, occ[:, None]], -1)
+        for b in range(0, max(pts.shape[0], 1), chunk):
+            pb = pts[b:b + chunk]
+            n = pb.shape[0]
+            ones = torch.ones(n, dtype=torch.float32, device=pts.device)
+            dyn = dynamic_r_query
+            if dyn is not None and dyn.numel() == pts.shape[0]:
+                dyn = dyn.reshape(-1)[b:b + chunk]
+            _, rc = fused_render(renderer, npc, decoders, torch.zeros_like(pb), pb, stage, ones, npc_geo_feats,
+                                 npc_col_feats, False, cloud_pos, dyn, exposure_feat, n_surface=1, force_save=True,
+                                 return_ctx=True, save_light=True)
+            v, m = _saved_views(rc)
+            occ = v['occ'][:m].clone()
+            hass.append(v['misc'][:m, 1] > 0.5)
+            rgb = v['rgbs'][:m, :3].clone() if rc.stage == 1 else torch.zeros(m, 3, device=pts.device)
+            raws.append(torch.cat([rgb, occ[:, None]], -1))
+    raw, has = torch.cat(raws), torch.cat(hass)
     ray_mask = None
     if pts_num:
         ray_mask = ~(has.view(-1, pts_num).sum(1) < int(decoders.cfg_flags['N_surface'] / 2 + 1))
@@ -461,7 +478,8 @@ class Renderer(object):
             R = g.shape[0]
             g32 = _f32c(g)
             far = torch.empty(1, dtype=torch.float32, device=g32.device)
-            check(lib().lsr_far_bound(ptr(g32), R, max(R, 1), ptr(far), stream_ptr(g32.device)), 'lsr_far_bound')
+            with torch.cuda.device(g32.device):
+                check(lib().lsr_far_bound(ptr(g32), R, max(R, 1), ptr(far), stream_ptr(g32.device)), 'lsr_far_bound')
             z0, not_near = npc.sample_near_pcl(rays_o[zero].clone().detach(), rays_d[zero].clone().detach(),
                                                self.near_end, float(far.item()), self.N_surface)   # Renderer.py:151-153
             z_zero = torch.zeros(R, self.N_surface, dtype=torch.float32, device=g32.device)

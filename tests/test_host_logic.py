@@ -198,3 +198,85 @@ def test_frustum_helpers_match_numpy_restatement():
     refp = np.array([ref_percent(verts, k) for k in kfs])
     assert pct.shape == (4,) and refp.max() > 0.05 and refp.min() == 0.0
     assert np.allclose(pct.numpy(), refp, atol=2.0 / verts.shape[0])      # at most a borderline vertex or two
+
+
+# ---------------------------------------------------------------------------------------- round-2 host fixes
+def test_config_loader_inherit_chain(tmp_path):
+    """load_config: inherit_from chain + default file, nested override semantics of the reference loader
+    (/root/reference/src/config.py:10-57)."""
+    import yaml
+    from loopy_slam_b200.config import load_config
+    (tmp_path / 'default.yaml').write_text(yaml.dump({'a': 1, 'm': {'x': 1, 'y': {'p': 1, 'q': 2}}, 'only_default': 7}))
+    (tmp_path / 'base.yaml').write_text(yaml.dump({'a': 2, 'm': {'y': {'q': 3}}, 'b': {'k': 1}}))
+    (tmp_path / 'scene.yaml').write_text(yaml.dump({'inherit_from': str(tmp_path / 'base.yaml'), 'm': {'x': 5}, 'b': 9}))
+    cfg = load_config(str(tmp_path / 'scene.yaml'), str(tmp_path / 'default.yaml'))
+    assert cfg['a'] == 2 and cfg['only_default'] == 7
+    assert cfg['m'] == {'x': 5, 'y': {'p': 1, 'q': 3}}
+    assert cfg['b'] == 9                      # a scalar replaces a mapping
+    import os
+    if os.path.isdir('/root/reference/configs'):   # build container only: identical to the real loader on the real files
+        import glob
+        from oracle import ref_import
+        _, _, _, rc = ref_import.import_reference()
+        cwd = os.getcwd()
+        os.chdir('/root/reference')
+        try:
+            for y in glob.glob('configs/*/*.yaml'):
+                assert rc.load_config(y, 'configs/point_slam.yaml') == load_config(y, 'configs/point_slam.yaml'), y
+        finally:
+            os.chdir(cwd)
+
+
+def test_npc_accessors_take_the_reference_bool():
+    """src/Mapper.py:490-493 calls get_geo_feats(self.end) / get_cloud_pos(self.end) with a BOOLEAN and
+    :773-777 update_*_feats(..., end=self.end): `end` must never be used as a row count."""
+    import loopy_slam_b200 as L
+    cfg = L.default_cfg('replica')
+    npc = L.NeuralPointCloud(cfg, device='cpu')
+    npc._pos = torch.arange(30, dtype=torch.float32).reshape(10, 3)
+    npc._n = npc._cap = 10
+    npc.geo_feats = torch.zeros(10, 32)
+    npc.col_feats = torch.zeros(10, 32)
+    for end in (False, True):
+        assert npc.get_cloud_pos(end).shape == (10, 3)
+        assert npc.get_geo_feats(end).shape == (10, 32) and npc.get_col_feats(end).shape == (10, 32)
+    npc.update_geo_feats(torch.ones(3, 32), indices=[1, 4, 5], end=False)
+    npc.update_col_feats(torch.ones(10, 32) * 2, end=False)
+    assert npc.get_geo_feats(False)[[1, 4, 5]].eq(1).all() and npc.get_geo_feats(False)[0].eq(0).all()
+    assert npc.get_col_feats(False).eq(2).all()
+
+
+def _child_step(model, q):
+    """runs in a spawned process: the blob must ADOPT the shared storage, and an optimiser step must land in it"""
+    import torch
+    flat, _ = model.blob.ensure('cpu')
+    p = model.color_decoder.output_linear.bias
+    aliased = p.data_ptr() >= flat.data_ptr() and p.data_ptr() < flat.data_ptr() + 4 * flat.numel()
+    opt = torch.optim.SGD([p], lr=1.0)
+    p.grad = torch.ones_like(p)
+    opt.step()
+    q.put((bool(aliased), bool(flat.is_shared())))
+
+
+def test_shared_decoders_stay_shared_across_processes():
+    """src/Point_SLAM.py shares `shared_decoders` between the tracker and mapper processes.  After
+    share_memory() + spawn, WeightBlob.ensure() in a child must adopt the shared flat buffer (not re-allocate a private
+    one), so that the mapper's optimiser steps reach the weights the tracker renders with."""
+    import torch.multiprocessing as mp
+    import loopy_slam_b200 as L
+    cfg = L.default_cfg('replica')
+    torch.manual_seed(0)
+    model = L.get_model(cfg)
+    model.share_memory()
+    before = model.color_decoder.output_linear.bias.detach().clone()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    pr = ctx.Process(target=_child_step, args=(model, q))
+    pr.start()
+    aliased, shared = q.get(timeout=120)
+    pr.join(60)
+    assert aliased and shared
+    after = model.color_decoder.output_linear.bias.detach()
+    assert torch.allclose(after, before - 1.0), 'the child\'s update did not reach the shared weights'
+    flat, _ = model.blob.ensure('cpu')      # and the parent's own blob still aliases the same memory
+    assert model.color_decoder.output_linear.bias.data_ptr() >= flat.data_ptr()
