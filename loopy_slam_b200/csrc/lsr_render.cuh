@@ -96,12 +96,13 @@ __host__ __device__ inline size_t scratch_legacy_floats() { return (size_t)Packe
 //      - the backward bulk-copies an atom column (F * 128 bytes, contiguous) into shared memory and the tensor
 //        core contracts over the ROWS directly (weight-gradient GEMMs), tools/umma_sw128_probe.cu test 1.
 struct SavedLayout {
-  size_t idx, w, D, misc, occ, rgbs, outraw, light_end, cg, gs, gh, cst, cht, cc1t, ect, u, sp, total;
+  size_t idx, w, D, misc, occ, rgbs, outraw, light_end, cg, gs, gh, cst, cht, cc1t, ect, ut, spt, qt, total;
   size_t P, Pp;
   int ntiles, rays_per_tile;
 };
 constexpr int TP_ROWS = 128;          // rows of a T-plane tile
 constexpr int TP_C1 = 40;             // features of the [c (32) | 1 | 0 x 7] plane
+constexpr int TP_Q = 64;              // lines of the transposed rel-pos MLP input [sin 10 | cos 10 | feature 32 | 1 | 0 x 11]
 __host__ __device__ inline size_t tplane_tile_floats(int F) { return (size_t)F * TP_ROWS; }
 __host__ __device__ inline int tplane_off(int F, int row, int f) {
   const int q = row >> 5, j = row & 31;
@@ -131,15 +132,16 @@ __host__ __device__ inline SavedLayout saved_layout(int64_t R, int S, int stage,
   L.cg = o;    o += Pp * CDIM;
   L.gs = o;    o += 5 * Pp * HG;
   L.gh = o;    o += 5 * Pp * HG;
-  L.cst = o; L.cht = o; L.cc1t = o; L.ect = o; L.u = o; L.sp = o;
+  L.cst = o; L.cht = o; L.cc1t = o; L.ect = o; L.ut = o; L.spt = o; L.qt = o;
   if (stage == LSR_STAGE_COLOR) {
     L.cst = o;     o += 5 * nt * tplane_tile_floats(HC);    // softplus outputs s_l          [layer][tile]
     L.cht = o;     o += 5 * nt * tplane_tile_floats(HC);    // layer outputs h_l             [layer][tile]
     L.cc1t = o;    o += nt * tplane_tile_floats(TP_C1);     // [c | 1 | 0]
     L.ect = o;     o += nt * tplane_tile_floats(ECC);       // colour Fourier features e' = [sin | cos]
-    if (flags & LSR_FLAG_REL_POS) {
-      L.u = o;     o += Pp * HC;
-      L.sp = o;    o += Pp * KNN * HC;
+    if (flags & LSR_FLAG_REL_POS) {   // rel-pos neighbour MLP: u = sum_k w_k softplus(.), the 8 softplus outputs, the 8 inputs Q_k
+      L.ut = o;    o += nt * tplane_tile_floats(HC);
+      L.spt = o;   o += nt * KNN * tplane_tile_floats(HC);
+      L.qt = o;    o += nt * KNN * tplane_tile_floats(TP_Q);
     }
   }
   L.total = o;
@@ -152,10 +154,10 @@ __host__ __device__ inline SavedLayout saved_layout(int64_t R, int S, int stage,
 constexpr int UMMA_PACKED_FLOATS_MAX = 2 * (93 * 32 + 3 * 32 * 32 + 128 * 32 + 5 * 32 * 32 +                  // geometry
                                             (40 + 128 + 128 + 168 + 128) * 128 + 5 * 32 * 128 + 56 * 128 +   // colour
                                             128 * 32 + 128 * 16) + 8192;                                     // V2, head, padding
-constexpr int BWD_PACK_FLOATS_MAX = 4 * 128 * 128 + (32 + 80 + 32 + 32 + 48) * 128 + 128 + 4096;   // W^hT x 4, extras, P_out
+constexpr int BWD_PACK_FLOATS_MAX = 4 * 128 * 128 + (32 + 80 + 32 + 32 + 48) * 128 + 128 * 32 + 64 * 128 + 128 + 4096;   // W^hT x 4, extras, V2^T, V1^T, P_out
 constexpr int BWD_ACC_SLOTS = 80;                 // per colour layer: [e' (40) | c (32) | 1 | pad (7)] x 128 outputs
 constexpr int BWD_ACC_FLOATS = 5 * BWD_ACC_SLOTS * 128 + 3 * TP_C1;   // + M_out [3][40]
-struct ScratchLayout { size_t legacy, umma, knn_idx, knn_rem, knn_w, knn_pos, knn_hw, bwd_pack, bwd_acc, bwd_dc, bwd_dp, total; };
+struct ScratchLayout { size_t legacy, umma, knn_idx, knn_rem, knn_w, knn_pos, knn_hw, bwd_pack, bwd_acc, bwd_dc, bwd_dp, bwd_dwh, bwd_dqt, total; };
 __host__ __device__ inline ScratchLayout scratch_layout(int64_t n_rays, int S) {
   ScratchLayout L;
   const size_t Pp = align_up((size_t)n_rays * S, 128) + 128;
@@ -171,6 +173,11 @@ __host__ __device__ inline ScratchLayout scratch_layout(int64_t n_rays, int S) {
   L.bwd_acc = o;  o = align_up(o + (size_t)BWD_ACC_FLOATS * sizeof(float), 256);
   L.bwd_dc = o;   o = align_up(o + Pp * CDIM * 4, 256);     // dL/dc (colour feature) per sample row
   L.bwd_dp = o;   o = align_up(o + Pp * 16, 256);           // dL/dp contribution of the colour Fourier features
+  L.bwd_dwh = o;  o = align_up(o + Pp * KNN * 4, 256);      // dL/d(normalised IDW weight) of the rel-pos path (tracker)
+  {   // d[sin | cos] of the rel-pos Fourier features: [tile][8][20][128]
+    const size_t rpt = (size_t)(128 / S), nt = ((size_t)n_rays + rpt - 1) / rpt;
+    L.bwd_dqt = o;  o = align_up(o + (nt > 0 ? nt : 1) * KNN * 20 * 128 * 4, 256);
+  }
   L.total = o + 256;
   return L;
 }

@@ -28,7 +28,7 @@ struct BwdArgs {
   const float *g_depth, *g_var, *g_rgb;
   int gflags;
   float *d_geo, *d_col, *d_w, *d_affine, *d_ro, *d_rd;
-  const float *ext_dc, *ext_dp;   // colour trunk hand-over (scratch planes)
+  const float *ext_dc, *ext_dp, *ext_dwh;   // colour backward hand-over (scratch planes)
   int rays_per_tile, ntiles;
 };
 
@@ -240,182 +240,10 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
 
       LSR_PHASE(1, 3);   // fourier bwd + dC
       if (relpos) {
-        // ------------------------------------------------------ rel-pos neighbour MLP backward
-        if (g_cw) {
-          float a2[TMW32][8];
-          zero_acc(a2);
-          tile_gemm<TMW32, 16, 2, false, false>(a2, sDC, CLD, nrows, sv + SL.u + p0 * HC, HC, HC, sB);
-#pragma unroll
-          for (int g = 0; g < 2; ++g)
-#pragma unroll
-            for (int i = 0; i < TMW32; ++i)
-              red_add_v4(dW + a.w.c_nb2_w + wm.row(i) * HC + wm.col(g), a2[i][g * 4 + 0], a2[i][g * 4 + 1],
-                         a2[i][g * 4 + 2], a2[i][g * 4 + 3]);
-          if (tid < CDIM) {
-            float s = 0.f;
-            for (int m = 0; m < nrows; ++m) s = fmaf(sDC[m * CLD + tid], sWsum[m], s);
-            atomicAdd(dW + a.w.c_nb2_b + tid, s);
-          }
-        }
-        prefetch_rows_l2(sv + SL.sp + p0 * KNN * HC, nrows * KNN, HC);
-        float dU[TMA][8];
-        zero_acc(dU);
-        tile_gemm<TMA, 16, 2, true, false>(dU, sDC, CLD, CDIM, blob + a.w.c_nb2_w, HC, HC, sB, nrows);
-        float dV1acc[TMW][4];
-        zero_acc(dV1acc);
-        float dv1 = 0.f;
-        float dBl[15];
-#pragma unroll
-        for (int k = 0; k < 15; ++k) dBl[k] = 0.f;
-        if (trk && tid < TILE_M) {      // dw_hat_k += dc . v2 (same for every valid k)
-          float rt = 0.f;
-          for (int c = 0; c < CDIM; ++c) rt = fmaf(sDC[tid * CLD + c], blob[a.w.c_nb2_b + c], rt);
-#pragma unroll
-          for (int k = 0; k < KNN; ++k)
-            if (sIdx[tid * KNN + k] >= 0) sDWh[tid * KNN + k] += rt;
-        }
-        for (int m = tid; m < TILE_M; m += NT) {
-          *reinterpret_cast<float4*>(sQ + m * QLD + QD) = make_float4(0.f, 0.f, 0.f, 0.f);
-          *reinterpret_cast<float4*>(sQ + m * QLD + QDP) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        __syncthreads();
-#pragma unroll 1
-        for (int k = 0; k < KNN; ++k) {
-          float part[TMA];
-#pragma unroll
-          for (int i = 0; i < TMA; ++i) part[i] = 0.f;
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            const int col = wm.col(g);
-            float4 sp4[TMA];
-#pragma unroll
-            for (int i = 0; i < TMA; ++i) {
-              const int r = wm.row(i);
-              sp4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (r < nrows) sp4[i] = __ldcs(reinterpret_cast<const float4*>(sv + SL.sp + ((p0 + r) * KNN + k) * HC + col));
-            }
-#pragma unroll
-            for (int i = 0; i < TMA; ++i) {
-              const int r = wm.row(i);
-              float4 dA = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (r < nrows) {
-                const float4 sp = sp4[i];
-                const float wk = sW[r * KNN + k];
-                dA = make_float4(wk * dU[i][g * 4 + 0] * softplus100_grad_from_out(sp.x),
-                                 wk * dU[i][g * 4 + 1] * softplus100_grad_from_out(sp.y),
-                                 wk * dU[i][g * 4 + 2] * softplus100_grad_from_out(sp.z),
-                                 wk * dU[i][g * 4 + 3] * softplus100_grad_from_out(sp.w));
-                part[i] += dU[i][g * 4 + 0] * sp.x + dU[i][g * 4 + 1] * sp.y + dU[i][g * 4 + 2] * sp.z +
-                           dU[i][g * 4 + 3] * sp.w;
-              }
-              *reinterpret_cast<float4*>(sD + r * DLD + col) = dA;
-            }
-          }
-          if (trk) {
-#pragma unroll
-            for (int i = 0; i < TMA; ++i) {
-              const float v = half_warp_sum(part[i]);
-              const int r = wm.row(i);
-              if (wm.tx == 0 && sIdx[r * KNN + k] >= 0) sDWh[r * KNN + k] += v;
-            }
-          }
-          // rebuild Q_k = [sin(phi) | cos(phi) | F^c[idx_k]]
-          for (int it = tid; it < TILE_M * ER; it += NT) {
-            const int m = it / ER, j = it - m * ER;
-            const int idx = sIdx[m * KNN + k];
-            float sn = 0.f, cs = 0.f;
-            if (idx >= 0) {
-              const float t0 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 0), sP[m * 4 + 0]);
-              const float t1 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 1), sP[m * 4 + 1]);
-              const float t2 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 2), sP[m * 4 + 2]);
-              const float arg = fmaf(t2, blob[a.w.c_Brel + 2 * ER + j],
-                                     fmaf(t1, blob[a.w.c_Brel + ER + j], t0 * blob[a.w.c_Brel + j]));
-              sincos_ff(arg, &sn, &cs);
-            }
-            sQ[m * QLD + j] = sn;
-            sQ[m * QLD + ER + j] = cs;
-          }
-          for (int it = tid; it < TILE_M * 8; it += NT) {
-            const int m = it >> 3, q = it & 7;
-            const int idx = sIdx[m * KNN + k];
-            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (idx >= 0) f = __ldg(reinterpret_cast<const float4*>(feat_row(a.col_feats, a.col_leaf, a.remap, idx)) + q);
-            *reinterpret_cast<float4*>(sQ + m * QLD + 2 * ER + q * 4) = f;
-          }
-          __syncthreads();
-          if (g_cw) {
-            tile_gemm<TMW, 16, 1, false, true>(dV1acc, sD, DLD, nrows, sQ, QLD, QDP, sB);
-            if (tid < HC)
-              for (int m = 0; m < nrows; ++m) dv1 += sD[m * DLD + tid];
-          }
-          float aq[TMA][4];
-          zero_acc(aq);
-          tile_gemm<TMA, 16, 1, true, false>(aq, sD, DLD, HC, blob + a.w.c_nb1_w, QD, QD, sB, nrows);
-          {
-            const int col = wm.tx * 4;
-            if (col < 2 * ER) {
-#pragma unroll
-              for (int i = 0; i < TMA; ++i)
-                *reinterpret_cast<float4*>(sDQ + wm.row(i) * DQLD + col) = make_float4(aq[i][0], aq[i][1], aq[i][2], aq[i][3]);
-            } else if (col < QD && g_cf) {
-#pragma unroll
-              for (int i = 0; i < TMA; ++i) {
-                const int r = wm.row(i);
-                const int idx = sIdx[r * KNN + k];
-                if (idx >= 0 && r < nrows) {
-                  float* dst = grad_row(a.d_col, a.remap, idx);
-                  if (dst) red_add_v4(dst + (col - 2 * ER), aq[i][0], aq[i][1], aq[i][2], aq[i][3]);
-                }
-              }
-            }
-          }
-          __syncthreads();
-          if ((g_cw || g_ry) && tid < 2 * TILE_M) {
-            const int m = tid % TILE_M, half = tid / TILE_M;
-            const int idx = sIdx[m * KNN + k];
-            if (idx >= 0) {
-              const float t0 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 0), sP[m * 4 + 0]);
-              const float t1 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 1), sP[m * 4 + 1]);
-              const float t2 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 2), sP[m * 4 + 2]);
-              float q0 = 0.f, q1 = 0.f, q2 = 0.f;
-#pragma unroll
-              for (int jj = 0; jj < 5; ++jj) {
-                const int j = half * 5 + jj;
-                const float dphi = sDQ[m * DQLD + j] * sQ[m * QLD + ER + j] - sDQ[m * DQLD + ER + j] * sQ[m * QLD + j];
-                dBl[jj] = fmaf(t0, dphi, dBl[jj]);
-                dBl[5 + jj] = fmaf(t1, dphi, dBl[5 + jj]);
-                dBl[10 + jj] = fmaf(t2, dphi, dBl[10 + jj]);
-                q0 = fmaf(blob[a.w.c_Brel + j], dphi, q0);
-                q1 = fmaf(blob[a.w.c_Brel + ER + j], dphi, q1);
-                q2 = fmaf(blob[a.w.c_Brel + 2 * ER + j], dphi, q2);
-              }
-              if (g_ry) {   // rel = x - p  ->  dp -= d rel
-                atomicAdd(&sDP[m * 4 + 0], -TWO_PI_F * q0);
-                atomicAdd(&sDP[m * 4 + 1], -TWO_PI_F * q1);
-                atomicAdd(&sDP[m * 4 + 2], -TWO_PI_F * q2);
-              }
-            }
-          }
-          __syncthreads();
-        }
-        if (g_cw) {
-          if (wm.tx * 4 < QD) {
-#pragma unroll
-            for (int i = 0; i < TMW; ++i)
-              red_add_v4(dW + a.w.c_nb1_w + wm.row(i) * QD + wm.tx * 4, dV1acc[i][0], dV1acc[i][1], dV1acc[i][2],
-                         dV1acc[i][3]);
-          }
-          if (tid < HC) atomicAdd(dW + a.w.c_nb1_b + tid, dv1);
-          const int half = (tid / TILE_M) & 1;   // uniform per warp; warps beyond 2*TILE_M threads carry zeros
-#pragma unroll
-          for (int c = 0; c < 3; ++c)
-#pragma unroll
-            for (int jj = 0; jj < 5; ++jj) {
-              float v = dBl[c * 5 + jj];
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-              if ((tid & 31) == 0) atomicAdd(&sRed[3 * EGP + c * ER + half * 5 + jj], v);
-            }
+        // the rel-pos neighbour MLP backward (feature scatter, dV1 / dV2 / dB_rel, pose part) ran in the tcgen05 kernel;
+        // what is left for the shared IDW-weight backward below is its d(w_hat) per neighbour
+        if (trk) {
+          for (int i = tid; i < nrows * KNN; i += NT) sDWh[i] += a.ext_dwh[p0 * KNN + i];
         }
       } else {
         scatter_idw(sDC, sIdx, sW, sHas, sDWh, a.col_feats, a.col_leaf, a.remap, a.d_col, g_cf, trk);
@@ -663,7 +491,8 @@ int sm_count();
 int balanced_rays_per_tile(int64_t n_rays, int n_surface, int nsm);
 int launch_trunk_bwd(const LsrParams* prm, const LsrWeights* w, const float* gt_depth, int64_t n_rays, const float* affine,
                      const void* saved, void* scratch, const float* g_depth, const float* g_var, const float* g_rgb, int grad_flags,
-                     float* d_weights, float* d_affine, cudaStream_t stream);
+                     float* d_weights, float* d_affine, const float* cloud_pos, const int32_t* row_remap, float* d_col_feats,
+                     int is_tracker, cudaStream_t stream);
 
 }  // namespace lsr
 
@@ -710,12 +539,13 @@ extern "C" int lsr_render_bwd(const LsrParams* prm, const void* grid_ws, const f
   const ScratchLayout CL = scratch_layout(n_rays, prm->n_surface);
   if (stage == LSR_STAGE_COLOR) {
     rc = launch_trunk_bwd(prm, w, gt_depth, n_rays, exposure_affine, saved, scratch, g_depth, g_var, g_rgb, grad_flags, d_weights,
-                          d_exposure_affine, stream);
+                          d_exposure_affine, cloud_pos, row_remap, d_col_feats, is_tracker, stream);
     if (rc) return rc;
   }
   BwdArgs a;
   a.ext_dc = (const float*)((const char*)scratch + CL.bwd_dc);
   a.ext_dp = (const float*)((const char*)scratch + CL.bwd_dp);
+  a.ext_dwh = (const float*)((const char*)scratch + CL.bwd_dwh);
   a.prm = *prm;
   a.cloud = cloud_pos;
   a.rays_o = rays_o; a.rays_d = rays_d; a.gt_depth = gt_depth;

@@ -89,7 +89,7 @@ __global__ void bwd_prep_kernel(const float* __restrict__ blob, float* __restric
 }
 
 // ------------------------------------------------------------------------------------------------ ring program
-enum { K_DXW = 0, K_DXE = 1, K_DWH = 2, K_DWE = 3 };
+enum { K_DXW = 0, K_DXE = 1, K_DWH = 2, K_DWE = 3, K_DV1 = 4, K_DV2 = 5 };
 enum { RF_WAIT_A = 1, RF_WAIT_B = 2, RF_COMMIT_D0 = 4, RF_COMMIT_D1 = 8, RF_FIRST = 16 };
 struct ROp {             // 32 bytes; one ring chunk = one bulk-copied (two-part) fp32 block + the MMAs that consume it
   uint32_t src0, src1;   // float offsets: weights -> backward pack buffer; T-planes -> saved buffer (+ tile * stride)
@@ -101,7 +101,7 @@ struct ROp {             // 32 bytes; one ring chunk = one bulk-copied (two-part
   uint32_t pad2;
 };
 static_assert(sizeof(ROp) == 32, "ROp");
-constexpr int MAX_ROPS = 80;
+constexpr int MAX_ROPS = 128;
 
 constexpr int BNS = 2;                                   // ring stages
 constexpr int BCW = 16;                                  // compute warps
@@ -117,14 +117,18 @@ constexpr int ZT_LO = 4 * ZT_ATOM;
 constexpr int SB_DOUT = SB_ZT + 2 * ZT_LO;               // [128][4] d(colour logits)
 constexpr int SB_HAS = SB_DOUT + 128 * 16;
 constexpr int SB_DP = SB_HAS + 128 * 4;                  // [128][4]
-constexpr int SB_TAB = SB_DP + 128 * 16;                 // W_out [3][128] | P_out [3][32] | c_B [3][20]
-constexpr int TAB_WOUT = 0, TAB_POUT = 3 * HC, TAB_CB = TAB_POUT + 3 * CDIM, TAB_TOTAL = TAB_CB + 3 * EC + 4;
+constexpr int SB_DWH = SB_DP + 128 * 16;                 // [128][8] d(normalised IDW weight) of the rel-pos path (tracker)
+constexpr int SB_BREL = SB_DWH + 128 * KNN * 4;          // [32] per-tile partial of d B_rel
+constexpr int SB_TAB = SB_BREL + 32 * 4;           // W_out [3][128] | P_out [3][32] | c_B [3][20] | B_rel | v2
+constexpr int TAB_WOUT = 0, TAB_POUT = 3 * HC, TAB_CB = TAB_POUT + 3 * CDIM, TAB_BREL = TAB_CB + 3 * EC + 4, TAB_V2B = TAB_BREL + 32,
+              TAB_TOTAL = TAB_V2B + CDIM;   // ... | rel-pos Fourier matrix [3][10] | v2 bias [32]
 constexpr int SB_PIPE = SB_TAB + TAB_TOTAL * 4;
 constexpr int BWD_UMMA_SMEM = SB_PIPE + 256;
+static_assert(2 * BNCT == 128 * KNN, "sDWh zeroing");
 static_assert(BWD_UMMA_SMEM <= 232448, "shared memory budget");
 static_assert(SB_ZT % 1024 == 0 && ZT_ATOM % 1024 == 0, "swizzle atoms need 1024-byte alignment");
 static_assert(HC * (HC + 4) * 4 + 80 * HC * 4 <= 2 * ZT_LO, "weight-gradient staging image fits the Z^T region");
-constexpr uint32_t TMB_ZHI = 0, TMB_ZLO = 128, TMB_G = 256, TMB_EX = 384;
+constexpr uint32_t TMB_ZHI = 0, TMB_ZLO = 128, TMB_G = 256, TMB_V1 = 320, TMB_EX = 384;
 constexpr uint32_t SW128_HIWORD = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
 
 struct BPipe {
@@ -148,6 +152,13 @@ struct TrunkArgs {
   float* acc;              // [5][80][128] + M_out [3][40]
   float* d_w;
   float *out_dc, *out_dp;  // [Pp][32], [Pp][4]
+  float* out_dwh;          // [Pp][8] d(normalised IDW weight) from the rel-pos path (tracker)
+  float* out_dqt;          // [tile][8][20][128] d[sin | cos] of the rel-pos Fourier features (-> relpos_trig_bwd_kernel)
+  const float* cloud;      // rel-pos: neighbour positions
+  const float4* knn_pos;   // forward scratch: sample positions (px, py, pz, z)
+  const int32_t* remap;
+  float* d_col;
+  int is_tracker;
   int gflags;
   int ntiles, rays_per_tile;
   int n_ops;
@@ -189,6 +200,11 @@ __device__ __forceinline__ void mma_ss2(uint32_t d, uint32_t a_lo, uint32_t a_hi
 __device__ __forceinline__ void bulk_prefetch_l2(const void* gmem, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gmem), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};\n" ::"r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(addr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -203,6 +219,8 @@ __global__ void __launch_bounds__(BT, 1) trunk_bwd_umma_kernel(const __grid_cons
   int* sHas = reinterpret_cast<int*>(smem + SB_HAS);
   float* sDP = reinterpret_cast<float*>(smem + SB_DP);
   float* sTab = reinterpret_cast<float*>(smem + SB_TAB);
+  float* sDWh = reinterpret_cast<float*>(smem + SB_DWH);
+  float* sBrel = reinterpret_cast<float*>(smem + SB_BREL);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = a.prm.n_surface;
@@ -211,6 +229,9 @@ __global__ void __launch_bounds__(BT, 1) trunk_bwd_umma_kernel(const __grid_cons
   const SavedLayout SL = saved_layout(a.R, S, LSR_STAGE_COLOR, a.prm.flags);
   const bool g_cw = (a.gflags & LSR_GRAD_COL_W) && a.d_w;
   const bool g_ry = (a.gflags & LSR_GRAD_RAYS) != 0;
+  const bool relpos = (a.prm.flags & LSR_FLAG_REL_POS) != 0;
+  const bool g_cf = (a.gflags & LSR_GRAD_COL_FEATS) && a.d_col;
+  const bool trk = a.is_tracker && g_ry;
   const bool g_af = (a.gflags & LSR_GRAD_AFFINE) && a.d_affine && a.prm.rgb_mode == LSR_RGB_AFFINE_SIGMOID;
 
   for (int i = tid; i < TAB_TOTAL; i += BT) {
@@ -218,6 +239,8 @@ __global__ void __launch_bounds__(BT, 1) trunk_bwd_umma_kernel(const __grid_cons
     if (i < TAB_POUT) v = blob[a.w.c_out_w + i];
     else if (i < TAB_CB) v = a.pack[BWD_PACK_FLOATS_MAX - 128 + (i - TAB_POUT)];
     else if (i < TAB_CB + 3 * EC) v = blob[a.w.c_B + (i - TAB_CB)];
+    else if (i >= TAB_BREL && i < TAB_BREL + 3 * ER && (a.prm.flags & LSR_FLAG_REL_POS)) v = blob[a.w.c_Brel + (i - TAB_BREL)];
+    else if (i >= TAB_V2B && (a.prm.flags & LSR_FLAG_REL_POS)) v = blob[a.w.c_nb2_b + (i - TAB_V2B)];
     sTab[i] = v;
   }
   if (warp == W_ISSUER) tmem_alloc(&pipe->tmem_base, 512);
@@ -351,15 +374,22 @@ __global__ void __launch_bounds__(BT, 1) trunk_bwd_umma_kernel(const __grid_cons
         } else {
           // row-contracted: D[out][feature] (+)= Z^T (atom column q, resident) . X^T (ring chunk); both operands
           // 128-byte-swizzled K-major with K = rows; K = 8 rows = 32 bytes inside the 128-byte line.
-          const uint32_t d = tb + (kind == K_DWH ? TMB_G : TMB_EX);
+          // K_DV2 has the roles swapped: A = ring chunk (u^T, 128 lines), B = the resident image (dC^T, 32 lines).
+          const uint32_t d = tb + (kind == K_DWH ? TMB_G : kind == K_DV1 ? TMB_V1 : TMB_EX);
           const uint32_t zh0 = ((zt_addr + q * ZT_ATOM) >> 4) & 0x3fffu, zl0 = ((zt_addr + ZT_LO + q * ZT_ATOM) >> 4) & 0x3fffu;
+          const bool swap = kind == K_DV2;
           if (elect_one()) {
             uint32_t rh = (st_hi >> 4) & 0x3fffu, zh = zh0, zl = zl0;
             uint32_t acc = acc0;
 #pragma unroll
             for (int k8 = 0; k8 < 4; ++k8) {
-              mma_ss2(d, zl, SW128_HIWORD, rh, SW128_HIWORD, idesc, acc);
-              mma_ss2(d, zh, SW128_HIWORD, rh, SW128_HIWORD, idesc, 1u);
+              if (swap) {
+                mma_ss2(d, rh, SW128_HIWORD, zl, SW128_HIWORD, idesc, acc);
+                mma_ss2(d, rh, SW128_HIWORD, zh, SW128_HIWORD, idesc, 1u);
+              } else {
+                mma_ss2(d, zl, SW128_HIWORD, rh, SW128_HIWORD, idesc, acc);
+                mma_ss2(d, zh, SW128_HIWORD, rh, SW128_HIWORD, idesc, 1u);
+              }
               acc = 1u; rh += 2; zh += 2; zl += 2;
             }
           }
@@ -370,7 +400,8 @@ __global__ void __launch_bounds__(BT, 1) trunk_bwd_umma_kernel(const __grid_cons
             uint32_t rl = (st_lo >> 4) & 0x3fffu, zh = zh0;
 #pragma unroll
             for (int k8 = 0; k8 < 4; ++k8) {
-              mma_ss2(d, zh, SW128_HIWORD, rl, SW128_HIWORD, idesc, 1u);
+              if (swap) mma_ss2(d, rl, SW128_HIWORD, zh, SW128_HIWORD, idesc, 1u);
+              else mma_ss2(d, zh, SW128_HIWORD, rl, SW128_HIWORD, idesc, 1u);
               rl += 2; zh += 2;
             }
           }
@@ -414,6 +445,9 @@ __global__ void __launch_bounds__(BT, 1) trunk_bwd_umma_kernel(const __grid_cons
 
       // ---------------------------------------------------------------- per-row state + compositing backward
       if (warp == 0) TRC(2, 0);
+      sDWh[tid] = 0.f;
+      sDWh[tid + BNCT] = 0.f;
+      if (tid < 32) sBrel[tid] = 0.f;
       float4 h_rgbs = make_float4(0.f, 0.f, 0.f, 0.f), h_raw = make_float4(0.f, 0.f, 0.f, 0.f);
       if (tid < 128) {   // all per-row loads of the head in flight together (one DRAM round trip)
         float4 mi = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -623,6 +657,10 @@ __global__ void __launch_bounds__(BT, 1) trunk_bwd_umma_kernel(const __grid_cons
       for (int l = 4; l >= 0; --l) {
         // ---- A: Z_l = G_l * softplus'(s_l) -> TMEM (hi, lo); kept in g[] for the transposed copy
         if (warp == 0) TRC(1, (4 - l) * 10 + 0);
+        if (l >= 1) {   // DRAM -> L2 one layer ahead: s_{l-1} (epilogue loads) and h_{l-2} (row-contraction pieces of layer l - 1)
+          prefetch_l2(sv + SL.cst + ((size_t)(l - 1) * SL.ntiles + tile) * tplane_tile_floats(HC) + (size_t)tid * 32);
+          if (g_cw && l >= 2) prefetch_l2(sv + SL.cht + ((size_t)(l - 2) * SL.ntiles + tile) * tplane_tile_floats(HC) + (size_t)tid * 32);
+        }
         {
           const float* tps = sv + SL.cst + ((size_t)l * SL.ntiles + tile) * tplane_tile_floats(HC) + tq * (HC * 32) + (tj & 3);
 #pragma unroll
@@ -723,6 +761,176 @@ __global__ void __launch_bounds__(BT, 1) trunk_bwd_umma_kernel(const __grid_cons
         o[0] = make_float4(dCacc[0], dCacc[1], dCacc[2], dCacc[3]);
         o[1] = make_float4(dCacc[4], dCacc[5], dCacc[6], dCacc[7]);
       }
+      // ---------------------------------------------------------------- rel-pos neighbour MLP backward (decoder.py:307-323,477-488)
+      //   c = V2 u + v2 sum_k w_k,  u = sum_k w_k softplus(V1 q_k + v1),  q_k = [sin(phi_k) | cos(phi_k) | F^c[I_k]],  phi_k = 2 pi (x_{I_k} - p) B_r
+      if (relpos) {
+        const size_t prow = p0 + row;
+        const bool has = sHas[row] != 0;
+        prefetch_l2(sv + SL.spt + ((size_t)tile * KNN) * tplane_tile_floats(HC) + (size_t)tid * 32);
+        if (tid < TP_Q * 4) prefetch_l2(sv + SL.qt + ((size_t)tile * KNN) * tplane_tile_floats(TP_Q) + (size_t)tid * 32);
+        if (g_cw) prefetch_l2(sv + SL.ut + (size_t)tile * tplane_tile_floats(HC) + (size_t)tid * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (!has || !rv) dCacc[j] = 0.f;    // rows without neighbours do not reach the features (decoder.py:489-490)
+        {   // dC -> TMEM A operand (K = 32) of dU = dC V2, and (weights train) dC^T -> row-contraction operand of dV2 = dC^T u
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) split_hi_lo(dCacc[j], hi[j], lo[j]);
+          tmem_st8(tmem_addr(tb, lane_base, TMB_ZHI + 8 * cg), hi);
+          tmem_st8(tmem_addr(tb, lane_base, TMB_ZLO + 8 * cg), lo);
+          if (g_cw) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = 8 * cg + j;
+              uint8_t* pz = zt_row + c * 128 + ((tchunk ^ (j & 7)) << 4);
+              *reinterpret_cast<uint32_t*>(pz) = __float_as_uint(dCacc[j]);
+              *reinterpret_cast<uint32_t*>(pz + ZT_LO) = lo[j];
+            }
+            // d v2 = sum_r dC[r] * sum_k w_k[r]
+            const float ws = rv ? reinterpret_cast<const float4*>(sv + SL.misc)[prow].z : 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float v = dCacc[j] * ws;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+              if (lane == 0) atomicAdd(a.d_w + a.w.c_nb2_b + 8 * cg + j, v);
+            }
+          }
+        }
+        signal(&pipe->a_ready);
+        if (g_cw) signal(&pipe->b_ready);
+        float rt = 0.f;   // tracker: d w_hat_k += dC . v2 for every listed neighbour
+        if (trk) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rt = fmaf(dCacc[j], sTab[TAB_V2B + 8 * cg + j], rt);
+        }
+        // dU = dC V2: this thread's 32 hidden columns, kept for all 8 neighbours
+        wait_d(0);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t x[16];
+          tmem_ld16(tmem_addr(tb, lane_base, TMB_G + 32 * cg + 16 * h), x);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) g[16 * h + j] = __uint_as_float(x[j]);
+        }
+        if (g_cw) {   // dV2^T[hid][c] (lane = hid, columns = c): coalesced over the lanes for every c
+          wait_d(1);
+          uint32_t x[8];
+          tmem_ld8(tmem_addr(tb, lane_base, TMB_EX + 8 * cg), x);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) red_add_f32(a.d_w + a.w.c_nb2_w + (size_t)(8 * cg + j) * HC + row, __uint_as_float(x[j]));
+        }
+        // Z_k = w_k dU * softplus'(.) for one neighbour: values in zk[], d w_hat_k partial = dU . softplus_k
+        float zk[32];
+        int idx = -1;
+        auto compute_z = [&](int k) {
+          if (k + 1 < KNN) {   // DRAM -> L2: what round k + 1 reads (512 + 256 lines: one or two per thread)
+            prefetch_l2(sv + SL.spt + ((size_t)tile * KNN + k + 1) * tplane_tile_floats(HC) + (size_t)tid * 32);
+            if (tid < TP_Q * 4) prefetch_l2(sv + SL.qt + ((size_t)tile * KNN + k + 1) * tplane_tile_floats(TP_Q) + (size_t)tid * 32);
+          }
+          const float wk = rv ? sv[SL.w + prow * KNN + k] : 0.f;
+          const int idk = rv ? reinterpret_cast<const int*>(sv + SL.idx)[prow * KNN + k] : -1;
+          const float* tsp = sv + SL.spt + ((size_t)tile * KNN + k) * tplane_tile_floats(HC) + tq * (HC * 32) + (tj & 3);
+          float part = 0.f;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float sp16[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sp16[j] = __ldcs(tsp + (32 * cg + 16 * h + j) * 32 + ((tchunk ^ (j & 7)) << 2));
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float du = g[16 * h + j];
+              part = fmaf(du, sp16[j], part);
+              zk[16 * h + j] = wk * du * softplus100_grad_from_out(sp16[j]);
+            }
+          }
+          if (trk && idk >= 0) atomicAdd(&sDWh[row * KNN + k], part + rt);
+          return idk;
+        };
+        int idx_next = compute_z(0);
+#pragma unroll 1
+        for (int k = 0; k < KNN; ++k) {
+          if (warp == 0) TRC(2, 16 + 6 * k);
+          idx = idx_next;
+          // ---- Z_k -> TMEM (A of dQ_k = Z_k V1); the accumulator columns of dQ_{k-1} were read at the end of the last round
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) split_hi_lo(zk[16 * h + j], hi[j], lo[j]);
+            tmem_st16(tmem_addr(tb, lane_base, TMB_ZHI + 32 * cg + 16 * h), hi);
+            tmem_st16(tmem_addr(tb, lane_base, TMB_ZLO + 32 * cg + 16 * h), lo);
+          }
+          signal(&pipe->a_ready);
+          if (warp == 0) TRC(2, 16 + 6 * k + 1);
+          if (g_cw) {                             // Z_k^T for dV1 += Z_k^T Q_k, once the previous round's MMAs have read the old image
+            if (k > 0) wait_d(1);
+            if (warp == 0) TRC(2, 16 + 6 * k + 2);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              uint32_t hi, lo;
+              split_hi_lo(zk[j], hi, lo);
+              uint8_t* pz = zt_row + (32 * cg + j) * 128 + ((tchunk ^ (j & 7)) << 4);
+              *reinterpret_cast<uint32_t*>(pz) = __float_as_uint(zk[j]);
+              *reinterpret_cast<uint32_t*>(pz + ZT_LO) = lo;
+            }
+            signal(&pipe->b_ready);
+          }
+          if (warp == 0) TRC(2, 16 + 6 * k + 3);
+          // ---- next round's Z values, computed while this round's MMAs run
+          if (k + 1 < KNN) idx_next = compute_z(k + 1);
+          // ---- dQ_k = Z_k V1: columns [0,20) -> Fourier / pose / B_rel, [20,52) -> the neighbour's colour feature row
+          wait_d(0);
+          if (warp == 0) TRC(2, 16 + 6 * k + 4);
+          if (cg == 0) {
+            // columns [0,20): gradients of [sin(phi_k) | cos(phi_k)].  Their chain rule (sincos recompute, d B_rel, pose part) is
+            // elementwise work with gathers and reductions: it runs in relpos_trig_bwd_kernel at full occupancy; here only
+            // a coalesced store (lane = row)
+            uint32_t x[16], y[8];
+            tmem_ld16(tmem_addr(tb, lane_base, TMB_G), x);
+            tmem_ld8(tmem_addr(tb, lane_base, TMB_G + 16), y);
+            tmem_wait_ld();
+            if (g_cw || g_ry) {
+              float* dq = a.out_dqt + (((size_t)tile * KNN + k) * (2 * ER)) * 128 + row;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) dq[j * 128] = __uint_as_float(x[j]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dq[(16 + j) * 128] = __uint_as_float(y[j]);
+            }
+          } else if (cg <= 2) {
+            // feature columns 20 + 16 (cg - 1) .. + 15, fetched as the two aligned 16-column blocks around them
+            uint32_t x[32];
+            tmem_ld16(tmem_addr(tb, lane_base, TMB_G + 16 * cg), *reinterpret_cast<uint32_t(*)[16]>(&x[0]));
+            tmem_ld16(tmem_addr(tb, lane_base, TMB_G + 16 * cg + 16), *reinterpret_cast<uint32_t(*)[16]>(&x[16]));
+            tmem_wait_ld();
+            if (g_cf && idx >= 0) {
+              float* dst = grad_row(a.d_col, a.remap, idx);
+              if (dst) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                  red_add_v4(dst + 16 * (cg - 1) + j, __uint_as_float(x[4 + j]), __uint_as_float(x[5 + j]), __uint_as_float(x[6 + j]),
+                             __uint_as_float(x[7 + j]));
+              }
+            }
+          }
+          tc_fence_before();
+          if (warp == 0) TRC(2, 16 + 6 * k + 5);
+        }
+        if (g_cw) {   // dV1^T[hid][q] accumulated over the 8 neighbours: lane = hid, columns = q (52) | bias | pad
+          wait_d(1);
+          float* stg = reinterpret_cast<float*>(smem + SB_ZT);            // [128 hid][68]: coalesced rows of d V1 afterwards
+          uint32_t x[16];
+          tmem_ld16(tmem_addr(tb, lane_base, TMB_V1 + 16 * cg), x);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) stg[row * 68 + 16 * cg + j] = __uint_as_float(x[j]);
+          bar_compute_b();
+          for (int e = tid; e < HC * QD; e += BNCT) red_add_f32(a.d_w + a.w.c_nb1_w + e, stg[(e / QD) * 68 + e % QD]);
+          if (tid < HC) red_add_f32(a.d_w + a.w.c_nb1_b + tid, stg[tid * 68 + QD]);
+          bar_compute_b();
+        }
+      }
       if (g_ry) {   // e' = [sin(arg) | cos(arg)], arg_j = 2 pi p . B_j  (decoder.py:34-43)
         const float* tpe = sv + SL.ect + (size_t)tile * tplane_tile_floats(ECC) + tq * (ECC * 32) + (tj & 3);
         float q0 = 0.f, q1 = 0.f, q2 = 0.f;
@@ -747,12 +955,74 @@ __global__ void __launch_bounds__(BT, 1) trunk_bwd_umma_kernel(const __grid_cons
       if (warp == 0) TRC(2, 3);
       if (g_ry && tid < nrows)
         reinterpret_cast<float4*>(a.out_dp)[p0 + tid] = make_float4(sDP[tid * 4 + 0], sDP[tid * 4 + 1], sDP[tid * 4 + 2], 0.f);
+      if (trk && relpos) {
+        for (int i = tid; i < nrows * KNN; i += BNCT) a.out_dwh[p0 * KNN + i] = sDWh[i];
+      }
       bar_compute_b();
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == W_ISSUER) tmem_dealloc(tb, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ rel-pos Fourier backward
+// q_k[0:20] = [sin(phi_k) | cos(phi_k)], phi_k = 2 pi (x_{I_k} - p) B_r (decoder.py:34-43,477-480).  Given d q_k[0:20] from the
+// tcgen05 kernel: d phi_j = dsin_j cos_j - dcos_j sin_j;  d B_r[c][j] += t_c d phi_j (t = 2 pi (x - p));  d p -= 2 pi B_r d phi.
+// One block per (tile, neighbour), one thread per sample row (sincos recomputed exactly as the forward does).
+struct TrigArgs {
+  const float* saved; const float* dqt; const float4* knn_pos; const float* cloud; const float* blob;
+  int brel; int R, S, rays_per_tile; int flags; int want_w, want_p;
+  float* d_w; float* out_dp;
+};
+__global__ void __launch_bounds__(128) relpos_trig_bwd_kernel(const __grid_constant__ TrigArgs a) {
+  const SavedLayout SL = saved_layout(a.R, a.S, LSR_STAGE_COLOR, a.flags);
+  __shared__ float sB[3 * ER];
+  __shared__ float sRed[4][3 * ER];
+  const int tile = blockIdx.x, k = blockIdx.y, row = threadIdx.x, lane = row & 31, warp = row >> 5;   // block = (tile, neighbour)
+  if (row < 3 * ER) sB[row] = a.blob[a.brel + row];
+  __syncthreads();
+  const int r0 = tile * a.rays_per_tile;
+  const int nrows = min(a.rays_per_tile, a.R - r0) * a.S;
+  const size_t p0 = (size_t)r0 * a.S;
+  float dB[3 * ER];
+#pragma unroll
+  for (int i = 0; i < 3 * ER; ++i) dB[i] = 0.f;
+  if (row < nrows) {
+    const int idx = reinterpret_cast<const int*>(a.saved + SL.idx)[(p0 + row) * KNN + k];
+    if (idx >= 0) {
+      const float4 pp = a.knn_pos[p0 + row];
+      const float t0 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 0), pp.x);
+      const float t1 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 1), pp.y);
+      const float t2 = TWO_PI_F * __fsub_rn(__ldg(a.cloud + 3 * (size_t)idx + 2), pp.z);
+      const float* dq = a.dqt + (((size_t)tile * KNN + k) * (2 * ER)) * 128 + row;
+      float q0 = 0.f, q1 = 0.f, q2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < ER; ++j) {
+        const float arg = fmaf(t2, sB[2 * ER + j], fmaf(t1, sB[ER + j], t0 * sB[j]));
+        float sn, cs;
+        sincos_ff(arg, &sn, &cs);
+        const float dphi = dq[j * 128] * cs - dq[(ER + j) * 128] * sn;
+        dB[j] = t0 * dphi; dB[ER + j] = t1 * dphi; dB[2 * ER + j] = t2 * dphi;
+        q0 = fmaf(sB[j], dphi, q0); q1 = fmaf(sB[ER + j], dphi, q1); q2 = fmaf(sB[2 * ER + j], dphi, q2);
+      }
+      if (a.want_p) {   // rel = x - p; the 8 neighbour blocks of a row add into the same slot
+        float* o = a.out_dp + (p0 + row) * 4;
+        atomicAdd(o + 0, -TWO_PI_F * q0); atomicAdd(o + 1, -TWO_PI_F * q1); atomicAdd(o + 2, -TWO_PI_F * q2);
+      }
+    }
+  }
+  if (a.want_w) {
+#pragma unroll
+    for (int i = 0; i < 3 * ER; ++i) {
+      float v = dB[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) sRed[warp][i] = v;
+    }
+    __syncthreads();
+    if (row < 3 * ER) atomicAdd(a.d_w + a.brel + row, (sRed[0][row] + sRed[1][row]) + (sRed[2][row] + sRed[3][row]));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ finalize
@@ -801,18 +1071,19 @@ __global__ void __launch_bounds__(HC) trunk_bwd_finalize_kernel(const float* __r
 }
 
 // ------------------------------------------------------------------------------------------------ host
-static int add_bjob(BJobs& J, int type, int wsrc, int ld, int col0, int u, int n0, int n_valid, int n_pad, int kc, int dst) {
+static int add_bjob(BJobs& J, int type, int wsrc, int ld, int col0, int u, int n0, int n_valid, int n_pad, int kc, int dst,
+                    int k_total = HC) {
   if (J.n >= MAX_BJOBS) return -1;
   BJob& j = J.j[J.n++];
   j.type = type; j.w = wsrc; j.ld = ld; j.col0 = col0; j.u = u; j.n0 = n0; j.n_valid = n_valid; j.n_pad = n_pad;
-  j.k_total = HC; j.kc = kc; j.dst = dst;
+  j.k_total = k_total; j.kc = kc; j.dst = dst;
   return 0;
 }
 
 struct TrunkProgram { ROp ops[MAX_ROPS]; int n_ops; BJobs jobs; int pack_floats; };
 
 // The ring program of one tile + the weight re-layout jobs.  Mirrors the epilogue code of trunk_bwd_umma_kernel.
-static void build_trunk_program(const LsrWeights* w, const SavedLayout& SL, bool g_cw, TrunkProgram* P) {
+static void build_trunk_program(const LsrWeights* w, const SavedLayout& SL, bool g_cw, bool relpos, TrunkProgram* P) {
   P->n_ops = 0;
   P->jobs.n = 0;
   int pk = 0;
@@ -877,6 +1148,30 @@ static void build_trunk_program(const LsrWeights* w, const SavedLayout& SL, bool
       first_dw = false;
     }
   }
+  if (relpos) {
+    // ---- rel-pos neighbour MLP: dU = dC V2 (K = 32), dV2^T = u^T . dC^T, then per neighbour dQ_k = Z_k V1 and dV1 += Z_k^T Q_k
+    add_bjob(P->jobs, 0, w->c_nb2_w, HC, 0, 0, 0, HC, HC, 32, pk, CDIM);          // B[n = hid][k = c] = V2[c][hid]
+    op(K_DXW, (uint32_t)pk, 0, HC * 32 * 4, 0, 0, 0, RF_WAIT_A | RF_FIRST | RF_COMMIT_D0, 4, 0, HC);
+    pk += HC * 32;
+    if (g_cw) {
+      for (int q = 0; q < 4; ++q)
+        op(K_DV2, (uint32_t)(SL.ut + q * (HC * 32)), tile_h, HC * 128, 0, 0, 0,
+           (q == 0 ? RF_WAIT_B | RF_FIRST : 0) | (q == 3 ? RF_COMMIT_D1 : 0), 4, q, CDIM);
+    }
+    const int v1t = pk;
+    add_bjob(P->jobs, 0, w->c_nb1_w, QD, 0, 0, 0, QD, 64, 64, pk, HC);             // B[n = q][k = hid] = V1[hid][q]
+    pk += 64 * HC;
+    const uint32_t tile_q = (uint32_t)tplane_tile_floats(TP_Q);
+    for (int k = 0; k < KNN; ++k) {
+      op(K_DXW, (uint32_t)v1t, 0, 64 * 64 * 4, 0, 0, 0, RF_WAIT_A | RF_FIRST, 8, 0, 64);
+      op(K_DXW, (uint32_t)(v1t + 64 * 64), 0, 64 * 64 * 4, 0, 0, 0, RF_COMMIT_D0, 8, 8, 64);
+      if (g_cw) {
+        for (int q = 0; q < 4; ++q)
+          op(K_DV1, (uint32_t)(SL.qt + (size_t)k * tile_q + q * (TP_Q * 32)), KNN * tile_q, TP_Q * 128, 0, 0, 0,
+             (q == 0 ? RF_WAIT_B : 0) | ((k == 0 && q == 0) ? RF_FIRST : 0) | (q == 3 ? RF_COMMIT_D1 : 0), 4, q, 64);
+      }
+    }
+  }
   P->pack_floats = pk;
   P->jobs.pout_dst = BWD_PACK_FLOATS_MAX - 128;
   P->jobs.w_out = w->c_out_w;
@@ -889,14 +1184,16 @@ int sm_count();
 // Fourier part of dL/dp (out_dp) per sample row for the remaining (rel-pos / geometry) backward.
 int launch_trunk_bwd(const LsrParams* prm, const LsrWeights* w, const float* gt_depth, int64_t n_rays, const float* affine,
                      const void* saved, void* scratch, const float* g_depth, const float* g_var, const float* g_rgb, int grad_flags,
-                     float* d_weights, float* d_affine, cudaStream_t stream) {
+                     float* d_weights, float* d_affine, const float* cloud_pos, const int32_t* row_remap, float* d_col_feats,
+                     int is_tracker, cudaStream_t stream) {
   const SavedLayout SL = saved_layout(n_rays, prm->n_surface, LSR_STAGE_COLOR, prm->flags);
   const ScratchLayout CL = scratch_layout(n_rays, prm->n_surface);
   if (SL.total >= (1ull << 32)) return LSR_ERR_UNSUPPORTED;   // ROp offsets are 32-bit float indices
   char* sbase = (char*)scratch;
   const bool g_cw = (grad_flags & LSR_GRAD_COL_W) && d_weights;
   static TrunkProgram P;   // host scratch (calls are serialised per process by the GIL / caller)
-  build_trunk_program(w, SL, g_cw, &P);
+  const bool relpos = (prm->flags & LSR_FLAG_REL_POS) != 0;
+  build_trunk_program(w, SL, g_cw, relpos, &P);
   if (P.pack_floats > BWD_PACK_FLOATS_MAX - 128 || P.n_ops > MAX_ROPS) return LSR_ERR_UNSUPPORTED;
   float* pack = (float*)(sbase + CL.bwd_pack);
   float* acc = (float*)(sbase + CL.bwd_acc);
@@ -920,6 +1217,13 @@ int launch_trunk_bwd(const LsrParams* prm, const LsrWeights* w, const float* gt_
   a.d_w = d_weights;
   a.out_dc = (float*)(sbase + CL.bwd_dc);
   a.out_dp = (float*)(sbase + CL.bwd_dp);
+  a.out_dwh = (float*)(sbase + CL.bwd_dwh);
+  a.out_dqt = (float*)(sbase + CL.bwd_dqt);
+  a.cloud = cloud_pos;
+  a.knn_pos = (const float4*)(sbase + CL.knn_pos);
+  a.remap = row_remap;
+  a.d_col = d_col_feats;
+  a.is_tracker = is_tracker;
   a.gflags = grad_flags;
   a.ntiles = SL.ntiles;
   a.rays_per_tile = SL.rays_per_tile;
@@ -932,6 +1236,16 @@ int launch_trunk_bwd(const LsrParams* prm, const LsrWeights* w, const float* gt_
   trunk_bwd_umma_kernel<<<grid, BT, BWD_UMMA_SMEM, stream>>>(a);
   LSR_LAUNCHED(1);
   LSR_CUDA_CHECK(cudaGetLastError());
+  if (relpos && (g_cw || (grad_flags & LSR_GRAD_RAYS))) {
+    TrigArgs t;
+    t.saved = (const float*)saved; t.dqt = a.out_dqt; t.knn_pos = a.knn_pos; t.cloud = cloud_pos; t.blob = w->blob;
+    t.brel = w->c_Brel; t.R = (int)n_rays; t.S = prm->n_surface; t.rays_per_tile = SL.rays_per_tile; t.flags = prm->flags;
+    t.want_w = g_cw ? 1 : 0; t.want_p = (grad_flags & LSR_GRAD_RAYS) ? 1 : 0;
+    t.d_w = d_weights; t.out_dp = a.out_dp;
+    relpos_trig_bwd_kernel<<<dim3(a.ntiles, KNN), 128, 0, stream>>>(t);
+    LSR_LAUNCHED(1);
+    LSR_CUDA_CHECK(cudaGetLastError());
+  }
   if (g_cw) {
     trunk_bwd_finalize_kernel<<<dim3(CDIM + 3, 5), HC, 0, stream>>>(w->blob, acc, d_weights, *w);
     LSR_LAUNCHED(1);
@@ -949,7 +1263,7 @@ extern "C" int lsr_debug_trace(long long* out) {
 }
 extern "C" int lsr_debug_trace_ops(const LsrWeights* w, int64_t n_rays, int S, int flags, int g_cw, unsigned char* kinds) {
   static lsr::TrunkProgram P;
-  lsr::build_trunk_program(w, lsr::saved_layout(n_rays, S, LSR_STAGE_COLOR, flags), g_cw != 0, &P);
+  lsr::build_trunk_program(w, lsr::saved_layout(n_rays, S, LSR_STAGE_COLOR, flags), g_cw != 0, (flags & LSR_FLAG_REL_POS) != 0, &P);
   for (int i = 0; i < P.n_ops; ++i) { kinds[2 * i] = P.ops[i].kind; kinds[2 * i + 1] = P.ops[i].flags; }
   return P.n_ops;
 }

@@ -503,6 +503,19 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
                 store_a_split1(smem + SM_Q_HI, smem + SM_Q_LO, m, grp * NJ + j, sn[j]);
                 store_a_split1(smem + SM_Q_HI, smem + SM_Q_LO, m, ER + grp * NJ + j, cs[j]);
               }
+              if (save_full) {   // Q_k^T for the backward's row-contracted dV1 GEMM (lane = row: one line per store)
+                float* tq_ = a.saved + SL.qt + ((size_t)tile * KNN + k) * tplane_tile_floats(TP_Q);
+                const bool ok = m < nrows;
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                  tq_[tplane_off(TP_Q, m, grp * NJ + j)] = ok ? sn[j] : 0.f;
+                  tq_[tplane_off(TP_Q, m, ER + grp * NJ + j)] = ok ? cs[j] : 0.f;
+                }
+                if (grp == 0) {   // ones line (bias gradient) + zero padding up to 64 lines
+#pragma unroll
+                  for (int f = QD; f < TP_Q; ++f) tq_[tplane_off(TP_Q, m, f)] = (ok && f == QD) ? 1.f : 0.f;
+                }
+              }
             } else {
               // neighbour feature row of row m: q[20..51]; this thread: 8 / HG2 float4
               constexpr int NF = 8 / HG2;
@@ -517,13 +530,21 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
               }
 #pragma unroll
               for (int i = 0; i < NF; ++i) store_a_split(smem + SM_Q_HI, smem + SM_Q_LO, m, 2 * ER + (f0 + i) * 4, f[i]);
+              if (save_full) {
+                float* tq_ = a.saved + SL.qt + ((size_t)tile * KNN + k) * tplane_tile_floats(TP_Q);
+                const bool ok = m < nrows;
+#pragma unroll
+                for (int i = 0; i < NF; ++i) {
+                  const float fv[4] = {f[i].x, f[i].y, f[i].z, f[i].w};
+#pragma unroll
+                  for (int t = 0; t < 4; ++t) tq_[tplane_off(TP_Q, m, 2 * ER + (f0 + i) * 4 + t)] = ok ? fv[t] : 0.f;
+                }
+              }
             }
           };
           float uf[CPT];
 #pragma unroll
           for (int i = 0; i < CPT; ++i) uf[i] = 0.f;
-          // saved-activation staging of this warp: [32][20] floats inside the (still unused) e' region
-          float* st = reinterpret_cast<float*>(smem + SM_EC_HI) + warp * (32 * 20);
           build_q(0);
           es.signal_a(pipe);
 #pragma unroll 1
@@ -532,7 +553,8 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
             if (k + 1 < KNN) { build_q(k + 1); es.signal_a(pipe); }   // GEMM k+1 runs under this epilogue
             const uint32_t accb = (k & 1) ? TM_ACC1 : TM_ACC0;
             const float wk = sW[row * KNN + k];
-            float* sp = a.saved + SL.sp + (pw0 * KNN + k) * HC + CPT * cg;
+            float* tsp = a.saved + SL.spt + ((size_t)tile * KNN + k) * tplane_tile_floats(HC) + (row >> 5) * (HC * 32) + (row & 3);
+            const int tchunk_r = (row & 31) >> 2;
             uint32_t x[2][16];
             tmem_ld16(tmem_addr(tb, lane_base, accb + CPT * cg), x[0]);
             tmem_wait_ld();
@@ -547,24 +569,29 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
                 const float s2 = softplus100(__uint_as_float(xc[j + 2]) + bb.z), s3 = softplus100(__uint_as_float(xc[j + 3]) + bb.w);
                 uf[16 * c + j + 0] = fmaf(wk, s0, uf[16 * c + j + 0]); uf[16 * c + j + 1] = fmaf(wk, s1, uf[16 * c + j + 1]);
                 uf[16 * c + j + 2] = fmaf(wk, s2, uf[16 * c + j + 2]); uf[16 * c + j + 3] = fmaf(wk, s3, uf[16 * c + j + 3]);
-                stage_put<20>(st, lane, j, s0, s1, s2, s3);
+                if (save_full) {
+                  const float sv4[4] = {s0, s1, s2, s3};
+#pragma unroll
+                  for (int t = 0; t < 4; ++t)
+                    tsp[(CPT * cg + 16 * c + j + t) * 32 + ((tchunk_r ^ ((j + t) & 7)) << 2)] = rv ? sv4[t] : 0.f;
+                }
               }
-              stage_flush<16, 20>(st, lane, sp + 16 * c, (size_t)KNN * HC, wvalid);
               if (c + 1 < STEPS) tmem_wait_ld();
             }
           }
           // u -> TMEM A operand of the V2 GEMM
           {
-            float* ug = a.saved + SL.u + pw0 * HC + CPT * cg;
+            float* tu = a.saved + SL.ut + (size_t)tile * tplane_tile_floats(HC) + (row >> 5) * (HC * 32) + (row & 3);
+            const int tchunk_r = (row & 31) >> 2;
 #pragma unroll
             for (int c = 0; c < STEPS; ++c) {
               uint32_t hi[16], lo[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) split_hi_lo(uf[16 * c + j], hi[j], lo[j]);
+              if (save_full) {
 #pragma unroll
-              for (int j = 0; j < 16; j += 4)
-                stage_put<20>(st, lane, j, uf[16 * c + j], uf[16 * c + j + 1], uf[16 * c + j + 2], uf[16 * c + j + 3]);
-              stage_flush<16, 20>(st, lane, ug + 16 * c, (size_t)HC, wvalid);
+                for (int j = 0; j < 16; ++j) tu[(CPT * cg + 16 * c + j) * 32 + ((tchunk_r ^ (j & 7)) << 2)] = rv ? uf[16 * c + j] : 0.f;
+              }
               tmem_st16(tmem_addr(tb, lane_base, TM_AHI + CPT * cg + 16 * c), hi);
               tmem_st16(tmem_addr(tb, lane_base, TM_ALO + CPT * cg + 16 * c), lo);
             }

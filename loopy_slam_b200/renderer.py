@@ -89,7 +89,7 @@ def _grid_for(npc, cloud_pos, cell, cache):
 class _RenderCtx:
     """Per-call constants shared by forward and backward."""
     __slots__ = ('prm', 'grid', 'stage', 'is_tracker', 'blob', 'wstruct', 'flat', 'saved', 'scratch', 'R',
-                 'r_query', 'device', 'far_group', 'force_save', 'timing', 'remap', 'renderer', 'z_zero')
+                 'r_query', 'device', 'far_group', 'force_save', 'timing', 'remap', 'renderer', 'z_zero', 'grad_enabled')
 
 
 def _tick(timing):
@@ -149,9 +149,10 @@ class _RenderFn(torch.autograd.Function):
         var = torch.empty(R, dtype=torch.float32, device=dev)
         rgb = torch.empty(R, 3, dtype=torch.float32, device=dev)
         valid = torch.empty(R, dtype=torch.uint8, device=dev)
-        # needs_input_grad stays True under torch.no_grad(): without this test every no_grad render (render_img: 816 k rays)
+        # needs_input_grad stays True under torch.no_grad() (and grad mode is always off INSIDE Function.forward, so the caller's
+        # mode is captured in fused_render): without this test every no_grad render (render_img: 816 k rays)
         # would allocate and write the multi-KB-per-sample saved activations
-        need_bwd = (torch.is_grad_enabled() and any(ctx.needs_input_grad)) or rc.force_save
+        need_bwd = (rc.grad_enabled and any(ctx.needs_input_grad)) or rc.force_save
         sb, cb = ctypes.c_size_t(), ctypes.c_size_t()
         check(lib().lsr_render_workspace_bytes(ctypes.byref(rc.prm), R, rc.stage, ctypes.byref(sb), ctypes.byref(cb)),
               'lsr_render_workspace_bytes')
@@ -348,6 +349,7 @@ def fused_render(renderer, npc, decoders, rays_d, rays_o, stage, gt_depth, npc_g
     rc.device = dev
     rc.far_group = fgroup
     rc.force_save = bool(force_save)
+    rc.grad_enabled = torch.is_grad_enabled()
     rc.timing = getattr(renderer, '_timing', None)
     out = _RenderFn.apply(rc, rays_o, rays_d, gt, geo, col, affine, far, geo_leaf, col_leaf, *params)
     if return_ctx:

@@ -29,6 +29,9 @@ print('tile: start 0, state loaded %d, compositing %d, head act %d, out_linear F
 names = ['A0', 'A1', 'B-waited-d1', 'B-loaded', 'C-signalled-a', 'flush-issued', 'E-start(ZT written)', 'E-waited-d0', 'E-read', 'F-signalled-b']
 for li in range(5):
     print('layer', 4 - li, ' '.join(f'{n}:{T[1][li * 10 + k] - t0}' for k, n in enumerate(names)))
+print('rel-pos per neighbour k: start, a-signalled, d1-waited, b-signalled, d0-waited, end')
+for k in range(8):
+    print(' k', k, [T[2][16 + 6 * k + j] - t0 for j in range(6)])
 print('issuer ops (i: wait-start conv-ready issued) relative to tile start:')
 i = 0
 while T[0][3 * i] != 0 and i < 170:
