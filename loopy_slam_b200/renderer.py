@@ -234,9 +234,16 @@ class _RenderFn(torch.autograd.Function):
                                        ptr(d_o), ptr(d_d), stream_ptr(dev)), 'lsr_render_bwd')
         _tock(rc.timing, 'bwd', ev)
         rc.saved = None
+        # Parameters the rendered stage does not touch get NO gradient (None), exactly like autograd on the reference's
+        # graph: a zero tensor instead would make the caller's Adam create state for them (src/Mapper.py:524-541 puts the
+        # whole colour decoder into the optimiser while 40 % of the iterations render stage 'geometry'), and its bias
+        # correction would then be off when the colour stage starts (caught by tests/test_gpu_trajectory.py).
+        relpos = bool(rc.prm.flags & _lib.FLAG_REL_POS)
         pgrads = []
         for k, (off, n, t) in enumerate(zip(blob.offsets, blob.numels, ctx.param_shapes)):
-            if pneed[k] and d_w is not None:
+            field = blob.entries[k][0]
+            used = field.startswith('g_') or (rc.stage == 1 and (relpos or field not in ('c_Brel', 'c_nb1_w', 'c_nb1_b', 'c_nb2_w', 'c_nb2_b')))
+            if pneed[k] and d_w is not None and used:
                 pgrads.append(d_w[off:off + n].view(t))
             else:
                 pgrads.append(None)

@@ -110,7 +110,8 @@ def grad_ok(ours, truth64, oracle32, floor=1e-4):
 
 
 def run_case_cuda_vs_oracle(name, device='cuda:0', verbose=False):
-    g = Golden(name)
+    g = name if isinstance(name, Golden) else Golden(name)
+    name = g.name
     ours = run_cuda(g, device)
     o32, o64 = run_oracle(g, torch.float32), run_oracle(g, torch.float64)
     res = {'ok': True}

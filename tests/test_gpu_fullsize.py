@@ -117,3 +117,54 @@ def test_fullsize_depth_l1_vs_oracle(scene):
     rgb_l1 = (rgb - cr).abs()[m].mean().item()
     assert depth_l1 < 2e-5 and rgb_l1 < 2e-5, (depth_l1, rgb_l1)      # metres / colour units; sensor depth is 1-5 m
     assert torch.allclose(depth[m], dr[m], rtol=1e-4, atol=1e-6) and torch.allclose(rgb[m], cr[m], rtol=1e-4, atol=2e-5)
+
+
+def test_fullsize_gradients_vs_fp64_oracle(scene):
+    """every gradient sink of the full 4 936-ray / 2e5-point mapper step against the fp64
+    restatement, with the SURVEY 8c noise-aware bound (<= max(1e-4, 2 x the fp32 oracle's own error vs fp64)).
+    The oracle finishes in seconds at this size because its neighbour search is the C grid k-NN."""
+    from oracle import render as orc
+    from oracle.knn_c import GridKNN
+    from helpers import rel_l2
+    sc = scene
+    R = sc['o'].shape[0]
+    gen = torch.Generator().manual_seed(11)
+    up_d, up_c = torch.randn(R, generator=gen), torch.randn(R, 3, generator=gen)
+    model = sc['model']
+    for p in model.parameters():
+        p.requires_grad_(True)
+        p.grad = None
+    geo = sc['geo'].clone().requires_grad_(True)
+    col = sc['col'].clone().requires_grad_(True)
+    depth, var, rgb, valid = sc['rend'].render_batch_ray(NPC(), model, sc['d'], sc['o'], DEV, 'color', gt_depth=sc['g'],
+                                                         npc_geo_feats=geo, npc_col_feats=col, cloud_pos=sc['cloud'])
+    ((depth * up_d.to(DEV)).sum() + (rgb * up_c.to(DEV)).sum()).backward()
+    ours = {'geo': geo.grad.cpu(), 'col': col.grad.cpu()}
+    ours.update({k: p.grad.detach().cpu() for k, p in model.named_parameters() if p.grad is not None})
+    W0 = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    W0['color_decoder.embedder._B'] = model.color_decoder.embedder._B.detach().cpu().clone()
+    ocfg = orc.OracleCfg.from_cfg(sc['cfg'])
+    o, d, g, cloud = sc['o'].cpu(), sc['d'].cpu(), sc['g'].cpu(), sc['cloud'].cpu()
+    z = orc.sample_z(g, ocfg)
+    pts = (o[:, None, :] + d[:, None, :] * z[:, :, None]).reshape(-1, 3)
+    knn = GridKNN(cloud, 0.08).query(pts, ocfg.radius_query)
+    res = {}
+    for dt in (torch.float32, torch.float64):
+        Wl = {k: v.clone().requires_grad_(True) for k, v in W0.items()}
+        gf = sc['geo'].cpu().clone().requires_grad_(True)
+        cf = sc['col'].cpu().clone().requires_grad_(True)
+        dr, vr, cr, validr, _ = orc.render_rays(Wl, ocfg, o, d, g, gf, cf, cloud, 'color', knn=knn, dtype=dt)
+        ((dr * up_d.to(dt)).sum() + (cr * up_c.to(dt)).sum()).backward()
+        res[dt] = {'geo': gf.grad, 'col': cf.grad}
+        res[dt].update({k: v.grad for k, v in Wl.items() if v.grad is not None})
+    bad = {}
+    for k, truth in res[torch.float64].items():
+        if k not in ours or truth.abs().max() == 0:
+            continue
+        e_ours, e_orc = rel_l2(ours[k], truth), rel_l2(res[torch.float32][k], truth)
+        if not e_ours <= max(1e-4, 2 * e_orc):
+            bad[k] = (e_ours, e_orc)
+    for p in model.parameters():
+        p.requires_grad_(False)
+        p.grad = None
+    assert not bad, bad

@@ -65,7 +65,9 @@ def test_render_matches_reference_golden(name):
     assert torch.equal(ours['valid'].bool(), g.t('valid'))
     torch.testing.assert_close(ours['depth'], g.t('depth'), rtol=1e-4, atol=1e-6)
     torch.testing.assert_close(ours['rgb'], g.t('rgb'), rtol=1e-4, atol=1e-5)
-    torch.testing.assert_close(ours['var'], g.t('var'), rtol=1e-3, atol=1e-7)
+    # var = sum w (z - depth)^2 cancels two nearly equal 1e-2 m terms: 1e-4 relative on var needs ~1e-6 on depth, so the
+    # bound is rtol 1e-4 plus an absolute floor of 3e-8 m^2 (= (0.17 mm)^2, fp32 rounding of z - depth at 3 m)
+    torch.testing.assert_close(ours['var'], g.t('var'), rtol=1e-4, atol=3e-8)
     assert rel_l2(ours['g_geo'], g.t('g_geo_feats')) < 5e-4
     if g.stage == 'color':
         assert rel_l2(ours['g_col'], g.t('g_col_feats')) < 5e-4
@@ -199,8 +201,9 @@ def test_render_img_matches_tiled_oracle():
     d_ref = torch.cat([o[0] for o in outs]).reshape(H, W)
     c_ref = torch.cat([o[2] for o in outs]).reshape(H, W, 3)
     assert (d_img.cpu()[gt == 0] == 0).all()
-    torch.testing.assert_close(d_img.cpu().float(), d_ref, rtol=2e-4, atol=1e-5)
-    torch.testing.assert_close(c_img.cpu(), c_ref, rtol=2e-3, atol=2e-4)
+    # SURVEY 8c forward contract (rtol 1e-4); atol = 2e-5 colour units / 1e-5 m for values that cancel to ~0
+    torch.testing.assert_close(d_img.cpu().float(), d_ref, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(c_img.cpu(), c_ref, rtol=1e-4, atol=2e-5)
 
 
 def test_eval_points_matches_oracle_decode():
@@ -224,7 +227,9 @@ def test_eval_points_matches_oracle_decode():
     assert torch.equal(point_mask.cpu(), has)
     assert torch.equal(ray_mask.cpu(), o32['valid'])
     torch.testing.assert_close(raw.cpu()[has][:, :3], ref_raw[has][:, :3], rtol=1e-4, atol=1e-5)
-    torch.testing.assert_close(raw.cpu()[has][:, 3], ref_raw[has][:, 3], rtol=1e-3, atol=1e-3)
+    # occupancy logits: the pretrained geometry decoder produces logits of magnitude 1e2..1e3 from cancelling terms, so
+    # 1e-4 relative + an absolute floor of 2e-3 logit units (sigmoid(0.1 * x) changes by < 5e-5 for that)
+    torch.testing.assert_close(raw.cpu()[has][:, 3], ref_raw[has][:, 3], rtol=1e-4, atol=2e-3)
 
 
 def test_neural_point_cloud_insert_and_query():
@@ -321,6 +326,17 @@ def test_edge_cases_empty_and_tiny():
     (dep.sum() + rgb.sum()).backward()
     assert torch.isfinite(geo.grad).all() and geo.grad.abs().sum() > 0
     assert ((dep >= 0.98 * g - 1e-5) & (dep <= 1.02 * g + 1e-5)).all()
+
+
+@pytest.mark.parametrize('name,S', [('replica_color_mapper', 3), ('replica_color_tracker', 3), ('tum_color_mapper_dynr', 7)])
+def test_other_n_surface_parity(name, S):
+    """N_surface != 5 (tiles of floor(128 / S) rays): full forward + gradient parity against the fp32 / fp64 oracle, not
+    just finiteness (goldens only cover N_surface = 5)."""
+    import dataclasses
+    g = Golden(name)
+    g.ocfg = dataclasses.replace(g.ocfg, N_surface=S)
+    res = run_case_cuda_vs_oracle(g, DEV, verbose=True)
+    assert res['ok'], res
 
 
 @pytest.mark.gpu
