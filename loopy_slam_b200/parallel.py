@@ -88,10 +88,19 @@ class GradAllReducer:
         works, nbytes = [], 0
         covered = set()
         if grad_buffer is not None and grad_buffer.numel() > 0:
-            covered = {id(p) for p in self.params if self._inside(p.grad, grad_buffer)}
+            cov = [p for p in self.params if self._inside(p.grad, grad_buffer)]
+            covered = {id(p) for p in cov}
             if covered:
-                works.append(dist.all_reduce(grad_buffer, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
-                nbytes += grad_buffer.numel() * 4
+                # only the span of the buffer that holds .grad views travels: with the reference's index_put flow the
+                # buffer also carries the two TABLE-sized feature gradients (N x 32 each), which nobody owns as .grad
+                # (autograd gathers the leaf rows out of them) and which must not be exchanged
+                lo = min(p.grad.data_ptr() for p in cov)
+                hi = max(p.grad.data_ptr() + p.grad.numel() * 4 for p in cov)
+                a = (lo - grad_buffer.data_ptr()) // 4
+                b = (hi - grad_buffer.data_ptr()) // 4
+                span = grad_buffer[a:b]
+                works.append(dist.all_reduce(span, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+                nbytes += span.numel() * 4
         if len(covered) == len(self.params):
             for w in works:
                 w.wait()
@@ -137,3 +146,39 @@ def max_over_ranks(value, device):
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def render_img_sharded(renderer, npc, decoders, c2w, device, stage, gt_depth=None, npc_geo_feats=None, npc_col_feats=None,
+                       dynamic_r_query=None, cloud_pos=None, exposure_feat=None, group=None):
+    """Renderer.render_img (/root/reference/src/utils/Renderer.py:203-276: 816 k forward-only rays on Replica) with the
+    ray tiles sharded over the ranks and ONE all-gather of the per-ray outputs.  Shards are whole groups of
+    `ray_batch_size` rays, so the per-tile far statistic of zero-depth rays (Renderer.py:102-121) is computed on exactly
+    the same rays as on one GPU: the result is bit-identical to render_img.  -> depth (H,W) f64, unc (H,W) f64, colour."""
+    from .common import get_rays
+    from .renderer import fused_render
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world == 1:
+        return renderer.render_img(npc, decoders, c2w, device, stage, gt_depth=gt_depth, npc_geo_feats=npc_geo_feats,
+                                   npc_col_feats=npc_col_feats, dynamic_r_query=dynamic_r_query, cloud_pos=cloud_pos,
+                                   exposure_feat=exposure_feat)
+    with torch.no_grad():
+        H, W = renderer.H, renderer.W
+        n = H * W
+        rbs = renderer.ray_batch_size
+        groups = (n + rbs - 1) // rbs
+        per = (groups + world - 1) // world                      # ray groups per rank
+        lo, hi = min(rank * per * rbs, n), min((rank + 1) * per * rbs, n)
+        rays_o, rays_d = get_rays(H, W, renderer.fx, renderer.fy, renderer.cx, renderer.cy, c2w, device)
+        rays_o, rays_d = rays_o.reshape(-1, 3)[lo:hi], rays_d.reshape(-1, 3)[lo:hi]
+        dyn = dynamic_r_query.reshape(-1)[lo:hi] if (renderer.use_dynamic_radius and dynamic_r_query is not None) else None
+        gt = gt_depth.reshape(-1)[lo:hi] if gt_depth is not None else None
+        out = torch.zeros(per * rbs, 5, dtype=torch.float32, device=rays_o.device)     # depth | var | rgb, padded to the shard size
+        if hi > lo:
+            depth, var, rgb, _ = fused_render(renderer, npc, decoders, rays_d, rays_o, stage, gt, npc_geo_feats, npc_col_feats,
+                                              False, cloud_pos, dyn, exposure_feat, far_group=rbs)
+            out[:hi - lo, 0], out[:hi - lo, 1], out[:hi - lo, 2:] = depth, var, rgb
+        full = torch.empty(world * per * rbs, 5, dtype=torch.float32, device=out.device)
+        dist.all_gather_into_tensor(full, out, group=group)
+        full = full[:n]
+        return full[:, 0].double().reshape(H, W), full[:, 1].double().reshape(H, W), full[:, 2:].reshape(H, W, 3).contiguous()
