@@ -165,6 +165,15 @@ int lsr_sample_rays_bwd(const float* d_rays_o, const float* d_rays_d, const int6
 int lsr_pose_fwd(const float* cam7, float* c2w12, lsr_stream_t stream);
 int lsr_pose_bwd(const float* cam7, const float* d_c2w12, float* d_cam7, lsr_stream_t stream);
 
+/* Frustum feature selection (Mapper.get_mask_from_c2w, src/Mapper.py:165-217): mask_out[i] = 1 when point i projects
+ * inside the edge-cropped image of the frame with world-to-camera matrix w2c (3x4 row-major, 12 HOST doubles) and its
+ * camera depth lies in [0, bilinear sensor depth + 0.5] (zero lookups count as the maximum lookup).  scratch: device,
+ * lsr_frustum_scratch_bytes(n_points). */
+int lsr_frustum_scratch_bytes(int64_t n_points, size_t* bytes);
+int lsr_frustum_mask(const float* cloud_pos, int64_t n_points, const double* w2c12_host, const float* depth_img,
+                     int32_t H, int32_t W, double fx, double fy, double cx, double cy, int32_t edge, void* scratch,
+                     uint8_t* mask_out, lsr_stream_t stream);
+
 /* Per-frame dynamic radius maps (use_dynamic_radius, src/Tracker.py:243-258, src/Mapper.py:854-869):
  * grey -> Sobel magnitude -> clip to [0, thr] -> linear map on [0, 0.01, thr]; r_add / r_query are (H,W)
  * float64 like the reference's numpy path.  Exactly one of color_f32 / color_f64 ((H,W,3)) is non-NULL. */

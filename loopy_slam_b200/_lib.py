@@ -20,7 +20,7 @@ GRAD_GEO_FEATS, GRAD_COL_FEATS, GRAD_GEO_W, GRAD_GEO_B, GRAD_COL_W, GRAD_RAYS, G
 EXPORTS = [
     'lsr_version', 'lsr_strerror', 'lsr_device_sm_count', 'lsr_launch_count', 'lsr_grid_workspace_bytes', 'lsr_grid_build',
     'lsr_knn_query', 'lsr_sample_rays', 'lsr_sample_rays_filtered', 'lsr_sample_rays_bwd', 'lsr_pose_fwd', 'lsr_pose_bwd',
-    'lsr_render_workspace_bytes', 'lsr_far_bound', 'lsr_render_fwd', 'lsr_render_bwd', 'lsr_dynamic_radius',
+    'lsr_render_workspace_bytes', 'lsr_far_bound', 'lsr_render_fwd', 'lsr_render_bwd', 'lsr_dynamic_radius', 'lsr_frustum_scratch_bytes', 'lsr_frustum_mask',
     'lsr_loss_scratch_bytes', 'lsr_mapper_loss', 'lsr_tracker_resid', 'lsr_tracker_loss', 'lsr_debug_program_stats',
 ]
 
@@ -76,6 +76,8 @@ def lib():
                                                  ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]
         L.lsr_far_bound.argtypes = [vp, i64, i64, vp, vp]
         L.lsr_dynamic_radius.argtypes = [vp, vp, i32, i32, f64, f64, f64, f64, vp, vp, vp]
+        L.lsr_frustum_scratch_bytes.argtypes = [i64, ctypes.POINTER(ctypes.c_size_t)]
+        L.lsr_frustum_mask.argtypes = [vp, i64, ctypes.POINTER(ctypes.c_double), vp, i32, i32, f64, f64, f64, f64, i32, vp, vp, vp]
         L.lsr_render_fwd.argtypes = [ctypes.POINTER(LsrParams), vp, vp, i64, vp, vp, vp, vp, vp, i64, vp, i64, vp, vp,
                                      vp, vp, vp,
                                      ctypes.POINTER(LsrWeights), vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp]

@@ -209,9 +209,94 @@ __global__ void dynamic_radius_kernel(const T* __restrict__ color, int H, int W,
   r_query[o] = map(ratio * r_add_max, ratio * r_add_min);
 }
 
+// ------------------------------------------------------------------------------------------------ frustum selection
+// Mapper.get_mask_from_c2w (/root/reference/src/Mapper.py:165-217): project every neural point into the current frame
+// (x axis flipped, :188-189), look the sensor depth up bilinearly at (u, v) (cv2.remap INTER_LINEAR, constant 0 border),
+// replace zero lookups by the maximum lookup (:210-211), keep points inside the edge-cropped image whose camera depth
+// -z lies in [0, depth + 0.5].  Pass 1: projection + lookup + global max; pass 2: the mask.  float64 projection like the
+// reference (numpy float64 points, float32 c2w inverse promoted).
+struct FrustumArgs {
+  const float* cloud; int64_t n;
+  double w2c[12];
+  const float* depth; int H, W;
+  double fx, fy, cx, cy; int edge;
+  float* u; float* v; float* negz; float* ds; unsigned int* maxbits; uint8_t* mask;
+};
+__device__ __forceinline__ float depth_at(const float* __restrict__ d, int H, int W, int x, int y) {
+  return (x >= 0 && x < W && y >= 0 && y < H) ? d[(size_t)y * W + x] : 0.f;
+}
+__global__ void frustum_project_kernel(const __grid_constant__ FrustumArgs a) {
+  float lmax = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double px = a.cloud[3 * i], py = a.cloud[3 * i + 1], pz = a.cloud[3 * i + 2];
+    double cx_ = a.w2c[0] * px + a.w2c[1] * py + a.w2c[2] * pz + a.w2c[3];
+    const double cy_ = a.w2c[4] * px + a.w2c[5] * py + a.w2c[6] * pz + a.w2c[7];
+    const double cz_ = a.w2c[8] * px + a.w2c[9] * py + a.w2c[10] * pz + a.w2c[11];
+    cx_ = -cx_;                                                       // :188-189
+    const double z = cz_ + 1e-5;                                      // uv = K @ cam; z = uv[2] + 1e-5  (:190-191)
+    const float u = (float)((a.fx * cx_ + a.cx * cz_) / z), v = (float)((a.fy * cy_ + a.cy * cz_) / z);   // :192-193 (float32 maps)
+    // bilinear lookup, pixel centres at integer coordinates, zeros outside the image
+    const float fu = floorf(u), fv = floorf(v);
+    float dsv = 0.f;
+    if (isfinite(u) && isfinite(v) && fu >= -1.f && fv >= -1.f && fu <= (float)a.W && fv <= (float)a.H) {
+      const int x0 = (int)fu, y0 = (int)fv;
+      const float ax = u - fu, ay = v - fv;
+      const float d00 = depth_at(a.depth, a.H, a.W, x0, y0), d10 = depth_at(a.depth, a.H, a.W, x0 + 1, y0);
+      const float d01 = depth_at(a.depth, a.H, a.W, x0, y0 + 1), d11 = depth_at(a.depth, a.H, a.W, x0 + 1, y0 + 1);
+      dsv = (d00 * (1.f - ax) + d10 * ax) * (1.f - ay) + (d01 * (1.f - ax) + d11 * ax) * ay;
+    }
+    a.u[i] = u; a.v[i] = v; a.negz[i] = (float)(-z); a.ds[i] = dsv;
+    lmax = fmaxf(lmax, dsv);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(a.maxbits, __float_as_uint(lmax));     // depths >= 0: bit order == value order
+}
+__global__ void frustum_mask_kernel(const __grid_constant__ FrustumArgs a) {
+  const float dmax = __uint_as_float(*a.maxbits);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float u = a.u[i], v = a.v[i], nz = a.negz[i];
+    float d = a.ds[i];
+    if (d == 0.f) d = dmax;                                           // :210-211
+    const bool in = u < (float)(a.W - a.edge) && u > (float)a.edge && v < (float)(a.H - a.edge) && v > (float)a.edge;
+    a.mask[i] = (in && 0.f <= nz && nz <= d + 0.5f) ? 1 : 0;          // :213
+  }
+}
+
 }  // namespace lsr
 
 using namespace lsr;
+
+extern "C" int lsr_frustum_scratch_bytes(int64_t n_points, size_t* bytes) {
+  if (n_points < 0 || !bytes) return LSR_ERR_ARG;
+  *bytes = (size_t)(n_points > 0 ? n_points : 1) * 16 + 256;
+  return LSR_OK;
+}
+
+extern "C" int lsr_frustum_mask(const float* cloud_pos, int64_t n_points, const double* w2c12_host, const float* depth_img,
+                                int32_t H, int32_t W, double fx, double fy, double cx, double cy, int32_t edge, void* scratch,
+                                uint8_t* mask_out, lsr_stream_t stream) {
+  if (n_points < 0 || !w2c12_host || !depth_img || H <= 0 || W <= 0 || !scratch || (n_points > 0 && (!cloud_pos || !mask_out)))
+    return LSR_ERR_ARG;
+  if (n_points == 0) return LSR_OK;
+  FrustumArgs a;
+  a.cloud = cloud_pos; a.n = n_points;
+  for (int i = 0; i < 12; ++i) a.w2c[i] = w2c12_host[i];
+  a.depth = depth_img; a.H = H; a.W = W; a.fx = fx; a.fy = fy; a.cx = cx; a.cy = cy; a.edge = edge;
+  char* sb = (char*)scratch;
+  a.maxbits = (unsigned int*)sb;
+  a.u = (float*)(sb + 256); a.v = a.u + n_points; a.negz = a.v + n_points; a.ds = a.negz + n_points;
+  a.mask = mask_out;
+  LSR_CUDA_CHECK(cudaMemsetAsync(a.maxbits, 0, sizeof(unsigned int), stream));
+  int blocks = (int)((n_points + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  frustum_project_kernel<<<blocks, 256, 0, stream>>>(a);
+  LSR_LAUNCHED(1);
+  frustum_mask_kernel<<<blocks, 256, 0, stream>>>(a);
+  LSR_LAUNCHED(1);
+  LSR_CUDA_CHECK(cudaGetLastError());
+  return LSR_OK;
+}
 
 extern "C" int lsr_dynamic_radius(const float* color_f32, const double* color_f64, int32_t H, int32_t W, double thr,
                                   double r_add_max, double r_add_min, double ratio, double* r_add, double* r_query,

@@ -9,8 +9,37 @@ import torch.nn.functional as F
 
 
 def get_mask_from_c2w(cloud_pos, c2w, depth, H, W, fx, fy, cx, cy, edge=-4):
-    """-> int64 indices of cloud rows that project inside the (edge-cropped) image and lie in front of
-    the camera no deeper than the bilinearly sampled sensor depth + 0.5 m (zero depth -> max depth)."""
+    """-> int64 indices of the cloud rows the mapper may optimise for this frame (src/Mapper.py:165-217): the points
+    that project inside the (edge-cropped) image and lie in front of the camera no deeper than the bilinearly looked-up
+    sensor depth + 0.5 m (zero lookups -> the maximum lookup).  CUDA tensors run the two-pass lsr_frustum_mask
+    kernels (float64 projection like the reference); CPU tensors (host-logic tests) take the torch restatement."""
+    if cloud_pos.is_cuda:
+        import ctypes
+        from ._lib import lib, check, ptr, stream_ptr
+        dev = cloud_pos.device
+        cloud = cloud_pos.detach()
+        if cloud.dtype != torch.float32 or not cloud.is_contiguous():
+            cloud = cloud.float().contiguous()
+        c = torch.as_tensor(c2w).detach().to('cpu', torch.float32)
+        if c.shape[0] == 3:
+            c = torch.cat([c, torch.tensor([[0., 0., 0., 1.]])], 0)
+        w2c = torch.linalg.inv(c).double()[:3].contiguous()        # np.linalg.inv(c2w) on the float32 pose, promoted (:180-181)
+        arr = (ctypes.c_double * 12)(*w2c.reshape(-1).tolist())
+        d = depth.detach().to(dev, torch.float32).contiguous()
+        n = cloud.shape[0]
+        nb = ctypes.c_size_t()
+        check(lib().lsr_frustum_scratch_bytes(n, ctypes.byref(nb)), 'lsr_frustum_scratch_bytes')
+        scratch = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+        mask = torch.empty(n, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().lsr_frustum_mask(ptr(cloud), n, arr, ptr(d), int(H), int(W), float(fx), float(fy), float(cx), float(cy),
+                                         int(edge), ptr(scratch), ptr(mask), stream_ptr(dev)), 'lsr_frustum_mask')
+        return torch.nonzero(mask, as_tuple=True)[0]
+    return _get_mask_from_c2w_torch(cloud_pos, c2w, depth, H, W, fx, fy, cx, cy, edge)
+
+
+def _get_mask_from_c2w_torch(cloud_pos, c2w, depth, H, W, fx, fy, cx, cy, edge=-4):
+    """The same selection as plain tensor ops (any device)."""
     dev = cloud_pos.device
     c2w = c2w.to(device=dev, dtype=torch.float32)
     if c2w.shape[0] == 3:

@@ -160,6 +160,26 @@ def test_get_samples_matches_reference_golden():
                 assert torch.equal(got, ref)
 
 
+def test_frustum_selection_kernel_matches_reference_restatement():
+    """lsr_frustum_mask (two-pass CUDA kernel) vs oracle/frustum.py = the reference's numpy + cv2.remap lines
+    (src/Mapper.py:165-217).  cv2.remap interpolates with 1/32-pixel fixed-point weights, so a point whose camera depth
+    sits within 1 mm of `lookup + 0.5` or whose projection sits within 1e-3 px of the crop edge may flip: at most 0.2 %
+    of the points may differ, and none that is not such a borderline case."""
+    from loopy_slam_b200.frustum import get_mask_from_c2w
+    from loopy_slam_b200.stream import SyntheticRoom, build_point_cloud
+    from oracle.frustum import get_mask_from_c2w as ref_mask
+    room = SyntheticRoom(H=96, W=128, fx=80., fy=80., cx=63.5, cy=47.5, n_frames=100, half=(1.0, 0.8, 0.6), hole_frac=0.02)
+    cloud, _, _ = build_point_cloud(room, 20000, pixels_per_frame=4000, frame_ids=[0, 10, 20, 30, 50, 70], max_frames=60)
+    for fid, edge in ((5, -4), (40, 0), (75, 10)):
+        color, depth, c2w = room.frame(fid)
+        got = get_mask_from_c2w(cloud.to(DEV), c2w, depth.to(DEV), room.H, room.W, room.fx, room.fy, room.cx, room.cy, edge=edge)
+        ref = ref_mask(cloud.numpy(), c2w.numpy(), depth.numpy(), room.H, room.W, room.fx, room.fy, room.cx, room.cy, edge)
+        a, b = set(got.cpu().tolist()), set(ref.tolist())
+        assert len(b) > 1000
+        assert len(a ^ b) <= 0.002 * cloud.shape[0], (fid, len(a), len(b), len(a ^ b))
+        assert got.dtype == torch.int64 and bool((got[1:] > got[:-1]).all())     # sorted row ids, like np.where
+
+
 def test_render_img_matches_tiled_oracle():
     """render_img (one fused launch, per-3000-ray far statistics) vs the oracle run tile by tile."""
     from oracle import render as orc
@@ -252,6 +272,54 @@ def test_neural_point_cloud_insert_and_query():
     _, Ie = _inradius(Dr, Ir, r2)
     assert torch.equal(I.cpu(), Ie) and (nn >= 1).all()
     assert npc.get_geo_feats().shape == (1200, 32) and abs(float(npc.get_geo_feats().std()) - 0.1) < 0.01
+
+
+def test_segmented_point_store_matches_oracle():
+    """f1: a stream of frames through NeuralPointCloud.add_neural_points on the device vs the CPU
+    restatement of the reference store (oracle/point_store.py: add_neural_points :1557-1631, check_index /
+    init_segment :1220-1315, update_fragments): same kept samples, same inserted positions, same segment boundaries and
+    inheritance masks, same merged end-of-run cloud and features."""
+    from loopy_slam_b200.stream import SyntheticRoom, sample_batch
+    from oracle.point_store import PointStoreOracle
+    room = SyntheticRoom(H=64, W=64, fx=40., fy=40., cx=31.5, cy=31.5, n_frames=60, half=(0.9, 0.7, 0.5), hole_frac=0.02)
+    cfg = L.default_cfg('replica')
+    cfg['mapping']['device'] = DEV
+    cfg['mapping']['segment_rot_cos'] = 0.985        # ~10 degrees: several segments within the short stream
+    cfg['mapping']['segment_rel_trans'] = 0.12
+
+    class Slam:
+        H, W, fx, fy, cx, cy = room.H, room.W, room.fx, room.fy, room.cx, room.cy
+    npc = L.NeuralPointCloud(cfg, Slam)
+    orc_ = PointStoreOracle(room.H, room.W, room.fx, room.fy, room.cx, room.cy, segment_rot_cos=0.985, segment_rel_trans=0.12)
+    feat = lambda p, which: torch.sin(p.cpu().double() @ torch.arange(1, 97, dtype=torch.float64).reshape(3, 32) * (1 + which)).float()
+    for fid in range(0, 60, 3):
+        o, d, g, c = sample_batch(room, [fid], 500, seed=100 + fid)
+        c2w = room.frame(fid)[2]
+        n_before = npc.fragments[-1].n if npc.fragments else 0
+        segs_before = len(npc.fragments)
+        kept = npc.add_neural_points(o.to(DEV), d.to(DEV), g.to(DEV), c.to(DEV), idx=torch.tensor(fid), cur_c2w=c2w)
+        seg = npc.fragments[-1]
+        first_new = seg.n_inherited if len(npc.fragments) != segs_before else n_before
+        new_pos = seg.pos[first_new:seg.n]
+        seg.geo[first_new:seg.n] = feat(new_pos, 0).to(DEV)          # deterministic features instead of N(0, 0.1) draws
+        seg.col[first_new:seg.n] = feat(new_pos, 1).to(DEV)
+        kept_ref = orc_.add_neural_points(o, d, g, fid, c2w, feat_fn=feat)
+        assert int(kept) == kept_ref, fid
+    keys = list(orc_.fragments_dict.keys())
+    assert len(npc.fragments) == len(keys) >= 3
+    for seg, k in zip(npc.fragments, keys):
+        f = orc_.fragments_dict[k]
+        assert seg.n == len(f['npc']) and seg.n_inherited == f['idx_start_segment_features']
+        torch.testing.assert_close(seg.pos[:seg.n].cpu(), torch.tensor(f['npc'], dtype=torch.float32), rtol=0, atol=1e-6)
+        if f['mask'] is not None:
+            assert torch.equal(seg.mask.cpu(), torch.from_numpy(f['mask']))
+    np.testing.assert_allclose(npc.get_cloud_pos(True).cpu().numpy(), orc_.merged('npc'), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(npc.get_geo_feats(True).cpu().numpy(), orc_.merged('geo_feats'), rtol=1e-5, atol=1e-6)
+    # the active index serves queries with row ids of the ACTIVE segment
+    D, I, nn = npc.find_neighbors_faiss(npc.get_cloud_pos()[:50], step='query')
+    assert bool((I[:, 0] == torch.arange(50, device=DEV)).all()) and bool((D[:, 0] == 0).all())
+    npc.train_index_global()
+    assert npc.index_ntotal() == orc_.merged('npc').shape[0]
 
 
 def test_dynamic_radius_map_matches_numpy_restatement():

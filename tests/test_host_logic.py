@@ -233,10 +233,7 @@ def test_npc_accessors_take_the_reference_bool():
     import loopy_slam_b200 as L
     cfg = L.default_cfg('replica')
     npc = L.NeuralPointCloud(cfg, device='cpu')
-    npc._pos = torch.arange(30, dtype=torch.float32).reshape(10, 3)
-    npc._n = npc._cap = 10
-    npc.geo_feats = torch.zeros(10, 32)
-    npc.col_feats = torch.zeros(10, 32)
+    npc.set_cloud(torch.arange(30, dtype=torch.float32).reshape(10, 3), torch.zeros(10, 32), torch.zeros(10, 32))
     for end in (False, True):
         assert npc.get_cloud_pos(end).shape == (10, 3)
         assert npc.get_geo_feats(end).shape == (10, 32) and npc.get_col_feats(end).shape == (10, 32)
@@ -280,3 +277,39 @@ def test_shared_decoders_stay_shared_across_processes():
     assert torch.allclose(after, before - 1.0), 'the child\'s update did not reach the shared weights'
     flat, _ = model.blob.ensure('cpu')      # and the parent's own blob still aliases the same memory
     assert model.color_decoder.output_linear.bias.data_ptr() >= flat.data_ptr()
+
+
+def test_segment_store_merge_matches_reference_restatement():
+    """The end-of-run merge of the segmented point store (inherited points averaged over the segments that carried them,
+    /root/reference/src/neural_point.py:1252-1281,1435-1510) on hand-built segments vs oracle/point_store.py."""
+    import numpy as np
+    import loopy_slam_b200 as L
+    from loopy_slam_b200.neural_point import _Segment
+    from oracle.point_store import PointStoreOracle
+    gen = torch.Generator().manual_seed(3)
+    cfg = L.default_cfg('replica')
+    npc = L.NeuralPointCloud(cfg, device='cpu')
+    orc = PointStoreOracle(64, 64, 40., 40., 31.5, 31.5)
+    orc.fragments_dict = {}
+    prev_keep = None
+    prev = None
+    for si, (n_new, frac) in enumerate(((40, 0.5), (30, 0.4), (25, None))):
+        inh_pos = prev['pos'][prev_keep] + 0.01 * (si) if prev is not None else torch.zeros(0, 3)   # inherited rows may have moved (PGO)
+        inh_geo = prev['geo'][prev_keep] if prev is not None else torch.zeros(0, 32)
+        inh_col = prev['col'][prev_keep] if prev is not None else torch.zeros(0, 32)
+        pos = torch.cat([inh_pos, torch.rand(n_new, 3, generator=gen)])
+        geo = torch.cat([inh_geo, torch.randn(n_new, 32, generator=gen)])
+        col = torch.cat([inh_col, torch.randn(n_new, 32, generator=gen)])
+        seg = _Segment('cpu', 32, torch.eye(4), si, inh_pos.shape[0])
+        seg.append(pos, geo, col)
+        mask = (torch.rand(pos.shape[0], generator=gen) < frac) if frac is not None else None
+        seg.mask = mask
+        npc.fragments.append(seg)
+        orc.fragments_dict[f'segment_{si}'] = {'npc': pos.tolist(), 'geo_feats': geo, 'col_feats': col,
+                                               'idx_start_segment_features': inh_pos.shape[0],
+                                               'mask': None if mask is None else mask.numpy()}
+        prev, prev_keep = {'pos': pos, 'geo': geo, 'col': col}, mask
+    np.testing.assert_allclose(npc.get_cloud_pos(True).numpy(), orc.merged('npc'), rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(npc.get_geo_feats(True).numpy(), orc.merged('geo_feats'), rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(npc.get_col_feats(True).numpy(), orc.merged('col_feats'), rtol=1e-6, atol=1e-7)
+    assert npc.get_cloud_pos(False).shape[0] == npc.fragments[-1].n
