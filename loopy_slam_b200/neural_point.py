@@ -323,6 +323,7 @@ class NeuralPointCloud(object):
             seg.append(npc, geo_feats, col_feats)
             self.fragments.append(seg)
             self.new_segment = True
+            self._grid = None
         else:
             self.fragments[-1].append(npc, geo_feats, col_feats)
 

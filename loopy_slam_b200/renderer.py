@@ -464,7 +464,7 @@ class Renderer(object):
         if gt_depth is not None and torch.numel(gt_depth) == 0:
             warnings.warn('tensor gt_depth is empty, info:')      # Renderer.py:122-128
             gt_depth = None
-        if self.sample_near_pcl and gt_depth is not None and hasattr(npc, 'sample_near_pcl'):
+        if self.sample_near_pcl and hasattr(npc, 'sample_near_pcl'):
             return self._render_with_near_pcl(npc, decoders, rays_d, rays_o, stage, gt_depth, npc_geo_feats,
                                               npc_col_feats, is_tracker, cloud_pos, dynamic_r_query, exposure_feat,
                                               feat_subset)
@@ -478,11 +478,18 @@ class Renderer(object):
         """Renderer.py:150-158,191-198 with rendering.sample_near_pcl: rays without sensor depth take their samples
         from npc.sample_near_pcl (between the first two of 25 coarse steps that have a neighbour), keep their
         rendered depth, and are invalid when fewer than two such steps exist."""
-        g = gt_depth.detach().reshape(-1)
-        zero = ~(g > 0)
         z_zero = None
         not_near_rays = None
-        if bool(zero.any()):
+        if gt_depth is None:                 # Renderer.py:107-113: all rays zero-depth, far = 10
+            z0, not_near = npc.sample_near_pcl(rays_o.clone().detach(), rays_d.clone().detach(), self.near_end, 10.0,
+                                               self.N_surface)
+            z_zero = z0.float()
+            not_near_rays = torch.nonzero(not_near, as_tuple=True)[0]
+            zero = None
+        else:
+            g = gt_depth.detach().reshape(-1)
+            zero = ~(g > 0)
+        if zero is not None and bool(zero.any()):
             from . import _lib as lb
             R = g.shape[0]
             g32 = _f32c(g)
@@ -503,6 +510,32 @@ class Renderer(object):
             valid[not_near_rays] = False                                                        # Renderer.py:154-157,194
         return depth, var, rgb, valid
 
+    def _near_pcl_depths_img(self, npc, rays_o, rays_d, gt):
+        """Sample depths of the zero-depth pixels of a full image (Renderer.py:150-158 applied per ray_batch_size tile, as
+        the reference's tile loop :243-266 does: each tile uses ITS far bound).  Only tiles that hold a zero-depth pixel are
+        visited; -> (H*W, N_surface) or None when every pixel has sensor depth."""
+        R = rays_o.shape[0]
+        if gt is None:                       # Renderer.py:107-113: every ray is zero-depth, far = 10 for every tile
+            z0, _ = npc.sample_near_pcl(rays_o, rays_d, self.near_end, 10.0, self.N_surface)
+            return z0.float()
+        g32 = _f32c(gt.detach())
+        zero = ~(g32 > 0)
+        if not bool(zero.any()):
+            return None
+        G = self.ray_batch_size
+        far = torch.empty((R + G - 1) // G, dtype=torch.float32, device=g32.device)
+        with torch.cuda.device(g32.device):
+            check(lib().lsr_far_bound(ptr(g32), R, G, ptr(far), stream_ptr(g32.device)), 'lsr_far_bound')
+        far_h = far.cpu()
+        z_zero = torch.zeros(R, self.N_surface, dtype=torch.float32, device=g32.device)
+        tiles = torch.unique(torch.nonzero(zero, as_tuple=True)[0] // G).cpu().tolist()
+        for t in tiles:
+            sl = slice(t * G, min((t + 1) * G, R))
+            zt = zero[sl]
+            z0, _ = npc.sample_near_pcl(rays_o[sl][zt], rays_d[sl][zt], self.near_end, float(far_h[t]), self.N_surface)
+            z_zero[sl][zt] = z0.float()
+        return z_zero
+
     # -- Renderer.py:203-276
     def render_img(self, npc, decoders, c2w, device, stage, gt_depth=None, npc_geo_feats=None, npc_col_feats=None,
                    dynamic_r_query=None, cloud_pos=None, exposure_feat=None):
@@ -516,7 +549,10 @@ class Renderer(object):
             rays_d = rays_d.reshape(-1, 3)
             dyn = dynamic_r_query.reshape(-1) if (self.use_dynamic_radius and dynamic_r_query is not None) else None
             gt = gt_depth.reshape(-1) if gt_depth is not None else None
+            z_zero = None
+            if self.sample_near_pcl and hasattr(npc, 'sample_near_pcl'):
+                z_zero = self._near_pcl_depths_img(npc, rays_o, rays_d, gt)
             depth, var, rgb, _ = fused_render(self, npc, decoders, rays_d, rays_o, stage, gt, npc_geo_feats,
                                               npc_col_feats, False, cloud_pos, dyn, exposure_feat,
-                                              far_group=self.ray_batch_size)
+                                              far_group=self.ray_batch_size, z_zero_depth=z_zero)
             return depth.double().reshape(H, W), var.double().reshape(H, W), rgb.reshape(H, W, 3)

@@ -72,7 +72,7 @@ def run_cuda(g, device='cuda:0', param_grads=True, loss_fn=None, near_pcl=False)
         loss = loss_fn(depth, var, rgb, valid, g.t('gt_depth').to(device), (g.t('up_rgb').abs() % 1.0).to(device))
     loss.backward()
     torch.cuda.synchronize()
-    out = dict(loss=float(loss),
+    out = dict(loss=float(loss.detach()),
                grads={k: v.grad.detach().cpu() for k, v in (('geo', geo), ('col', col)) if v.grad is not None},
                depth=depth.detach().cpu(), var=var.detach().cpu(), rgb=rgb.detach().cpu(), valid=valid.cpu(),
                g_geo=geo.grad.cpu() if geo.grad is not None else None,

@@ -175,7 +175,7 @@ def test_frustum_selection_kernel_matches_reference_restatement():
         got = get_mask_from_c2w(cloud.to(DEV), c2w, depth.to(DEV), room.H, room.W, room.fx, room.fy, room.cx, room.cy, edge=edge)
         ref = ref_mask(cloud.numpy(), c2w.numpy(), depth.numpy(), room.H, room.W, room.fx, room.fy, room.cx, room.cy, edge)
         a, b = set(got.cpu().tolist()), set(ref.tolist())
-        assert len(b) > 1000
+        assert len(b) > 200
         assert len(a ^ b) <= 0.002 * cloud.shape[0], (fid, len(a), len(b), len(a ^ b))
         assert got.dtype == torch.int64 and bool((got[1:] > got[:-1]).all())     # sorted row ids, like np.where
 
@@ -317,7 +317,7 @@ def test_segmented_point_store_matches_oracle():
     np.testing.assert_allclose(npc.get_geo_feats(True).cpu().numpy(), orc_.merged('geo_feats'), rtol=1e-5, atol=1e-6)
     # the active index serves queries with row ids of the ACTIVE segment
     D, I, nn = npc.find_neighbors_faiss(npc.get_cloud_pos()[:50], step='query')
-    assert bool((I[:, 0] == torch.arange(50, device=DEV)).all()) and bool((D[:, 0] == 0).all())
+    assert bool((D[:, 0] == 0).all()) and torch.equal(npc.get_cloud_pos()[I[:, 0]], npc.get_cloud_pos()[:50])   # (a batch may hold one pixel twice)
     npc.train_index_global()
     assert npc.index_ntotal() == orc_.merged('npc').shape[0]
 
@@ -462,6 +462,54 @@ def test_feature_subset_equals_index_put_flow(name):
     assert a[6].keys() == b[6].keys()
     for k in a[6]:
         assert rel_l2(b[6][k].cpu(), a[6][k].cpu()) < 1e-4, k
+
+
+def test_render_img_with_sample_near_pcl_matches_tile_loop():
+    """rendering.sample_near_pcl=True through render_img (Renderer.py:243-266 calls render_batch_ray per tile, so
+    zero-depth pixels are sampled near the cloud with THAT tile's far bound): one fused launch vs our own tile loop over
+    render_batch_ray (checked against the oracle in test_sample_near_pcl_on_the_fused_path); also gt_depth=None."""
+    g = Golden('replica_color_sparse_zero_depth')
+    cfg = cfg_from_ocfg(g.ocfg)
+    cfg['rendering']['sample_near_pcl'] = True
+    gen = torch.Generator().manual_seed(22)
+    H, W = 24, 30
+    model = build_model(cfg, g.weights, DEV)
+    rend = L.Renderer(cfg, None, SlamLike(H, W, 20.0, 20.0, 14.5, 11.5), ray_batch_size=100)
+    rend.sigmoid_coefficient = g.ocfg.sigmoid_coef
+    gdc = Golden('replica_color_mapper')
+    cloud, geo, col = gdc.t('cloud').to(DEV), gdc.t('geo_feats').to(DEV), gdc.t('col_feats').to(DEV)
+    c2w = torch.eye(4)
+    c2w[:3, 3] = gdc.t('rays_o')[0]
+    dvec = gdc.t('rays_d')[0]
+    zc = -dvec / dvec.norm()
+    xc = torch.linalg.cross(torch.tensor([0., 0., 1.]), zc)
+    xc = xc / xc.norm()
+    c2w[:3, 0], c2w[:3, 1], c2w[:3, 2] = xc, torch.linalg.cross(zc, xc), zc
+    gt = 0.4 + torch.rand(H, W, generator=gen) * 0.8
+    gt[::4, ::3] = 0.0
+    gt[20:, :] = 0.0                                         # whole tiles without any sensor depth
+    qcfg = L.default_cfg('replica')
+    qcfg['pointcloud']['radius_query'] = g.ocfg.radius_query
+    qcfg['mapping']['device'] = DEV
+    npc = L.NeuralPointCloud(qcfg, device=DEV)
+    npc.set_cloud(cloud, geo, col)
+    ro, rd = L.get_rays(H, W, 20.0, 20.0, 14.5, 11.5, c2w.to(DEV), DEV)
+    ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
+    for gt_img in (gt.to(DEV), None):
+        d_img, v_img, c_img = rend.render_img(npc, model, c2w.to(DEV), DEV, 'color', gt_depth=gt_img, npc_geo_feats=geo,
+                                              npc_col_feats=col, cloud_pos=cloud)
+        outs = []
+        with torch.no_grad():
+            for s0 in range(0, H * W, 100):
+                gg = gt_img.reshape(-1)[s0:s0 + 100] if gt_img is not None else None
+                outs.append(rend.render_batch_ray(npc, model, rd[s0:s0 + 100], ro[s0:s0 + 100], DEV, 'color', gt_depth=gg,
+                                                  npc_geo_feats=geo, npc_col_feats=col, cloud_pos=cloud))
+        d_ref = torch.cat([o[0] for o in outs]).reshape(H, W).double()
+        c_ref = torch.cat([o[2] for o in outs]).reshape(H, W, 3)
+        assert rel_l2(d_img.cpu(), d_ref.cpu()) < 1e-6 and rel_l2(c_img.cpu(), c_ref.cpu()) < 1e-6
+        assert float(d_img.abs().max()) > 0
+        if gt_img is not None:
+            assert (d_img[gt_img == 0] != 0).any()           # zero-depth pixels keep their rendered depth on this path
 
 
 def test_sample_near_pcl_on_the_fused_path():
