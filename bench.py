@@ -40,6 +40,8 @@ import time
 
 import torch
 
+T_START = time.time()
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -133,10 +135,19 @@ def build_scene(dataset, n_points, cache=True):
     path = f'/tmp/lsr_bench_cloud_{dataset}_{n_points}.pt'
     if cache and os.path.exists(path):
         cloud, geo, col = torch.load(path)
+    elif n_points > 300000:
+        # The insertion rule saturates near 2.3e5 points in this room (locations >= radius_add apart on ~100 m^2 of wall), so
+        # the large-N sweep point is the 2e5 cloud replicated with a 1 cm jitter: same geometry, proportionally denser cells.
+        base = build_scene(dataset, N_POINTS, cache)
+        reps = (n_points + base['cloud'].shape[0] - 1) // base['cloud'].shape[0]
+        gen = torch.Generator().manual_seed(SEED + 7)
+        cloud = torch.cat([base['cloud'] + (0.01 * torch.randn(base['cloud'].shape, generator=gen) if r else 0.0)
+                           for r in range(reps)])[:n_points].contiguous()
+        geo = torch.zeros(cloud.shape[0], 32).normal_(0, 0.1, generator=gen)
+        col = torch.zeros(cloud.shape[0], 32).normal_(0, 0.1, generator=gen)
     else:
-        ppf = 20000 if n_points <= 300000 else 60000
-        cloud, geo, col = build_point_cloud(room, n_points, frame_stride=40, pixels_per_frame=ppf, seed=SEED,
-                                            max_frames=2000 if n_points > 300000 else 400)
+        cloud, geo, col = build_point_cloud(room, n_points, frame_stride=40, pixels_per_frame=20000, seed=SEED, max_frames=400)
+    if not (cache and os.path.exists(path)):
         if cache:
             try:
                 torch.save((cloud, geo, col), path + f'.{os.getpid()}')
@@ -422,6 +433,9 @@ def run_lsr(args, rank, world, local):
             for ds, npts in (('tum', N_POINTS), ('scannet', N_POINTS), (args.config, 2000), (args.config, 1000000)):
                 if ds == args.config and npts == args.n_points:
                     continue
+                if time.time() - T_START > args.sweep_budget_s:      # keep the default run within minutes
+                    extra[f'mapper_iteration_{ds}_N{npts}'] = {'skipped': f'wall-clock budget of {args.sweep_budget_s} s for side measurements spent'}
+                    continue
                 try:
                     it2 = MapperIteration(ds, npts, dev, 0, 1, None, 'color')
                     ms, r = time_steps(lambda k: (it2.step(), it2.rays_last)[1], n_extra, flush, dev)
@@ -681,6 +695,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extra', action='store_true', help='skip the labelled side measurements')
     ap.add_argument('--no-sweep', action='store_true', help='skip the TUM / ScanNet / N-sweep lines of `extra`')
+    ap.add_argument('--sweep-budget-s', type=float, default=150.0, help='side measurements of `extra` start only while the run is younger than this')
     ap.add_argument('--cpu-budget', type=float, default=20.0)
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -280,7 +280,8 @@ def _make_params(renderer, decoders, stage, coef):
 
 def fused_render(renderer, npc, decoders, rays_d, rays_o, stage, gt_depth, npc_geo_feats, npc_col_feats,
                  is_tracker, cloud_pos, dynamic_r_query, exposure_feat, far_group=None, n_surface=None,
-                 force_save=False, return_ctx=False, feat_subset=None, z_zero_depth=None, save_light=False):
+                 force_save=False, return_ctx=False, feat_subset=None, z_zero_depth=None, save_light=False,
+                 radius_override=None):
     """The one place that marshals a render call into lsr_render_fwd / lsr_render_bwd."""
     _lib.require_cuda(rays_o, 'rays_o')
     dev = rays_o.device
@@ -295,6 +296,8 @@ def fused_render(renderer, npc, decoders, rays_d, rays_o, stage, gt_depth, npc_g
     if save_light:
         prm.flags |= _lib.FLAG_SAVE_LIGHT
     radius = npc.get_radius_query() if npc is not None and hasattr(npc, 'get_radius_query') else renderer.radius_query
+    if radius_override is not None:        # NICER.forward stage 'mesh': find_neighbors_faiss(step='mesh') -> radius_mesh
+        radius = radius_override
     prm.radius_query = float(radius)
     rc = _RenderCtx()
     rc.prm = prm
@@ -387,11 +390,21 @@ def _saved_views(rc):
 
 def decode_points(decoders, p, npc, stage, npc_geo_feats, npc_col_feats, pts_num, cloud_pos, dynamic_r_query,
                   exposure_feat, renderer=None):
-    """NICER.forward semantics (decoder.py:573-610), forward only: runs the fused kernel with one
+    """NICER.forward semantics (decoder.py:573-626), forward only: runs the fused kernel with one
     sample per "ray" (origin = the point, direction = 0, so the sample point is the origin exactly)
     and reads the per-sample occupancy / colour out of a LIGHT save (148 B per point), in chunks of
     renderer.points_batch_size points like Renderer.eval_points (Renderer.py:40-60).
-    -> raw (P,4) [r,g,b,occ-logit], ray_mask (P/pts_num,) bool or None, point_mask (P,) bool."""
+    -> raw (P,4) [r,g,b,occ-logit], ray_mask (P/pts_num,) bool or None, point_mask (P,) bool.
+    stage 'mesh' (:611-620) = 'color' with the mesher's radius (radius_mesh, neural_point.py:1694-1696) and no ray mask
+    (:257-262); stage 'color_only' (:621-626) returns the (P,3) colour alone."""
+    mesh, color_only = stage == 'mesh', stage == 'color_only'
+    radius_override = None
+    if mesh:
+        radius_override = getattr(npc, 'radius_mesh', None)
+        if radius_override is None:
+            raise ValueError("stage 'mesh' needs npc.radius_mesh (pointcloud.radius_mesh)")
+    if mesh or color_only:
+        stage = 'color'
     if renderer is None:
         renderer = getattr(decoders, '_lsr_renderer', None)
         if renderer is None:
@@ -409,15 +422,17 @@ def decode_points(decoders, p, npc, stage, npc_geo_feats, npc_col_feats, pts_num
                 dyn = dyn.reshape(-1)[b:b + chunk]
             _, rc = fused_render(renderer, npc, decoders, torch.zeros_like(pb), pb, stage, ones, npc_geo_feats,
                                  npc_col_feats, False, cloud_pos, dyn, exposure_feat, n_surface=1, force_save=True,
-                                 return_ctx=True, save_light=True)
+                                 return_ctx=True, save_light=True, radius_override=radius_override)
             v, m = _saved_views(rc)
             occ = v['occ'][:m].clone()
             hass.append(v['misc'][:m, 1] > 0.5)
             rgb = v['rgbs'][:m, :3].clone() if rc.stage == 1 else torch.zeros(m, 3, device=pts.device)
             raws.append(torch.cat([rgb, occ[:, None]], -1))
     raw, has = torch.cat(raws), torch.cat(hass)
+    if color_only:
+        return raw[:, :3]
     ray_mask = None
-    if pts_num:
+    if pts_num and not mesh:
         ray_mask = ~(has.view(-1, pts_num).sum(1) < int(decoders.cfg_flags['N_surface'] / 2 + 1))
     return raw, ray_mask, has
 

@@ -252,6 +252,34 @@ def test_eval_points_matches_oracle_decode():
     torch.testing.assert_close(raw.cpu()[has][:, 3], ref_raw[has][:, 3], rtol=1e-4, atol=2e-3)
 
 
+def test_nicer_forward_mesh_and_color_only_stages():
+    """NICER.forward stages 'mesh' (decoder.py:611-620: the mesher's radius, no ray mask) and 'color_only' (:621-626)."""
+    g = Golden('replica_color_mapper')
+    cfg = cfg_from_ocfg(g.ocfg)
+    model = build_model(cfg, g.weights, DEV)
+    H, W, fx, fy, cx, cy = g.raw['intrinsics']
+    rend = L.Renderer(cfg, None, SlamLike(H, W, fx, fy, cx, cy))
+    pts = (g.t('rays_o') + g.t('rays_d') * g.t('gt_depth').reshape(-1, 1)).to(DEV)
+    geo, col, cloud = g.t('geo_feats').to(DEV), g.t('col_feats').to(DEV), g.t('cloud').to(DEV)
+
+    class NPC:
+        radius_mesh = 0.6 * g.ocfg.radius_query
+
+        def __init__(self, r):
+            self.r = r
+
+        def get_radius_query(self):
+            return self.r
+    model._lsr_renderer = rend
+    full, ray_mask, pm = model(pts, NPC(g.ocfg.radius_query), 'color', geo, col, pts_num=1, cloud_pos=cloud)
+    only = model(pts, NPC(g.ocfg.radius_query), 'color_only', geo, col, pts_num=1, cloud_pos=cloud)
+    assert only.shape == (pts.shape[0], 3) and torch.equal(only, full[:, :3])
+    mesh, rm, pm_mesh = model(pts, NPC(g.ocfg.radius_query), 'mesh', geo, col, pts_num=1, cloud_pos=cloud)
+    small, _, pm_small = model(pts, NPC(NPC.radius_mesh), 'color', geo, col, pts_num=1, cloud_pos=cloud)
+    assert rm is None and torch.equal(mesh, small) and torch.equal(pm_mesh, pm_small)
+    assert not torch.equal(mesh, full)                      # the smaller radius really changed the neighbourhoods
+
+
 def test_neural_point_cloud_insert_and_query():
     cfg = L.default_cfg('replica')
     cfg['mapping']['device'] = DEV
