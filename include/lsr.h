@@ -157,6 +157,14 @@ int lsr_sample_rays_filtered(const float* depth_img, const float* color_img, int
                              int64_t n, int32_t H0, int32_t H1, int32_t W0, int32_t W1, float depth_limit,
                              float* rays_o, float* rays_d, float* depth, float* color, int64_t* i_out,
                              int64_t* j_out, int32_t* count, lsr_stream_t stream);
+/* As lsr_sample_rays_filtered, but RETURNS the count to the host (*count_host, a plain host int): the kernel posts it to a
+ * host-mapped pinned word and the call spins on that word instead of copying + synchronising the stream.  This is the size
+ * the reference's get_samples needs on the host to shape its return values (src/common.py:249-259). */
+int lsr_sample_rays_filtered_sync(const float* depth_img, const float* color_img, int32_t H, int32_t W, float fx,
+                                  float fy, float cx, float cy, const float* c2w, int32_t c2w_ld, const int64_t* pix,
+                                  int64_t n, int32_t H0, int32_t H1, int32_t W0, int32_t W1, float depth_limit,
+                                  float* rays_o, float* rays_d, float* depth, float* color, int64_t* i_out,
+                                  int64_t* j_out, int32_t* count_host, lsr_stream_t stream);
 /* d_c2w (3x4 row-major, 12 floats, overwritten) from d_rays_o/d_rays_d and the pixel coords */
 int lsr_sample_rays_bwd(const float* d_rays_o, const float* d_rays_d, const int64_t* i_pix,
                         const int64_t* j_pix, int64_t n, float fx, float fy, float cx, float cy,

@@ -19,7 +19,7 @@ GRAD_GEO_FEATS, GRAD_COL_FEATS, GRAD_GEO_W, GRAD_GEO_B, GRAD_COL_W, GRAD_RAYS, G
 # every exported symbol declared in include/lsr.h (checked by tests/test_abi.py)
 EXPORTS = [
     'lsr_version', 'lsr_strerror', 'lsr_device_sm_count', 'lsr_launch_count', 'lsr_grid_workspace_bytes', 'lsr_grid_build',
-    'lsr_knn_query', 'lsr_sample_rays', 'lsr_sample_rays_filtered', 'lsr_sample_rays_bwd', 'lsr_pose_fwd', 'lsr_pose_bwd',
+    'lsr_knn_query', 'lsr_sample_rays', 'lsr_sample_rays_filtered', 'lsr_sample_rays_filtered_sync', 'lsr_sample_rays_bwd', 'lsr_pose_fwd', 'lsr_pose_bwd',
     'lsr_render_workspace_bytes', 'lsr_far_bound', 'lsr_render_fwd', 'lsr_render_bwd', 'lsr_dynamic_radius', 'lsr_frustum_scratch_bytes', 'lsr_frustum_mask',
     'lsr_loss_scratch_bytes', 'lsr_mapper_loss', 'lsr_tracker_resid', 'lsr_tracker_loss', 'lsr_debug_program_stats',
 ]
@@ -69,6 +69,8 @@ def lib():
                                       vp, vp, vp, vp, vp, vp, vp]
         L.lsr_sample_rays_filtered.argtypes = [vp, vp, i32, i32, f32, f32, f32, f32, vp, i32, vp, i64, i32, i32, i32, i32, f32,
                                                vp, vp, vp, vp, vp, vp, vp, vp]
+        L.lsr_sample_rays_filtered_sync.argtypes = [vp, vp, i32, i32, f32, f32, f32, f32, vp, i32, vp, i64, i32, i32, i32, i32, f32,
+                                                    vp, vp, vp, vp, vp, vp, ctypes.POINTER(ctypes.c_int32), vp]
         L.lsr_sample_rays_bwd.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, vp]
         L.lsr_pose_fwd.argtypes = [vp, vp, vp]
         L.lsr_pose_bwd.argtypes = [vp, vp, vp, vp]

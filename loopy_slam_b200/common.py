@@ -9,6 +9,8 @@ The reference rebuilds an H x W meshgrid and launches ~10 tiny kernels per get_s
 it is torch.randint (kept so the pixel sequence follows the same global generator, Appendix D of
 SURVEY.md) plus ONE fused kernel, with a hand-written backward to the camera matrix.
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -64,20 +66,22 @@ class _SampleRaysFn(torch.autograd.Function):
 
 
 def _sample_rays_filtered(c2w_f, depth_img, color_img, pix, geom, depth_limit):
-    """lsr_sample_rays_filtered + ONE count readback.  One allocation for all outputs, one launch, one host sync."""
+    """lsr_sample_rays_filtered_sync: one allocation for all outputs, one launch; the number of kept pixels (the size of the
+    returned tensors) comes back through a host-mapped word the C side spins on -- no D2H copy, no stream synchronise."""
     H, W, fx, fy, cx, cy, H0, H1, W0, W1 = geom
     dev = pix.device
     n = pix.shape[0]
-    # [rays_o 3n | rays_d 3n | depth n | colour 3n] f32 and [i n | j n | count] i64 in two buffers
+    # [rays_o 3n | rays_d 3n | depth n | colour 3n] f32 and [i n | j n] i64 in two buffers
     fbuf = torch.empty(10 * n, dtype=torch.float32, device=dev)
-    ibuf = torch.empty(2 * n + 1, dtype=torch.int64, device=dev)
+    ibuf = torch.empty(2 * n, dtype=torch.int64, device=dev)
     base_f, base_i = fbuf.data_ptr(), ibuf.data_ptr()
-    check(lib().lsr_sample_rays_filtered(depth_img.data_ptr(), color_img.data_ptr(), H, W, fx, fy, cx, cy, c2w_f.data_ptr(),
-                                         c2w_f.shape[-1], pix.data_ptr(), n, H0, H1, W0, W1,
-                                         float(depth_limit) if depth_limit is not None else 0.0, base_f, base_f + 12 * n,
-                                         base_f + 24 * n, base_f + 28 * n, base_i, base_i + 8 * n, base_i + 16 * n,
-                                         stream_ptr(dev)), 'lsr_sample_rays_filtered')
-    m = int(ibuf[2 * n:].view(torch.int32)[0].item())    # the one host sync of the call: the size of the returned tensors
+    cnt = ctypes.c_int32(0)
+    check(lib().lsr_sample_rays_filtered_sync(depth_img.data_ptr(), color_img.data_ptr(), H, W, fx, fy, cx, cy, c2w_f.data_ptr(),
+                                              c2w_f.shape[-1], pix.data_ptr(), n, H0, H1, W0, W1,
+                                              float(depth_limit) if depth_limit is not None else 0.0, base_f, base_f + 12 * n,
+                                              base_f + 24 * n, base_f + 28 * n, base_i, base_i + 8 * n, ctypes.byref(cnt),
+                                              stream_ptr(dev)), 'lsr_sample_rays_filtered_sync')
+    m = cnt.value
     return (fbuf[:3 * m].view(m, 3), fbuf[3 * n:3 * n + 3 * m].view(m, 3), fbuf[6 * n:6 * n + m],
             fbuf[7 * n:7 * n + 3 * m].view(m, 3), ibuf[:m], ibuf[n:n + m])
 

@@ -194,7 +194,6 @@ constexpr int SM_PIPE = SM_BIAS + 2200 * 4;
 constexpr int FWD_SMEM_BYTES = SM_PIPE + 128;
 static_assert(SM_Q_LO + 14 * UM_A_SLAB <= SM_C_HI && SM_EG_LO + 24 * UM_A_SLAB <= SM_C_HI, "union region");
 static_assert(FWD_SMEM_BYTES <= 232448, "shared memory budget");
-static_assert(CW * 32 * 20 * 4 <= 20 * UM_A_SLAB, "store staging ([32][20] floats per warp) fits the dead e' / Q operand regions");
 struct Bias {   // float offsets inside the shared bias table
   static constexpr int gb = 0, gu = 160, gow = 320, gob = 352;            // geometry: 5x32, 5x32, 32, 1
   static constexpr int cb = 356, cu = cb + 640, v1b = cu + 640, v2b = v1b + 128, cob = v2b + 32;   // colour
@@ -242,29 +241,9 @@ struct FwdArgs {
 #endif
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;\n" ::"n"(NCT) : "memory"); }
 
-// Saved-activation stores.  An epilogue thread owns ONE ROW (its TMEM lane), so a direct st.global of its
-// values touches 32 different 128-byte lines per warp instruction -- measured at ~2 cycles per line in the
-// LSU, that made the stores (not the MMAs) the bottleneck of the first version of this kernel.  Instead the
-// values go through a per-warp shared-memory staging block [32 rows][NC + 4] and leave as full row segments:
-// NC = 32 -> 8 lanes cover one 128-byte line, 4 lines per instruction.
-template <int LD>
-__device__ __forceinline__ void stage_put(float* stage, int lane, int col, float a, float b, float c, float d) {
-  *reinterpret_cast<float4*>(stage + lane * LD + col) = make_float4(a, b, c, d);
-}
-// rows [0, nvalid) of the staged block -> g[row * pitch + 0 .. NC)
-template <int NC, int LD>
-__device__ __forceinline__ void stage_flush(const float* stage, int lane, float* g, size_t pitch, int nvalid) {
-  constexpr int LPR = NC / 4, RPI = 32 / LPR;
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < LPR; ++i) {
-    const int r = i * RPI + lane / LPR, c = (lane % LPR) * 4;
-    const float4 x = *reinterpret_cast<const float4*>(stage + r * LD + c);
-    if (r < nvalid) *reinterpret_cast<float4*>(g + (size_t)r * pitch + c) = x;
-  }
-  __syncwarp();
-}
-
+// Saved activations leave as T-planes (lsr_render.cuh: tplane_off): per 128-row tile [feature][row], so that the store of one
+// feature by the 32 row-owner lanes of a warp is one full 128-byte line, and the backward can bulk-copy a plane as a
+// ready-made K-major (K = rows) tensor-core operand.
 __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant__ FwdArgs a) {
   // NB: no pointer re-alignment through integer casts here -- it makes the compiler lose the shared address
   // space and turns every LDS / STS below into a generic LD / ST (measured: 5x slower epilogues)
@@ -343,8 +322,6 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
       const size_t p0 = (size_t)r0 * S;
       const bool rv = row < nrows;
       const size_t prow = p0 + row;
-      const size_t pw0 = p0 + lane_base;                                   // first row of this warp's lane quadrant
-      const int wvalid = save_full ? min(max(nrows - (int)lane_base, 0), 32) : 0;   // rows of it that are saved
       LSR_PHASE_BEGIN();
 
       // ---------------------------------------------------------------- neighbour lists of the tile

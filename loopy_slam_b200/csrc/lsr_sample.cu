@@ -3,6 +3,7 @@
 //   quad2rotation / get_camera_from_tensor                       /root/reference/src/common.py:301-343
 // The reference rebuilds a full H x W meshgrid per call and launches ~10 tiny kernels; here one
 // launch turns n pixel indices into rays + gathered depth/colour.
+#include <cstring>
 #include "lsr_common.cuh"
 
 namespace lsr {
@@ -52,7 +53,8 @@ __global__ void __launch_bounds__(1024) sample_rays_filtered_kernel(
     const float* __restrict__ depth_img, const float* __restrict__ color_img, int H, int W, float fx, float fy, float cx, float cy,
     const float* __restrict__ c2w, int ld, const int64_t* __restrict__ pix, int64_t n, int H0, int H1, int W0, int W1,
     float depth_limit, float* __restrict__ rays_o, float* __restrict__ rays_d, float* __restrict__ depth,
-    float* __restrict__ color, int64_t* __restrict__ i_out, int64_t* __restrict__ j_out, int32_t* __restrict__ count) {
+    float* __restrict__ color, int64_t* __restrict__ i_out, int64_t* __restrict__ j_out, int32_t* __restrict__ count,
+    unsigned long long* __restrict__ host_word, uint32_t ticket) {
   __shared__ int warp_cnt[32];
   __shared__ int base_s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -104,7 +106,12 @@ __global__ void __launch_bounds__(1024) sample_rays_filtered_kernel(
     if (threadIdx.x == 0) base_s = base + total;
     __syncthreads();
   }
-  if (threadIdx.x == 0) *count = base_s;
+  if (threadIdx.x == 0) {
+    if (count) *count = base_s;
+    // host-mapped result word of lsr_sample_rays_filtered_sync: (ticket << 32) | count in ONE 8-byte store, so the spinning
+    // host thread can never see a count without its ticket
+    if (host_word) *reinterpret_cast<volatile unsigned long long*>(host_word) = ((unsigned long long)ticket << 32) | (uint32_t)base_s;
+  }
 }
 
 __global__ void sample_rays_bwd_kernel(const float* __restrict__ g_o, const float* __restrict__ g_d,
@@ -339,10 +346,64 @@ extern "C" int lsr_sample_rays_filtered(const float* depth_img, const float* col
   if (n == 0) { LSR_CUDA_CHECK(cudaMemsetAsync(count, 0, sizeof(int32_t), stream)); return LSR_OK; }
   if (!depth_img || !c2w || !pix || !rays_o || !rays_d || !depth || !i_out || !j_out) return LSR_ERR_ARG;
   sample_rays_filtered_kernel<<<1, 1024, 0, stream>>>(depth_img, color_img, H, W, fx, fy, cx, cy, c2w, c2w_ld, pix, n, H0, H1,
-                                                      W0, W1, depth_limit, rays_o, rays_d, depth, color, i_out, j_out, count);
+                                                      W0, W1, depth_limit, rays_o, rays_d, depth, color, i_out, j_out, count,
+                                                      nullptr, 0u);
   LSR_LAUNCHED(1);
   LSR_CUDA_CHECK(cudaGetLastError());
   return LSR_OK;
+}
+
+// The reference's get_samples returns tensors whose LENGTH is the number of kept pixels (src/common.py:249-255), so every call
+// has to bring one integer back to the host.  Instead of a D2H copy + stream synchronize (~20 us of driver work per call, twelve
+// calls per mapping iteration), the kernel stores the count together with a per-call ticket into a host-mapped pinned word and
+// this function spins on it.  Everything else the call wrote stays ordered by the stream as usual.
+namespace {
+struct HostWords {
+  unsigned long long* w = nullptr;   // 64 words, cudaHostAllocPortable | cudaHostAllocMapped (UVA: same pointer on every device)
+  unsigned int next = 0;
+};
+HostWords g_words;
+}  // namespace
+
+extern "C" int lsr_sample_rays_filtered_sync(const float* depth_img, const float* color_img, int32_t H, int32_t W, float fx,
+                                             float fy, float cx, float cy, const float* c2w, int32_t c2w_ld,
+                                             const int64_t* pix, int64_t n, int32_t H0, int32_t H1, int32_t W0, int32_t W1,
+                                             float depth_limit, float* rays_o, float* rays_d, float* depth, float* color,
+                                             int64_t* i_out, int64_t* j_out, int32_t* count_host, lsr_stream_t stream) {
+  if (n < 0 || H <= 0 || W <= 0 || H0 < 0 || W0 < 0 || H1 > H || W1 > W || H0 >= H1 || W0 >= W1 || c2w_ld < 4 || !count_host)
+    return LSR_ERR_ARG;
+  *count_host = 0;
+  if (n == 0) return LSR_OK;
+  if (!depth_img || !c2w || !pix || !rays_o || !rays_d || !depth || !i_out || !j_out) return LSR_ERR_ARG;
+  if (!g_words.w) {
+    void* p = nullptr;
+    LSR_CUDA_CHECK(cudaHostAlloc(&p, 64 * sizeof(unsigned long long), cudaHostAllocPortable | cudaHostAllocMapped));
+    memset(p, 0, 64 * sizeof(unsigned long long));
+    unsigned long long* expect = nullptr;
+    if (!__atomic_compare_exchange_n(&g_words.w, &expect, (unsigned long long*)p, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE))
+      cudaFreeHost(p);                                   // another thread won the race
+  }
+  const unsigned int t = __atomic_add_fetch(&g_words.next, 1u, __ATOMIC_RELAXED);
+  const uint32_t ticket = t | 0x80000000u;               // never 0: a fresh (zeroed) word cannot match
+  unsigned long long* word = g_words.w + (t & 63u);
+  sample_rays_filtered_kernel<<<1, 1024, 0, stream>>>(depth_img, color_img, H, W, fx, fy, cx, cy, c2w, c2w_ld, pix, n, H0, H1,
+                                                      W0, W1, depth_limit, rays_o, rays_d, depth, color, i_out, j_out, nullptr,
+                                                      word, ticket);
+  LSR_LAUNCHED(1);
+  LSR_CUDA_CHECK(cudaGetLastError());
+  for (unsigned long long spins = 1;; ++spins) {
+    const unsigned long long v = __atomic_load_n(word, __ATOMIC_ACQUIRE);
+    if ((uint32_t)(v >> 32) == ticket) { *count_host = (int32_t)(uint32_t)v; return LSR_OK; }
+    if ((spins & 0xfffu) == 0) {                          // a faulted kernel never writes its ticket: ask the stream
+      const cudaError_t q = cudaStreamQuery(stream);
+      if (q == cudaSuccess) {
+        const unsigned long long v2 = __atomic_load_n(word, __ATOMIC_ACQUIRE);
+        if ((uint32_t)(v2 >> 32) == ticket) { *count_host = (int32_t)(uint32_t)v2; return LSR_OK; }
+        return LSR_ERR_CUDA;
+      }
+      if (q != cudaErrorNotReady) return LSR_ERR_CUDA;
+    }
+  }
 }
 
 extern "C" int lsr_sample_rays_bwd(const float* d_rays_o, const float* d_rays_d, const int64_t* i_pix,
