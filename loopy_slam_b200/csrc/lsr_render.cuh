@@ -96,7 +96,7 @@ __host__ __device__ inline size_t scratch_legacy_floats() { return (size_t)Packe
 //      - the backward bulk-copies an atom column (F * 128 bytes, contiguous) into shared memory and the tensor
 //        core contracts over the ROWS directly (weight-gradient GEMMs), tools/umma_sw128_probe.cu test 1.
 struct SavedLayout {
-  size_t idx, w, D, misc, occ, rgbs, outraw, light_end, cg, gs, gh, cst, cht, cc1t, ect, ut, spt, qt, total;
+  size_t idx, w, D, misc, occ, rgbs, outraw, light_end, cg, gs, gh, cst, cc1t, ect, ut, spt, qt, total;
   size_t P, Pp;
   int ntiles, rays_per_tile;
 };
@@ -132,10 +132,11 @@ __host__ __device__ inline SavedLayout saved_layout(int64_t R, int S, int stage,
   L.cg = o;    o += Pp * CDIM;
   L.gs = o;    o += 5 * Pp * HG;
   L.gh = o;    o += 5 * Pp * HG;
-  L.cst = o; L.cht = o; L.cc1t = o; L.ect = o; L.ut = o; L.spt = o; L.qt = o;
+  L.cst = o; L.cc1t = o; L.ect = o; L.ut = o; L.spt = o; L.qt = o;
   if (stage == LSR_STAGE_COLOR) {
     L.cst = o;     o += 5 * nt * tplane_tile_floats(HC);    // softplus outputs s_l          [layer][tile]
-    L.cht = o;     o += 5 * nt * tplane_tile_floats(HC);    // layer outputs h_l             [layer][tile]
+    // (the layer outputs h_l = s_l + U_l c + u_l are NOT saved: the backward needs them only inside Z^T h, which is
+    //  Z^T s + (Z^T [c | 1]) [U | u]^T -- the second factor is accumulated anyway for the fc_c gradients)
     L.cc1t = o;    o += nt * tplane_tile_floats(TP_C1);     // [c | 1 | 0]
     L.ect = o;     o += nt * tplane_tile_floats(ECC);       // colour Fourier features e' = [sin | cos]
     if (flags & LSR_FLAG_REL_POS) {   // rel-pos neighbour MLP: u = sum_k w_k softplus(.), the 8 softplus outputs, the 8 inputs Q_k

@@ -299,23 +299,23 @@ __global__ void __launch_bounds__(BT, 1) trunk_bwd_umma_kernel(const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(&pipe->conv[stage]);
         // DRAM -> L2 prefetch (LSU path: the TMA queue stays free for the ring) of what the NEXT tile of this CTA reads
-        // from the saved planes -- s_l and h_l T-planes, [c|1], e' -- one request per 128-byte line, spread over the ops
+        // from the saved planes -- s_l T-planes, [c|1], e' -- one request per 128-byte line, spread over the ops
         const int tt = tile + (int)gridDim.x;
         if (tt < a.ntiles) {
-          constexpr int LINES = 10 * HC * 4 + (TP_C1 + ECC) * 4;
+          constexpr int LINES = 5 * HC * 4 + (TP_C1 + ECC) * 4;
           const int per = (LINES + a.n_ops - 1) / a.n_ops;
           for (int e = i * per + cw * 32 + lane; e < min((i + 1) * per, LINES); e += 32 * BCONV) {
             const float* base;
             int ln = e;
-            if (ln < 10 * HC * 4) {
+            if (ln < 5 * HC * 4) {
               const int pl = ln / (HC * 4);
               ln -= pl * HC * 4;
-              base = sv + (pl < 5 ? SL.cst : SL.cht) + ((size_t)(pl % 5) * SL.ntiles + tt) * tplane_tile_floats(HC);
-            } else if (ln < 10 * HC * 4 + TP_C1 * 4) {
-              ln -= 10 * HC * 4;
+              base = sv + SL.cst + ((size_t)pl * SL.ntiles + tt) * tplane_tile_floats(HC);
+            } else if (ln < 5 * HC * 4 + TP_C1 * 4) {
+              ln -= 5 * HC * 4;
               base = sv + SL.cc1t + (size_t)tt * tplane_tile_floats(TP_C1);
             } else {
-              ln -= 10 * HC * 4 + TP_C1 * 4;
+              ln -= 5 * HC * 4 + TP_C1 * 4;
               base = sv + SL.ect + (size_t)tt * tplane_tile_floats(ECC);
             }
             prefetch_l2(base + (size_t)ln * 32);
@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(BT, 1) trunk_bwd_umma_kernel(const __grid_cons
       // ---------------------------------------------------------------- output_linear gradients + M_out = dOut^T [c | 1]
       // thread-per-feature-line FMAs: lane l reads 4 rows of the (swizzled) 128-byte lines of feature f
       if (g_cw) {
-        const float* tph4 = sv + SL.cht + ((size_t)4 * SL.ntiles + tile) * tplane_tile_floats(HC);
+        const float* tph4 = sv + SL.cst + ((size_t)4 * SL.ntiles + tile) * tplane_tile_floats(HC);   // s_4; the (U_4 c + u_4) part of h_4 is added by the finalize kernel
         const float* tpc1 = sv + SL.cc1t + (size_t)tile * tplane_tile_floats(TP_C1);
         constexpr int NL = (HC + CDIM + 1 + BCW - 1) / BCW;   // feature lines per warp (11)
         float4 xs[NL];
@@ -659,7 +659,6 @@ __global__ void __launch_bounds__(BT, 1) trunk_bwd_umma_kernel(const __grid_cons
         if (warp == 0) TRC(1, (4 - l) * 10 + 0);
         if (l >= 1) {   // DRAM -> L2 one layer ahead: s_{l-1} (epilogue loads) and h_{l-2} (row-contraction pieces of layer l - 1)
           prefetch_l2(sv + SL.cst + ((size_t)(l - 1) * SL.ntiles + tile) * tplane_tile_floats(HC) + (size_t)tid * 32);
-          if (g_cw && l >= 2) prefetch_l2(sv + SL.cht + ((size_t)(l - 2) * SL.ntiles + tile) * tplane_tile_floats(HC) + (size_t)tid * 32);
         }
         {
           const float* tps = sv + SL.cst + ((size_t)l * SL.ntiles + tile) * tplane_tile_floats(HC) + tq * (HC * 32) + (tj & 3);
@@ -1033,8 +1032,9 @@ __global__ void __launch_bounds__(128) relpos_trig_bwd_kernel(const __grid_const
 //   d c_fc_w[4][i][c]     = sum_o W_out[o][i] M_out[o][c];     d c_fc_b[4][i] = sum_o W_out[o][i] M_out[o][ones];  d c_out_b = M_out[:, ones]
 __global__ void __launch_bounds__(HC) trunk_bwd_finalize_kernel(const float* __restrict__ blob, const float* __restrict__ acc,
                                                                 float* __restrict__ dW, const __grid_constant__ LsrWeights w) {
-  // grid (33 + 2, 5): blockIdx.x = c < 33 -> column c of fc_c[l] (32: bias) for all 128 i (threadIdx.x);
-  //                   33 -> lin bias of layer l; 34 -> e' columns of c_lin_w[l] (l = 0, 3) and the head bias
+  // grid (33 + 2 + 128, 5): blockIdx.x = c < 33 -> column c of fc_c[l] (32: bias) for all 128 i (threadIdx.x);
+  //                   33 -> lin bias of layer l; 34 -> e' columns of c_lin_w[l] (l = 0, 3) and the head bias;
+  //                   35 + o -> the (U c + u) part of the h-columns of row o of c_lin_w[l] (l >= 1) / c_out_w (l == 0)
   const int l = blockIdx.y, c = blockIdx.x, i = threadIdx.x;
   const float* mo = acc + 5 * BWD_ACC_SLOTS * 128;
   __shared__ float sm[HC];
@@ -1061,6 +1061,22 @@ __global__ void __launch_bounds__(HC) trunk_bwd_finalize_kernel(const float* __r
     else dW[w.c_fc_b[l] + i] += s;
   } else if (c == CDIM + 1) {
     dW[w.c_lin_b[l] + i] += acc[((size_t)l * BWD_ACC_SLOTS + 40 + CDIM) * 128 + i];
+  } else if (c >= CDIM + 3) {
+    // The tensor-core pass contracted Z_l with the SAVED softplus outputs s_{l-1} only; the rest of h_{l-1} = s_{l-1} + U_{l-1} c +
+    // u_{l-1} enters through M_l:  d c_lin_w[l][o][hoff + i] += sum_c M_l[c][o] U_{l-1}[i][c] + M_l[ones][o] u_{l-1}[i]   (l = 1..4),
+    // and for the head (blockIdx.y == 0):  d c_out_w[o][i] += sum_c M_out[o][c] U_4[i][c] + M_out[o][ones] u_4[i].
+    const int o = c - (CDIM + 3);
+    if (l == 0 && o >= 3) return;
+    const int lu = l == 0 ? 4 : l - 1;                       // the fc_c layer whose output is part of the contracted h
+    sm[i] = 0.f;
+    if (i <= CDIM) sm[i] = l == 0 ? mo[o * TP_C1 + i] : acc[((size_t)l * BWD_ACC_SLOTS + 40 + i) * 128 + o];
+    __syncthreads();
+    const float* ur = blob + w.c_fc_w[lu] + (size_t)i * CDIM;
+    float s = sm[CDIM] * blob[w.c_fc_b[lu] + i];
+#pragma unroll 8
+    for (int cc = 0; cc < CDIM; ++cc) s = fmaf(sm[cc], ur[cc], s);
+    if (l == 0) dW[w.c_out_w + o * HC + i] += s;
+    else dW[w.c_lin_w[l] + (size_t)o * (l == 3 ? ECC + HC : HC) + (l == 3 ? ECC : 0) + i] += s;
   } else {
     if (l == 0 || l == 3) {
       const int ldw = l == 3 ? ECC + HC : ECC;
@@ -1133,7 +1149,7 @@ static void build_trunk_program(const LsrWeights* w, const SavedLayout& SL, bool
     bool first_dw = true;
     if (l >= 1) {
       for (int q = 0; q < 4; ++q) {
-        op(K_DWH, (uint32_t)(SL.cht + (size_t)(l - 1) * SL.ntiles * tile_h + q * (HC * 32)), tile_h, HC * 128, 0, 0, 0,
+        op(K_DWH, (uint32_t)(SL.cst + (size_t)(l - 1) * SL.ntiles * tile_h + q * (HC * 32)), tile_h, HC * 128, 0, 0, 0,
            (first_dw ? RF_WAIT_B : 0) | (q == 0 ? RF_FIRST : 0), 4, q, HC);
         first_dw = false;
       }
@@ -1247,7 +1263,7 @@ int launch_trunk_bwd(const LsrParams* prm, const LsrWeights* w, const float* gt_
     LSR_CUDA_CHECK(cudaGetLastError());
   }
   if (g_cw) {
-    trunk_bwd_finalize_kernel<<<dim3(CDIM + 3, 5), HC, 0, stream>>>(w->blob, acc, d_weights, *w);
+    trunk_bwd_finalize_kernel<<<dim3(CDIM + 3 + HC, 5), HC, 0, stream>>>(w->blob, acc, d_weights, *w);
     LSR_LAUNCHED(1);
     LSR_CUDA_CHECK(cudaGetLastError());
   }

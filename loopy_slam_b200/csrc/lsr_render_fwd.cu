@@ -663,9 +663,8 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
 #pragma unroll 1
         for (int li = 0; li < 5; ++li) {
           es.wait_d(pipe, 0);
-          // s_l / h_l T-planes: this thread's row inside the tile's atom column, chunk swizzle folded per feature
+          // s_l T-plane: this thread's row inside the tile's atom column, chunk swizzle folded per feature
           float* tps = a.saved + SL.cst + ((size_t)li * SL.ntiles + tile) * tplane_tile_floats(HC) + (row >> 5) * (HC * 32) + (row & 3);
-          float* tph = a.saved + SL.cht + ((size_t)li * SL.ntiles + tile) * tplane_tile_floats(HC) + (row >> 5) * (HC * 32) + (row & 3);
           const int tchunk = (row & 31) >> 2;
           uint32_t v1[2][16], v2[2][16];
           tmem_ld16(tmem_addr(tb, lane_base, TM_ACC0 + CPT * cg), v1[0]);
@@ -698,7 +697,6 @@ __global__ void __launch_bounds__(FT, 1) render_fwd_kernel(const __grid_constant
                   const int f = col0 + j + t;
                   const int off = f * 32 + ((tchunk ^ ((j + t) & 7)) << 2);
                   tps[off] = rv ? s[t] : 0.f;
-                  tph[off] = rv ? hk[j + t] : 0.f;
                 }
               }
             }
