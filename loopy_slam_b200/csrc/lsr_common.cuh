@@ -95,6 +95,7 @@ __device__ __forceinline__ float sqdist_rn(float ax, float ay, float az, float b
 // float64 tensor); else in float against r2f.
 constexpr unsigned KNN_INF = 0x7f800000u;   // +inf bits; squared distances are >= 0 so bit order == value order
 constexpr int KNN_NOID = 0x7fffffff;
+constexpr int KNN_PEND = 64;               // pending-candidate slots per query of knn_warp_multi (warp-private shared memory)
 
 // Conservative lower bound of |p - x| over every x binned into cell c along one axis (0 when p may be
 // inside).  Points land in cell c when floor(fl(fl(x - o) * inv)) == c, i.e. x in [o + c*cell, o + (c+1)*cell)
@@ -117,11 +118,47 @@ template <int NQ>
 __device__ __forceinline__ void knn_warp_multi(const GridView& g, const float (&px)[NQ], const float (&py)[NQ],
                                                const float (&pz)[NQ], const float (&rr)[NQ], const bool (&active)[NQ],
                                                bool dyn, const float (&r2f)[NQ], const double (&r2d)[NQ],
-                                               unsigned (&bestD)[NQ], int (&bestI)[NQ]) {
+                                               unsigned (&bestD)[NQ], int (&bestI)[NQ], uint2* __restrict__ pend) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
+  // In-radius candidates that beat the current 8th best are only APPENDED to a warp-private list in shared memory
+  // (pend: KNN_PEND entries per query); the 8-round selection -- by far the most expensive part of the walk, and it was run
+  // for nearly every 32-candidate chunk -- runs when 32 of them are waiting or at the end: typically once per query
+  // (a query ball holds ~15-25 points).  The result does not depend on the processing order: (D, id) is a total order.
+  int npend[NQ];
+  unsigned b7D[NQ];
+  int b7I[NQ];
 #pragma unroll
-  for (int q = 0; q < NQ; ++q) { bestD[q] = KNN_INF; bestI[q] = KNN_NOID; }
+  for (int q = 0; q < NQ; ++q) { bestD[q] = KNN_INF; bestI[q] = KNN_NOID; npend[q] = 0; b7D[q] = KNN_INF; b7I[q] = KNN_NOID; }
+  auto flush = [&](int q) {
+    __syncwarp();
+    for (int base = 0; base < npend[q]; base += 32) {
+      unsigned cD = KNN_INF;
+      int cI = KNN_NOID;
+      if (base + lane < npend[q]) { const uint2 e = pend[q * KNN_PEND + base + lane]; cD = e.x; cI = (int)e.y; }
+      unsigned oD = lane < KNN ? bestD[q] : KNN_INF;
+      int oI = lane < KNN ? bestI[q] : KNN_NOID;
+      unsigned nD = KNN_INF;
+      int nI = KNN_NOID;
+#pragma unroll
+      for (int k = 0; k < KNN; ++k) {
+        const bool c_lt = (cD < oD) || (cD == oD && cI < oI);
+        const unsigned lD = c_lt ? cD : oD;
+        const int lI = c_lt ? cI : oI;
+        const unsigned mD = __reduce_min_sync(FULL, lD);
+        const int mI = __reduce_min_sync(FULL, lD == mD ? lI : KNN_NOID);
+        if (lane == k) { nD = mD; nI = mI; }
+        if (cD == mD && cI == mI) { cD = KNN_INF; cI = KNN_NOID; }
+        else if (oD == mD && oI == mI) { oD = KNN_INF; oI = KNN_NOID; }
+      }
+      bestD[q] = nD;
+      bestI[q] = nI;
+    }
+    npend[q] = 0;
+    b7D[q] = __shfl_sync(FULL, bestD[q], KNN - 1);
+    b7I[q] = __shfl_sync(FULL, bestI[q], KNN - 1);
+    __syncwarp();
+  };
   const GridHeader* h = g.hdr;
   if (h->n_points <= 0) return;
   const float inv = h->inv_cell, ce = h->cell;
@@ -207,30 +244,19 @@ __device__ __forceinline__ void knn_warp_multi(const GridView& g, const float (&
           const bool outside = dyn ? ((double)D > r2d[q]) : (D > r2f[q]);
           if (!outside) { cD = __float_as_uint(D); cI = __float_as_int(q4[q].w); }
         }
-        const unsigned b7D = __shfl_sync(FULL, bestD[q], KNN - 1);
-        const int b7I = __shfl_sync(FULL, bestI[q], KNN - 1);
-        if (__any_sync(FULL, (cD < b7D) || (cD == b7D && cI < b7I))) {
-          unsigned oD = lane < KNN ? bestD[q] : KNN_INF;
-          int oI = lane < KNN ? bestI[q] : KNN_NOID;
-          unsigned nD = KNN_INF;
-          int nI = KNN_NOID;
-#pragma unroll
-          for (int k = 0; k < KNN; ++k) {
-            const bool c_lt = (cD < oD) || (cD == oD && cI < oI);
-            const unsigned lD = c_lt ? cD : oD;
-            const int lI = c_lt ? cI : oI;
-            const unsigned mD = __reduce_min_sync(FULL, lD);
-            const int mI = __reduce_min_sync(FULL, lD == mD ? lI : KNN_NOID);
-            if (lane == k) { nD = mD; nI = mI; }
-            if (cD == mD && cI == mI) { cD = KNN_INF; cI = KNN_NOID; }
-            else if (oD == mD && oI == mI) { oD = KNN_INF; oI = KNN_NOID; }
-          }
-          bestD[q] = nD;
-          bestI[q] = nI;
+        const bool better = (cD < b7D[q]) || (cD == b7D[q] && cI < b7I[q]);   // cD == INF (outside / no candidate) never is
+        const unsigned bal = __ballot_sync(FULL, better);
+        if (bal) {
+          if (better) pend[q * KNN_PEND + npend[q] + __popc(bal & ((1u << lane) - 1u))] = make_uint2(cD, (unsigned)cI);
+          npend[q] += __popc(bal);
+          if (npend[q] > 32) flush(q);
         }
       }
     }
   }
+#pragma unroll
+  for (int q = 0; q < NQ; ++q)
+    if (npend[q] > 0) flush(q);
 }
 #endif  // __CUDACC__
 

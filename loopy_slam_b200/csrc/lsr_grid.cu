@@ -210,7 +210,8 @@ __global__ void __launch_bounds__(KQ_NT) knn_query_kernel(const void* ws, const 
       px[t] = q[3 * i]; py[t] = q[3 * i + 1]; pz[t] = q[3 * i + 2];
     }
   }
-  knn_warp_multi<KQ_NQ>(g, px, py, pz, rr, act, dyn, r2f, r2d, bD, bI);
+  __shared__ uint2 pend_s[KQ_NT / 32][KQ_NQ * KNN_PEND];
+  knn_warp_multi<KQ_NQ>(g, px, py, pz, rr, act, dyn, r2f, r2d, bD, bI, pend_s[threadIdx.x >> 5]);
 #pragma unroll
   for (int t = 0; t < KQ_NQ; ++t) {
     const int64_t i = i0 + t;

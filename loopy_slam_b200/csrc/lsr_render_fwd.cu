@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(256, LSR_KNN_BLOCKS) sample_knn_kernel(const _
   const SavedLayout SL = saved_layout(a.R, S, a.stage, a.prm.flags);
   const GridHeader* gh_ = reinterpret_cast<const GridHeader*>(a.grid);
   const GridView gv = grid_view(a.grid, gh_->n_points, gh_->max_cells);
+  __shared__ uint2 pend_s[8][NQ * KNN_PEND];
   const int lane = threadIdx.x & 31;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
   for (int pair = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pair * NQ < P; pair += warps_total) {
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(256, LSR_KNN_BLOCKS) sample_knn_kernel(const _
         rr[q] = (float)r * 1.00001f + 1e-7f;
       }
     }
-    knn_warp_multi<NQ>(gv, px, py, pz, rr, rowvalid, dynr, r2f, r2d, bD, bI);
+    knn_warp_multi<NQ>(gv, px, py, pz, rr, rowvalid, dynr, r2f, r2d, bD, bI, pend_s[threadIdx.x >> 5]);
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
       const int m = m0 + q;
