@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('LSR_LIB', os.path.join(_HERE, 'liblsr.so'))   # LSR_LIB: A/B experiments only
 
 LSR_STAGE = {'geometry': 0, 'color': 1}
-FLAG_REL_POS, FLAG_DYNAMIC_R, FLAG_SKIP_ZERO_DEPTH, FLAG_SAMPLE_NEAR_PCL, FLAG_SAVE_LIGHT = 1, 2, 4, 8, 16
+FLAG_REL_POS, FLAG_DYNAMIC_R, FLAG_SKIP_ZERO_DEPTH, FLAG_SAMPLE_NEAR_PCL, FLAG_SAVE_LIGHT, FLAG_FWD_ONLY = 1, 2, 4, 8, 16, 32
 RGB_SIGMOID, RGB_RAW, RGB_AFFINE_SIGMOID = 0, 1, 2
 GRAD_GEO_FEATS, GRAD_COL_FEATS, GRAD_GEO_W, GRAD_GEO_B, GRAD_COL_W, GRAD_RAYS, GRAD_AFFINE = 1, 2, 4, 8, 16, 32, 64
 

@@ -158,7 +158,11 @@ constexpr int UMMA_PACKED_FLOATS_MAX = 2 * (93 * 32 + 3 * 32 * 32 + 128 * 32 + 5
 constexpr int BWD_PACK_FLOATS_MAX = 4 * 128 * 128 + (32 + 80 + 32 + 32 + 48) * 128 + 128 * 32 + 64 * 128 + 128 + 4096;   // W^hT x 4, extras, V2^T, V1^T, P_out
 constexpr int BWD_ACC_SLOTS = 80;                 // per colour layer: [e' (40) | c (32) | 1 | pad (7)] x 128 outputs
 constexpr int BWD_ACC_FLOATS = 5 * BWD_ACC_SLOTS * 128 + 3 * TP_C1;   // + M_out [3][40]
-struct ScratchLayout { size_t legacy, umma, knn_idx, knn_rem, knn_w, knn_pos, knn_hw, bwd_pack, bwd_acc, bwd_dc, bwd_dp, bwd_dwh, bwd_dqt, total; };
+constexpr int GEO_PACK_FLOATS = 14336 + 32;        // geometry backward: per-layer B blocks [W_l^h | P_l (| W^e)] + v = w_out U_4 (lsr_geo_bwd_umma.cu)
+struct ScratchLayout {
+  size_t legacy, umma, knn_idx, knn_rem, knn_w, knn_pos, knn_hw, fwd_end, bwd_pack, bwd_acc, bwd_dc, bwd_dp, bwd_dwh, bwd_dqt, bwd_gpack,
+      bwd_gdc, bwd_gde, bwd_gdh, total;
+};
 __host__ __device__ inline ScratchLayout scratch_layout(int64_t n_rays, int S) {
   ScratchLayout L;
   const size_t Pp = align_up((size_t)n_rays * S, 128) + 128;
@@ -170,6 +174,7 @@ __host__ __device__ inline ScratchLayout scratch_layout(int64_t n_rays, int S) {
   L.knn_w = o;    o = align_up(o + Pp * KNN * 4, 256);
   L.knn_pos = o;  o = align_up(o + Pp * 16, 256);
   L.knn_hw = o;   o = align_up(o + Pp * 8, 256);
+  L.fwd_end = o + 256;                                      // LSR_FLAG_FWD_ONLY: nothing behind this point is needed
   L.bwd_pack = o; o = align_up(o + (size_t)BWD_PACK_FLOATS_MAX * sizeof(float), 256);
   L.bwd_acc = o;  o = align_up(o + (size_t)BWD_ACC_FLOATS * sizeof(float), 256);
   L.bwd_dc = o;   o = align_up(o + Pp * CDIM * 4, 256);     // dL/dc (colour feature) per sample row
@@ -179,6 +184,10 @@ __host__ __device__ inline ScratchLayout scratch_layout(int64_t n_rays, int S) {
     const size_t rpt = (size_t)(128 / S), nt = ((size_t)n_rays + rpt - 1) / rpt;
     L.bwd_dqt = o;  o = align_up(o + (nt > 0 ? nt : 1) * KNN * 20 * 128 * 4, 256);
   }
+  L.bwd_gpack = o; o = align_up(o + (size_t)GEO_PACK_FLOATS * sizeof(float), 256);
+  L.bwd_gdc = o;   o = align_up(o + Pp * CDIM * 4, 256);    // geometry chain hand-over: dL/dc^g, dL/de (96), dL/dh_l (5 x 32)
+  L.bwd_gde = o;   o = align_up(o + Pp * EGP * 4, 256);
+  L.bwd_gdh = o;   o = align_up(o + 5 * Pp * HG * 4, 256);
   L.total = o + 256;
   return L;
 }
@@ -267,6 +276,73 @@ __device__ __forceinline__ void sincos_ff(float x, float* s, float* c) {
 }
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.f / (1.f + expf(-x)); }
+
+// Compositing backward of ONE ray (Renderer.py:184-201, common.py:382-422): dL/d(occupancy logit) of its S samples -> dOcc[s],
+// and (colour stage, dOut != nullptr) dL/d(rgb of sample s) -> dOut[4 s + {0,1,2}].  prow0 = global row of the ray's first sample.
+__device__ __forceinline__ void composite_bwd_ray(const LsrParams& prm, bool color, const float* __restrict__ sv, const SavedLayout& SL,
+                                                  size_t prow0, int ray, const float* __restrict__ gt_depth,
+                                                  const float* __restrict__ g_depth, const float* __restrict__ g_var,
+                                                  const float* __restrict__ g_rgb, float* dOcc, float* dOut) {
+  const int S = prm.n_surface;
+  const float g = gt_depth[ray];
+  const float coef = prm.sigmoid_coef;
+  const bool nz = g > 0.f;
+  const float gD = (nz || (prm.flags & LSR_FLAG_SAMPLE_NEAR_PCL)) ? g_depth[ray] : 0.f;   // Renderer.py:197-198
+  const float gV = g_var ? g_var[ray] : 0.f;
+  float gC[3] = {0.f, 0.f, 0.f};
+  if (color && g_rgb && (nz || !(prm.flags & LSR_FLAG_SKIP_ZERO_DEPTH))) {
+    gC[0] = g_rgb[3 * ray + 0]; gC[1] = g_rgb[3 * ray + 1]; gC[2] = g_rgb[3 * ray + 2];
+  }
+  float al[8], Tv[8], wv[8], zv[8], rg[8][3];
+  float T = 1.f, sw = 0.f, swz = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    if (s < S) {
+      const float4 mi = reinterpret_cast<const float4*>(sv + SL.misc)[prow0 + s];   // (z, has, sum w, cnt)
+      const float occ = mi.y > 0.5f ? sv[SL.occ + prow0 + s] : -100.f;
+      const float alpha = sigmoidf_acc(coef * occ);
+      al[s] = alpha; Tv[s] = T;
+      const float w = alpha * T;
+      wv[s] = w;
+      T = T * ((1.f - alpha) + 1e-10f);
+      zv[s] = mi.x;
+      float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (color) rs = reinterpret_cast<const float4*>(sv + SL.rgbs)[prow0 + s];
+      rg[s][0] = rs.x; rg[s][1] = rs.y; rg[s][2] = rs.z;
+      sw += w; swz += w * zv[s];
+      c0 += w * rs.x; c1 += w * rs.y; c2 += w * rs.z;
+    }
+  }
+  const float wsum = sw + 1e-10f;
+  const float depth = swz / wsum;
+  const float m0 = c0 / wsum, m1 = c1 / wsum, m2 = c2 / wsum;
+  float dvar_ddepth = 0.f;
+#pragma unroll
+  for (int s = 0; s < 8; ++s)
+    if (s < S) dvar_ddepth += -2.f * wv[s] * (zv[s] - depth);
+  const float gDe = gD + gV * dvar_ddepth;
+  float dwv[8];
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    if (s < S) {
+      const float dz = zv[s] - depth;
+      dwv[s] = (gDe * dz + gC[0] * (rg[s][0] - m0) + gC[1] * (rg[s][1] - m1) + gC[2] * (rg[s][2] - m2)) / wsum + gV * dz * dz;
+    }
+  }
+  float suffix = 0.f;
+#pragma unroll
+  for (int s = 7; s >= 0; --s) {
+    if (s < S) {
+      const float dalpha = Tv[s] * dwv[s] - suffix / ((1.f - al[s]) + 1e-10f);
+      suffix += wv[s] * dwv[s];
+      dOcc[s] = coef * al[s] * (1.f - al[s]) * dalpha;
+      if (dOut) {
+        const float f = wv[s] / wsum;
+        dOut[4 * s + 0] = gC[0] * f; dOut[4 * s + 1] = gC[1] * f; dOut[4 * s + 2] = gC[2] * f;
+      }
+    }
+  }
+}
 
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);

@@ -4,6 +4,7 @@
 // graph of Renderer.render_batch_ray (/root/reference/src/utils/Renderer.py:71-201) that the
 // reference differentiates with loss.backward() (src/Mapper.py:722, src/Tracker.py:193).
 // Math: SURVEY.md Appendix A ("Backward of step 10") + the chain rule through Appendix A steps 2-7.
+#define LSR_FFMA_GEMM 1   // the only GEMMs left in this file are the (rare) geometry-decoder weight gradients: plain FP32 FFMA, no mma.sync
 #include "lsr_render.cuh"
 
 namespace lsr {
@@ -29,6 +30,7 @@ struct BwdArgs {
   int gflags;
   float *d_geo, *d_col, *d_w, *d_affine, *d_ro, *d_rd;
   const float *ext_dc, *ext_dp, *ext_dwh;   // colour backward hand-over (scratch planes)
+  const float *ext_gdc, *ext_gde, *ext_gdh; // geometry chain hand-over (lsr_geo_bwd_umma.cu): dL/dc^g (P x 32), dL/de (P x 96), dL/dh_l (5 x P x 32)
   int rays_per_tile, ntiles;
 };
 
@@ -159,67 +161,11 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
     __syncthreads();
 
     // ------------------------------------------------------------ 1: compositing backward
-    if (tid < nr) {
-      const int ray = r0 + tid;
-      const float g = a.gt_depth[ray];
-      const float coef = a.prm.sigmoid_coef;
-      const bool nz = g > 0.f;
-      const float gD = (nz || (a.prm.flags & LSR_FLAG_SAMPLE_NEAR_PCL)) ? a.g_depth[ray] : 0.f;   // Renderer.py:197-198
-      const float gV = a.g_var ? a.g_var[ray] : 0.f;
-      float gC[3] = {0.f, 0.f, 0.f};
-      if (color && a.g_rgb && (nz || !(a.prm.flags & LSR_FLAG_SKIP_ZERO_DEPTH))) {
-        gC[0] = a.g_rgb[3 * ray + 0]; gC[1] = a.g_rgb[3 * ray + 1]; gC[2] = a.g_rgb[3 * ray + 2];
-      }
-      float al[8], Tv[8], wv[8], zv[8], rg[8][3];
-      float T = 1.f, sw = 0.f, swz = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
-#pragma unroll
-      for (int s = 0; s < 8; ++s) {
-        if (s < S) {
-          const int m = tid * S + s;
-          const float occ = sHas[m] ? sv[SL.occ + p0 + m] : -100.f;
-          const float alpha = sigmoidf_acc(coef * occ);
-          al[s] = alpha; Tv[s] = T;
-          const float w = alpha * T;
-          wv[s] = w;
-          T = T * ((1.f - alpha) + 1e-10f);
-          zv[s] = sP[m * 4 + 3];
-          float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (color) rs = reinterpret_cast<const float4*>(sv + SL.rgbs)[p0 + m];
-          rg[s][0] = rs.x; rg[s][1] = rs.y; rg[s][2] = rs.z;
-          sw += w; swz += w * zv[s];
-          c0 += w * rs.x; c1 += w * rs.y; c2 += w * rs.z;
-        }
-      }
-      const float wsum = sw + 1e-10f;
-      const float depth = swz / wsum;
-      const float m0 = c0 / wsum, m1 = c1 / wsum, m2 = c2 / wsum;
-      float dvar_ddepth = 0.f;
-#pragma unroll
-      for (int s = 0; s < 8; ++s)
-        if (s < S) dvar_ddepth += -2.f * wv[s] * (zv[s] - depth);
-      const float gDe = gD + gV * dvar_ddepth;
-      float dwv[8];
-#pragma unroll
-      for (int s = 0; s < 8; ++s) {
-        if (s < S) {
-          const float dz = zv[s] - depth;
-          dwv[s] = (gDe * dz + gC[0] * (rg[s][0] - m0) + gC[1] * (rg[s][1] - m1) + gC[2] * (rg[s][2] - m2)) / wsum +
-                   gV * dz * dz;
-        }
-      }
-      float suffix = 0.f;
-#pragma unroll
-      for (int s = 7; s >= 0; --s) {
-        if (s < S) {
-          const int m = tid * S + s;
-          const float dalpha = Tv[s] * dwv[s] - suffix / ((1.f - al[s]) + 1e-10f);
-          suffix += wv[s] * dwv[s];
-          sDOcc[m] = coef * al[s] * (1.f - al[s]) * dalpha;
-          const float f = wv[s] / wsum;
-          sDOut[m * 4 + 0] = gC[0] * f; sDOut[m * 4 + 1] = gC[1] * f; sDOut[m * 4 + 2] = gC[2] * f;
-        }
-      }
-    }
+    // (only the output-layer gradients of a TRAINABLE geometry decoder still need dL/d(occupancy logit) here: the colour head
+    //  and both MLP chains take it inside their tensor-core kernels)
+    if (g_gw && tid < nr)
+      composite_bwd_ray(a.prm, color, sv, SL, p0 + (size_t)tid * S, r0 + tid, a.gt_depth, a.g_depth, a.g_var, a.g_rgb, sDOcc + tid * S,
+                        sDOut + tid * S * 4);
     __syncthreads();
 
     LSR_PHASE(1, 0);   // load state + compositing backward
@@ -254,13 +200,13 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
     LSR_PHASE(1, 4);   // rel-pos backward / colour scatter
     // -------------------------------------------------------------- geometry MLP backward
     {
-      for (int it = tid; it < TILE_M * 8; it += NT) {
-        const int m = it >> 3, q = it & 7;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m < nrows) v = reinterpret_cast<const float4*>(sv + SL.cg)[(p0 + m) * 8 + q];
-        *reinterpret_cast<float4*>(sC + m * CLD + q * 4) = v;
-      }
       if (g_gw) {
+        for (int it = tid; it < TILE_M * 8; it += NT) {
+          const int m = it >> 3, q = it & 7;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m < nrows) v = reinterpret_cast<const float4*>(sv + SL.cg)[(p0 + m) * 8 + q];
+          *reinterpret_cast<float4*>(sC + m * CLD + q * 4) = v;
+        }
         for (int it = tid; it < TILE_M * EGP; it += NT) {
           const int m = it / EGP, j = it - m * EGP;
           float v = 0.f;
@@ -283,52 +229,70 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
           atomicAdd(dW + a.w.g_out_b, s);
         }
       }
-      float dHg[TMNA][4];
-      {
-        const float4 wo = *reinterpret_cast<const float4*>(blob + a.w.g_out_w + nm.col());
+      // The dX chain (dH_l, dL/dc^g, dL/de) ran on the tensor cores (geo_bwd_umma_kernel); pick up its results.
+      float dCacc[TMNA][4], dEacc[TMA][8];
 #pragma unroll
-        for (int i = 0; i < TMNA; ++i) {
-          const float d = sDOcc[nm.row(i)];
-          dHg[i][0] = d * wo.x; dHg[i][1] = d * wo.y; dHg[i][2] = d * wo.z; dHg[i][3] = d * wo.w;
+      for (int i = 0; i < TMNA; ++i) {
+        const int r = nm.row(i);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nrows) v = *reinterpret_cast<const float4*>(a.ext_gdc + (p0 + r) * CDIM + nm.col());
+        dCacc[i][0] = v.x; dCacc[i][1] = v.y; dCacc[i][2] = v.z; dCacc[i][3] = v.w;
+      }
+      zero_acc(dEacc);
+      if (g_gb || g_ry) {
+#pragma unroll
+        for (int i = 0; i < TMA; ++i) {
+          const int r = wm.row(i);
+          if (r < nrows) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              if (wm.col(g) < EGP) {
+                const float4 v = *reinterpret_cast<const float4*>(a.ext_gde + (p0 + r) * EGP + wm.col(g));
+                dEacc[i][g * 4 + 0] = v.x; dEacc[i][g * 4 + 1] = v.y; dEacc[i][g * 4 + 2] = v.z; dEacc[i][g * 4 + 3] = v.w;
+              }
+            }
+          }
         }
       }
-      for (int li = 0; li < 5; ++li) prefetch_rows_l2(sv + SL.gs + ((size_t)li * Pp + p0) * HG, nrows, HG);
-      float dCacc[TMNA][4], dEacc[TMA][8];
-      zero_acc(dCacc);
-      zero_acc(dEacc);
+      if (g_gw) {
+        // geometry decoder weight gradients (only when mapping.fix_geo_decoder is off): per layer dU = dH^T c, dW = dA^T h_prev
 #pragma unroll 1
-      for (int li = 4; li >= 0; --li) {
+        for (int li = 4; li >= 0; --li) {
+          float dHg[TMNA][4];
 #pragma unroll
-        for (int i = 0; i < TMNA; ++i)
-          *reinterpret_cast<float4*>(sD + nm.row(i) * CLD + nm.col()) = make_float4(dHg[i][0], dHg[i][1], dHg[i][2], dHg[i][3]);
-        __syncthreads();
-        if (g_gw) {
+          for (int i = 0; i < TMNA; ++i) {
+            const int r = nm.row(i);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < nrows) v = *reinterpret_cast<const float4*>(a.ext_gdh + ((size_t)li * Pp + p0 + r) * HG + nm.col());
+            dHg[i][0] = v.x; dHg[i][1] = v.y; dHg[i][2] = v.z; dHg[i][3] = v.w;
+            *reinterpret_cast<float4*>(sD + r * CLD + nm.col()) = v;
+          }
+          __syncthreads();
           if (tid < HG) {
             float s = 0.f;
             for (int m = 0; m < nrows; ++m) s += sD[m * CLD + tid];
             atomicAdd(dW + a.w.g_fc_b[li] + tid, s);
           }
-          float au[TMN32][4];
-          zero_acc(au);
-          tile_gemm<TMN32, 8, 1, false, true>(au, sD, CLD, nrows, sC, CLD, CDIM, sB);
+          {
+            float au[TMN32][4];
+            zero_acc(au);
+            tile_gemm<TMN32, 8, 1, false, true>(au, sD, CLD, nrows, sC, CLD, CDIM, sB);
 #pragma unroll
-          for (int i = 0; i < TMN32; ++i)
-            red_add_v4(dW + a.w.g_fc_w[li] + nm.row(i) * CDIM + nm.col(), au[i][0], au[i][1], au[i][2], au[i][3]);
-        }
-        tile_gemm<TMNA, 8, 1, true, false>(dCacc, sD, CLD, HG, blob + a.w.g_fc_w[li], CDIM, CDIM, sB, nrows);
-#pragma unroll
-        for (int i = 0; i < TMNA; ++i) {
-          const int r = nm.row(i);
-          float4 dA = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (r < nrows) {
-            const float4 s4 = *reinterpret_cast<const float4*>(sv + SL.gs + ((size_t)li * Pp + p0 + r) * HG + nm.col());
-            dA = make_float4(s4.x > 0.f ? dHg[i][0] : 0.f, s4.y > 0.f ? dHg[i][1] : 0.f, s4.z > 0.f ? dHg[i][2] : 0.f,
-                             s4.w > 0.f ? dHg[i][3] : 0.f);
+            for (int i = 0; i < TMN32; ++i)
+              red_add_v4(dW + a.w.g_fc_w[li] + nm.row(i) * CDIM + nm.col(), au[i][0], au[i][1], au[i][2], au[i][3]);
           }
-          *reinterpret_cast<float4*>(sD + r * CLD + nm.col()) = dA;
-        }
-        __syncthreads();
-        if (g_gw) {
+#pragma unroll
+          for (int i = 0; i < TMNA; ++i) {
+            const int r = nm.row(i);
+            float4 dA = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < nrows) {
+              const float4 s4 = *reinterpret_cast<const float4*>(sv + SL.gs + ((size_t)li * Pp + p0 + r) * HG + nm.col());
+              dA = make_float4(s4.x > 0.f ? dHg[i][0] : 0.f, s4.y > 0.f ? dHg[i][1] : 0.f, s4.z > 0.f ? dHg[i][2] : 0.f,
+                               s4.w > 0.f ? dHg[i][3] : 0.f);
+            }
+            *reinterpret_cast<float4*>(sD + r * CLD + nm.col()) = dA;
+          }
+          __syncthreads();
           if (tid < HG) {
             float s = 0.f;
             for (int m = 0; m < nrows; ++m) s += sD[m * CLD + tid];
@@ -366,16 +330,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
                   if (col < EG) atomicAdd(dW + a.w.g_lin_w[li] + wm.row(i) * ldw + col, ae2[i][g * 4 + j]);
                 }
           }
-        }
-        if (li == 1 || li == 2 || li == 4) {
-          zero_acc(dHg);
-          tile_gemm<TMNA, 8, 1, true, false>(dHg, sD, CLD, HG, blob + a.w.g_lin_w[li], HG, HG, sB, nrows);
-        } else if (li == 3) {
-          zero_acc(dHg);
-          tile_gemm<TMNA, 8, 1, true, false>(dHg, sD, CLD, HG, packed + Packed::gW3n + EGP, 128, HG, sB, nrows);
-          tile_gemm<TMA, 16, 2, true, false>(dEacc, sD, CLD, HG, packed + Packed::gW3n, 128, EGP, sB, nrows);
-        } else {
-          tile_gemm<TMA, 16, 2, true, false>(dEacc, sD, CLD, HG, packed + Packed::gW0n, EGP, EGP, sB, nrows);
+          __syncthreads();
         }
       }
       // geometry Fourier backward: e_j = sin(arg_j)
@@ -489,6 +444,9 @@ int check_weights(const LsrWeights* w);
 int check_params(const LsrParams* p);
 int sm_count();
 int balanced_rays_per_tile(int64_t n_rays, int n_surface, int nsm);
+int launch_geo_bwd(const LsrParams* prm, const LsrWeights* w, const float* gt_depth, int64_t n_rays, int stage, const void* saved,
+                   float* gpack, const float* g_depth, const float* g_var, const float* g_rgb, int grad_flags, float* gdc, float* gde,
+                   float* gdh, cudaStream_t stream);
 int launch_trunk_bwd(const LsrParams* prm, const LsrWeights* w, const float* gt_depth, int64_t n_rays, const float* affine,
                      const void* saved, void* scratch, const float* g_depth, const float* g_var, const float* g_rgb, int grad_flags,
                      float* d_weights, float* d_affine, const float* cloud_pos, const int32_t* row_remap, float* d_col_feats,
@@ -523,7 +481,7 @@ extern "C" int lsr_render_bwd(const LsrParams* prm, const void* grid_ws, const f
   if (n_rays < 0 || n_rays > (1ll << 27) || n_points < 0) return LSR_ERR_ARG;
   if (n_rays == 0) return LSR_OK;
   if (!saved || !scratch || !rays_o || !rays_d || !gt_depth || !g_depth) return LSR_ERR_ARG;
-  if (prm->flags & LSR_FLAG_SAVE_LIGHT) return LSR_ERR_ARG;   // a light save holds no activations to differentiate
+  if (prm->flags & (LSR_FLAG_SAVE_LIGHT | LSR_FLAG_FWD_ONLY)) return LSR_ERR_ARG;   // no activations / no backward scratch to differentiate with
   if (n_points > 0 && (!cloud_pos || !geo_feats)) return LSR_ERR_ARG;
   if (n_points > 0 && stage == LSR_STAGE_COLOR && !col_feats) return LSR_ERR_ARG;
   if (row_remap && (!geo_leaf || (stage == LSR_STAGE_COLOR && !col_leaf))) return LSR_ERR_ARG;
@@ -542,7 +500,17 @@ extern "C" int lsr_render_bwd(const LsrParams* prm, const void* grid_ws, const f
                           d_exposure_affine, cloud_pos, row_remap, d_col_feats, is_tracker, stream);
     if (rc) return rc;
   }
+  {
+    const bool need_e = (grad_flags & (LSR_GRAD_GEO_B | LSR_GRAD_GEO_W | LSR_GRAD_RAYS)) != 0;
+    rc = launch_geo_bwd(prm, w, gt_depth, n_rays, stage, saved, (float*)((char*)scratch + CL.bwd_gpack), g_depth, g_var, g_rgb,
+                        grad_flags, (float*)((char*)scratch + CL.bwd_gdc), need_e ? (float*)((char*)scratch + CL.bwd_gde) : nullptr,
+                        (grad_flags & LSR_GRAD_GEO_W) ? (float*)((char*)scratch + CL.bwd_gdh) : nullptr, stream);
+    if (rc) return rc;
+  }
   BwdArgs a;
+  a.ext_gdc = (const float*)((const char*)scratch + CL.bwd_gdc);
+  a.ext_gde = (const float*)((const char*)scratch + CL.bwd_gde);
+  a.ext_gdh = (const float*)((const char*)scratch + CL.bwd_gdh);
   a.ext_dc = (const float*)((const char*)scratch + CL.bwd_dc);
   a.ext_dp = (const float*)((const char*)scratch + CL.bwd_dp);
   a.ext_dwh = (const float*)((const char*)scratch + CL.bwd_dwh);

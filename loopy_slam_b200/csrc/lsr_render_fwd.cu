@@ -970,7 +970,10 @@ extern "C" int lsr_render_workspace_bytes(const LsrParams* prm, int64_t n_rays, 
     const SavedLayout SLh = saved_layout(n_rays, prm->n_surface, stage, prm->flags);
     *saved_bytes = ((prm->flags & LSR_FLAG_SAVE_LIGHT) ? SLh.light_end : SLh.total) * sizeof(float);
   }
-  if (scratch_bytes) *scratch_bytes = scratch_layout(n_rays, prm->n_surface).total;
+  if (scratch_bytes) {
+    const ScratchLayout CLh = scratch_layout(n_rays, prm->n_surface);
+    *scratch_bytes = (prm->flags & LSR_FLAG_FWD_ONLY) ? CLh.fwd_end : CLh.total;
+  }
   return LSR_OK;
 }
 

@@ -153,6 +153,8 @@ class _RenderFn(torch.autograd.Function):
         # mode is captured in fused_render): without this test every no_grad render (render_img: 816 k rays)
         # would allocate and write the multi-KB-per-sample saved activations
         need_bwd = (rc.grad_enabled and any(ctx.needs_input_grad)) or rc.force_save
+        if not need_bwd or (rc.prm.flags & _lib.FLAG_SAVE_LIGHT):
+            rc.prm.flags |= _lib.FLAG_FWD_ONLY      # scratch without the backward's hand-over planes
         sb, cb = ctypes.c_size_t(), ctypes.c_size_t()
         check(lib().lsr_render_workspace_bytes(ctypes.byref(rc.prm), R, rc.stage, ctypes.byref(sb), ctypes.byref(cb)),
               'lsr_render_workspace_bytes')

@@ -12,7 +12,7 @@ SO = os.path.join(ROOT, 'loopy_slam_b200', 'liblsr_phase.so')
 
 def build():
     csrc = os.path.join(ROOT, 'loopy_slam_b200', 'csrc')
-    srcs = [os.path.join(csrc, f) for f in ('lsr_grid.cu', 'lsr_sample.cu', 'lsr_loss.cu', 'lsr_render_fwd.cu', 'lsr_render_bwd.cu', 'lsr_render_bwd_umma.cu')]
+    srcs = [os.path.join(csrc, f) for f in ('lsr_grid.cu', 'lsr_sample.cu', 'lsr_loss.cu', 'lsr_render_fwd.cu', 'lsr_render_bwd.cu', 'lsr_render_bwd_umma.cu', 'lsr_geo_bwd_umma.cu')]
     subprocess.check_call(['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-rdc=true',
                            '-DLSR_PHASE_TIMING', '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '-shared', '-cudart', 'static',
                            '-o', SO] + srcs)
