@@ -73,25 +73,31 @@ struct GeoArgs {
   int ntiles, rays_per_tile;
 };
 
-constexpr int GB_NT = 128;
+// Two independent 128-thread groups per CTA, each walking its own tiles with its own TMEM columns and mbarrier: the chain of a
+// tile is latency (five dependent MMA round trips), so a second tile in flight on the SM hides most of it, and the 112 KB of
+// weight images are shared.
+constexpr int GB_GROUPS = 2;
+constexpr int GB_NT = 128 * GB_GROUPS;
 constexpr int GSM_WHI = 0;
 constexpr int GSM_WLO = GSM_WHI + GPK_V * 4;
-constexpr int GSM_DOCC = GSM_WLO + GPK_V * 4;
-constexpr int GSM_TAB = GSM_DOCC + 128 * 4;         // w_out (32) | v (32)
+constexpr int GSM_DOCC = GSM_WLO + GPK_V * 4;       // [group][128]
+constexpr int GSM_TAB = GSM_DOCC + GB_GROUPS * 128 * 4;   // w_out (32) | v (32)
 constexpr int GSM_BAR = GSM_TAB + 64 * 4;
 constexpr int GEO_SMEM_BYTES = GSM_BAR + 64;
-constexpr uint32_t GT_AHI = 0, GT_ALO = 32, GT_D = 64, GT_DE = 128;   // TMEM columns (256 allocated)
+constexpr uint32_t GT_AHI = 0, GT_ALO = 32, GT_D = 64, GT_DE = 128, GT_GROUP = 224;   // TMEM columns per group (512 allocated)
+
+__device__ __forceinline__ void bar_group(int g) { asm volatile("bar.sync %0, 128;\n" ::"r"(1 + g) : "memory"); }
 
 __global__ void __launch_bounds__(GB_NT, 1) geo_bwd_umma_kernel(const __grid_constant__ GeoArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   float* sWhi = reinterpret_cast<float*>(smem + GSM_WHI);
   float* sWlo = reinterpret_cast<float*>(smem + GSM_WLO);
-  float* sDOcc = reinterpret_cast<float*>(smem + GSM_DOCC);
   float* sTab = reinterpret_cast<float*>(smem + GSM_TAB);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + GSM_BAR);
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + GSM_BAR + 16);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + GSM_BAR + 32);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int grp = threadIdx.x >> 7, tid = threadIdx.x & 127, warp = tid >> 5;     // tid / warp: inside the group
+  float* sDOcc = reinterpret_cast<float*>(smem + GSM_DOCC) + grp * 128;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + GSM_BAR) + grp;
   const int S = a.prm.n_surface;
   const float* __restrict__ sv = a.saved;
   const bool color = a.stage == LSR_STAGE_COLOR;
@@ -101,21 +107,28 @@ __global__ void __launch_bounds__(GB_NT, 1) geo_bwd_umma_kernel(const __grid_con
   const size_t Pp = SL.Pp;
 
   // weights: raw image (= hi operand, the tensor core reads the top 19 bits) and lo residual image
-  for (int i = tid; i < GPK_V / 4; i += GB_NT) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(a.gpack) + i);
-    uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-    split_hi_lo(v.x, h0, l0); split_hi_lo(v.y, h1, l1); split_hi_lo(v.z, h2, l2); split_hi_lo(v.w, h3, l3);
-    reinterpret_cast<float4*>(sWhi)[i] = v;
-    reinterpret_cast<uint4*>(sWlo)[i] = make_uint4(l0, l1, l2, l3);
+  {
+    constexpr int PER = GPK_V / 4 / GB_NT;          // 14 float4 per thread: every load in flight before the first use
+    static_assert(PER * GB_NT * 4 == GPK_V, "pack size");
+    float4 v[PER];
+#pragma unroll
+    for (int t = 0; t < PER; ++t) v[t] = __ldg(reinterpret_cast<const float4*>(a.gpack) + threadIdx.x + t * GB_NT);
+#pragma unroll
+    for (int t = 0; t < PER; ++t) {
+      uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+      split_hi_lo(v[t].x, h0, l0); split_hi_lo(v[t].y, h1, l1); split_hi_lo(v[t].z, h2, l2); split_hi_lo(v[t].w, h3, l3);
+      reinterpret_cast<float4*>(sWhi)[threadIdx.x + t * GB_NT] = v[t];
+      reinterpret_cast<uint4*>(sWlo)[threadIdx.x + t * GB_NT] = make_uint4(l0, l1, l2, l3);
+    }
   }
-  if (tid < 32) { sTab[tid] = a.w.blob[a.w.g_out_w + tid]; sTab[32 + tid] = a.gpack[GPK_V + tid]; }
-  if (warp == 0) tmem_alloc(tslot, 256);
+  if (threadIdx.x < 32) { sTab[threadIdx.x] = a.w.blob[a.w.g_out_w + threadIdx.x]; sTab[32 + threadIdx.x] = a.gpack[GPK_V + threadIdx.x]; }
+  if (threadIdx.x < 32) tmem_alloc(tslot, 512);
   if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tb = *tslot;
+  const uint32_t tb = *tslot + (uint32_t)grp * GT_GROUP;
   const uint32_t lane_base = 32u * (uint32_t)warp;
   const uint32_t whi = smem_u32(sWhi), wlo = smem_u32(sWlo);
   uint32_t parity = 0;
@@ -137,7 +150,7 @@ __global__ void __launch_bounds__(GB_NT, 1) geo_bwd_umma_kernel(const __grid_con
     }
   };
 
-  for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+  for (int tile = blockIdx.x + grp * (int)gridDim.x; tile < a.ntiles; tile += GB_GROUPS * (int)gridDim.x) {
     const int r0 = tile * a.rays_per_tile;
     const int nr = min(a.rays_per_tile, a.R - r0);
     const int nrows = nr * S;
@@ -145,18 +158,34 @@ __global__ void __launch_bounds__(GB_NT, 1) geo_bwd_umma_kernel(const __grid_con
     const int row = tid;
     const bool rv = row < nrows;
 
+    // ReLU masks of all five layers up front (one DRAM round trip instead of five): bit j of mbits[l] = s_l[row][j] > 0
+    uint32_t mbits[5];
+#pragma unroll
+    for (int l = 0; l < 5; ++l) {
+      const float4* srow = reinterpret_cast<const float4*>(sv + SL.gs + ((size_t)l * Pp + p0 + row) * HG);
+      uint32_t m = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rv) s4 = __ldg(srow + j);
+        m |= (s4.x > 0.f ? 1u : 0u) << (4 * j) | (s4.y > 0.f ? 2u : 0u) << (4 * j) | (s4.z > 0.f ? 4u : 0u) << (4 * j) |
+             (s4.w > 0.f ? 8u : 0u) << (4 * j);
+      }
+      mbits[l] = m;
+    }
+
     // ---- compositing backward (Renderer.py:184-201, common.py:382-422): d(occupancy logit) per sample row
     sDOcc[tid] = 0.f;
-    __syncthreads();
+    bar_group(grp);
     if (tid < nr) composite_bwd_ray(a.prm, color, sv, SL, p0 + (size_t)tid * S, r0 + tid, a.gt_depth, a.g_depth, a.g_var, a.g_rgb,
                                     sDOcc + tid * S, nullptr);
-    __syncthreads();
+    bar_group(grp);
     const float docc = sDOcc[row];
     float dH[32], dC[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) { dH[j] = docc * sTab[j]; dC[j] = docc * sTab[32 + j]; }
 
-#pragma unroll 1
+#pragma unroll
     for (int l = 4; l >= 0; --l) {
       if (g_gw && rv) {
         float4* dst = reinterpret_cast<float4*>(a.gdh + ((size_t)l * Pp + p0 + row) * HG);
@@ -164,22 +193,13 @@ __global__ void __launch_bounds__(GB_NT, 1) geo_bwd_umma_kernel(const __grid_con
         for (int j = 0; j < 8; ++j) dst[j] = make_float4(dH[4 * j], dH[4 * j + 1], dH[4 * j + 2], dH[4 * j + 3]);
       }
       uint32_t hi[32], lo[32];
-      {
-        const float4* srow = reinterpret_cast<const float4*>(sv + SL.gs + ((size_t)l * Pp + p0 + row) * HG);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (rv) s4 = __ldg(srow + j);
-          const float sj[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-          for (int t = 0; t < 4; ++t) split_hi_lo(sj[t] > 0.f ? dH[4 * j + t] : 0.f, hi[4 * j + t], lo[4 * j + t]);
-        }
-      }
+      for (int j = 0; j < 32; ++j) split_hi_lo((mbits[l] >> j) & 1u ? dH[j] : 0.f, hi[j], lo[j]);
       tmem_st32(tmem_addr(tb, lane_base, GT_AHI), hi);
       tmem_st32(tmem_addr(tb, lane_base, GT_ALO), lo);
       tmem_wait_st();
       tc_fence_before();
-      __syncthreads();
+      bar_group(grp);
       if (warp == 0 && elect_one()) {
         tc_fence_after();
         if (l == 0) issue(0, GT_DE, 1u);          // dE += dA_0 . W_0
@@ -219,11 +239,11 @@ __global__ void __launch_bounds__(GB_NT, 1) geo_bwd_umma_kernel(const __grid_con
       }
     }
     tc_fence_before();
-    __syncthreads();     // every TMEM read of this tile is done before the next tile's first MMA overwrites the columns
+    bar_group(grp);      // every TMEM read of this tile is done before the group's next tile overwrites the columns
     tc_fence_after();
   }
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tb, 256);
+  if (threadIdx.x < 32) tmem_dealloc(*tslot, 512);
 }
 
 int sm_count();
