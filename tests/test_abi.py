@@ -45,6 +45,15 @@ def test_argument_validation_without_gpu(lib):
     sb, cb = ctypes.c_size_t(), ctypes.c_size_t()
     assert lib.lsr_render_workspace_bytes(ctypes.byref(prm), 4992, 1, ctypes.byref(sb), ctypes.byref(cb)) == 0
     assert sb.value > 4992 * 5 * 4 * 2500 and cb.value > 400000
+    full_scratch, full_saved = cb.value, sb.value
+    assert full_saved < 4992 * 5 * 4 * 2900                     # the h planes are not saved: 11.3 KB per sample
+    prm.flags = 1 | _lib.FLAG_FWD_ONLY                          # forward-only: scratch without the backward's hand-over planes
+    assert lib.lsr_render_workspace_bytes(ctypes.byref(prm), 4992, 1, ctypes.byref(sb), ctypes.byref(cb)) == 0
+    assert cb.value < full_scratch / 4 and cb.value > 4992 * 5 * 120
+    prm.flags = 1 | _lib.FLAG_SAVE_LIGHT
+    assert lib.lsr_render_workspace_bytes(ctypes.byref(prm), 4992, 1, ctypes.byref(sb), ctypes.byref(cb)) == 0
+    assert sb.value < 4992 * 5 * 200                            # light save: 148 B per sample (+ padding)
+    prm.flags = 1
     prm.nn_num = 7
     assert lib.lsr_render_workspace_bytes(ctypes.byref(prm), 10, 1, ctypes.byref(sb), ctypes.byref(cb)) == 4
     assert lib.lsr_strerror(4) == b'unsupported configuration'
