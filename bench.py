@@ -414,6 +414,25 @@ def run_lsr(args, rank, world, local):
         ms, r = time_steps(lambda k: (it.step(literal=False), it.rays_last)[1], n_extra, flush, dev)
         extra['mapper_iteration_lsr_extensions'] = line(ms, r, what='FeatureSubset/row_remap instead of the per-iteration index_put, '
                                                         'lsr_mapper_loss instead of the inline torch loss (callers must opt in)')
+        # (1b) the render hot path alone: rays of eight iterations pre-sampled and resident on the device, row_remap + fused
+        # loss, no host synchronisation inside the step -- what the kernels sustain when the caller does not serialise them
+        with torch.no_grad():
+            pre = [it.sample() for _ in range(8)]
+
+        def hot(k):
+            o, d, g, c, rq, _ = pre[k % 8]
+            for p in it.train_params:
+                p.grad = None
+            depth, var, color, valid = it.rend.render_batch_ray(it.npc, it.model, d, o, dev, stage, gt_depth=g,
+                                                                npc_geo_feats=it.npc_geo, npc_col_feats=it.npc_col,
+                                                                is_tracker=False, cloud_pos=it.cloud, dynamic_r_query=rq,
+                                                                feat_subset=(it.subset, it.geo_leaf, it.col_leaf))
+            it.L.mapper_loss(depth, color, valid, g, c, stage, it.w_color)[0].backward()
+            return o.shape[0]
+        if not it.exposure:
+            ms, r = time_steps(hot, n_extra, flush, dev)
+            extra['render_hot_path_only'] = line(ms, r, what='render_batch_ray + fused loss + backward on pre-sampled device-resident '
+                                                 'rays (row_remap), no host synchronisation in the step')
         # (2) geometry stage (40 % of the mapping iterations, Mapper.py:588-591)
         ms, r = time_steps(lambda k: (it.step(stage='geometry'), it.rays_last)[1], n_extra, flush, dev)
         extra['mapper_iteration_geometry_stage'] = line(ms, r)

@@ -74,3 +74,24 @@ def test_no_cpu_fallback():
         r.render_batch_ray(None, m, torch.zeros(4, 3), torch.zeros(4, 3), 'cpu', 'color', gt_depth=torch.ones(4),
                            npc_geo_feats=torch.zeros(8, 32), npc_col_feats=torch.zeros(8, 32),
                            cloud_pos=torch.zeros(8, 3))
+
+
+def test_library_sass_is_tcgen05_only():
+    """Every MLP layer of both passes runs on the 5th-generation tensor cores: the sm_100a SASS of the library holds
+    tcgen05 MMAs (UTCHMMA) with TMEM loads / stores (LDTM / STTM) and bulk copies (UBLKCP), and no legacy mma.sync (HMMA)."""
+    import re
+    import shutil
+    import subprocess
+    from loopy_slam_b200 import _lib
+    exe = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(exe):
+        pytest.skip('cuobjdump not available')
+    sass = subprocess.run([exe, '-sass', _lib.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    ops = re.findall(r'^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)', sass, flags=re.M)
+    names = {o.split('.')[0] for o in ops}
+    assert 'UTCHMMA' in names and 'LDTM' in names and 'STTM' in names and 'UBLKCP' in names, sorted(names)[:50]
+    assert 'HMMA' not in names and 'IMMA' not in names
+    per_kernel = re.split(r'Function : ', sass)[1:]
+    with_umma = [k.split('\n')[0] for k in per_kernel if 'UTCHMMA' in k]
+    assert any('render_fwd_kernel' in k for k in with_umma) and any('trunk_bwd_umma_kernel' in k for k in with_umma) \
+        and any('geo_bwd_umma_kernel' in k for k in with_umma), with_umma
