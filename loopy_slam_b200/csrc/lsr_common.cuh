@@ -7,6 +7,17 @@
 
 // every kernel launch of the library bumps this counter (lsr_launch_count; bench.py reports it as gpu_launches)
 namespace lsr { extern long long g_launch_count; }
+// cudaFuncAttributeMaxDynamicSharedMemorySize of a kernel, set once per device (it was ~2 us of host time per call)
+#define LSR_SMEM_ATTR_ONCE(kernel, bytes)                                                                        \
+  do {                                                                                                           \
+    static unsigned long long done_mask_ = 0ull;                                                                 \
+    int dev_ = 0;                                                                                                \
+    LSR_CUDA_CHECK(cudaGetDevice(&dev_));                                                                        \
+    if (!((done_mask_ >> (dev_ & 63)) & 1ull)) {                                                                 \
+      LSR_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));   \
+      done_mask_ |= 1ull << (dev_ & 63);                                                                         \
+    }                                                                                                            \
+  } while (0)
 #define LSR_LAUNCHED(n) (__atomic_fetch_add(&lsr::g_launch_count, (long long)(n), __ATOMIC_RELAXED))
 
 #define LSR_CUDA_CHECK(expr)                          \

@@ -265,7 +265,7 @@ int launch_geo_bwd(const LsrParams* prm, const LsrWeights* w, const float* gt_de
   const SavedLayout SL = saved_layout(n_rays, prm->n_surface, stage, prm->flags);
   a.rays_per_tile = SL.rays_per_tile;
   a.ntiles = SL.ntiles;
-  LSR_CUDA_CHECK(cudaFuncSetAttribute(geo_bwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEO_SMEM_BYTES));
+  LSR_SMEM_ATTR_ONCE(geo_bwd_umma_kernel, GEO_SMEM_BYTES);
   const int grid = a.ntiles < nsm ? a.ntiles : nsm;
   geo_bwd_umma_kernel<<<grid, GB_NT, GEO_SMEM_BYTES, stream>>>(a);
   LSR_LAUNCHED(1);

@@ -450,7 +450,31 @@ int launch_geo_bwd(const LsrParams* prm, const LsrWeights* w, const float* gt_de
 int launch_trunk_bwd(const LsrParams* prm, const LsrWeights* w, const float* gt_depth, int64_t n_rays, const float* affine,
                      const void* saved, void* scratch, const float* g_depth, const float* g_var, const float* g_rgb, int grad_flags,
                      float* d_weights, float* d_affine, const float* cloud_pos, const int32_t* row_remap, float* d_col_feats,
-                     int is_tracker, cudaStream_t stream);
+                     int is_tracker, cudaStream_t stream, int phase);
+
+// Side stream of the colour-stage backward.  trunk_bwd_umma_kernel keeps one CTA per SM and 45 of the 148 SMs get a second
+// tile, so the other SMs idle for the second half of it; the geometry chain (independent of the colour trunk) is enqueued on a
+// second stream right behind it and fills those SMs, and the finalize kernel runs beside the scatter kernel.
+struct SideStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t e_fork = nullptr, e_geo = nullptr, e_trunk = nullptr, e_fin = nullptr;
+  int state = 0;   // 0: not created, 1: ok, -1: creation failed (fall back to one stream)
+};
+static SideStream* side_stream() {
+  static SideStream side[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStream& S = side[dev];
+  if (S.state == 0) {
+    bool ok = cudaStreamCreateWithFlags(&S.s, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&S.e_fork, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&S.e_geo, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&S.e_trunk, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&S.e_fin, cudaEventDisableTiming) == cudaSuccess;
+    S.state = ok ? 1 : -1;
+  }
+  return S.state == 1 ? &S : nullptr;
+}
 
 }  // namespace lsr
 
@@ -495,17 +519,32 @@ extern "C" int lsr_render_bwd(const LsrParams* prm, const void* grid_ws, const f
   if (nsm <= 0) return LSR_ERR_CUDA;
 
   const ScratchLayout CL = scratch_layout(n_rays, prm->n_surface);
-  if (stage == LSR_STAGE_COLOR) {
+  SideStream* side = stage == LSR_STAGE_COLOR ? side_stream() : nullptr;
+  if (side) {   // fork: the side stream starts behind everything already enqueued on the caller's stream
+    LSR_CUDA_CHECK(cudaEventRecord(side->e_fork, stream));
+    LSR_CUDA_CHECK(cudaStreamWaitEvent(side->s, side->e_fork, 0));
+  }
+  if (stage == LSR_STAGE_COLOR) {   // weight re-layout, trunk kernel, rel-pos trig kernel
     rc = launch_trunk_bwd(prm, w, gt_depth, n_rays, exposure_affine, saved, scratch, g_depth, g_var, g_rgb, grad_flags, d_weights,
-                          d_exposure_affine, cloud_pos, row_remap, d_col_feats, is_tracker, stream);
+                          d_exposure_affine, cloud_pos, row_remap, d_col_feats, is_tracker, stream, side ? 1 : 0);
     if (rc) return rc;
+    if (side) LSR_CUDA_CHECK(cudaEventRecord(side->e_trunk, stream));
   }
   {
     const bool need_e = (grad_flags & (LSR_GRAD_GEO_B | LSR_GRAD_GEO_W | LSR_GRAD_RAYS)) != 0;
     rc = launch_geo_bwd(prm, w, gt_depth, n_rays, stage, saved, (float*)((char*)scratch + CL.bwd_gpack), g_depth, g_var, g_rgb,
                         grad_flags, (float*)((char*)scratch + CL.bwd_gdc), need_e ? (float*)((char*)scratch + CL.bwd_gde) : nullptr,
-                        (grad_flags & LSR_GRAD_GEO_W) ? (float*)((char*)scratch + CL.bwd_gdh) : nullptr, stream);
+                        (grad_flags & LSR_GRAD_GEO_W) ? (float*)((char*)scratch + CL.bwd_gdh) : nullptr, side ? side->s : stream);
     if (rc) return rc;
+    if (side) {
+      LSR_CUDA_CHECK(cudaEventRecord(side->e_geo, side->s));
+      LSR_CUDA_CHECK(cudaStreamWaitEvent(stream, side->e_geo, 0));          // the scatter kernel below needs the geometry planes
+      LSR_CUDA_CHECK(cudaStreamWaitEvent(side->s, side->e_trunk, 0));       // finalize: behind the trunk kernel, beside the scatter kernel
+      rc = launch_trunk_bwd(prm, w, gt_depth, n_rays, exposure_affine, saved, scratch, g_depth, g_var, g_rgb, grad_flags, d_weights,
+                            d_exposure_affine, cloud_pos, row_remap, d_col_feats, is_tracker, side->s, 2);
+      if (rc) return rc;
+      LSR_CUDA_CHECK(cudaEventRecord(side->e_fin, side->s));
+    }
   }
   BwdArgs a;
   a.ext_gdc = (const float*)((const char*)scratch + CL.bwd_gdc);
@@ -532,11 +571,12 @@ extern "C" int lsr_render_bwd(const LsrParams* prm, const void* grid_ws, const f
   a.rays_per_tile = balanced_rays_per_tile(n_rays, prm->n_surface, nsm);
   a.ntiles = (int)((n_rays + a.rays_per_tile - 1) / a.rays_per_tile);
   const size_t smem = BWD_SMEM_FLOATS * sizeof(float);
-  LSR_CUDA_CHECK(cudaFuncSetAttribute(render_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LSR_SMEM_ATTR_ONCE(render_bwd_kernel, smem);
   const int slots = nsm * CTAS_PER_SM;
   const int grid = a.ntiles < slots ? a.ntiles : slots;
   render_bwd_kernel<<<grid, NT, smem, stream>>>(a);
   LSR_LAUNCHED(1);
   LSR_CUDA_CHECK(cudaGetLastError());
+  if (side) LSR_CUDA_CHECK(cudaStreamWaitEvent(stream, side->e_fin, 0));   // join: everything is ordered on the caller's stream again
   return LSR_OK;
 }

@@ -1201,12 +1201,22 @@ int sm_count();
 int launch_trunk_bwd(const LsrParams* prm, const LsrWeights* w, const float* gt_depth, int64_t n_rays, const float* affine,
                      const void* saved, void* scratch, const float* g_depth, const float* g_var, const float* g_rgb, int grad_flags,
                      float* d_weights, float* d_affine, const float* cloud_pos, const int32_t* row_remap, float* d_col_feats,
-                     int is_tracker, cudaStream_t stream) {
+                     int is_tracker, cudaStream_t stream, int phase) {
+  // phase 0: everything on `stream`; 1: all but the finalize kernel; 2: only the finalize kernel (the caller orders it behind
+  // the trunk kernel and may put it on another stream)
   const SavedLayout SL = saved_layout(n_rays, prm->n_surface, LSR_STAGE_COLOR, prm->flags);
   const ScratchLayout CL = scratch_layout(n_rays, prm->n_surface);
   if (SL.total >= (1ull << 32)) return LSR_ERR_UNSUPPORTED;   // ROp offsets are 32-bit float indices
   char* sbase = (char*)scratch;
   const bool g_cw = (grad_flags & LSR_GRAD_COL_W) && d_weights;
+  if (phase == 2) {
+    if (g_cw) {
+      trunk_bwd_finalize_kernel<<<dim3(CDIM + 3 + HC, 5), HC, 0, stream>>>(w->blob, (const float*)(sbase + CL.bwd_acc), d_weights, *w);
+      LSR_LAUNCHED(1);
+      LSR_CUDA_CHECK(cudaGetLastError());
+    }
+    return LSR_OK;
+  }
   static TrunkProgram P;   // host scratch (calls are serialised per process by the GIL / caller)
   const bool relpos = (prm->flags & LSR_FLAG_REL_POS) != 0;
   build_trunk_program(w, SL, g_cw, relpos, &P);
@@ -1247,7 +1257,7 @@ int launch_trunk_bwd(const LsrParams* prm, const LsrWeights* w, const float* gt_
   memcpy(a.ops, P.ops, sizeof(ROp) * P.n_ops);
   const int nsm = sm_count();
   if (nsm <= 0) return LSR_ERR_CUDA;
-  LSR_CUDA_CHECK(cudaFuncSetAttribute(trunk_bwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_UMMA_SMEM));
+  LSR_SMEM_ATTR_ONCE(trunk_bwd_umma_kernel, BWD_UMMA_SMEM);
   const int grid = a.ntiles < nsm ? a.ntiles : nsm;
   trunk_bwd_umma_kernel<<<grid, BT, BWD_UMMA_SMEM, stream>>>(a);
   LSR_LAUNCHED(1);
@@ -1262,7 +1272,7 @@ int launch_trunk_bwd(const LsrParams* prm, const LsrWeights* w, const float* gt_
     LSR_LAUNCHED(1);
     LSR_CUDA_CHECK(cudaGetLastError());
   }
-  if (g_cw) {
+  if (g_cw && phase == 0) {
     trunk_bwd_finalize_kernel<<<dim3(CDIM + 3 + HC, 5), HC, 0, stream>>>(w->blob, acc, d_weights, *w);
     LSR_LAUNCHED(1);
     LSR_CUDA_CHECK(cudaGetLastError());

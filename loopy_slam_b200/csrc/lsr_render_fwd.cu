@@ -1079,7 +1079,7 @@ extern "C" int lsr_render_fwd(const LsrParams* prm, const void* grid_ws, const f
   a.ntiles = (int)((n_rays + a.rays_per_tile - 1) / a.rays_per_tile);
   a.n_ops = P.n_ops;
   memcpy(a.ops, P.ops, sizeof(UOp) * P.n_ops);
-  LSR_CUDA_CHECK(cudaFuncSetAttribute(render_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES));
+  LSR_SMEM_ATTR_ONCE(render_fwd_kernel, FWD_SMEM_BYTES);
   const int grid = a.ntiles < nsm ? a.ntiles : nsm;
   render_fwd_kernel<<<grid, FT, FWD_SMEM_BYTES, stream>>>(a);
   LSR_LAUNCHED(1);
