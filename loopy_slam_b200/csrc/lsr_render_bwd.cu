@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
       for (int it = tid; it < TILE_M * 8; it += NT) {
         const int m = it >> 3, q = it & 7;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m < nrows && sHas[m]) v = reinterpret_cast<const float4*>(a.ext_dc)[(p0 + m) * 8 + q];
+        if (!relpos && m < nrows && sHas[m]) v = reinterpret_cast<const float4*>(a.ext_dc)[(p0 + m) * 8 + q];   // rel-pos: scattered by the trunk kernel
         *reinterpret_cast<float4*>(sDC + m * CLD + q * 4) = v;
       }
       if (g_ry && tid < nrows) {
@@ -435,7 +435,6 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) render_bwd_kernel(const __gri
         if (j < EG) atomicAdd(dW + a.w.g_B + c * EG + j, sRed[i]);
       }
     }
-    if (g_cw && relpos && tid < 3 * ER) atomicAdd(dW + a.w.c_Brel + tid, sRed[3 * EGP + tid]);
     __syncthreads();
   }
 }
@@ -524,11 +523,14 @@ extern "C" int lsr_render_bwd(const LsrParams* prm, const void* grid_ws, const f
     LSR_CUDA_CHECK(cudaEventRecord(side->e_fork, stream));
     LSR_CUDA_CHECK(cudaStreamWaitEvent(side->s, side->e_fork, 0));
   }
-  if (stage == LSR_STAGE_COLOR) {   // weight re-layout, trunk kernel, rel-pos trig kernel
+  // With the rel-pos decoder and no pose gradient the scatter kernel needs nothing from the colour trunk (its feature scatter and
+  // Fourier pose terms happen in the trunk kernel): the whole geometry side -- chain + scatter kernel -- runs on the side stream.
+  const bool geo_side_only = side && (prm->flags & LSR_FLAG_REL_POS) && !(grad_flags & LSR_GRAD_RAYS) && !is_tracker;
+  if (stage == LSR_STAGE_COLOR) {   // weight re-layout, trunk kernel, rel-pos trig kernel (+ finalize when it stays on this stream)
     rc = launch_trunk_bwd(prm, w, gt_depth, n_rays, exposure_affine, saved, scratch, g_depth, g_var, g_rgb, grad_flags, d_weights,
-                          d_exposure_affine, cloud_pos, row_remap, d_col_feats, is_tracker, stream, side ? 1 : 0);
+                          d_exposure_affine, cloud_pos, row_remap, d_col_feats, is_tracker, stream, (side && !geo_side_only) ? 1 : 0);
     if (rc) return rc;
-    if (side) LSR_CUDA_CHECK(cudaEventRecord(side->e_trunk, stream));
+    if (side && !geo_side_only) LSR_CUDA_CHECK(cudaEventRecord(side->e_trunk, stream));
   }
   {
     const bool need_e = (grad_flags & (LSR_GRAD_GEO_B | LSR_GRAD_GEO_W | LSR_GRAD_RAYS)) != 0;
@@ -536,7 +538,7 @@ extern "C" int lsr_render_bwd(const LsrParams* prm, const void* grid_ws, const f
                         grad_flags, (float*)((char*)scratch + CL.bwd_gdc), need_e ? (float*)((char*)scratch + CL.bwd_gde) : nullptr,
                         (grad_flags & LSR_GRAD_GEO_W) ? (float*)((char*)scratch + CL.bwd_gdh) : nullptr, side ? side->s : stream);
     if (rc) return rc;
-    if (side) {
+    if (side && !geo_side_only) {
       LSR_CUDA_CHECK(cudaEventRecord(side->e_geo, side->s));
       LSR_CUDA_CHECK(cudaStreamWaitEvent(stream, side->e_geo, 0));          // the scatter kernel below needs the geometry planes
       LSR_CUDA_CHECK(cudaStreamWaitEvent(side->s, side->e_trunk, 0));       // finalize: behind the trunk kernel, beside the scatter kernel
@@ -546,6 +548,7 @@ extern "C" int lsr_render_bwd(const LsrParams* prm, const void* grid_ws, const f
       LSR_CUDA_CHECK(cudaEventRecord(side->e_fin, side->s));
     }
   }
+  cudaStream_t scatter_stream = geo_side_only ? side->s : stream;
   BwdArgs a;
   a.ext_gdc = (const float*)((const char*)scratch + CL.bwd_gdc);
   a.ext_gde = (const float*)((const char*)scratch + CL.bwd_gde);
@@ -574,9 +577,10 @@ extern "C" int lsr_render_bwd(const LsrParams* prm, const void* grid_ws, const f
   LSR_SMEM_ATTR_ONCE(render_bwd_kernel, smem);
   const int slots = nsm * CTAS_PER_SM;
   const int grid = a.ntiles < slots ? a.ntiles : slots;
-  render_bwd_kernel<<<grid, NT, smem, stream>>>(a);
+  render_bwd_kernel<<<grid, NT, smem, scatter_stream>>>(a);
   LSR_LAUNCHED(1);
   LSR_CUDA_CHECK(cudaGetLastError());
+  if (geo_side_only) LSR_CUDA_CHECK(cudaEventRecord(side->e_fin, side->s));
   if (side) LSR_CUDA_CHECK(cudaStreamWaitEvent(stream, side->e_fin, 0));   // join: everything is ordered on the caller's stream again
   return LSR_OK;
 }
