@@ -234,7 +234,10 @@ int lsr_debug_program_stats(const LsrWeights* w, int stage, int flags, int64_t* 
  * d_geo_feats/d_col_feats (N,C), d_weights (layout of w->blob), d_exposure_affine (12),
  * d_rays_o/d_rays_d (R,3, plain stores).  Unwanted sinks may be NULL (and unset in grad_flags).
  * With row_remap, d_geo_feats / d_col_feats are the (n_sel,C) gradients of geo_leaf / col_leaf; rows that
- * are not remapped are not trainable and receive nothing. */
+ * are not remapped are not trainable and receive nothing. 
+ * `scratch` must be the buffer the matching lsr_render_fwd call used (it holds the k-NN results).  In the colour stage part
+ * of the work runs on a library-owned side stream; everything is ordered on `stream` again when the call returns.
+ */
 int lsr_render_bwd(const LsrParams* prm, const void* grid_ws, const float* cloud_pos, int64_t n_points,
                    const float* rays_o, const float* rays_d, const float* gt_depth,
                    const double* r_query, int64_t n_rays, const float* geo_feats,

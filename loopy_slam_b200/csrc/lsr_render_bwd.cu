@@ -449,7 +449,7 @@ int launch_geo_bwd(const LsrParams* prm, const LsrWeights* w, const float* gt_de
 int launch_trunk_bwd(const LsrParams* prm, const LsrWeights* w, const float* gt_depth, int64_t n_rays, const float* affine,
                      const void* saved, void* scratch, const float* g_depth, const float* g_var, const float* g_rgb, int grad_flags,
                      float* d_weights, float* d_affine, const float* cloud_pos, const int32_t* row_remap, float* d_col_feats,
-                     int is_tracker, cudaStream_t stream, int phase);
+                     int is_tracker, cudaStream_t stream, int phase, cudaEvent_t ev_after_trunk);
 
 // Side stream of the colour-stage backward.  trunk_bwd_umma_kernel keeps one CTA per SM and 45 of the 148 SMs get a second
 // tile, so the other SMs idle for the second half of it; the geometry chain (independent of the colour trunk) is enqueued on a
@@ -526,11 +526,11 @@ extern "C" int lsr_render_bwd(const LsrParams* prm, const void* grid_ws, const f
   // With the rel-pos decoder and no pose gradient the scatter kernel needs nothing from the colour trunk (its feature scatter and
   // Fourier pose terms happen in the trunk kernel): the whole geometry side -- chain + scatter kernel -- runs on the side stream.
   const bool geo_side_only = side && (prm->flags & LSR_FLAG_REL_POS) && !(grad_flags & LSR_GRAD_RAYS) && !is_tracker;
-  if (stage == LSR_STAGE_COLOR) {   // weight re-layout, trunk kernel, rel-pos trig kernel (+ finalize when it stays on this stream)
+  if (stage == LSR_STAGE_COLOR) {   // trunk kernel, rel-pos trig kernel (+ finalize when there is no side stream)
     rc = launch_trunk_bwd(prm, w, gt_depth, n_rays, exposure_affine, saved, scratch, g_depth, g_var, g_rgb, grad_flags, d_weights,
-                          d_exposure_affine, cloud_pos, row_remap, d_col_feats, is_tracker, stream, (side && !geo_side_only) ? 1 : 0);
+                          d_exposure_affine, cloud_pos, row_remap, d_col_feats, is_tracker, stream, side ? 1 : 0,
+                          side ? side->e_trunk : nullptr);
     if (rc) return rc;
-    if (side && !geo_side_only) LSR_CUDA_CHECK(cudaEventRecord(side->e_trunk, stream));
   }
   {
     const bool need_e = (grad_flags & (LSR_GRAD_GEO_B | LSR_GRAD_GEO_W | LSR_GRAD_RAYS)) != 0;
@@ -541,11 +541,6 @@ extern "C" int lsr_render_bwd(const LsrParams* prm, const void* grid_ws, const f
     if (side && !geo_side_only) {
       LSR_CUDA_CHECK(cudaEventRecord(side->e_geo, side->s));
       LSR_CUDA_CHECK(cudaStreamWaitEvent(stream, side->e_geo, 0));          // the scatter kernel below needs the geometry planes
-      LSR_CUDA_CHECK(cudaStreamWaitEvent(side->s, side->e_trunk, 0));       // finalize: behind the trunk kernel, beside the scatter kernel
-      rc = launch_trunk_bwd(prm, w, gt_depth, n_rays, exposure_affine, saved, scratch, g_depth, g_var, g_rgb, grad_flags, d_weights,
-                            d_exposure_affine, cloud_pos, row_remap, d_col_feats, is_tracker, side->s, 2);
-      if (rc) return rc;
-      LSR_CUDA_CHECK(cudaEventRecord(side->e_fin, side->s));
     }
   }
   cudaStream_t scatter_stream = geo_side_only ? side->s : stream;
@@ -580,7 +575,13 @@ extern "C" int lsr_render_bwd(const LsrParams* prm, const void* grid_ws, const f
   render_bwd_kernel<<<grid, NT, smem, scatter_stream>>>(a);
   LSR_LAUNCHED(1);
   LSR_CUDA_CHECK(cudaGetLastError());
-  if (geo_side_only) LSR_CUDA_CHECK(cudaEventRecord(side->e_fin, side->s));
-  if (side) LSR_CUDA_CHECK(cudaStreamWaitEvent(stream, side->e_fin, 0));   // join: everything is ordered on the caller's stream again
+  if (side) {   // finalize: behind the trunk kernel, beside the rel-pos trig kernel / the scatter kernel; then join
+    LSR_CUDA_CHECK(cudaStreamWaitEvent(side->s, side->e_trunk, 0));
+    rc = launch_trunk_bwd(prm, w, gt_depth, n_rays, exposure_affine, saved, scratch, g_depth, g_var, g_rgb, grad_flags, d_weights,
+                          d_exposure_affine, cloud_pos, row_remap, d_col_feats, is_tracker, side->s, 2, nullptr);
+    if (rc) return rc;
+    LSR_CUDA_CHECK(cudaEventRecord(side->e_fin, side->s));
+    LSR_CUDA_CHECK(cudaStreamWaitEvent(stream, side->e_fin, 0));   // everything is ordered on the caller's stream again
+  }
   return LSR_OK;
 }

@@ -1201,9 +1201,9 @@ int sm_count();
 int launch_trunk_bwd(const LsrParams* prm, const LsrWeights* w, const float* gt_depth, int64_t n_rays, const float* affine,
                      const void* saved, void* scratch, const float* g_depth, const float* g_var, const float* g_rgb, int grad_flags,
                      float* d_weights, float* d_affine, const float* cloud_pos, const int32_t* row_remap, float* d_col_feats,
-                     int is_tracker, cudaStream_t stream, int phase) {
-  // phase 0: everything on `stream`; 1: all but the finalize kernel; 2: only the finalize kernel (the caller orders it behind
-  // the trunk kernel and may put it on another stream)
+                     int is_tracker, cudaStream_t stream, int phase, cudaEvent_t ev_after_trunk) {
+  // phase 0: weight images, trunk, trig, finalize on `stream`; 1: without the finalize kernel; 2: only the finalize kernel (the
+  // caller orders it behind the trunk kernel -- ev_after_trunk -- and may put it on another stream)
   const SavedLayout SL = saved_layout(n_rays, prm->n_surface, LSR_STAGE_COLOR, prm->flags);
   const ScratchLayout CL = scratch_layout(n_rays, prm->n_surface);
   if (SL.total >= (1ull << 32)) return LSR_ERR_UNSUPPORTED;   // ROp offsets are 32-bit float indices
@@ -1262,6 +1262,7 @@ int launch_trunk_bwd(const LsrParams* prm, const LsrWeights* w, const float* gt_
   trunk_bwd_umma_kernel<<<grid, BT, BWD_UMMA_SMEM, stream>>>(a);
   LSR_LAUNCHED(1);
   LSR_CUDA_CHECK(cudaGetLastError());
+  if (ev_after_trunk) LSR_CUDA_CHECK(cudaEventRecord(ev_after_trunk, stream));
   if (relpos && (g_cw || (grad_flags & LSR_GRAD_RAYS))) {
     TrigArgs t;
     t.saved = (const float*)saved; t.dqt = a.out_dqt; t.knn_pos = a.knn_pos; t.cloud = cloud_pos; t.blob = w->blob;
