@@ -500,7 +500,7 @@ def run_lsr(args, rank, world, local):
                 'note': f'{poses_host.numel() * 4} B of poses every step + the current RGB-D frame ({frame_bytes} B) once inside the '
                         f'timed region; keyframe images stay on the device as in the reference'},
         'gpu_launches': n_launch,
-        'roofline': {'bound': 'hbm', 'kernel': 'lsr_render_bwd (bwd_prep + trunk_bwd_umma + render_bwd + finalize kernels)' if dom_bwd
+        'roofline': {'bound': 'hbm', 'kernel': 'lsr_render_bwd (trunk_bwd_umma + geo_bwd_umma + render_bwd and their prep / trig / finalize kernels, two streams)' if dom_bwd
                      else 'lsr_render_fwd (sample_knn + render_fwd kernels)',
                      'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
                      'traffic': (traffic or {}).get('bwd_bytes' if dom_bwd else 'fwd_bytes'), 'peak_source': peak_src,
