@@ -375,29 +375,11 @@ __device__ __forceinline__ void prefetch_rows_l2(const float* base, int nrows, i
 //   Columns >= ncols_valid (multiple of 4) contribute zeros.  All NT threads must call; ends with
 //   __syncthreads() so callers may immediately overwrite A or reuse sBuf.
 //
-// Default implementation: tensor cores with an error-compensated 3xTF32 split.  Every fp32 operand
-// x is split into hi = x with the low 13 mantissa bits cleared (exactly what the tensor core reads of
-// an fp32 word) and lo = x - hi (exact), and each product is evaluated as hi*hi + lo*hi + hi*lo with
-// fp32 accumulation: relative error ~2^-21 per operand, i.e. fp32-grade (the 1e-4 parity contract
-// rules out single-pass TF32).  mma.sync.m16n8k8 (HMMA.1688.F32.TF32) measured on this
-// B200 at 478 MAC/clk/SM = 3.9x the FFMA pipe (tools/mma_rate.cu), i.e. 1.3x FFMA peak after the 3x
-// split but with ~4x fewer issued instructions and ~3x less shared-memory traffic per MAC.
-// The 8 warps tile the output as 2 (rows) x 4 (cols): warp (wm, wn) owns 16-row tiles wm, wm+2, ... and
-// 8-column tiles wn, wn+4, ...; the fragments are then re-laid-out through shared memory (32 rows per
-// pass) into the WIDE / NARROW per-thread register tiles every epilogue of the kernels is written for.
-// Define LSR_FFMA_GEMM to compile the plain FP32 FFMA version instead (A/B comparisons only).
+// Plain FP32 FFMA: the only callers left are the weight gradients of a TRAINABLE geometry decoder (render_bwd_kernel), a rare
+// path; every other contraction of the library runs on tcgen05 (lsr_render_fwd.cu, lsr_render_bwd_umma.cu, lsr_geo_bwd_umma.cu).
+// (Rounds 1-2 had an mma.sync 3xTF32 body here; it left with the last kernel that used it.)
 constexpr int SB_LD_PAD = 8;                         // chunk / staging row pitch = cols + 8 (== 8 mod 32)
 constexpr int SB_FLOATS = NSTAGE * KC * (128 + SB_LD_PAD);
-
-__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
-  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-__device__ __forceinline__ void split_tf32(float x, unsigned& hi, unsigned& lo) {
-  hi = __float_as_uint(x) & 0xffffe000u;
-  lo = __float_as_uint(x - __uint_as_float(hi));
-}
 
 // Feature rows may live in two places: the full (N,C) table, or -- for the rows the mapper is optimising --
 // a compact (n_sel,C) leaf block addressed through row_remap[id] >= 0 (replaces the per-iteration
@@ -423,233 +405,6 @@ __device__ __forceinline__ float* grad_row(float* __restrict__ d, const int32_t*
   return d + (size_t)idx * CDIM;
 }
 
-#ifndef LSR_RING_FASTPATH
-#define LSR_RING_FASTPATH 0   // 1: separate predicate-free copy loop for interior chunks (costs code size)
-#endif
-// One KC-row chunk of a streamed B operand -> ring stage (chunk % NSTAGE); always commits a group.
-template <int NCOLS>
-__device__ __forceinline__ void ring_prefetch_chunk(const float* __restrict__ B, int ldb, int Kc, int ncols_valid,
-                                                    float* sBuf, int chunk) {
-  constexpr int CLD_ = NCOLS + SB_LD_PAD;
-  constexpr int PIECES = KC * NCOLS / 4;   // float4 pieces per chunk
-  constexpr int PPR = NCOLS / 4;           // pieces per chunk row
-  const int nchunks = (Kc + KC - 1) / KC;
-  if (chunk < nchunks) {
-    float* dst = sBuf + (chunk % NSTAGE) * (KC * CLD_);
-    const int k0 = chunk * KC;
-    static_assert(PIECES % NT == 0 || PIECES < NT, "chunk pieces per thread");
-    constexpr int PER = (PIECES + NT - 1) / NT;           // float4 pieces per thread
-    constexpr int RSTEP = NT / PPR;                       // chunk rows covered by one sweep of the CTA
-    // thread -> (row0 + i * RSTEP, c4): the column is fixed, only the row advances
-    const int row0 = threadIdx.x / PPR, c4 = threadIdx.x % PPR;
-    const bool active = PIECES >= NT || threadIdx.x < PIECES;
-    float* d = dst + row0 * CLD_ + c4 * 4;
-    const float* src = B + (size_t)(k0 + row0) * ldb + c4 * 4;
-    if (LSR_RING_FASTPATH && k0 + KC <= Kc && ncols_valid == NCOLS) {   // interior chunk: no predicates
-      if (active) {
-#pragma unroll
-        for (int i = 0; i < PER; ++i) cp_async16(d + i * RSTEP * CLD_, src + (size_t)i * RSTEP * ldb);
-      }
-    } else if (active) {
-      const bool colok = c4 * 4 < ncols_valid;
-#pragma unroll
-      for (int i = 0; i < PER; ++i) {
-        if (colok && k0 + row0 + i * RSTEP < Kc) cp_async16(d + i * RSTEP * CLD_, src + (size_t)i * RSTEP * ldb);
-        else *reinterpret_cast<float4*>(d + i * RSTEP * CLD_) = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-  }
-  cp_async_commit();
-}
-// Issue the ring prologue (chunks 0 .. NSTAGE-2) of the NEXT streamed GEMM early -- typically right
-// before an epilogue -- so the L2 latency of its first weight chunk hides behind that epilogue.  The
-// matching mma_core / tile_gemm call must then pass PRE = true.  Only legal when the ring is idle
-// (i.e. after the previous mma_core / tile_gemm returned).
-template <int NCOLS>
-__device__ __forceinline__ void gemm_prefetch(const float* __restrict__ B, int ldb, int Kc, int ncols_valid, float* sBuf) {
-#pragma unroll
-  for (int st = 0; st < NSTAGE - 1; ++st) ring_prefetch_chunk<NCOLS>(B, ldb, Kc, ncols_valid, sBuf, st);
-}
-
-#ifndef LSR_FFMA_GEMM
-// Accumulator fragments of an M_OUT x NCOLS output tile, distributed over the 8 warps as 2 (rows) x 4
-// (cols): warp (wm, wn) owns 16-row tiles wm, wm+2, ... and 8-column tiles wn, wn+4, ...; inside a
-// fragment, thread (g = lane/4, t = lane%4) holds rows g, g+8 and columns 2t, 2t+1.
-template <int M_OUT, int NCOLS>
-struct FragTile {
-  static constexpr int MTT = M_OUT / 16, NTT = NCOLS / 8;
-  static constexpr int MI = (MTT + 1) / 2, NJ = (NTT + 3) / 4;
-  float c[MI][NJ][4];
-  __device__ __forceinline__ void zero() {
-#pragma unroll
-    for (int i = 0; i < MI; ++i)
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) { c[i][j][0] = 0.f; c[i][j][1] = 0.f; c[i][j][2] = 0.f; c[i][j][3] = 0.f; }
-  }
-  // row of the (c[i][j][2h], c[i][j][2h+1]) pair and its first column
-  __device__ __forceinline__ static int row(int i, int h) {
-    return (((threadIdx.x >> 5) >> 2) + 2 * i) * 16 + ((threadIdx.x & 31) >> 2) + 8 * h;
-  }
-  __device__ __forceinline__ static int col(int j) { return (((threadIdx.x >> 5) & 3) + 4 * j) * 8 + 2 * (threadIdx.x & 3); }
-  __device__ __forceinline__ static bool col_ok(int j) { return NTT % 4 == 0 || ((threadIdx.x >> 5) & 3) + 4 * j < NTT; }
-};
-
-// c += A . B on the tensor cores (3xTF32); semantics of the operands as in tile_gemm below.  Ends with
-// __syncthreads().  mvalid: output rows >= mvalid are not needed, their 16-row MMA tiles are skipped.
-template <int M_OUT, int NCOLS, bool A_ROWMAJOR, bool B_SMEM, bool PRE = false>
-__device__ __forceinline__ void mma_core(float (&c)[FragTile<M_OUT, NCOLS>::MI][FragTile<M_OUT, NCOLS>::NJ][4],
-                                         const float* __restrict__ A, int lda, int Kc, const float* __restrict__ B,
-                                         int ldb, int ncols_valid, float* sBuf, int mvalid) {
-  constexpr int MTT = M_OUT / 16, NTT = NCOLS / 8;
-  constexpr int MI = (MTT + 1) / 2, NJ = (NTT + 3) / 4;
-  constexpr int CLD_ = NCOLS + SB_LD_PAD;   // chunk row pitch
-  static_assert(NT == 256 && M_OUT % 32 == 0, "mma_core thread layout");
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int wm = warp >> 2, wn = warp & 3;
-
-  // one k8 step: A fragments from A (shared), B fragments from bs (shared, row pitch bld).
-  // The three partial products of one accumulator are issued in three separate sweeps over the
-  // (i, j) tiles so that consecutive HMMAs never depend on each other.
-  const float* Abase = A_ROWMAJOR ? A + (size_t)(wm * 16 + g) * lda + t : A + (size_t)t * lda + wm * 16 + g;
-  auto k8_step = [&](int k, const float* bs, int bld, int kb) {
-    unsigned bh[NJ][2], bl[NJ][2];
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      float b0 = 0.f, b1 = 0.f;
-      if ((NTT % 4 == 0 || wn + 4 * j < NTT) && (!B_SMEM || (wn + 4 * j) * 8 < ncols_valid)) {
-        const float* bp = bs + (size_t)(kb + t) * bld + (wn + 4 * j) * 8 + g;
-        b0 = bp[0];
-        b1 = bp[4 * bld];
-      }
-      split_tf32(b0, bh[j][0], bl[j][0]);
-      split_tf32(b1, bh[j][1], bl[j][1]);
-    }
-#pragma unroll
-    for (int i0 = 0; i0 < MI; i0 += 2) {
-      constexpr int IB = MI >= 2 ? 2 : 1;
-      if ((wm + 2 * i0) * 16 >= mvalid) break;             // warp-uniform: this and all later row tiles are unused
-      const bool second = IB > 1 && (wm + 2 * (i0 + 1)) * 16 < mvalid;
-      unsigned ah[IB][4], al[IB][4];
-#pragma unroll
-      for (int ii = 0; ii < IB; ++ii) {
-        if (ii == 1 && !second) break;
-        const int i = i0 + ii;
-        float a0, a1, a2, a3;
-        if (A_ROWMAJOR) {
-          const float* ap = Abase + (size_t)(32 * i) * lda + k;
-          a0 = ap[0]; a1 = ap[8 * lda]; a2 = ap[4]; a3 = ap[8 * lda + 4];
-        } else {
-          const float* ap = Abase + (size_t)k * lda + 32 * i;
-          a0 = ap[0]; a1 = ap[8]; a2 = ap[4 * lda]; a3 = ap[4 * lda + 8];
-        }
-        if (MTT % 2 && wm + 2 * i >= MTT) { a0 = 0.f; a1 = 0.f; a2 = 0.f; a3 = 0.f; }
-        split_tf32(a0, ah[ii][0], al[ii][0]); split_tf32(a1, ah[ii][1], al[ii][1]);
-        split_tf32(a2, ah[ii][2], al[ii][2]); split_tf32(a3, ah[ii][3], al[ii][3]);
-      }
-      if (IB == 1 || second) {
-#pragma unroll
-        for (int j = 0; j < NJ; ++j)
-#pragma unroll
-          for (int ii = 0; ii < IB; ++ii) mma_tf32_16x8x8(c[i0 + ii][j], al[ii], bh[j]);
-#pragma unroll
-        for (int j = 0; j < NJ; ++j)
-#pragma unroll
-          for (int ii = 0; ii < IB; ++ii) mma_tf32_16x8x8(c[i0 + ii][j], ah[ii], bl[j]);
-#pragma unroll
-        for (int j = 0; j < NJ; ++j)
-#pragma unroll
-          for (int ii = 0; ii < IB; ++ii) mma_tf32_16x8x8(c[i0 + ii][j], ah[ii], bh[j]);
-      } else {                                             // only the first row tile of the pair is live
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) mma_tf32_16x8x8(c[i0][j], al[0], bh[j]);
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) mma_tf32_16x8x8(c[i0][j], ah[0], bl[j]);
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) mma_tf32_16x8x8(c[i0][j], ah[0], bh[j]);
-      }
-    }
-  };
-
-  if constexpr (B_SMEM) {
-    __syncthreads();   // A / B tiles written by the caller must be visible
-    const int K8 = (Kc + 7) / 8;
-    for (int k8 = 0; k8 < K8; ++k8) k8_step(k8 * 8, B, ldb, k8 * 8);
-    __syncthreads();
-  } else {
-    constexpr int PIECES = KC * NCOLS / 4;   // float4 pieces per chunk
-    constexpr int PPR = NCOLS / 4;           // pieces per chunk row
-    const int nchunks = (Kc + KC - 1) / KC;
-    auto prefetch = [&](int chunk) { ring_prefetch_chunk<NCOLS>(B, ldb, Kc, ncols_valid, sBuf, chunk); };
-    if (!PRE) {
-#pragma unroll
-      for (int st = 0; st < NSTAGE - 1; ++st) prefetch(st);
-    }
-    for (int cix = 0; cix < nchunks; ++cix) {
-      cp_async_wait<NSTAGE - 2>();
-      __syncthreads();          // chunk visible to all; everyone is done with the previous chunk's buffer
-      prefetch(cix + NSTAGE - 1);
-      const float* sb = sBuf + (cix % NSTAGE) * (KC * CLD_);
-      const int k0 = cix * KC;
-#pragma unroll
-      for (int kb = 0; kb < KC; kb += 8)
-        if (k0 + kb < Kc) k8_step(k0 + kb, sb, CLD_, kb);
-    }
-    cp_async_wait<0>();
-    __syncthreads();
-  }
-
-}
-
-template <int TM, int TXN, int NCG, bool A_ROWMAJOR, bool B_SMEM, bool PRE = false>
-__device__ __forceinline__ void tile_gemm(float (&acc)[TM][NCG * 4], const float* __restrict__ A, int lda,
-                                          int Kc, const float* __restrict__ B, int ldb, int ncols_valid,
-                                          float* sBuf, int mvalid = 1 << 30) {
-  constexpr int NCOLS = TXN * 4 * NCG;      // 32 / 64 / 128 output columns
-  constexpr int RS = NT / TXN;
-  constexpr int M_OUT = TM * RS;            // 32 / 64 / 128 output rows
-  constexpr int MTT = M_OUT / 16, NTT = NCOLS / 8;
-  constexpr int NJ = (NTT + 3) / 4;
-  constexpr int CLD_ = NCOLS + SB_LD_PAD;
-  const int tid = threadIdx.x;
-  const int tx = tid % TXN, ty = tid / TXN;
-  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int wm = warp >> 2, wn = warp & 3;
-  FragTile<M_OUT, NCOLS> f;
-  f.zero();
-  mma_core<M_OUT, NCOLS, A_ROWMAJOR, B_SMEM, PRE>(f.c, A, lda, Kc, B, ldb, ncols_valid, sBuf, mvalid);
-  float (&c)[FragTile<M_OUT, NCOLS>::MI][NJ][4] = f.c;
-
-  // fragments -> per-thread register tiles, 32 output rows per pass through sBuf
-  float* stage = sBuf;
-#pragma unroll
-  for (int p = 0; p < M_OUT / 32; ++p) {
-    if (MTT % 2 == 0 || wm + 2 * p < MTT) {
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        const int nt = wn + 4 * j;
-        if (NTT % 4 == 0 || nt < NTT) {
-          *reinterpret_cast<float2*>(stage + (wm * 16 + g) * CLD_ + nt * 8 + 2 * t) = make_float2(c[p][j][0], c[p][j][1]);
-          *reinterpret_cast<float2*>(stage + (wm * 16 + g + 8) * CLD_ + nt * 8 + 2 * t) = make_float2(c[p][j][2], c[p][j][3]);
-        }
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < TM; ++i) {
-      if ((ty + RS * i) / 32 == p) {     // RS = 16: i in {2p, 2p+1};  RS = 32: i == p  (folds at compile time per i)
-        const int rl = ty + RS * i - 32 * p;
-#pragma unroll
-        for (int gq = 0; gq < NCG; ++gq) {
-          const float4 v = *reinterpret_cast<const float4*>(stage + rl * CLD_ + gq * TXN * 4 + tx * 4);
-          acc[i][gq * 4 + 0] += v.x; acc[i][gq * 4 + 1] += v.y; acc[i][gq * 4 + 2] += v.z; acc[i][gq * 4 + 3] += v.w;
-        }
-      }
-    }
-    __syncthreads();
-  }
-}
-#else
 template <int TM, int TXN, int NCG, bool A_ROWMAJOR, bool B_SMEM>
 __device__ __forceinline__ void tile_gemm(float (&acc)[TM][NCG * 4], const float* __restrict__ A, int lda,
                                           int Kc, const float* __restrict__ B, int ldb, int ncols_valid,
@@ -756,7 +511,6 @@ __device__ __forceinline__ void tile_gemm(float (&acc)[TM][NCG * 4], const float
   }
 }
 
-#endif  // LSR_FFMA_GEMM
 
 template <int TM, int NC>
 __device__ __forceinline__ void zero_acc(float (&acc)[TM][NC]) {

@@ -4,7 +4,6 @@
 // graph of Renderer.render_batch_ray (/root/reference/src/utils/Renderer.py:71-201) that the
 // reference differentiates with loss.backward() (src/Mapper.py:722, src/Tracker.py:193).
 // Math: SURVEY.md Appendix A ("Backward of step 10") + the chain rule through Appendix A steps 2-7.
-#define LSR_FFMA_GEMM 1   // the only GEMMs left in this file are the (rare) geometry-decoder weight gradients: plain FP32 FFMA, no mma.sync
 #include "lsr_render.cuh"
 
 namespace lsr {
