@@ -4,6 +4,8 @@
 // graph of Renderer.render_batch_ray (/root/reference/src/utils/Renderer.py:71-201) that the
 // reference differentiates with loss.backward() (src/Mapper.py:722, src/Tracker.py:193).
 // Math: SURVEY.md Appendix A ("Backward of step 10") + the chain rule through Appendix A steps 2-7.
+#include <mutex>
+
 #include "lsr_render.cuh"
 
 namespace lsr {
@@ -457,12 +459,14 @@ struct SideStream {
   cudaStream_t s = nullptr;
   cudaEvent_t e_fork = nullptr, e_geo = nullptr, e_trunk = nullptr, e_fin = nullptr;
   int state = 0;   // 0: not created, 1: ok, -1: creation failed (fall back to one stream)
+  std::mutex mu;   // the fork / join events are reused: enqueueing a backward is atomic per device
 };
 static SideStream* side_stream() {
   static SideStream side[64];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   SideStream& S = side[dev];
+  std::lock_guard<std::mutex> lock(S.mu);
   if (S.state == 0) {
     bool ok = cudaStreamCreateWithFlags(&S.s, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&S.e_fork, cudaEventDisableTiming) == cudaSuccess;
@@ -518,6 +522,8 @@ extern "C" int lsr_render_bwd(const LsrParams* prm, const void* grid_ws, const f
 
   const ScratchLayout CL = scratch_layout(n_rays, prm->n_surface);
   SideStream* side = stage == LSR_STAGE_COLOR ? side_stream() : nullptr;
+  std::unique_lock<std::mutex> side_lock;
+  if (side) side_lock = std::unique_lock<std::mutex>(side->mu);
   if (side) {   // fork: the side stream starts behind everything already enqueued on the caller's stream
     LSR_CUDA_CHECK(cudaEventRecord(side->e_fork, stream));
     LSR_CUDA_CHECK(cudaStreamWaitEvent(side->s, side->e_fork, 0));

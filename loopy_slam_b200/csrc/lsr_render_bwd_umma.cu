@@ -1217,7 +1217,7 @@ int launch_trunk_bwd(const LsrParams* prm, const LsrWeights* w, const float* gt_
     }
     return LSR_OK;
   }
-  static TrunkProgram P;   // host scratch (calls are serialised per process by the GIL / caller)
+  static thread_local TrunkProgram P;   // host scratch, too large for the stack of a small thread
   const bool relpos = (prm->flags & LSR_FLAG_REL_POS) != 0;
   build_trunk_program(w, SL, g_cw, relpos, &P);
   if (P.pack_floats > BWD_PACK_FLOATS_MAX - 128 || P.n_ops > MAX_ROPS) return LSR_ERR_UNSUPPORTED;
@@ -1229,7 +1229,7 @@ int launch_trunk_bwd(const LsrParams* prm, const LsrWeights* w, const float* gt_
   LSR_LAUNCHED(1);
   LSR_CUDA_CHECK(cudaGetLastError());
 
-  static TrunkArgs a;
+  static thread_local TrunkArgs a;
   a.prm = *prm;
   a.w = *w;
   a.gt_depth = gt_depth;
