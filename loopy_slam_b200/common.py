@@ -35,7 +35,7 @@ class _SampleRaysFn(torch.autograd.Function):
         j = torch.empty(n, dtype=torch.int64, device=dev)
         if c2w_f.device != dev:
             c2w_f = c2w_f.to(dev)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             check(lib().lsr_sample_rays(ptr(depth_img), ptr(color_img), H, W, fx, fy, cx, cy, ptr(c2w_f),
                                         c2w_f.shape[-1], ptr(pix), n, H0, H1, W0, W1, ptr(rays_o), ptr(rays_d),
                                         ptr(depth), ptr(color), ptr(i), ptr(j), stream_ptr(dev)), 'lsr_sample_rays')
@@ -57,7 +57,7 @@ class _SampleRaysFn(torch.autograd.Function):
         d12 = torch.empty(12, dtype=torch.float32, device=dev)
         g_o = g_o.contiguous().float() if g_o is not None else None
         g_d = g_d.contiguous().float() if g_d is not None else None
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             check(lib().lsr_sample_rays_bwd(ptr(g_o), ptr(g_d), ptr(i), ptr(j), i.shape[0], fx, fy, cx, cy, ptr(d12),
                                             stream_ptr(dev)), 'lsr_sample_rays_bwd')
         g = torch.zeros(ctx.c2w_shape, dtype=torch.float32, device=dev)
@@ -94,7 +94,7 @@ class _SampleRaysFilteredFn(torch.autograd.Function):
         c2w_f = c2w.to(torch.float32)
         if not c2w_f.is_contiguous():
             c2w_f = c2w_f.contiguous()
-        with torch.cuda.device(pix.device):
+        with _lib.on_device(pix.device):
             rays_o, rays_d, depth, color, i, j = _sample_rays_filtered(c2w_f, depth_img, color_img, pix, geom, depth_limit)
         ctx.geom = geom
         ctx.c2w_shape = c2w.shape
@@ -111,7 +111,7 @@ class _SampleRaysFilteredFn(torch.autograd.Function):
         d12 = torch.empty(12, dtype=torch.float32, device=dev)
         g_o = g_o.contiguous().float() if g_o is not None else None
         g_d = g_d.contiguous().float() if g_d is not None else None
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             check(lib().lsr_sample_rays_bwd(ptr(g_o), ptr(g_d), ptr(i), ptr(j), i.shape[0], fx, fy, cx, cy, ptr(d12),
                                             stream_ptr(dev)), 'lsr_sample_rays_bwd')
         g = torch.zeros(ctx.c2w_shape, dtype=torch.float32, device=dev)
@@ -146,7 +146,7 @@ def get_samples(H0, H1, W0, W1, n, H, W, fx, fy, cx, cy, c2w, depth, color, devi
             c2w_f = c2w.detach()
             if c2w_f.dtype != torch.float32 or not c2w_f.is_contiguous():
                 c2w_f = c2w_f.to(torch.float32).contiguous()
-            with torch.cuda.device(pix.device):
+            with _lib.on_device(pix.device):
                 out = _sample_rays_filtered(c2w_f, depth_f, color, pix, geom, depth_limit)
         return out if return_index else out[:4]
     out = _SampleRaysFn.apply(c2w, depth_f, color if fused_color else None, pix, geom)
@@ -198,7 +198,7 @@ class _PoseFn(torch.autograd.Function):
     def forward(ctx, cam):
         cam_f = cam.detach().to(torch.float32).contiguous()
         out = torch.empty(3, 4, dtype=torch.float32, device=cam.device)
-        with torch.cuda.device(cam.device):
+        with _lib.on_device(cam.device):
             check(lib().lsr_pose_fwd(ptr(cam_f), ptr(out), stream_ptr(cam.device)), 'lsr_pose_fwd')
         ctx.save_for_backward(cam_f)
         ctx.dtype = cam.dtype
@@ -208,7 +208,7 @@ class _PoseFn(torch.autograd.Function):
     def backward(ctx, g):
         cam_f, = ctx.saved_tensors
         d = torch.empty(7, dtype=torch.float32, device=cam_f.device)
-        with torch.cuda.device(cam_f.device):
+        with _lib.on_device(cam_f.device):
             check(lib().lsr_pose_bwd(ptr(cam_f), ptr(g.contiguous().float()), ptr(d), stream_ptr(cam_f.device)),
                   'lsr_pose_bwd')
         return d.to(ctx.dtype)

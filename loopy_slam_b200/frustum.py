@@ -15,6 +15,7 @@ def get_mask_from_c2w(cloud_pos, c2w, depth, H, W, fx, fy, cx, cy, edge=-4):
     kernels (float64 projection like the reference); CPU tensors (host-logic tests) take the torch restatement."""
     if cloud_pos.is_cuda:
         import ctypes
+        from . import _lib
         from ._lib import lib, check, ptr, stream_ptr
         dev = cloud_pos.device
         cloud = cloud_pos.detach()
@@ -31,7 +32,7 @@ def get_mask_from_c2w(cloud_pos, c2w, depth, H, W, fx, fy, cx, cy, edge=-4):
         check(lib().lsr_frustum_scratch_bytes(n, ctypes.byref(nb)), 'lsr_frustum_scratch_bytes')
         scratch = torch.empty(nb.value, dtype=torch.uint8, device=dev)
         mask = torch.empty(n, dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             check(lib().lsr_frustum_mask(ptr(cloud), n, arr, ptr(d), int(H), int(W), float(fx), float(fy), float(cx), float(cy),
                                          int(edge), ptr(scratch), ptr(mask), stream_ptr(dev)), 'lsr_frustum_mask')
         return torch.nonzero(mask, as_tuple=True)[0]

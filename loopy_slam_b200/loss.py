@@ -49,7 +49,7 @@ class _MapperLossFn(torch.autograd.Function):
         d_depth = torch.empty(R, dtype=torch.float32, device=dev)
         d_color = torch.empty(R, 3, dtype=torch.float32, device=dev) if use_color else None
         scratch = _scratch(dev)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             check(lib().lsr_mapper_loss(ptr(d), ptr(c), ptr(v), ptr(g), ptr(gc), R, LSR_STAGE[stage], float(w_color),
                                         ptr(scratch), ptr(loss3), ptr(d_depth), ptr(d_color), stream_ptr(dev)),
                   'lsr_mapper_loss')
@@ -87,7 +87,7 @@ class _TrackerLossFn(torch.autograd.Function):
         d_color = torch.empty(R, 3, dtype=torch.float32, device=dev)
         mask = torch.empty(R, dtype=torch.uint8, device=dev)
         scratch = _scratch(dev)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             st = stream_ptr(dev)
             check(lib().lsr_tracker_resid(ptr(d), ptr(u), ptr(g), R, int(bool(handle_dynamic)), ptr(scratch), ptr(tmp),
                                           st), 'lsr_tracker_resid')

@@ -36,7 +36,7 @@ class GridIndex:
         nbytes = ctypes.c_size_t()
         check(lib().lsr_grid_workspace_bytes(self.n, self.max_cells, ctypes.byref(nbytes)), 'lsr_grid_workspace_bytes')
         self.ws = torch.empty(nbytes.value, dtype=torch.uint8, device=cloud.device)
-        with torch.cuda.device(cloud.device):
+        with _lib.on_device(cloud.device):
             check(lib().lsr_grid_build(ptr(self.cloud), self.n, self.cell, self.max_cells, ptr(self.ws), nbytes.value,
                                        stream_ptr(cloud.device)), 'lsr_grid_build')
 
@@ -52,7 +52,7 @@ class GridIndex:
         if dynamic_radius is not None:
             rd = dynamic_radius.detach().to(torch.float64).reshape(-1).contiguous()
             assert rd.shape[0] == P, 'shape mis-match for input points and dynamic radius'
-        with torch.cuda.device(q.device):
+        with _lib.on_device(q.device):
             check(lib().lsr_knn_query(ptr(self.ws), ptr(q), ptr(rd), float(radius), P, ptr(D), ptr(I), ptr(n),
                                       stream_ptr(q.device)), 'lsr_knn_query')
         return D, I, n
@@ -161,7 +161,7 @@ class _RenderFn(torch.autograd.Function):
         rc.scratch = torch.empty(cb.value, dtype=torch.uint8, device=dev)
         rc.saved = torch.empty(sb.value, dtype=torch.uint8, device=dev) if need_bwd else None
         ev = _tick(rc.timing)
-        with torch.cuda.device(dev):      # the kernels launch on dev's stream: make it the current device
+        with _lib.on_device(dev):      # the kernels launch on dev's stream: make it the current device
             check(lib().lsr_render_fwd(ctypes.byref(rc.prm), ptr(rc.grid.ws), ptr(rc.grid.cloud), rc.grid.n,
                                        ptr(rays_o), ptr(rays_d), ptr(gt_depth), ptr(rc.r_query), ptr(far_zero),
                                        rc.far_group, ptr(rc.z_zero), R, ptr(geo_feats), ptr(col_feats), ptr(rc.remap), ptr(geo_leaf),
@@ -226,7 +226,7 @@ class _RenderFn(torch.autograd.Function):
         g_var = _f32c(g_var) if g_var is not None else None
         g_rgb = _f32c(g_rgb) if g_rgb is not None else None
         ev = _tick(rc.timing)
-        with torch.cuda.device(dev):      # the kernels launch on dev's stream: make it the current device
+        with _lib.on_device(dev):      # the kernels launch on dev's stream: make it the current device
             check(lib().lsr_render_bwd(ctypes.byref(rc.prm), ptr(rc.grid.ws), ptr(rc.grid.cloud), rc.grid.n,
                                        ptr(rays_o), ptr(rays_d), ptr(gt_depth), ptr(rc.r_query), R, ptr(geo_feats),
                                        ptr(col_feats), ptr(rc.remap), ptr(geo_leaf), ptr(col_leaf),
@@ -333,7 +333,7 @@ def fused_render(renderer, npc, decoders, rays_d, rays_o, stage, gt_depth, npc_g
         gt = _f32c(gt_depth.detach().reshape(-1))
         fgroup = int(far_group) if far_group else max(R, 1)
         far = torch.empty((R + fgroup - 1) // fgroup if R else 1, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             check(lib().lsr_far_bound(ptr(gt), R, fgroup, ptr(far), stream_ptr(dev)), 'lsr_far_bound')
     geo = _f32c(npc_geo_feats)
     col = _f32c(npc_col_feats) if npc_col_feats is not None else None
@@ -511,7 +511,7 @@ class Renderer(object):
             R = g.shape[0]
             g32 = _f32c(g)
             far = torch.empty(1, dtype=torch.float32, device=g32.device)
-            with torch.cuda.device(g32.device):
+            with _lib.on_device(g32.device):
                 check(lib().lsr_far_bound(ptr(g32), R, max(R, 1), ptr(far), stream_ptr(g32.device)), 'lsr_far_bound')
             z0, not_near = npc.sample_near_pcl(rays_o[zero].clone().detach(), rays_d[zero].clone().detach(),
                                                self.near_end, float(far.item()), self.N_surface)   # Renderer.py:151-153
@@ -541,7 +541,7 @@ class Renderer(object):
             return None
         G = self.ray_batch_size
         far = torch.empty((R + G - 1) // G, dtype=torch.float32, device=g32.device)
-        with torch.cuda.device(g32.device):
+        with _lib.on_device(g32.device):
             check(lib().lsr_far_bound(ptr(g32), R, G, ptr(far), stream_ptr(g32.device)), 'lsr_far_bound')
         far_h = far.cpu()
         z_zero = torch.zeros(R, self.N_surface, dtype=torch.float32, device=g32.device)
