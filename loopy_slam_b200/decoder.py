@@ -168,6 +168,8 @@ class WeightBlob:
             self.numels.append(n)
             off += (n + 3) // 4 * 4
         self.n_elems = off
+        self.shapes = None      # filled by the renderer on first use (parameter shapes / strides, for the gradient views)
+        self.strides = None
         self.flat = None
         self.struct = None
         self.geo_w_idx = [k for k, e in enumerate(ent) if e[0].startswith('g_') and e[0] != 'g_B']

@@ -85,6 +85,9 @@ def _grid_for(npc, cloud_pos, cell, cache):
     return cache.get(cloud_pos, cell)
 
 
+_RELPOS_FIELDS = ('c_Brel', 'c_nb1_w', 'c_nb1_b', 'c_nb2_w', 'c_nb2_b')
+
+
 # ----------------------------------------------------------------------------- fused render op
 class _RenderCtx:
     """Per-call constants shared by forward and backward."""
@@ -170,7 +173,9 @@ class _RenderFn(torch.autograd.Function):
                                        ptr(rc.saved), ptr(rc.scratch), stream_ptr(dev)), 'lsr_render_fwd')
         _tock(rc.timing, 'fwd', ev)
         ctx.rc = rc
-        ctx.param_shapes = [p.shape for p in params]
+        if rc.blob.shapes is None:      # shapes / contiguous strides of the parameters, once per blob
+            rc.blob.shapes = [tuple(p.shape) for p in params]
+            rc.blob.strides = [tuple(p.stride()) for p in params]
         ctx.save_for_backward(rays_o, rays_d, gt_depth, geo_feats, col_feats, affine, geo_leaf, col_leaf)
         ctx.mark_non_differentiable(valid)
         return depth, var, rgb, valid
@@ -241,14 +246,17 @@ class _RenderFn(torch.autograd.Function):
         # whole colour decoder into the optimiser while 40 % of the iterations render stage 'geometry'), and its bias
         # correction would then be off when the colour stage starts (caught by tests/test_gpu_trajectory.py).
         relpos = bool(rc.prm.flags & _lib.FLAG_REL_POS)
-        pgrads = []
-        for k, (off, n, t) in enumerate(zip(blob.offsets, blob.numels, ctx.param_shapes)):
-            field = blob.entries[k][0]
-            used = field.startswith('g_') or (rc.stage == 1 and (relpos or field not in ('c_Brel', 'c_nb1_w', 'c_nb1_b', 'c_nb2_w', 'c_nb2_b')))
-            if pneed[k] and d_w is not None and used:
-                pgrads.append(d_w[off:off + n].view(t))
-            else:
-                pgrads.append(None)
+        pgrads = [None] * len(blob.offsets)
+        if d_w is not None:
+            base = d_w.storage_offset()
+            color = rc.stage == 1
+            for k in range(len(pgrads)):
+                if not pneed[k]:
+                    continue
+                field = blob.entries[k][0]
+                if field[0] != 'g' and not (color and (relpos or field not in _RELPOS_FIELDS)):
+                    continue
+                pgrads[k] = d_w.as_strided(blob.shapes[k], blob.strides[k], base + blob.offsets[k])   # one op per view
         if sub:
             return (None, d_o if need[1] else None, d_d if need[2] else None, None, None, None, d_aff, None,
                     d_geo, d_col, *pgrads)
