@@ -3,7 +3,10 @@ store, /root/reference/src/neural_point.py -- add_neural_points :1557-1631, chec
 :1220-1250, update_fragments :1138-1218 (point / feature bookkeeping only), get_cloud_pos :1252-1281, get_geo_feats /
 get_col_feats :1435-1510 -- with the FAISS index replaced by the exact k-NN of oracle/knn.py (the index holds the active
 segment's points: inherited ones first, :1247-1248, then every insertion, :1627).  Python lists as in the reference.
-"parity unpinned" against FAISS itself (third-party, approximate); everything else follows the cited lines."""
+PINNED: tests/golden/make_golden_point_store.py runs the REAL reference methods (as unbound functions on a stand-in object
+with an exhaustive-search index) over a 20-frame stream for both segment strategies; tests/test_oracle_golden.py checks this
+restatement against those vectors bit for bit (positions, masks, segment boundaries, features, merged tables).  Only the
+approximate FAISS IVF search itself stays "parity unpinned" (third-party, absent)."""
 import numpy as np
 import torch
 

@@ -350,6 +350,43 @@ def test_segmented_point_store_matches_oracle():
     assert npc.index_ntotal() == orc_.merged('npc').shape[0]
 
 
+@pytest.mark.parametrize('strategy', ['rot_trans', 'fixed'])
+def test_point_store_matches_reference_golden(strategy):
+    """The device point store against vectors minted from the REAL reference methods (tests/golden/make_golden_point_store.py):
+    same kept samples, segment boundaries, inherited-point masks, inserted positions and merged end-of-run cloud."""
+    import os
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'point_store.npz'))
+    H, W, fx, fy, cx, cy = G['intr']
+    rel_trans, rot_cos, fixed = G[f'{strategy}_cfg']
+    cfg = L.default_cfg('replica')
+    cfg['mapping'].update(device=DEV, segment_strategy=strategy, fixed_segment_size=int(fixed), segment_rel_trans=float(rel_trans),
+                          segment_rot_cos=float(rot_cos))
+
+    class Slam:
+        pass
+    Slam.H, Slam.W, Slam.fx, Slam.fy, Slam.cx, Slam.cy = int(H), int(W), float(fx), float(fy), float(cx), float(cy)
+    npc = L.NeuralPointCloud(cfg, Slam)
+    kept = []
+    for fid in G[f'{strategy}_fids']:
+        t = lambda k: torch.from_numpy(G[f'{strategy}_{k}{fid}'])
+        o = t('o').to(DEV)
+        kept.append(int(npc.add_neural_points(o, t('d').to(DEV), t('g').to(DEV), torch.zeros_like(o), idx=torch.tensor(int(fid)),
+                                              cur_c2w=t('c2w'))))
+    assert kept == G[f'{strategy}_kept'].tolist()
+    nseg = int(G[f'{strategy}_nseg'])
+    assert len(npc.fragments) == nseg
+    for k, seg in enumerate(npc.fragments):
+        ref = G[f'{strategy}_seg{k}_npc']
+        assert [seg.start_idx, seg.n_inherited] == G[f'{strategy}_seg{k}_start'].tolist() and seg.n == ref.shape[0]
+        torch.testing.assert_close(seg.pos[:seg.n].cpu().double(), torch.from_numpy(ref), rtol=0, atol=1e-6)
+        m = G[f'{strategy}_seg{k}_mask']
+        if k < nseg - 1:
+            assert torch.equal(seg.mask.cpu(), torch.from_numpy(m))
+        else:
+            assert seg.mask is None and m.size == 0
+    np.testing.assert_allclose(npc.get_cloud_pos(True).cpu().numpy(), G[f'{strategy}_end_pos'], rtol=1e-5, atol=1e-6)
+
+
 def test_dynamic_radius_map_matches_numpy_restatement():
     """vs a scipy/numpy restatement of skimage 0.19.3 rgb2gray + sobel_h/sobel_v (reflect) + interp1d
     (src/Tracker.py:243-258).  skimage itself is not installed: pinned to its documented kernels."""

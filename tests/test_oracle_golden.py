@@ -1,5 +1,7 @@
 """CPU: pin the oracle restatement (oracle/render.py, oracle/knn.py) against golden vectors
 produced by the REAL reference code (tests/golden/make_golden.py)."""
+import os
+
 import pytest
 import torch
 
@@ -119,3 +121,43 @@ def test_oracle_sampling_matches_reference_golden():
                                              c2w, depth, color, depth_filter=bool(filt), depth_limit=None if lim < 0 else lim)
         for got, name in ((o, 'o'), (d, 'd'), (sd, 'sd'), (sc, 'sc'), (i, 'i'), (j, 'j')):
             assert torch.equal(got, torch.from_numpy(z[f'{name}{k}'])), (k, name)
+
+
+@pytest.mark.parametrize('strategy', ['rot_trans', 'fixed'])
+def test_oracle_point_store_matches_reference_golden(strategy):
+    """oracle/point_store.py vs the REAL reference methods (add_neural_points, check_index, init_segment, update_fragments,
+    get_*(end=True) of /root/reference/src/neural_point.py) run on a 20-frame stream with an exhaustive-search index
+    (tests/golden/make_golden_point_store.py): same kept samples, segment boundaries, inherited-point masks, positions,
+    features (same generator draws) and merged end-of-run tables."""
+    import numpy as np
+    import torch
+    from oracle.point_store import PointStoreOracle
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'point_store.npz'))
+    H, W, fx, fy, cx, cy = G['intr']
+    rel_trans, rot_cos, fixed = G[f'{strategy}_cfg']
+    st = PointStoreOracle(int(H), int(W), fx, fy, cx, cy, segment_strategy=strategy, fixed_segment_size=int(fixed),
+                          segment_rel_trans=rel_trans, segment_rot_cos=rot_cos, c_dim=4)
+    torch.manual_seed(77)
+    feat = lambda p, which: torch.zeros([p.shape[0], 4]).normal_(mean=0, std=0.1)     # neural_point.py:1614-1617, geo then col
+    kept = []
+    for fid in G[f'{strategy}_fids']:
+        t = lambda k: torch.from_numpy(G[f'{strategy}_{k}{fid}'])
+        kept.append(st.add_neural_points(t('o'), t('d'), t('g'), int(fid), t('c2w'), feat_fn=feat))
+    assert kept == G[f'{strategy}_kept'].tolist()
+    keys = list(st.fragments_dict.keys())
+    assert len(keys) == int(G[f'{strategy}_nseg']) >= 5
+    for k, key in enumerate(keys):
+        f = st.fragments_dict[key]
+        assert int(key.split('_')[-1]) == int(G[f'{strategy}_seg{k}_name'])
+        assert [f['start_idx'], f['idx_start_segment_features']] == G[f'{strategy}_seg{k}_start'].tolist()
+        np.testing.assert_array_equal(np.array(f['npc'], dtype=np.float64), G[f'{strategy}_seg{k}_npc'])
+        np.testing.assert_array_equal(f['geo_feats'].numpy(), G[f'{strategy}_seg{k}_geo'])
+        np.testing.assert_array_equal(f['col_feats'].numpy(), G[f'{strategy}_seg{k}_col'])
+        m = G[f'{strategy}_seg{k}_mask']
+        if k == len(keys) - 1:
+            assert f['mask'] is None and m.size == 0
+        else:
+            np.testing.assert_array_equal(np.asarray(f['mask']), m)
+    np.testing.assert_allclose(st.merged('npc'), G[f'{strategy}_end_pos'], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(st.merged('geo_feats'), G[f'{strategy}_end_geo'], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(st.merged('col_feats'), G[f'{strategy}_end_col'], rtol=1e-6, atol=1e-7)
