@@ -1,5 +1,7 @@
 """ORACLE (test infrastructure, never imported by the product): Mapper.get_mask_from_c2w restated with the reference's own
-numpy + cv2 calls (/root/reference/src/Mapper.py:165-217), cv2.remap included (cv2 is available on both boxes)."""
+numpy + cv2 calls (/root/reference/src/Mapper.py:165-217), cv2.remap included (cv2 is available on both boxes).
+PINNED: tests/golden/make_golden_frustum.py runs the REAL Mapper.get_mask_from_c2w / filter_point_before_add (unbound, on a
+stand-in object) and tests/test_oracle_golden.py checks this restatement against those row ids bit for bit."""
 import numpy as np
 
 

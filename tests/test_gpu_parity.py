@@ -180,6 +180,24 @@ def test_frustum_selection_kernel_matches_reference_restatement():
         assert got.dtype == torch.int64 and bool((got[1:] > got[:-1]).all())     # sorted row ids, like np.where
 
 
+def test_frustum_kernel_matches_reference_golden():
+    """lsr_frustum_mask vs row ids minted from the REAL Mapper.get_mask_from_c2w (tests/golden/make_golden_frustum.py): the
+    only admissible differences are points whose bilinear depth test sits on the 0.5 m threshold within fp32 rounding."""
+    import os
+    from loopy_slam_b200.frustum import get_mask_from_c2w, filter_point_before_add
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'frustum.npz'))
+    H, W, fx, fy, cx, cy = G['intr']
+    cloud = torch.from_numpy(G['cloud']).to(DEV)
+    for k, (fid, edge) in enumerate(G['cases']):
+        got = get_mask_from_c2w(cloud, torch.from_numpy(G[f'c2w{k}']), torch.from_numpy(G[f'depth{k}']).to(DEV), int(H), int(W),
+                                fx, fy, cx, cy, edge=int(edge))
+        a, b = set(got.cpu().tolist()), set(G[f'idx{k}'].tolist())
+        assert len(b) > 300 and len(a ^ b) <= 0.002 * cloud.shape[0], (int(fid), len(a), len(b), len(a ^ b))
+    m = filter_point_before_add(torch.from_numpy(G['f_o']).to(DEV), torch.from_numpy(G['f_d']).to(DEV),
+                                torch.from_numpy(G['f_g']).to(DEV), torch.from_numpy(G['f_prev']), int(H), int(W), fx, fy, cx, cy)
+    assert torch.equal(m.cpu(), torch.from_numpy(G['f_mask']))
+
+
 def test_render_img_matches_tiled_oracle():
     """render_img (one fused launch, per-3000-ray far statistics) vs the oracle run tile by tile."""
     from oracle import render as orc

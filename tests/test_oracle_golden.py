@@ -161,3 +161,28 @@ def test_oracle_point_store_matches_reference_golden(strategy):
     np.testing.assert_allclose(st.merged('npc'), G[f'{strategy}_end_pos'], rtol=0, atol=1e-12)
     np.testing.assert_allclose(st.merged('geo_feats'), G[f'{strategy}_end_geo'], rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(st.merged('col_feats'), G[f'{strategy}_end_col'], rtol=1e-6, atol=1e-7)
+
+
+def test_oracle_frustum_matches_reference_golden():
+    """oracle/frustum.py and the package's host path vs the REAL Mapper.get_mask_from_c2w / filter_point_before_add
+    (/root/reference/src/Mapper.py:137-217, numpy + cv2.remap; tests/golden/make_golden_frustum.py)."""
+    import numpy as np
+    import torch
+    from oracle.frustum import get_mask_from_c2w as oracle_mask
+    from loopy_slam_b200.frustum import get_mask_from_c2w, filter_point_before_add
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'frustum.npz'))
+    H, W, fx, fy, cx, cy = G['intr']
+    H, W = int(H), int(W)
+    cloud = G['cloud']
+    for k, (fid, edge) in enumerate(G['cases']):
+        ref = G[f'idx{k}']
+        assert ref.size > 300
+        got = oracle_mask(cloud, G[f'c2w{k}'], G[f'depth{k}'], H, W, fx, fy, cx, cy, int(edge))
+        np.testing.assert_array_equal(np.asarray(got), ref)                      # the restatement: bit-exact row ids
+        host = get_mask_from_c2w(torch.from_numpy(cloud), torch.from_numpy(G[f'c2w{k}']), torch.from_numpy(G[f'depth{k}']), H, W,
+                                 fx, fy, cx, cy, edge=int(edge))                 # torch path for CPU tensors
+        a, b = set(host.tolist()), set(ref.tolist())
+        assert len(a ^ b) <= 0.002 * cloud.shape[0], (int(fid), len(a), len(b), len(a ^ b))
+    m = filter_point_before_add(torch.from_numpy(G['f_o']), torch.from_numpy(G['f_d']), torch.from_numpy(G['f_g']),
+                                torch.from_numpy(G['f_prev']), H, W, fx, fy, cx, cy)
+    assert torch.equal(m.cpu(), torch.from_numpy(G['f_mask']))
