@@ -71,7 +71,7 @@ def make_store(npm, strategy, H, W, fx, fy, cx, cy, rel_trans, rot_cos, fixed_si
     s.add_orb_features = lambda *a, **k: None
     C = npm.NeuralPointCloud
     for name in ('check_index', 'init_segment', 'update_fragments', 'find_neighbors_faiss', 'get_cloud_pos', 'get_geo_feats',
-                 'get_col_feats', 'add_neural_points'):
+                 'get_col_feats', 'add_neural_points', 'sample_near_pcl'):
         setattr(s, name, types.MethodType(getattr(C, name), s))
     return s
 
@@ -118,6 +118,14 @@ def main():
         finally:
             torch.Tensor.cuda = _cuda
         print(strategy, 'segments', len(keys), 'kept', kept, 'end points', out[f'{strategy}_end_pos'].shape)
+        if strategy == 'rot_trans':
+            # sample_near_pcl :1734-1786 on the active index (what the renderer asks for the zero-depth rays of a batch)
+            o, d, g, _ = sample_batch(room, [57, 30], 40, seed=9)
+            far = torch.max(g * 1.2)
+            z, invalid = s.sample_near_pcl(o, d, 0.3, far, 5)
+            out.update(snp_o=o.numpy(), snp_d=d.numpy(), snp_far=far.numpy(), snp_z=z.numpy(), snp_invalid=invalid.numpy(),
+                       snp_cloud=s.index.x.numpy())
+            print('sample_near_pcl: invalid', int(invalid.sum()), 'of', invalid.numel())
     np.savez_compressed(OUT, **out)
     print('wrote', OUT, os.path.getsize(OUT), 'bytes')
 

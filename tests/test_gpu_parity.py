@@ -198,6 +198,21 @@ def test_frustum_kernel_matches_reference_golden():
     assert torch.equal(m.cpu(), torch.from_numpy(G['f_mask']))
 
 
+def test_sample_near_pcl_matches_reference_golden():
+    """NeuralPointCloud.sample_near_pcl on the device (grid k-NN, torch glue) vs the REAL reference method on the same cloud
+    (tests/golden/make_golden_point_store.py): same invalid rays, sample depths to fp32 rounding of the float64 linspace."""
+    import os
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'point_store.npz'))
+    cfg = L.default_cfg('replica')
+    cfg['mapping']['device'] = DEV
+    npc = L.NeuralPointCloud(cfg, device=DEV)
+    npc.set_cloud(torch.from_numpy(G['snp_cloud']).to(DEV))
+    z, invalid = npc.sample_near_pcl(torch.from_numpy(G['snp_o']).to(DEV), torch.from_numpy(G['snp_d']).to(DEV), 0.3,
+                                     float(G['snp_far']), 5)
+    assert torch.equal(invalid.cpu(), torch.from_numpy(G['snp_invalid']))
+    torch.testing.assert_close(z.cpu(), torch.from_numpy(G['snp_z']), rtol=0, atol=2e-7)
+
+
 def test_render_img_matches_tiled_oracle():
     """render_img (one fused launch, per-3000-ray far statistics) vs the oracle run tile by tile."""
     from oracle import render as orc

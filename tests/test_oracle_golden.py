@@ -186,3 +186,17 @@ def test_oracle_frustum_matches_reference_golden():
     m = filter_point_before_add(torch.from_numpy(G['f_o']), torch.from_numpy(G['f_d']), torch.from_numpy(G['f_g']),
                                 torch.from_numpy(G['f_prev']), H, W, fx, fy, cx, cy)
     assert torch.equal(m.cpu(), torch.from_numpy(G['f_mask']))
+
+
+def test_oracle_sample_near_pcl_matches_reference_golden():
+    """oracle.render.sample_near_pcl vs the REAL NeuralPointCloud.sample_near_pcl (neural_point.py:1734-1786) run on the active
+    index of the golden stream (exhaustive search): sample depths bit for bit, same invalid rays."""
+    import numpy as np
+    import torch
+    from oracle import render as orc
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'point_store.npz'))
+    z, invalid = orc.sample_near_pcl(torch.from_numpy(G['snp_o']), torch.from_numpy(G['snp_d']), 0.3, float(G['snp_far']), 5,
+                                     torch.from_numpy(G['snp_cloud']), 0.08)
+    assert 0 < int(G['snp_invalid'].sum()) < G['snp_invalid'].size
+    np.testing.assert_array_equal(invalid.numpy(), G['snp_invalid'])
+    np.testing.assert_array_equal(z.numpy(), G['snp_z'])
