@@ -515,7 +515,6 @@ class Renderer(object):
             g = gt_depth.detach().reshape(-1)
             zero = ~(g > 0)
         if zero is not None and bool(zero.any()):
-            from . import _lib as lb
             R = g.shape[0]
             g32 = _f32c(g)
             far = torch.empty(1, dtype=torch.float32, device=g32.device)
